@@ -1,0 +1,344 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference on seeded inputs.
+
+Runs only in the build container (needs /root/reference); the fixtures it writes
+are committed, and nothing at test/bench time reads /root/reference.
+
+    python tests/golden/make_golden.py
+
+Third-party imports the reference needs but this image lacks are stubbed in
+sys.modules: matplotlib, fvcore, pycocotools.  The
+pycocotools stub is NOT the real rasteriser: its ``iou`` is an independent
+pure-Python exact polygon-clipping IoU, used only to pin nms_rotbb's CONTROL FLOW
+(utils/bbox_ops.py:276-306) -- rotated IoU values remain "parity unpinned".
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = os.environ.get('MYDET_REFERENCE', '/root/reference')
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+# ----------------------------------------------------------------------------- stubs
+def _poly_area(p):
+    return 0.5 * sum(p[i][0] * p[(i + 1) % len(p)][1] - p[(i + 1) % len(p)][0] * p[i][1]
+                     for i in range(len(p)))
+
+
+def _clip(subject, clipper):
+    """Sutherland-Hodgman, pure Python, independent of oracle/rotiou.c."""
+    sgn = 1.0 if _poly_area(clipper) >= 0 else -1.0
+    out = list(subject)
+    for i in range(len(clipper)):
+        a, b = clipper[i], clipper[(i + 1) % len(clipper)]
+        ex, ey = b[0] - a[0], b[1] - a[1]
+        src, out = out, []
+        if not src:
+            break
+        for k in range(len(src)):
+            p, q = src[k], src[(k + 1) % len(src)]
+            dp = sgn * (ex * (p[1] - a[1]) - ey * (p[0] - a[0]))
+            dq = sgn * (ex * (q[1] - a[1]) - ey * (q[0] - a[0]))
+            if dp >= 0:
+                out.append(p)
+            if (dp >= 0) != (dq >= 0):
+                t = dp / (dp - dq)
+                out.append((p[0] + t * (q[0] - p[0]), p[1] + t * (q[1] - p[1])))
+    return out
+
+
+def _poly_iou(v1, v2):
+    p1 = [(v1[2 * i], v1[2 * i + 1]) for i in range(4)]
+    p2 = [(v2[2 * i], v2[2 * i + 1]) for i in range(4)]
+    inter_poly = _clip(p1, p2)
+    inter = abs(_poly_area(inter_poly)) if len(inter_poly) >= 3 else 0.0
+    union = abs(_poly_area(p1)) + abs(_poly_area(p2)) - inter
+    return inter / union if union > 0 else 0.0
+
+
+def install_stubs():
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    mask = mod('pycocotools.mask',
+               frPyObjects=lambda polys, h, w: polys,
+               iou=lambda d, g, crowd: np.array([[_poly_iou(a, b) for b in g] for a in d], dtype=np.float64))
+    mod('pycocotools', mask=mask)
+    mod('pycocotools.coco', COCO=object)
+    mod('pycocotools.cocoeval', COCOeval=object)
+    plt = mod('matplotlib.pyplot')
+    mod('matplotlib', pyplot=plt)
+    nn = mod('fvcore.nn', smooth_l1_loss=None, sigmoid_focal_loss=None)
+    mod('fvcore', nn=nn)
+
+
+def import_reference():
+    install_stubs()
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import warnings
+    warnings.filterwarnings('ignore')
+
+
+# ----------------------------------------------------------------------------- inputs
+def head_views(gen, n_b, n_a, n_h, n_w, n_p, n_c, conf_mu=0.0, separate=False):
+    """NCHW head output + the permuted views the reference heads hand to the det layers
+    (models/rpns.py:29-41 for the YOLO head, :175-189 for the EfficientDet head)."""
+    if separate:  # EfDetHead: bbox tensor and (conf+class) tensor, nA == 1
+        bb = torch.randn(n_b, n_p, n_h, n_w, generator=gen) * 0.5
+        cc = torch.randn(n_b, 1 + n_c, n_h, n_w, generator=gen) * 1.5
+        cc[:, 0] += conf_mu
+        cc[:, 1:] -= 1.0
+        raw = {'bbox': bb.permute(0, 2, 3, 1), 'conf': cc.permute(0, 2, 3, 1)[..., 0:1],
+               'class': cc.permute(0, 2, 3, 1)[..., 1:]}
+        return {'bbox_nchw': bb, 'cls_nchw': cc}, raw
+    ch = n_p + 1 + n_c
+    t = torch.randn(n_b, n_a * ch, n_h, n_w, generator=gen)
+    v = t.view(n_b, n_a, ch, n_h, n_w)
+    v[:, :, :n_p] *= 0.5
+    v[:, :, n_p] = v[:, :, n_p] * 1.5 + conf_mu
+    v[:, :, n_p + 1:] = v[:, :, n_p + 1:] * 1.5 - 1.0
+    raw = {'bbox': v[:, :, 0:n_p].permute(0, 1, 3, 4, 2),
+           'conf': v[:, :, n_p:n_p + 1].permute(0, 1, 3, 4, 2),
+           'class': v[:, :, n_p + 1:].permute(0, 1, 3, 4, 2)}
+    return {'nchw': t}, raw
+
+
+def np_(d):
+    return {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in d.items()}
+
+
+def save(name, **arrays):
+    path = os.path.join(OUT, name + '.npz')
+    np.savez_compressed(path, **np_(arrays))
+    print(f'{name}: {os.path.getsize(path) / 1024:.1f} kB')
+
+
+YOLO_ANCHORS = [[10, 13], [16, 30], [33, 23], [30, 61], [62, 45], [59, 119], [116, 90], [156, 198], [373, 326]]
+RAPID_ANCHORS = [[18.7807, 33.4659], [28.8912, 61.7536], [48.6849, 68.3897], [45.0668, 101.4673],
+                 [63.0952, 113.5382], [81.3909, 134.4554], [91.7364, 144.9949], [137.5189, 178.4791],
+                 [194.4429, 250.7985]]
+IDX3 = [[0, 1, 2], [3, 4, 5], [6, 7, 8]]
+
+
+# ----------------------------------------------------------------------------- cases
+def gen_decode():
+    from models.detlayers.yolov3 import YOLOLayer
+    from models.detlayers.fcos2 import FCOSLayer as FCOS2Layer, FCOS_ATSS_Layer
+    from models.detlayers.fcos import FCOSLayer as FCOS1Layer
+    from models.detlayers.rapid import RAPiDLayer
+    from models.detlayers.retinanet import RetinaLayer
+    from models.detlayers.uv5 import DetectLayer
+
+    gen = torch.Generator().manual_seed(1001)
+    img_hw = (96, 128)
+    strides = [8, 16, 32]
+    out = {}
+    # --- YOLOv3, 3 anchors, 5 classes; level 2 is 3x4 (odd plane, exercises the scalar path)
+    cfg = {'model.yolo.anchors': YOLO_ANCHORS, 'model.yolo.anchor_indices': IDX3,
+           'model.yolo.anchor.negative_threshold': 0.7, 'model.fpn.out_strides': strides,
+           'general.num_class': 5}
+    for li, s in enumerate(strides):
+        store, raw = head_views(gen, 2, 3, img_hw[0] // s, img_hw[1] // s, 4, 5)
+        p, _ = YOLOLayer(li, cfg)(raw, img_hw, None)
+        out.update({f'yolo{li}_in': store['nchw'], f'yolo{li}_bbox': p['bbox'],
+                    f'yolo{li}_cls': p['class_idx'], f'yolo{li}_score': p['score']})
+    # --- YOLOv3 with zero classes (score = sigmoid(conf))
+    cfg0 = dict(cfg, **{'general.num_class': 0})
+    store, raw = head_views(gen, 2, 3, 6, 8, 4, 0)
+    p, _ = YOLOLayer(1, cfg0)(raw, img_hw, None)
+    out.update({'yolo_c0_in': store['nchw'], 'yolo_c0_bbox': p['bbox'], 'yolo_c0_cls': p['class_idx'],
+                'yolo_c0_score': p['score']})
+    # --- RAPiD, zero classes (configs/rapid.json) and 3 classes
+    for tag, nc in (('rapid_c0', 0), ('rapid_c3', 3)):
+        cfgr = {'model.rapid.anchors': RAPID_ANCHORS, 'model.rapid.anchor_indices': IDX3,
+                'model.fpn.out_strides': strides, 'general.num_class': nc,
+                'model.rapid.wh_smooth_l1_beta': 1, 'model.angle.loss_angle': 'Periodic_L1',
+                'model.angle.pred_range': 360}
+        for li, s in enumerate(strides):
+            store, raw = head_views(gen, 2, 3, img_hw[0] // s, img_hw[1] // s, 5, nc)
+            raw['bbox'][..., 4].mul_(4.0)  # angle logits spread over (-3, 3)-ish
+            p, _ = RAPiDLayer(li, cfgr)(raw, img_hw, None)
+            out.update({f'{tag}_{li}_in': store['nchw'], f'{tag}_{li}_bbox': p['bbox'],
+                        f'{tag}_{li}_cls': p['class_idx'], f'{tag}_{li}_score': p['score']})
+    # --- FCOS2 / FCOS2_ATSS / FCOS v1 on an EfficientDet-style head, 5 levels, 6 classes
+    img2 = (256, 384)
+    strides5 = [8, 16, 32, 64, 128]
+    cfgf = {'model.fcos.anchors': [0, 64, 128, 256, 512, 100000000], 'model.fpn.out_strides': strides5,
+            'general.num_class': 6, 'model.fcos2.ignored_threshold': 0.7,
+            'general.pred_bbox_format': 'cxcywh', 'model.atss.anchors': [24, 48, 96, 192, 384],
+            'model.atss.topk_per_level': 9}
+    for li, s in enumerate(strides5):
+        store, raw = head_views(gen, 2, 1, img2[0] // s, img2[1] // s, 4, 6, separate=True)
+        raw['bbox'].mul_(3.0)  # make some boxes hit the image-border clamp
+        p, _ = FCOS2Layer(li, cfgf)(raw, img2, None)
+        p_atss, _ = FCOS_ATSS_Layer(li, cfgf)(raw, img2, None)
+        assert all(torch.equal(p[k], p_atss[k]) for k in p)
+        raw1 = {'bbox': raw['bbox'], 'center': raw['conf'], 'class': raw['class']}
+        p1, _ = FCOS1Layer(li, cfgf)(raw1, img2, None)
+        assert all(torch.equal(p[k], p1[k]) for k in p)
+        out.update({f'fcos{li}_bbox_in': store['bbox_nchw'], f'fcos{li}_cls_in': store['cls_nchw'],
+                    f'fcos{li}_bbox': p['bbox'], f'fcos{li}_cls': p['class_idx'], f'fcos{li}_score': p['score']})
+    # --- RetinaNet (9 anchors), plain and rotated
+    for tag, npar, fmt in (('retina', 4, 'cxcywh'), ('retina_rot', 5, 'cxcywhd')):
+        cfgt = {'model.fpn.out_strides': strides, 'model.retina.anchor.base': 4,
+                'model.retina.anchor.scales': [1, 1.26, 1.5874],
+                'model.retina.anchor.ratios': [[1, 1], [1.4, 0.7], [0.7, 1.4]],
+                'model.retina.anchor.positive_threshold': 0.5, 'model.retina.anchor.negative_threshold': 0.5,
+                'general.num_class': 4, 'general.pred_bbox_format': fmt, 'general.bbox_param': npar,
+                'model.angle.loss_name': 'Periodic_L1'}
+        li, s = 1, 16
+        n_h, n_w = img_hw[0] // s, img_hw[1] // s
+        bb = torch.randn(2, 9 * npar, n_h, n_w, generator=gen) * 0.5
+        cc = torch.randn(2, 9 * 4, n_h, n_w, generator=gen) * 1.5
+        raw = {'bbox': bb.view(2, 9, npar, n_h, n_w).permute(0, 1, 3, 4, 2),
+               'class': cc.view(2, 9, 4, n_h, n_w).permute(0, 1, 3, 4, 2)}
+        # the 'cxcywhd' constructor branch is broken at HEAD (retinanet.py:36 imports a module
+        # that does not exist), so build the plain layer and switch the two attributes the
+        # decode branch reads (:71, :53)
+        layer = RetinaLayer(li, dict(cfgt, **{'general.pred_bbox_format': 'cxcywh'}))
+        layer.pred_bbox_format, layer.n_bbparam = fmt, npar
+        p, _ = layer(raw, img_hw, None)
+        out.update({f'{tag}_bbox_in': bb, f'{tag}_cls_in': cc, f'{tag}_anchors': layer.anchor_wh,
+                    f'{tag}_bbox': p['bbox'], f'{tag}_cls': p['class_idx'], f'{tag}_score': p['score']})
+    # --- Ultralytics / YOLOv5
+    cfgu = {'model.detect.anchors': YOLO_ANCHORS, 'model.detect.anchor_indices': IDX3,
+            'model.fpn.out_strides': strides, 'general.num_class': 5,
+            'model.detect.sample_selection': 'best', 'model.detect.confidence_target': 'zero-one',
+            'model.detect.loss_bbox': 'smooth_L1', 'general.pred_bbox_format': 'cxcywh'}
+    store, raw = head_views(gen, 2, 3, 12, 16, 4, 5)
+    p, _ = DetectLayer(0, cfgu)(raw, img_hw, None)
+    out.update({'uv5_in': store['nchw'], 'uv5_bbox': p['bbox'], 'uv5_cls': p['class_idx'], 'uv5_score': p['score']})
+    save('decode', **out)
+
+
+def gen_postprocess():
+    from utils.structures import ImageObjects
+    gen = torch.Generator().manual_seed(1002)
+    out = {}
+
+    def boxes_(n, p, span=400.0):
+        b = torch.empty(n, p)
+        b[:, 0:2] = torch.rand(n, 2, generator=gen) * span
+        b[:, 2:4] = torch.rand(n, 2, generator=gen) * 80 + 4
+        if p == 5:
+            b[:, 4] = torch.rand(n, generator=gen) * 360 - 180
+        return b
+
+    def run(tag, n, p, n_cls, fmt, conf, nms, direct=False):
+        bxs = boxes_(n, p)
+        sc = torch.rand(n, generator=gen)
+        cats = torch.randint(0, max(n_cls, 1), (n,), generator=gen)
+        keys = torch.cat([bxs, sc[:, None], cats[:, None].float()], dim=1)
+        obj = ImageObjects(bxs.clone(), cats.clone(), scores=sc.clone(), bb_format=fmt, img_hw=(512, 512))
+        res = obj.nms(nms) if direct else obj.post_process(conf, nms)
+        # recover kept indices: rows are unique with probability 1
+        got = torch.cat([res.bboxes, res.scores[:, None], res.cats[:, None].float()], dim=1)
+        idx = torch.tensor([int(torch.nonzero((keys == g).all(dim=1))[0, 0]) for g in got], dtype=torch.int64)
+        assert idx.unique().numel() == idx.numel()
+        out.update({f'{tag}_boxes': bxs, f'{tag}_scores': sc, f'{tag}_cats': cats, f'{tag}_keep': idx,
+                    f'{tag}_params': np.array([conf, nms], dtype=np.float64)})
+
+    run('pp_small', 300, 4, 5, 'cxcywh', 0.3, 0.45)           # below the 512 cap
+    run('pp_cap', 2000, 4, 7, 'cxcywh', 0.05, 0.5)            # top-512 kicks in
+    run('pp_rot', 1500, 5, 1, 'cxcywhd', 0.01, 0.45)          # angle ignored, single class
+    run('pp_empty', 50, 4, 3, 'cxcywh', 2.0, 0.5)             # nothing survives
+    run('nms_direct', 1200, 4, 3, 'cxcywh', 0.0, 0.3, direct=True)   # un-capped ImageObjects.nms
+    # adversarial: duplicates, zero-area and contained boxes, exact-threshold IoU, all one class
+    b = torch.tensor([[10., 10, 20, 20], [10, 10, 20, 20], [10, 10, 0, 0], [12, 10, 20, 20],
+                      [100, 100, 30, 30], [100, 100, 10, 10], [30, 10, 20, 20], [10, 30, 20, 20]])
+    s = torch.tensor([0.9, 0.8, 0.7, 0.6, 0.5, 0.4, 0.3, 0.2])
+    obj = ImageObjects(b.clone(), torch.zeros(8, dtype=torch.int64), scores=s.clone(), bb_format='cxcywh')
+    res = obj.nms(1.0 / 9.0)   # IoU(100,100,30,30 vs 10x10 inside) == 1/9 exactly?  strict '>' keeps it
+    out.update({'adv_boxes': b, 'adv_scores': s, 'adv_keep_scores': res.scores,
+                'adv_thr': np.array([1.0 / 9.0])})
+    save('postprocess', **out)
+
+
+def gen_iou():
+    from utils.bbox_ops import bboxes_iou, nms_rotbb, xywha2vertex, cxcywh_to_x1y1x2y2
+    import json
+    gen = torch.Generator().manual_seed(1003)
+    a = torch.rand(37, 4, generator=gen) * 100 + 1
+    b = torch.rand(11, 4, generator=gen) * 100 + 1
+    ax = cxcywh_to_x1y1x2y2(a)
+    bx = cxcywh_to_x1y1x2y2(b)
+    out = {'a': a, 'b': b, 'iou_cxcywh': bboxes_iou(a, b, xyxy=False), 'iou_xyxy': bboxes_iou(ax, bx, xyxy=True),
+           'a_xyxy': ax}
+    # realistic GT from the reference's own debug fixture (datasets/debug/debug3.json, x1y1wh)
+    anns = json.load(open(os.path.join(REF, 'datasets/debug/debug3.json')))['annotations']
+    gt = torch.tensor([[x + w / 2, y + h / 2, w, h] for x, y, w, h in (an['bbox'] for an in anns)], dtype=torch.float32)
+    out.update({'gt_debug3': gt, 'iou_gt_self': bboxes_iou(gt, gt)})
+    # rotated: corners, and nms_rotbb control flow under the stub polygon IoU
+    rb = torch.empty(120, 5)
+    rb[:, 0:2] = torch.rand(120, 2, generator=gen) * 300 + 50
+    rb[:, 2:4] = torch.rand(120, 2, generator=gen) * 90 + 10
+    rb[:, 4] = torch.rand(120, generator=gen) * 360 - 180
+    rs = torch.rand(120, generator=gen)
+    rad = rb.clone()
+    rad[:, 4] = rad[:, 4] * np.pi / 180
+    out.update({'rot_boxes': rb, 'rot_scores': rs, 'rot_vertices': xywha2vertex(rad, is_degree=False),
+                'rot_keep_045': nms_rotbb(rb, rs, 0.45), 'rot_keep_02': nms_rotbb(rb, rs, 0.2),
+                'rot_keep_maj2': nms_rotbb(rb, rs, 0.3, majority=2)})
+    rot_anns = json.load(open(os.path.join(REF, 'datasets/debug/rotbb_debug3.json')))['annotations']
+    rgt = torch.tensor([an['bbox'] for an in rot_anns], dtype=torch.float32)
+    from utils.bbox_ops import iou_rle
+    out.update({'rot_gt_debug3': rgt, 'rot_gt_iou_stub': iou_rle(rgt[:40], rgt[:40])})
+    save('iou', **out)
+
+
+def gen_atss():
+    from models.detlayers.fcos2 import FCOS_ATSS_Layer
+    from utils.structures import ImageObjects
+    gen = torch.Generator().manual_seed(1004)
+    img_hw = (384, 512)   # the coarsest level must still hold >= k=9 anchors (torch.topk, fcos2.py:397)
+    strides = [8, 16, 32, 64, 128]
+    cfg = {'model.fpn.out_strides': strides, 'general.num_class': 6, 'model.fcos2.ignored_threshold': 0.7,
+           'model.atss.anchors': [24, 48, 96, 192, 384], 'model.atss.topk_per_level': 9}
+    n_b = 2
+    labels = []
+    gts = {}
+    for b in range(n_b):
+        n = 12 if b == 0 else 5
+        bx = torch.empty(n, 4)
+        bx[:, 0] = torch.rand(n, generator=gen) * (img_hw[1] - 40) + 20
+        bx[:, 1] = torch.rand(n, generator=gen) * (img_hw[0] - 40) + 20
+        bx[:, 2:4] = torch.rand(n, 2, generator=gen) * 120 + 12
+        ct = torch.randint(0, 6, (n,), generator=gen)
+        assert (bx[:, 2] * bx[:, 3]).unique().numel() == n
+        labels.append(ImageObjects(bx, ct, bb_format='cxcywh', img_hw=img_hw))
+        gts[f'gt{b}_boxes'] = bx
+        gts[f'gt{b}_cats'] = ct
+    out = dict(gts)
+    for li, s in enumerate(strides):
+        store, raw = head_views(gen, n_b, 1, img_hw[0] // s, img_hw[1] // s, 4, 6, separate=True)
+        layer = FCOS_ATSS_Layer(li, cfg)
+        grabbed = {}
+
+        def prof(frame, event, arg):
+            if event == 'return' and frame.f_code.co_name == 'forward' and 'PositiveMask' in frame.f_locals:
+                for k in ('PositiveMask', 'IgnoredMask', 'TargetConf', 'TargetLTRB', 'TargetCls'):
+                    grabbed[k] = frame.f_locals[k].clone()
+        sys.setprofile(prof)
+        try:
+            layer(raw, img_hw, labels)
+        finally:
+            sys.setprofile(None)
+        out.update({f'atss{li}_bbox_in': store['bbox_nchw'], f'atss{li}_cls_in': store['cls_nchw']})
+        out.update({f'atss{li}_{k}': v for k, v in grabbed.items()})
+    save('atss', **out)
+
+
+if __name__ == '__main__':
+    import_reference()
+    torch.set_grad_enabled(False)
+    gen_decode()
+    gen_postprocess()
+    gen_iou()
+    gen_atss()

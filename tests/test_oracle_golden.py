@@ -1,0 +1,130 @@
+"""CPU: the oracle against fixtures produced by the real reference (tests/golden/make_golden.py)
+and against the installed torchvision.  Bit-exact unless stated."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import decode as od, postprocess as opp, iou as oi, atss as oa
+from helpers import T, level_anchors, yolo_views, efdet_views, anchor_views, YOLO_ANCHORS, RAPID_ANCHORS
+
+
+def same(got, g, key):
+    b, c, s = got
+    assert torch.equal(b, T(g[key + '_bbox'])), key
+    assert torch.equal(c, T(g[key + '_cls'])), key
+    assert torch.equal(s, T(g[key + '_score'])), key
+
+
+def test_decode_yolo(golden):
+    g = golden('decode')
+    for li, s in enumerate((8, 16, 32)):
+        raw = yolo_views(T(g[f'yolo{li}_in']), 3, 4, 5)
+        same(od.decode_yolo(raw, level_anchors(YOLO_ANCHORS, li), s, 5), g, f'yolo{li}')
+    raw = yolo_views(T(g['yolo_c0_in']), 3, 4, 0)
+    same(od.decode_yolo(raw, level_anchors(YOLO_ANCHORS, 1), 16, 0), g, 'yolo_c0')
+
+
+def test_decode_rapid(golden):
+    g = golden('decode')
+    for tag, nc in (('rapid_c0', 0), ('rapid_c3', 3)):
+        for li, s in enumerate((8, 16, 32)):
+            raw = yolo_views(T(g[f'{tag}_{li}_in']), 3, 5, nc)
+            same(od.decode_rapid(raw, level_anchors(RAPID_ANCHORS, li), s, nc), g, f'{tag}_{li}')
+
+
+def test_decode_fcos(golden):
+    g = golden('decode')
+    for li, s in enumerate((8, 16, 32, 64, 128)):
+        raw = efdet_views(T(g[f'fcos{li}_bbox_in']), T(g[f'fcos{li}_cls_in']))
+        same(od.decode_fcos(raw, s, (256, 384)), g, f'fcos{li}')
+
+
+def test_decode_retina_uv5(golden):
+    g = golden('decode')
+    for tag, rot in (('retina', False), ('retina_rot', True)):
+        raw = anchor_views(T(g[f'{tag}_bbox_in']), T(g[f'{tag}_cls_in']), 9)
+        same(od.decode_retina(raw, T(g[f'{tag}_anchors']), 16, (96, 128), with_angle=rot), g, tag)
+    raw = yolo_views(T(g['uv5_in']), 3, 4, 5)
+    same(od.decode_uv5(raw, level_anchors(YOLO_ANCHORS, 0), 8), g, 'uv5')
+
+
+@pytest.mark.parametrize('tag,fmt,cap', [('pp_small', 'cxcywh', 512), ('pp_cap', 'cxcywh', 512),
+                                         ('pp_rot', 'cxcywhd', 512), ('pp_empty', 'cxcywh', 512)])
+def test_post_process(golden, tag, fmt, cap):
+    g = golden('postprocess')
+    boxes, scores, cats = T(g[tag + '_boxes']), T(g[tag + '_scores']), T(g[tag + '_cats'])
+    conf, nms = g[tag + '_params']
+    assert opp.top_boundary_is_tie_free(scores, conf, cap)
+    keep = opp.post_process(boxes, cats, scores, float(conf), float(nms), fmt, cap)
+    assert torch.equal(keep, T(g[tag + '_keep']))
+
+
+def test_nms_direct_and_adversarial(golden):
+    g = golden('postprocess')
+    boxes, scores, cats = T(g['nms_direct_boxes']), T(g['nms_direct_scores']), T(g['nms_direct_cats'])
+    keep = opp.class_nms(boxes, scores, cats, float(g['nms_direct_params'][1]))
+    assert torch.equal(keep, T(g['nms_direct_keep']))
+    keep = opp.class_nms(T(g['adv_boxes']), T(g['adv_scores']), torch.zeros(8, dtype=torch.int64), float(g['adv_thr'][0]))
+    assert torch.equal(T(g['adv_scores'])[keep], T(g['adv_keep_scores']))
+
+
+def test_nms_restatement_matches_torchvision():
+    tv = pytest.importorskip('torchvision')
+    gen = torch.Generator().manual_seed(7)
+    for n, thr in ((1, 0.5), (64, 0.5), (777, 0.3), (2000, 0.7)):
+        xy = torch.rand(n, 2, generator=gen) * 200
+        wh = torch.rand(n, 2, generator=gen) * 60
+        box = torch.cat([xy, xy + wh], 1)
+        sc = (torch.rand(n, generator=gen) * 50).round() / 50      # many exact score ties
+        assert torch.equal(opp.nms_aabb(box, sc, thr), tv.ops.nms(box, sc, thr))
+    # threshold semantics: float IoU against a DOUBLE threshold, strict '>'
+    box = torch.tensor([[0., 0, 10, 10], [0, 0, 10, 4.5]])
+    sc = torch.tensor([1.0, 0.5])
+    for thr in (0.45, float(np.float32(0.45)), 0.4499999):
+        assert torch.equal(opp.nms_aabb(box, sc, thr), tv.ops.nms(box, sc, thr))
+
+
+def test_bboxes_iou(golden):
+    g = golden('iou')
+    a, b = T(g['a']), T(g['b'])
+    assert torch.equal(oi.bboxes_iou(a, b), T(g['iou_cxcywh']))
+    assert torch.equal(oi.cxcywh_to_x1y1x2y2(a), T(g['a_xyxy']))
+    assert torch.equal(oi.bboxes_iou(oi.cxcywh_to_x1y1x2y2(a), oi.cxcywh_to_x1y1x2y2(b), xyxy=True), T(g['iou_xyxy']))
+    gt = T(g['gt_debug3'])
+    assert torch.equal(oi.bboxes_iou(gt, gt), T(g['iou_gt_self']))
+    with pytest.raises(IndexError):
+        oi.bboxes_iou(torch.zeros(3, 5), b)
+
+
+def test_rotated(golden):
+    g = golden('iou')
+    rb, rs = T(g['rot_boxes']), T(g['rot_scores'])
+    rad = rb.clone()
+    rad[:, 4] = oi.deg2rad_f32(rad[:, 4])
+    assert torch.equal(oi.xywha2vertex(rad), T(g['rot_vertices']))
+    # control flow of nms_rotbb, pinned against the reference driven by an independent polygon IoU
+    assert torch.equal(oi.nms_rot(rb, rs, 0.45), T(g['rot_keep_045']))
+    assert torch.equal(oi.nms_rot(rb, rs, 0.2), T(g['rot_keep_02']))
+    assert torch.equal(oi.nms_rot(rb, rs, 0.3, majority=2), T(g['rot_keep_maj2']))
+    rgt = T(g['rot_gt_debug3'])[:40]
+    np.testing.assert_allclose(oi.iou_rot(rgt, rgt).numpy(), g['rot_gt_iou_stub'], rtol=0, atol=2e-6)
+    # geometric known answers
+    sq = torch.tensor([[50., 50, 20, 20, 0]])
+    assert abs(float(oi.iou_rot(sq, torch.tensor([[50., 50, 20, 20, 90]]))) - 1.0) < 1e-6
+    assert abs(float(oi.iou_rot(sq, torch.tensor([[60., 50, 20, 20, 0]]))) - 1.0 / 3.0) < 1e-6
+    octo = float(oi.iou_rot(sq, torch.tensor([[50., 50, 20, 20, 45]])))       # square vs 45-deg square
+    inter = 400 * 2 * (2 ** 0.5 - 1)
+    assert abs(octo - inter / (800 - inter)) < 1e-6
+    assert float(oi.iou_rot(sq, torch.tensor([[500., 50, 20, 20, 10]]))) == 0.0
+
+
+def test_atss(golden):
+    g = golden('atss')
+    gts = [(T(g[f'gt{b}_boxes']), T(g[f'gt{b}_cats'])) for b in range(2)]
+    strides, sides = [8, 16, 32, 64, 128], [24, 48, 96, 192, 384]
+    for li in range(5):
+        t = T(g[f'atss{li}_bbox_in']).permute(0, 2, 3, 1)
+        out = oa.assign_level(li, t, gts, (384, 512), strides, sides, 9, 0.7, 6)
+        for k, v in out.items():
+            assert torch.equal(v, T(g[f'atss{li}_{k}'])), (li, k)
+    assert sum(int(g[f'atss{li}_PositiveMask'].sum()) for li in range(5)) > 0
