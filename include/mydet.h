@@ -1,0 +1,182 @@
+/* mydet.h -- C ABI of libmydet.so: the myDetection post-processing hot path on B200 (sm_100a).
+ *
+ * The reference (duanzhiihao/myDetection) is pure Python and has NO native/FFI boundary; its
+ * plug-in boundary is Python duck typing.  This header is the boundary a
+ * native replacement needs: every entry point names the reference routine it replaces
+ * (paths relative to the reference root).  INTEGRATION.md shows the ctypes binding and the
+ * three reference modules a maintainer would swap.
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers unless a parameter is documented as host memory.
+ *     The library never allocates device memory: outputs and workspaces are caller-owned.
+ *   - Every call is asynchronous and stream-ordered on `stream` (a cudaStream_t passed as
+ *     void*; NULL = the legacy default stream).  No call synchronises the device.
+ *   - Re-entrant, no global mutable state besides a thread-local last-error string.
+ *   - Return value: 0 = ok; > 0 = a cudaError_t; < 0 = one of the MYDET_ERR_* codes.
+ *   - Strides are in ELEMENTS, so the permuted NCHW views the reference heads hand to the
+ *     det layers (models/rpns.py:29-41, :175-189) are consumed in place, without a copy.
+ *   - Tie policy (the reference leaves it open): wherever scores are ranked,
+ *     equal scores are ordered by ascending candidate index.
+ */
+#ifndef MYDET_H_
+#define MYDET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MYDET_VERSION 100
+#define MYDET_MAX_LEVELS 8
+#define MYDET_MAX_ANCHORS 16
+#define MYDET_MAX_CLASS_ID 4095      /* class ids must lie in [0, 4095]                    */
+#define MYDET_MAX_CANDIDATES 1048575 /* candidates per image must be < 2^20                */
+#define MYDET_SMALL_K 1024           /* <= this many survivors: single fused kernel per image */
+
+enum {
+    MYDET_OK = 0,
+    MYDET_ERR_INVALID = -1,     /* bad argument (see mydet_last_error)            */
+    MYDET_ERR_WORKSPACE = -2,   /* workspace too small                             */
+    MYDET_ERR_UNSUPPORTED = -3  /* shape outside the documented limits             */
+};
+
+/* Which det layer's decode arithmetic to apply (models/registry.py:119-146). */
+typedef enum {
+    MYDET_KIND_YOLO = 0,   /* models/detlayers/yolov3.py:41-69   YOLOLayer                   */
+    MYDET_KIND_FCOS = 1,   /* models/detlayers/fcos2.py:40-69, :222-251; fcos.py:41-68       */
+    MYDET_KIND_RAPID = 2,  /* models/detlayers/rapid.py:48-82    RAPiDLayer (cx,cy,w,h,deg)  */
+    MYDET_KIND_RETINA = 3, /* models/detlayers/retinanet.py:63-82 RetinaLayer                */
+    MYDET_KIND_UV5 = 4     /* models/detlayers/uv5.py:60-91      DetectLayer                 */
+} mydet_kind_t;
+
+typedef enum {
+    MYDET_BOX_CXCYWH = 0,  /* also 'cxcywhd': the angle is carried but ignored by AABB NMS    */
+    MYDET_BOX_X1Y1X2Y2 = 1
+} mydet_box_format_t;
+
+/* One pyramid level of raw head output: the tensors of the reference's raw dict
+ * ('bbox', 'conf' or 'center', 'class').  Logical shapes (B,nA,nH,nW,P), (B,nA,nH,nW),
+ * (B,nA,nH,nW,C); for single-anchor heads pass n_anchor = 1 and stride_a = 0. */
+typedef struct {
+    const float* bbox;        /* element (b=0,a=0,h=0,w=0,p=0)                                  */
+    const float* conf;        /* objectness / centerness logits; NULL for MYDET_KIND_RETINA     */
+    const float* cls;         /* class logits, class 0; NULL when n_cls == 0                    */
+    int64_t bbox_stride[5];   /* b, a, h, w, p                                                  */
+    int64_t conf_stride[4];   /* b, a, h, w                                                     */
+    int64_t cls_stride[5];    /* b, a, h, w, c                                                  */
+    int32_t n_anchor, n_h, n_w;
+    float stride;             /* cfg['model.fpn.out_strides'][level]                            */
+    float anchor_w[MYDET_MAX_ANCHORS]; /* pixels; unused by MYDET_KIND_FCOS                      */
+    float anchor_h[MYDET_MAX_ANCHORS];
+} mydet_level_t;
+
+int mydet_version(void);
+const char* mydet_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Decode, dense.  Replaces the test-mode branch of every det layer's forward(raw, img_size, None)
+ * (files above) AND the level concatenation of OneStageBBox.forward (models/general.py:74-76):
+ * all levels are decoded by ONE launch straight into the level-concatenated buffers.
+ *   levels        HOST array of n_levels descriptors, stride-ascending (reference order)
+ *   out_box       (B, n_total, P) float32     n_total = sum_l nA*nH*nW, candidate order a->h->w
+ *   out_cls       (B, n_total)    int64       first index of the maximal class probability
+ *   out_score     (B, n_total)    float32
+ * n_param P is 4, or 5 for rotated kinds.  img_h/img_w: network input size (FCOS/Retina clamps). */
+int mydet_decode_dense(int kind, const mydet_level_t* levels, int n_levels, int batch, int n_cls,
+                       int n_param, float img_h, float img_w, float* out_box, int64_t* out_cls,
+                       float* out_score, int64_t n_total, void* stream);
+
+/* Decode fused with the score threshold of ImageObjects.post_process (utils/structures.py:98):
+ * only candidates with score >= conf_thres (float32 compare) are written, compacted per image with
+ * a warp-ballot + one atomic per warp.  Slot order is unspecified; cand_idx carries the flat
+ * candidate index (position in the dense layout above), which later ranking uses as tie-break.
+ *   cand_box (B,capacity,P) f32, cand_score (B,capacity) f32, cand_cls (B,capacity) i32,
+ *   cand_idx (B,capacity) i32, cand_count (B) i32 -- zeroed by this call; may exceed capacity
+ *   (the overflow is dropped, consumers clamp). */
+int mydet_decode_compact(int kind, const mydet_level_t* levels, int n_levels, int batch, int n_cls,
+                         int n_param, float img_h, float img_w, float conf_thres, float* cand_box,
+                         float* cand_score, int32_t* cand_cls, int32_t* cand_idx,
+                         int32_t* cand_count, int32_t capacity, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Threshold -> top-k -> class-aware axis-aligned NMS, batched.  Replaces
+ * ImageObjects.post_process / nms / non_max_suppression (utils/structures.py:92-173), including
+ * torchvision.ops.nms's arithmetic (float32 IoU = inter/(a_i+a_j-inter), suppressed iff
+ * (double)iou > nms_thres, visiting order = stable descending score).
+ *   boxes  (B, pitch, P) f32; scores (B, pitch) f32; cls (B, pitch) int32 or int64 (cls_is_i64)
+ *   src_idx  optional (B,pitch) i32: value reported in out_idx instead of the slot number
+ *   counts   optional (B) i32: valid candidates per image (clamped to n_per_image); else all
+ *   conf_thres: candidates with score < conf_thres (or NaN) are ignored; pass -INFINITY for none
+ *   topk     > 0: keep the topk best survivors before NMS (reference: 512); <= 0: no cap
+ *   outputs  out_box (B,out_cap,P), out_score (B,out_cap), out_cls (B,out_cap) i64,
+ *            out_idx (B,out_cap) i32, out_count (B) i32; rows ordered class ascending, then score
+ *            descending, exactly as the reference concatenates its per-class groups.
+ *   status   optional (B) i32 written with a bit mask: 1 = class id out of range, 2 = output
+ *            truncated to out_cap, 4 = input count exceeded n_per_image.
+ * Workspace: mydet_postprocess_workspace_bytes(...) bytes, 256-byte aligned. */
+size_t mydet_postprocess_workspace_bytes(int batch, int n_per_image, int topk);
+int mydet_postprocess(const float* boxes, const float* scores, const void* cls, int cls_is_i64,
+                      const int32_t* src_idx, const int32_t* counts, int batch, int64_t pitch,
+                      int n_per_image, int n_param, int box_format, float conf_thres, int topk,
+                      double nms_thres, float* out_box, float* out_score, int64_t* out_cls,
+                      int32_t* out_idx, int32_t* out_count, int32_t* status, int out_cap,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Whole path in one call: decode_compact + postprocess (what api/detection.py:168-172 does per
+ * image, here for the batch).  Workspace: mydet_detect_workspace_bytes(...). */
+size_t mydet_detect_workspace_bytes(int batch, int64_t n_total, int n_param, int topk);
+int mydet_detect(int kind, const mydet_level_t* levels, int n_levels, int batch, int n_cls,
+                 int n_param, float img_h, float img_w, float conf_thres, int topk,
+                 double nms_thres, float* out_box, float* out_score, int64_t* out_cls,
+                 int32_t* out_idx, int32_t* out_count, int32_t* status, int out_cap,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Rotated greedy NMS, batched, single class per image.  Replaces nms_rotbb
+ * (utils/bbox_ops.py:250-306) with exact polygon clipping instead of the pycocotools raster
+ * (parity unpinned for the IoU values).  Box i is dropped iff its IoU with an
+ * already kept, higher-scored box is >= thr (ge_mode != 0, the reference) or > thr.
+ *   boxes (B,pitch,5) (cx,cy,w,h,degrees clockwise), scores (B,pitch), counts optional (B)
+ *   keep  (B,pitch) i64: kept indices into the image's boxes, descending score; keep_count (B)
+ *   votes optional (B,pitch) i32: per kept box, 1 + number of dropped boxes whose best IoU was
+ *         with it (the reference's majority-vote bookkeeping, :291-306) */
+size_t mydet_nms_rot_workspace_bytes(int batch, int n_per_image);
+int mydet_nms_rot(const float* boxes, const float* scores, const int32_t* counts, int batch,
+                  int64_t pitch, int n_per_image, double thr, int ge_mode, int64_t* keep,
+                  int32_t* keep_count, int32_t* votes, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pairwise IoU matrices. */
+/* bboxes_iou (utils/bbox_ops.py:6-49): a (N,4), b (K,4) -> out (N,K) f32, bit-exact arithmetic. */
+int mydet_iou_aabb_pairwise(const float* a, int64_t n, const float* b, int64_t k, int xyxy,
+                            float* out, void* stream);
+/* iou_rle (utils/bbox_ops.py:52-100): a (N,5), b (K,5) degrees -> out (N,K) f64, exact clipping. */
+int mydet_iou_rot_pairwise(const float* a, int64_t n, const float* b, int64_t k, double* out,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ATSS assignment of one pyramid level.  Replaces the target construction of
+ * FCOS_ATSS_Layer.forward (models/detlayers/fcos2.py:253-341) and _get_atss_threshold (:385-405).
+ *   t_ltrb      this level's raw regression logits, logical (B,nH,nW,4), strides b,h,w,p
+ *   gt_box      (B, max_gt, 4) cxcywh f32, gt_cls (B, max_gt) i64, gt_count (B) i32
+ *   strides / anchor_sides  HOST arrays of n_levels entries (cfg 'model.fpn.out_strides',
+ *                           'model.atss.anchors'); level = index of this level
+ *   outputs     positive, ignored (B,nH,nW) u8; target_ltrb (B,nH,nW,4), target_conf (B,nH,nW),
+ *               target_cls (B,nH,nW,C) f32 -- all fully written by the call
+ *   thr_out     optional (B, max_gt) f32: the adaptive threshold of every GT (mean + std) */
+size_t mydet_atss_workspace_bytes(int batch, int max_gt);
+int mydet_atss_assign(const float* t_ltrb, const int64_t t_stride[4], int batch, int level,
+                      int n_levels, const int32_t* strides, const float* anchor_sides, int img_h,
+                      int img_w, const float* gt_box, const int64_t* gt_cls,
+                      const int32_t* gt_count, int max_gt, int topk, float ignore_thres, int n_cls,
+                      uint8_t* positive, uint8_t* ignored, float* target_ltrb, float* target_conf,
+                      float* target_cls, float* thr_out, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MYDET_H_ */

@@ -1,0 +1,261 @@
+// ATSS anchor-to-GT assignment for one pyramid level.
+//
+// Replaces the target construction of FCOS_ATSS_Layer.forward (models/detlayers/fcos2.py:253-341)
+// and _get_atss_threshold (:385-405).  Three kernels, everything stays on the device (the
+// reference moves predictions to the CPU, loops over images and GTs in Python and copies the
+// dense targets back):
+//   prepare   : per image, GTs ordered by area descending (stable)                     (:299-303)
+//   threshold : per (image, GT): the k nearest anchor centres of EVERY level (one warp per
+//               level, exhaustive (d2, index)-ordered selection = torch.topk(largest=False)),
+//               IoU of those L*k square anchors with the GT, thr = mean + unbiased std  (:385-405)
+//   assign    : per (image, cell) of this level: ignore mask = max_GT IoU(pred, GT) > t (:306-308),
+//               then the GTs in area order; positive iff IoU(anchor, GT) > thr and the cell lies
+//               strictly inside the GT; the last (= smallest) positive GT owns TargetLTRB, classes
+//               accumulate multi-hot                                                    (:312-341)
+// IoU arithmetic is bboxes_iou's (utils/bbox_ops.py:38-49), bit-exact.
+#include "internal.cuh"
+
+namespace mydet {
+
+constexpr int kAtssMaxK = 16;
+
+struct AtssWs {
+    float4* gt_sorted;   // B*max_gt   cxcywh, area-descending
+    int* cls_sorted;     // B*max_gt
+    int* src_sorted;     // B*max_gt   original GT index
+    float* thr;          // B*max_gt   in sorted order
+};
+
+static size_t carve_atss(AtssWs& w, void* base, int batch, int max_gt) {
+    size_t off = 0;
+    auto take = [&](size_t b) { size_t o = off; off = align_up(off + b, 256); return o; };
+    const size_t bg = (size_t)batch * (size_t)(max_gt > 0 ? max_gt : 1);
+    const size_t o0 = take(bg * 16), o1 = take(bg * 4), o2 = take(bg * 4), o3 = take(bg * 4);
+    if (base) {
+        char* p = static_cast<char*>(base);
+        w.gt_sorted = (float4*)(p + o0); w.cls_sorted = (int*)(p + o1); w.src_sorted = (int*)(p + o2); w.thr = (float*)(p + o3);
+    }
+    return off;
+}
+
+// bboxes_iou(a, b, xyxy=False) for one pair, cxcywh inputs.
+__device__ __forceinline__ float iou_cxcywh(float acx, float acy, float aw, float ah, float bcx, float bcy, float bw, float bh) {
+    const float ahw = __fmul_rn(aw, 0.5f), ahh = __fmul_rn(ah, 0.5f), bhw = __fmul_rn(bw, 0.5f), bhh = __fmul_rn(bh, 0.5f);
+    const float tlx = fmaxf(__fsub_rn(acx, ahw), __fsub_rn(bcx, bhw)), tly = fmaxf(__fsub_rn(acy, ahh), __fsub_rn(bcy, bhh));
+    const float brx = fminf(__fadd_rn(acx, ahw), __fadd_rn(bcx, bhw)), bry = fminf(__fadd_rn(acy, ahh), __fadd_rn(bcy, bhh));
+    const float en = (tlx < brx && tly < bry) ? 1.0f : 0.0f;
+    const float inter = __fmul_rn(__fmul_rn(__fsub_rn(brx, tlx), __fsub_rn(bry, tly)), en);
+    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(__fmul_rn(aw, ah), __fmul_rn(bw, bh)), inter));
+}
+
+__global__ void atss_prepare_kernel(const float* gt_box, const long long* gt_cls, const int* gt_count, int max_gt, AtssWs w) {
+    extern __shared__ float s_area[];
+    const int b = blockIdx.x;
+    const int n = min(max(gt_count[b], 0), max_gt);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float* g = gt_box + ((long long)b * max_gt + i) * 4;
+        s_area[i] = __fmul_rn(g[2], g[3]);                              // fcos2.py:299
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float ai = s_area[i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += (s_area[j] > ai || (s_area[j] == ai && j < i)) ? 1 : 0;
+        const float* g = gt_box + ((long long)b * max_gt + i) * 4;
+        const long long o = (long long)b * max_gt + rank;
+        w.gt_sorted[o] = make_float4(g[0], g[1], g[2], g[3]);
+        w.cls_sorted[o] = (int)gt_cls[(long long)b * max_gt + i];
+        w.src_sorted[o] = i;
+    }
+}
+
+struct AtssGeom {
+    int n_levels, k, img_h, img_w;
+    int stride[MYDET_MAX_LEVELS];
+    float side[MYDET_MAX_LEVELS];
+};
+
+// grid (max_gt, B); one warp per level.
+__global__ void atss_threshold_kernel(AtssGeom G, const int* gt_count, int max_gt, AtssWs w, float* thr_user) {
+    __shared__ float s_iou[MYDET_MAX_LEVELS * kAtssMaxK];
+    const int b = blockIdx.y, g = blockIdx.x;
+    const int n_gt = min(max(gt_count[b], 0), max_gt);
+    if (g >= n_gt) return;
+    const int level = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float4 gt = w.gt_sorted[(long long)b * max_gt + g];
+    if (level < G.n_levels) {
+        const int s = G.stride[level];
+        const int n_w = G.img_w / s, n_h = G.img_h / s, n = n_w * n_h;
+        const float fs = (float)s, half = __fmul_rn(0.5f, fs);
+        float last_d = -1.0f;
+        int last_i = -1;
+        for (int round = 0; round < G.k; ++round) {
+            float best_d = INFINITY;
+            int best_i = 0x7fffffff;
+            for (int i = lane; i < n; i += 32) {
+                const int row = i / n_w, col = i - row * n_w;
+                const float ax = __fadd_rn(__fmul_rn((float)col, fs), half);
+                const float ay = __fadd_rn(__fmul_rn((float)row, fs), half);
+                const float dx = __fsub_rn(gt.x, ax), dy = __fsub_rn(gt.y, ay);
+                const float d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));           // :396
+                const bool after_last = d > last_d || (d == last_d && i > last_i);
+                if (after_last && (d < best_d || (d == best_d && i < best_i))) { best_d = d; best_i = i; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, best_d, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+                if (od < best_d || (od == best_d && oi < best_i)) { best_d = od; best_i = oi; }
+            }
+            last_d = best_d; last_i = best_i;
+            if (lane == 0) {
+                const int row = best_i / n_w, col = best_i - row * n_w;
+                const float ax = __fadd_rn(__fmul_rn((float)col, fs), half);
+                const float ay = __fadd_rn(__fmul_rn((float)row, fs), half);
+                s_iou[level * G.k + round] = iou_cxcywh(gt.x, gt.y, gt.z, gt.w, ax, ay, G.side[level], G.side[level]);  // :401
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int cnt = G.n_levels * G.k;
+        double sum = 0.0;
+        for (int i = 0; i < cnt; ++i) sum += (double)s_iou[i];
+        const double mean = sum / cnt;
+        double ss = 0.0;
+        for (int i = 0; i < cnt; ++i) { const double d = (double)s_iou[i] - mean; ss += d * d; }
+        const float fmean = (float)mean;
+        const float fstd = (float)sqrt(ss / (cnt - 1));                                    // unbiased, :403
+        const float thr = __fadd_rn(fmean, fstd);                                          // :404
+        w.thr[(long long)b * max_gt + g] = thr;
+        if (thr_user) thr_user[(long long)b * max_gt + w.src_sorted[(long long)b * max_gt + g]] = thr;
+    }
+}
+
+struct AssignParams {
+    const float* t; long long ts_b, ts_h, ts_w, ts_p;
+    int n_h, n_w, n_cls, max_gt;
+    float stride, side, ignore_thres;
+    const int* gt_count;
+    unsigned char* positive; unsigned char* ignored;
+    float* target_ltrb; float* target_conf; float* target_cls;
+};
+
+constexpr int kAssignThreads = 128;
+
+__global__ void __launch_bounds__(kAssignThreads) atss_assign_kernel(AssignParams P, AtssWs w) {
+    extern __shared__ float4 s_gt[];                       // max_gt boxes, then thr, then cls
+    float* s_thr = reinterpret_cast<float*>(s_gt + P.max_gt);
+    int* s_cls = reinterpret_cast<int*>(s_thr + P.max_gt);
+    const int b = blockIdx.y;
+    const int n_hw = P.n_h * P.n_w;
+    const int cell0 = blockIdx.x * kAssignThreads;
+    const int n_gt = min(max(P.gt_count[b], 0), P.max_gt);
+    for (int i = threadIdx.x; i < n_gt; i += kAssignThreads) {
+        s_gt[i] = w.gt_sorted[(long long)b * P.max_gt + i];
+        s_thr[i] = w.thr[(long long)b * P.max_gt + i];
+        s_cls[i] = w.cls_sorted[(long long)b * P.max_gt + i];
+    }
+    // zero this CTA's slab of the class target (coalesced), ones are scattered after the barrier
+    {
+        const int cells = min(kAssignThreads, n_hw - cell0);
+        float* slab = P.target_cls + ((long long)b * n_hw + cell0) * P.n_cls;
+        const long long total = (long long)cells * P.n_cls;
+        for (long long i = threadIdx.x; i < total; i += kAssignThreads) slab[i] = 0.0f;
+    }
+    __syncthreads();
+    const int cell = cell0 + threadIdx.x;
+    if (cell >= n_hw) return;
+    const int row = cell / P.n_w, col = cell - row * P.n_w;
+    const float half = __fmul_rn(P.stride, 0.5f);
+    // fcos2.py:256-259  linspace(0,img,n+1)[:-1] + 0.5*stride  == col*stride + stride/2 for integer strides
+    const float gx = __fadd_rn(__fmul_rn((float)col, P.stride), half);
+    const float gy = __fadd_rn(__fmul_rn((float)row, P.stride), half);
+    // un-clamped predicted box of this cell (fcos2.py:42, :253, :444-450)
+    const float* t = P.t + b * P.ts_b + row * P.ts_h + col * P.ts_w;
+    const float l = __fmul_rn(expf(t[0]), P.stride), tp = __fmul_rn(expf(t[P.ts_p]), P.stride);
+    const float r = __fmul_rn(expf(t[2 * P.ts_p]), P.stride), bt = __fmul_rn(expf(t[3 * P.ts_p]), P.stride);
+    const float pcx = __fadd_rn(gx, __fmul_rn(__fsub_rn(r, l), 0.5f)), pcy = __fadd_rn(gy, __fmul_rn(__fsub_rn(bt, tp), 0.5f));
+    const float pw = __fadd_rn(l, r), ph = __fadd_rn(tp, bt);
+
+    float best_iou = -INFINITY;
+    bool positive = false;
+    float4 ltrb = make_float4(0.f, 0.f, 0.f, 0.f);
+    float* cls_row = P.target_cls + ((long long)b * n_hw + cell) * P.n_cls;
+    for (int g = 0; g < n_gt; ++g) {
+        const float4 gt = s_gt[g];
+        best_iou = fmaxf(best_iou, iou_cxcywh(pcx, pcy, pw, ph, gt.x, gt.y, gt.z, gt.w));   // :306-307
+        const float hw = __fmul_rn(gt.z, 0.5f), hh = __fmul_rn(gt.w, 0.5f);                  // :408-414, cr = 1
+        const float tl = __fsub_rn(gx, __fsub_rn(gt.x, hw)), tt = __fsub_rn(gy, __fsub_rn(gt.y, hh));
+        const float tr = __fsub_rn(__fadd_rn(gt.x, hw), gx), tb = __fsub_rn(__fadd_rn(gt.y, hh), gy);
+        const bool inside = tl > 0.f && tt > 0.f && tr > 0.f && tb > 0.f;                    // :321
+        const float iou = iou_cxcywh(gx, gy, P.side, P.side, gt.x, gt.y, gt.z, gt.w);        // :329
+        if (inside && iou > s_thr[g]) {                                                      // :330-331
+            positive = true;
+            ltrb = make_float4(tl, tt, tr, tb);                                              // :335, last writer wins
+            const int c = s_cls[g];
+            if (c >= 0 && c < P.n_cls) cls_row[c] = 1.0f;                                    // :339-340
+        }
+    }
+    const long long o = (long long)b * n_hw + cell;
+    P.positive[o] = positive ? 1 : 0;
+    P.ignored[o] = (n_gt > 0 && best_iou > P.ignore_thres) ? 1 : 0;                          // :308
+    reinterpret_cast<float4*>(P.target_ltrb)[o] = ltrb;
+    P.target_conf[o] = positive ? 1.0f : 0.0f;                                               // :337
+}
+
+}  // namespace mydet
+
+using namespace mydet;
+
+MYDET_API size_t mydet_atss_workspace_bytes(int batch, int max_gt) {
+    AtssWs w;
+    return carve_atss(w, nullptr, batch, max_gt);
+}
+
+MYDET_API int mydet_atss_assign(const float* t_ltrb, const int64_t t_stride[4], int batch, int level, int n_levels,
+                                const int32_t* strides, const float* anchor_sides, int img_h, int img_w,
+                                const float* gt_box, const int64_t* gt_cls, const int32_t* gt_count, int max_gt,
+                                int topk, float ignore_thres, int n_cls, uint8_t* positive, uint8_t* ignored,
+                                float* target_ltrb, float* target_conf, float* target_cls, float* thr_out,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    MYDET_REQUIRE(n_levels >= 1 && n_levels <= MYDET_MAX_LEVELS && level >= 0 && level < n_levels, "bad level / n_levels");
+    MYDET_REQUIRE(strides && anchor_sides && t_stride, "NULL host array");
+    MYDET_REQUIRE(topk >= 1 && topk <= kAtssMaxK, "topk must be in [1,%d]", kAtssMaxK);
+    MYDET_REQUIRE(n_levels * topk >= 2, "need at least two candidate anchors for the std");
+    MYDET_REQUIRE(batch >= 0 && max_gt >= 0 && n_cls > 0, "bad batch / max_gt / n_cls");
+    MYDET_REQUIRE(max_gt <= 2048, "more than 2048 GT boxes per image");
+    AtssGeom G;
+    G.n_levels = n_levels; G.k = topk; G.img_h = img_h; G.img_w = img_w;
+    for (int i = 0; i < n_levels; ++i) {
+        MYDET_REQUIRE(strides[i] > 0 && img_h % strides[i] == 0 && img_w % strides[i] == 0,
+                      "image size must be divisible by every stride (fcos2.py:266)");
+        MYDET_REQUIRE((img_h / strides[i]) * (img_w / strides[i]) >= topk,
+                      "level %d has fewer than k anchors (torch.topk would raise, fcos2.py:397)", i);
+        G.stride[i] = strides[i]; G.side[i] = anchor_sides[i];
+    }
+    if (batch == 0) return 0;
+    MYDET_REQUIRE(t_ltrb && gt_count && positive && ignored && target_ltrb && target_conf && target_cls, "NULL tensor pointer");
+    MYDET_REQUIRE(max_gt == 0 || (gt_box && gt_cls), "NULL GT pointer");
+    AtssWs w;
+    const size_t need = carve_atss(w, workspace, batch, max_gt);
+    if (!workspace || need > workspace_bytes) {
+        set_error("workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+        return MYDET_ERR_WORKSPACE;
+    }
+    if (max_gt > 0) {
+        atss_prepare_kernel<<<batch, 128, sizeof(float) * max_gt, st>>>(gt_box, reinterpret_cast<const long long*>(gt_cls), gt_count, max_gt, w);
+        atss_threshold_kernel<<<dim3(max_gt, batch), 32 * n_levels, 0, st>>>(G, gt_count, max_gt, w, thr_out);
+    }
+    AssignParams P;
+    P.t = t_ltrb; P.ts_b = t_stride[0]; P.ts_h = t_stride[1]; P.ts_w = t_stride[2]; P.ts_p = t_stride[3];
+    P.n_h = img_h / strides[level]; P.n_w = img_w / strides[level]; P.n_cls = n_cls; P.max_gt = max_gt;
+    P.stride = (float)strides[level]; P.side = anchor_sides[level]; P.ignore_thres = ignore_thres;
+    P.gt_count = gt_count; P.positive = positive; P.ignored = ignored;
+    P.target_ltrb = target_ltrb; P.target_conf = target_conf; P.target_cls = target_cls;
+    const int n_hw = P.n_h * P.n_w;
+    const size_t smem = (size_t)max_gt * (16 + 4 + 4);
+    atss_assign_kernel<<<dim3((n_hw + kAssignThreads - 1) / kAssignThreads, batch), kAssignThreads, smem, st>>>(P, w);
+    return launch_status("atss kernels");
+}

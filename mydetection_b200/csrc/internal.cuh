@@ -1,0 +1,46 @@
+// Structures and launchers shared between the translation units of libmydet.
+#pragma once
+#include "common.cuh"
+
+namespace mydet {
+
+// postprocess_small.cu
+struct PPParams {
+    const float* boxes;
+    const float* scores;
+    const void* cls;
+    const int* src_idx;
+    const int* counts;
+    long long pitch;
+    int n_per_image, n_param, box_format, cls_is_i64;
+    float conf_thres;
+    int topk;          // effective K (<= kpad)
+    float nms_thr_f;   // float_at_or_below(nms_thres)
+    int kpad;          // power of two >= K, >= 32
+    float* out_box;
+    float* out_score;
+    long long* out_cls;
+    int* out_idx;
+    int* out_count;
+    int* status;
+    int out_cap;
+};
+int launch_postprocess_small(const PPParams& P, int batch, cudaStream_t st);
+
+// nms_large.cu
+struct LargeArgs {
+    const float* boxes; const float* scores; const void* cls; int cls_is_i64; const int* src_idx; const int* counts;
+    int batch; long long pitch; int n, n_param, box_format; float conf_thres; int topk; double thr; int ge; bool rot;
+    float* out_box; float* out_score; long long* out_cls; int* out_idx; int* out_count; int* status; int out_cap;
+    long long* keep64;
+};
+int run_large(const LargeArgs& A, void* workspace, size_t workspace_bytes, cudaStream_t st);
+size_t large_workspace_bytes(int batch, int n, bool rot);
+
+// decode.cu
+int decode_compact_impl(int kind, const mydet_level_t* levels, int n_levels, int batch, int n_cls, int n_param,
+                        float img_h, float img_w, float conf_thres, float* cand_box, float* cand_score,
+                        int32_t* cand_cls, int32_t* cand_idx, int32_t* cand_count, int32_t capacity,
+                        int64_t* n_total_out, cudaStream_t st);
+
+}  // namespace mydet

@@ -1,0 +1,114 @@
+// Pairwise IoU matrices.
+//   mydet_iou_aabb_pairwise replaces bboxes_iou (utils/bbox_ops.py:6-49), bit-exact: the same
+//   float32 operations in the same order (c -/+ wh/2, max/min, (br-tl).x*(br-tl).y*en,
+//   area_i/(area_a+area_b-area_i)), no FMA contraction.
+//   mydet_iou_rot_pairwise replaces iou_rle (utils/bbox_ops.py:52-100) with exact float64 polygon
+//   clipping (rotgeom.cuh); like the reference it returns float64.
+// Layout: each CTA computes a 32 (rows of a) x 128 (columns of b) tile; the b-tile is staged in
+// shared memory once and reused by the 32 rows; stores are coalesced along K.
+#include "internal.cuh"
+#include "rotgeom.cuh"
+
+namespace mydet {
+
+constexpr int kIouCols = 128;
+constexpr int kIouRows = 32;
+
+__global__ void __launch_bounds__(kIouCols) iou_aabb_kernel(const float* __restrict__ a, long long n,
+                                                           const float* __restrict__ b, long long k, int xyxy,
+                                                           float* __restrict__ out) {
+    __shared__ float4 lo_hi_a[kIouRows];   // tl.x tl.y br.x br.y of the row boxes
+    __shared__ float area_a[kIouRows];
+    const long long col = (long long)blockIdx.x * kIouCols + threadIdx.x;
+    const long long row0 = (long long)blockIdx.y * kIouRows;
+    if (threadIdx.x < kIouRows && row0 + threadIdx.x < n) {
+        const float4 v = reinterpret_cast<const float4*>(a)[row0 + threadIdx.x];
+        if (xyxy) {
+            lo_hi_a[threadIdx.x] = v;
+            area_a[threadIdx.x] = __fmul_rn(__fsub_rn(v.z, v.x), __fsub_rn(v.w, v.y));   // :36 prod(hi-lo)
+        } else {
+            const float hw = __fmul_rn(v.z, 0.5f), hh = __fmul_rn(v.w, 0.5f);
+            lo_hi_a[threadIdx.x] = make_float4(__fsub_rn(v.x, hw), __fsub_rn(v.y, hh), __fadd_rn(v.x, hw), __fadd_rn(v.y, hh));
+            area_a[threadIdx.x] = __fmul_rn(v.z, v.w);                                    // :45 prod(wh)
+        }
+    }
+    __syncthreads();
+    if (col >= k) return;
+    const float4 vb = reinterpret_cast<const float4*>(b)[col];
+    float4 cb;
+    float area_b;
+    if (xyxy) {
+        cb = vb;
+        area_b = __fmul_rn(__fsub_rn(vb.z, vb.x), __fsub_rn(vb.w, vb.y));
+    } else {
+        const float hw = __fmul_rn(vb.z, 0.5f), hh = __fmul_rn(vb.w, 0.5f);
+        cb = make_float4(__fsub_rn(vb.x, hw), __fsub_rn(vb.y, hh), __fadd_rn(vb.x, hw), __fadd_rn(vb.y, hh));
+        area_b = __fmul_rn(vb.z, vb.w);
+    }
+    const int rows = (int)min((long long)kIouRows, n - row0);
+#pragma unroll 4
+    for (int r = 0; r < rows; ++r) {
+        const float4 ca = lo_hi_a[r];
+        const float tlx = fmaxf(ca.x, cb.x), tly = fmaxf(ca.y, cb.y);
+        const float brx = fminf(ca.z, cb.z), bry = fminf(ca.w, cb.w);
+        const float en = (tlx < brx && tly < bry) ? 1.0f : 0.0f;                            // :47
+        const float inter = __fmul_rn(__fmul_rn(__fsub_rn(brx, tlx), __fsub_rn(bry, tly)), en);  // :48
+        out[(row0 + r) * k + col] = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a[r], area_b), inter));  // :49
+    }
+}
+
+__global__ void __launch_bounds__(kIouCols) iou_rot_kernel(const float* __restrict__ a, long long n,
+                                                          const float* __restrict__ b, long long k,
+                                                          double* __restrict__ out) {
+    __shared__ float ax[kIouRows][4], ay[kIouRows][4], acx[kIouRows], acy[kIouRows], ar[kIouRows];
+    const long long col = (long long)blockIdx.x * kIouCols + threadIdx.x;
+    const long long row0 = (long long)blockIdx.y * kIouRows;
+    if (threadIdx.x < kIouRows && row0 + threadIdx.x < n) {
+        const float* p = a + (row0 + threadIdx.x) * 5;
+        float v[5] = {p[0], p[1], p[2], p[3], p[4]};
+        float r;
+        make_rot_box(v, ax[threadIdx.x], ay[threadIdx.x], r);
+        acx[threadIdx.x] = v[0]; acy[threadIdx.x] = v[1]; ar[threadIdx.x] = r;
+    }
+    __syncthreads();
+    if (col >= k) return;
+    const float* p = b + col * 5;
+    float v[5] = {p[0], p[1], p[2], p[3], p[4]};
+    float bx[4], by[4], br;
+    make_rot_box(v, bx, by, br);
+    const int rows = (int)min((long long)kIouRows, n - row0);
+    for (int r = 0; r < rows; ++r) {
+        // same cull as the oracle: circumscribed circles apart => IoU is exactly 0
+        const double dx = (double)acx[r] - (double)v[0], dy = (double)acy[r] - (double)v[1];
+        const double rr = (double)ar[r] + (double)br + 1e-3;
+        double iou = 0.0;
+        if (dx * dx + dy * dy <= rr * rr) iou = rot_iou_f64(ax[r], ay[r], bx, by);
+        out[(row0 + r) * k + col] = iou;
+    }
+}
+
+}  // namespace mydet
+
+using namespace mydet;
+
+MYDET_API int mydet_iou_aabb_pairwise(const float* a, int64_t n, const float* b, int64_t k, int xyxy, float* out,
+                                      void* stream) {
+    MYDET_REQUIRE(n >= 0 && k >= 0, "negative size");
+    if (n == 0 || k == 0) return 0;
+    MYDET_REQUIRE(a && b && out, "NULL tensor pointer");
+    MYDET_REQUIRE(((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0, "box arrays must be 16-byte aligned");
+    const dim3 grid((unsigned)((k + kIouCols - 1) / kIouCols), (unsigned)((n + kIouRows - 1) / kIouRows));
+    MYDET_REQUIRE(grid.y <= 65535, "too many rows for one launch");
+    iou_aabb_kernel<<<grid, kIouCols, 0, (cudaStream_t)stream>>>(a, n, b, k, xyxy, out);
+    return launch_status("iou_aabb_kernel");
+}
+
+MYDET_API int mydet_iou_rot_pairwise(const float* a, int64_t n, const float* b, int64_t k, double* out, void* stream) {
+    MYDET_REQUIRE(n >= 0 && k >= 0, "negative size");
+    if (n == 0 || k == 0) return 0;
+    MYDET_REQUIRE(a && b && out, "NULL tensor pointer");
+    const dim3 grid((unsigned)((k + kIouCols - 1) / kIouCols), (unsigned)((n + kIouRows - 1) / kIouRows));
+    MYDET_REQUIRE(grid.y <= 65535, "too many rows for one launch");
+    iou_rot_kernel<<<grid, kIouCols, 0, (cudaStream_t)stream>>>(a, n, b, k, out);
+    return launch_status("iou_rot_kernel");
+}

@@ -1,0 +1,333 @@
+// NMS for candidate sets that do not fit one CTA (> MYDET_SMALL_K boxes per image): the dense
+// scene sweep (10k-50k boxes, BASELINE.json configs[4]) and rotated NMS at 10k boxes (configs[2]).
+//
+// Replaces ImageObjects.non_max_suppression (utils/structures.py:111-173, via torchvision.ops.nms)
+// and nms_rotbb (utils/bbox_ops.py:250-306).  Pipeline, all stream-ordered, no host round trip:
+//   keys   : 64-bit sort key per candidate (class asc, score desc, index asc); failed threshold = ~0
+//   rank   : rank[i] = #{j : key[j] < key[i]}  (tiled all-pairs count; keys are unique) -> order
+//   gather : sorted corner boxes / rotated quads
+//   mask   : upper-triangular 64x64-tile IoU bit matrix, column tile staged in shared memory,
+//            one row per thread; rotated boxes use the cull + polygon clipping of rotgeom.cuh
+//   sweep  : one CTA per image walks the 64-row blocks; the diagonal word chain is resolved in
+//            registers by one thread, the kept rows are OR-ed into the removed vector by all
+//   emit   : ordered compaction of the survivors
+#include "internal.cuh"
+#include "rotgeom.cuh"
+
+namespace mydet {
+
+constexpr int kTile = 64;
+
+struct LargeWs {          // carved out of the caller's workspace
+    unsigned long long* keys;   // B*n
+    int* order;                 // B*n   sorted position -> candidate slot
+    int* m;                     // B     number of valid (thresholded / selected) candidates
+    float4* box;                // B*n   sorted corners (AABB)
+    float* area;                // B*n
+    int* cls;                   // B*n
+    RotBox* rbox;               // B*n   sorted rotated quads (ROT)
+    unsigned long long* mask;   // B*n*words
+    unsigned long long* kept;   // B*words
+    int words;                  // ceil(n/64)
+};
+
+static size_t carve(LargeWs& w, void* base, int batch, int n, bool rot) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t bn = (size_t)batch * n;
+    w.words = (n + 63) / 64;
+    const size_t o_keys = take(bn * 8), o_order = take(bn * 4), o_m = take((size_t)batch * 4);
+    const size_t o_box = take(rot ? 0 : bn * 16), o_area = take(rot ? 0 : bn * 4), o_cls = take(rot ? 0 : bn * 4);
+    const size_t o_rbox = take(rot ? bn * sizeof(RotBox) : 0);
+    const size_t o_mask = take(bn * (size_t)w.words * 8), o_kept = take((size_t)batch * w.words * 8);
+    if (base) {
+        char* p = static_cast<char*>(base);
+        w.keys = (unsigned long long*)(p + o_keys); w.order = (int*)(p + o_order); w.m = (int*)(p + o_m);
+        w.box = (float4*)(p + o_box); w.area = (float*)(p + o_area); w.cls = (int*)(p + o_cls);
+        w.rbox = (RotBox*)(p + o_rbox);
+        w.mask = (unsigned long long*)(p + o_mask); w.kept = (unsigned long long*)(p + o_kept);
+    }
+    return off;
+}
+
+size_t large_workspace_bytes(int batch, int n, bool rot) {
+    LargeWs w;
+    return carve(w, nullptr, batch, n, rot);
+}
+
+// ---------------------------------------------------------------------------- keys
+struct KeyParams {
+    const float* scores; const void* cls; const int* counts;
+    long long pitch; int n, cls_is_i64, use_cls; float thr;
+    int* status;
+};
+
+__global__ void keys_kernel(KeyParams P, unsigned long long* keys, int* m) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = P.n;
+    if (P.counts) { const int c = P.counts[b]; n = c < n ? (c < 0 ? 0 : c) : n; }
+    bool valid = false;
+    unsigned long long key = ~0ull;
+    if (i < n) {
+        const float s = P.scores[(long long)b * P.pitch + i];
+        if (s >= P.thr) {
+            int c = 0;
+            if (P.use_cls) {
+                const long long ci = (long long)b * P.pitch + i;
+                c = P.cls_is_i64 ? (int)reinterpret_cast<const long long*>(P.cls)[ci] : reinterpret_cast<const int*>(P.cls)[ci];
+                if (c < 0 || c > MYDET_MAX_CLASS_ID) { if (P.status) atomicOr(P.status + b, 1); c = c < 0 ? 0 : MYDET_MAX_CLASS_ID; }
+            }
+            key = ((unsigned long long)c << 52) | ((unsigned long long)(~float_key(s)) << 20) | (unsigned long long)i;
+            valid = true;
+        }
+    }
+    if (i < P.n) keys[(long long)b * P.n + i] = key;
+    const unsigned bal = __ballot_sync(0xffffffffu, valid);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(m + b, __popc(bal));
+}
+
+// ---------------------------------------------------------------------------- rank (sort)
+constexpr int kRankThreads = 256;
+__global__ void __launch_bounds__(kRankThreads) rank_kernel(const unsigned long long* keys, int* order, int n) {
+    __shared__ unsigned long long tile[kRankThreads];
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * kRankThreads + threadIdx.x;
+    const unsigned long long* kb = keys + (long long)b * n;
+    const unsigned long long mine = (i < n) ? kb[i] : ~0ull;
+    int rank = 0;
+    for (int base = 0; base < n; base += kRankThreads) {
+        const int j = base + threadIdx.x;
+        tile[threadIdx.x] = (j < n) ? kb[j] : ~0ull;
+        __syncthreads();
+#pragma unroll 8
+        for (int t = 0; t < kRankThreads; ++t) rank += (tile[t] < mine) ? 1 : 0;
+        __syncthreads();
+    }
+    if (i < n && mine != ~0ull) order[(long long)b * n + rank] = i;
+}
+
+// ---------------------------------------------------------------------------- gather
+struct GatherParams {
+    const float* boxes; long long pitch; int n, n_param, box_format;
+};
+template <bool ROT>
+__global__ void gather_kernel(GatherParams P, const unsigned long long* keys, const int* order, const int* m, LargeWs w) {
+    const int b = blockIdx.y;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m[b]) return;
+    const long long row = (long long)b * P.n + r;
+    const int i = order[row];
+    const float* bx = P.boxes + ((long long)b * P.pitch + i) * P.n_param;
+    if (ROT) {
+        float v[5] = {bx[0], bx[1], bx[2], bx[3], bx[4]};
+        RotBox q;
+        make_rot_box(v, q.x, q.y, q.r);
+        q.cx = v[0]; q.cy = v[1];
+        q.area2 = (float)signed_area2_f64(q.x, q.y);
+        w.rbox[row] = q;
+    } else {
+        const float v0 = bx[0], v1 = bx[1], v2 = bx[2], v3 = bx[3];
+        float4 c4;
+        if (P.box_format == MYDET_BOX_CXCYWH) {
+            const float hw = __fmul_rn(v2, 0.5f), hh = __fmul_rn(v3, 0.5f);
+            c4 = make_float4(__fsub_rn(v0, hw), __fsub_rn(v1, hh), __fadd_rn(v0, hw), __fadd_rn(v1, hh));
+        } else {
+            c4 = make_float4(v0, v1, v2, v3);
+        }
+        w.box[row] = c4;
+        w.area[row] = __fmul_rn(__fsub_rn(c4.z, c4.x), __fsub_rn(c4.w, c4.y));
+        w.cls[row] = (int)(keys[(long long)b * P.n + i] >> 52);
+    }
+}
+
+// ---------------------------------------------------------------------------- mask
+// grid (col_tile, row_tile, image); 64 threads; thread t owns row row_tile*64+t.
+template <bool ROT>
+__global__ void __launch_bounds__(kTile) mask_kernel(LargeWs w, const int* m, int n, float thr_f, double thr_d, int ge) {
+    const int ct = blockIdx.x, rt = blockIdx.y, b = blockIdx.z;
+    if (ct < rt) return;
+    const int mb = m[b];
+    if (rt * kTile >= mb || ct * kTile >= mb) return;
+    const long long base = (long long)b * n;
+    const int t = threadIdx.x;
+    const int r = rt * kTile + t;
+    const int c0 = ct * kTile;
+    unsigned long long bits = 0ull;
+    if (ROT) {
+        __shared__ RotBox cols[kTile];
+        if (c0 + t < mb) cols[t] = w.rbox[base + c0 + t];
+        __syncthreads();
+        if (r < mb) {
+            const RotBox me = w.rbox[base + r];
+            const int lim = min(kTile, mb - c0);
+            for (int j = 0; j < lim; ++j)
+                if (c0 + j > r && rot_overlaps(me, cols[j], thr_d, ge != 0)) bits |= 1ull << j;
+        }
+    } else {
+        __shared__ float4 cbox[kTile];
+        __shared__ float carea[kTile];
+        __shared__ int ccls[kTile];
+        if (c0 + t < mb) { cbox[t] = w.box[base + c0 + t]; carea[t] = w.area[base + c0 + t]; ccls[t] = w.cls[base + c0 + t]; }
+        __syncthreads();
+        if (r < mb) {
+            const float4 a = w.box[base + r];
+            const float aarea = w.area[base + r];
+            const int ac = w.cls[base + r];
+            const int lim = min(kTile, mb - c0);
+            // sorted by class: the tile can only match if its class range reaches ac
+            if (ccls[0] <= ac && ccls[lim - 1] >= ac) {
+#pragma unroll 4
+                for (int j = 0; j < lim; ++j) {
+                    const float4 c4 = cbox[j];
+                    const float ovr = iou_corners(a.x, a.y, a.z, a.w, aarea, c4.x, c4.y, c4.z, c4.w, carea[j]);
+                    if (c0 + j > r && ccls[j] == ac && ovr > thr_f) bits |= 1ull << j;
+                }
+            }
+        }
+    }
+    if (r < mb) w.mask[(base + r) * w.words + ct] = bits;
+}
+
+// ---------------------------------------------------------------------------- sweep + emit
+constexpr int kSweepThreads = 256;
+
+struct EmitParams {
+    const float* boxes; const float* scores; const void* cls; const int* src_idx;
+    long long pitch; int n, n_param, cls_is_i64;
+    float* out_box; float* out_score; long long* out_cls; int* out_idx; int* out_count; int* status; int out_cap;
+    long long* keep64;   // rotated API: kept candidate indices as int64 (B, pitch)
+};
+
+__global__ void __launch_bounds__(kSweepThreads) sweep_kernel(LargeWs w, const int* m, int n, EmitParams E) {
+    extern __shared__ unsigned long long sm[];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int mb = m[b];
+    const int words = (mb + 63) / 64;
+    unsigned long long* removed = sm;                    // w.words
+    unsigned long long* keptw = sm + w.words;            // w.words
+    unsigned long long* diag = keptw + w.words;          // 64
+    __shared__ unsigned long long s_kept;
+    __shared__ int s_prefix_total;
+    const unsigned long long* mask = w.mask + (long long)b * n * w.words;
+
+    for (int i = tid; i < w.words; i += kSweepThreads) { removed[i] = 0ull; keptw[i] = 0ull; }
+    __syncthreads();
+
+    for (int t = 0; t < words; ++t) {
+        const int r0 = t * kTile;
+        const int rows = min(kTile, mb - r0);
+        if (tid < kTile) diag[tid] = (tid < rows) ? mask[(long long)(r0 + tid) * w.words + t] : 0ull;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long d[kTile];
+#pragma unroll
+            for (int j = 0; j < kTile; ++j) d[j] = diag[j];
+            unsigned long long cur = removed[t];
+            if (rows < kTile) cur |= ~0ull << rows;
+            unsigned long long kept = 0ull;
+#pragma unroll
+            for (int j = 0; j < kTile; ++j) {
+                const bool alive = !((cur >> j) & 1ull);
+                if (alive) { kept |= 1ull << j; cur |= d[j]; }
+            }
+            s_kept = kept;
+            keptw[t] = kept;
+        }
+        __syncthreads();
+        const unsigned long long kept = s_kept;
+        // OR the kept rows of this block into the removed words that are still ahead
+        for (int wd = t + 1 + tid; wd < words; wd += kSweepThreads) {
+            unsigned long long acc = 0ull;
+            unsigned long long k = kept;
+            while (k) {
+                const int j = __ffsll((long long)k) - 1;
+                k &= k - 1;
+                acc |= mask[(long long)(r0 + j) * w.words + wd];
+            }
+            removed[wd] |= acc;
+        }
+        __syncthreads();
+    }
+
+    // ---- emit survivors in sorted order
+    // exclusive prefix of popcounts over keptw (serial per 256-word chunk is fine: words <= 16384)
+    __shared__ int chunk_sum[kSweepThreads];
+    const int per = (words + kSweepThreads - 1) / kSweepThreads;
+    int local = 0;
+    for (int k = 0; k < per; ++k) { const int wd = tid * per + k; if (wd < words) local += __popcll(keptw[wd]); }
+    chunk_sum[tid] = local;
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int k = 0; k < kSweepThreads; ++k) { const int v = chunk_sum[k]; chunk_sum[k] = acc; acc += v; }
+        s_prefix_total = acc;
+    }
+    __syncthreads();
+    int pos = chunk_sum[tid];
+    const int* order = w.order + (long long)b * n;
+    for (int k = 0; k < per; ++k) {
+        const int wd = tid * per + k;
+        if (wd >= words) break;
+        unsigned long long kw = keptw[wd];
+        while (kw) {
+            const int j = __ffsll((long long)kw) - 1;
+            kw &= kw - 1;
+            const int i = order[wd * kTile + j];
+            if (E.keep64) {
+                E.keep64[(long long)b * E.pitch + pos] = i;
+            } else if (pos < E.out_cap) {
+                const long long orow = (long long)b * E.out_cap + pos;
+                const long long irow = (long long)b * E.pitch + i;
+                for (int p = 0; p < E.n_param; ++p) E.out_box[orow * E.n_param + p] = E.boxes[irow * E.n_param + p];
+                E.out_score[orow] = E.scores[irow];
+                E.out_cls[orow] = E.cls ? (E.cls_is_i64 ? reinterpret_cast<const long long*>(E.cls)[irow]
+                                                        : (long long)reinterpret_cast<const int*>(E.cls)[irow]) : 0ll;
+                E.out_idx[orow] = E.src_idx ? E.src_idx[irow] : i;
+            }
+            ++pos;
+        }
+    }
+    if (tid == 0) {
+        int total = s_prefix_total;
+        if (!E.keep64 && total > E.out_cap) { total = E.out_cap; if (E.status) atomicOr(E.status + b, 2); }
+        E.out_count[b] = total;
+    }
+}
+
+// ---------------------------------------------------------------------------- host orchestration
+int run_large(const LargeArgs& A, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    LargeWs w;
+    const size_t need = carve(w, workspace, A.batch, A.n, A.rot);
+    if (need > workspace_bytes || !workspace) {
+        set_error("workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+        return MYDET_ERR_WORKSPACE;
+    }
+    MYDET_REQUIRE(A.topk <= 0 || A.topk >= A.n, "top-k above %d with more candidates than k is not supported yet "
+                  "(topk=%d, n=%d)", MYDET_SMALL_K, A.topk, A.n);
+    MYDET_REQUIRE(A.batch <= 65535, "batch too large for one launch (<= 65535)");
+    const int B = A.batch, n = A.n;
+    MYDET_CUDA(cudaMemsetAsync(w.m, 0, sizeof(int) * (size_t)B, st));
+    if (A.status) MYDET_CUDA(cudaMemsetAsync(A.status, 0, sizeof(int) * (size_t)B, st));
+    KeyParams K{A.scores, A.cls, A.counts, A.pitch, n, A.cls_is_i64, (A.cls && !A.rot) ? 1 : 0, A.conf_thres, A.status};
+    keys_kernel<<<dim3((n + 255) / 256, B), 256, 0, st>>>(K, w.keys, w.m);
+    rank_kernel<<<dim3((n + kRankThreads - 1) / kRankThreads, B), kRankThreads, 0, st>>>(w.keys, w.order, n);
+    GatherParams G{A.boxes, A.pitch, n, A.n_param, A.box_format};
+    const int tiles = (n + kTile - 1) / kTile;
+    if (A.rot) {
+        gather_kernel<true><<<dim3((n + 255) / 256, B), 256, 0, st>>>(G, w.keys, w.order, w.m, w);
+        mask_kernel<true><<<dim3(tiles, tiles, B), kTile, 0, st>>>(w, w.m, n, 0.f, A.thr, A.ge);
+    } else {
+        gather_kernel<false><<<dim3((n + 255) / 256, B), 256, 0, st>>>(G, w.keys, w.order, w.m, w);
+        mask_kernel<false><<<dim3(tiles, tiles, B), kTile, 0, st>>>(w, w.m, n, float_at_or_below(A.thr), A.thr, 0);
+    }
+    EmitParams E{A.boxes, A.scores, A.cls, A.src_idx, A.pitch, n, A.n_param, A.cls_is_i64,
+                 A.out_box, A.out_score, A.out_cls, A.out_idx, A.out_count, A.status, A.out_cap, A.keep64};
+    const size_t smem = ((size_t)w.words * 2 + kTile) * sizeof(unsigned long long);
+    MYDET_REQUIRE(smem <= 200 * 1024, "too many candidates per image for the sweep kernel");
+    MYDET_CUDA(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem > 48 * 1024 ? (int)smem : 48 * 1024));
+    sweep_kernel<<<B, kSweepThreads, smem, st>>>(w, w.m, n, E);
+    return launch_status("large NMS pipeline");
+}
+
+}  // namespace mydet

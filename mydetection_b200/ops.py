@@ -1,0 +1,292 @@
+"""Tensor-level wrappers over the C ABI (include/mydet.h).
+
+PyTorch is used here only for device memory, the current stream and dtype/shape checks; every
+result is produced by the hand-written CUDA kernels of libmydet.so.  CPU tensors are rejected --
+there is no fallback path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (KIND_YOLO, KIND_FCOS, KIND_RAPID, KIND_RETINA, KIND_UV5,  # noqa: F401
+                   BOX_CXCYWH, BOX_X1Y1X2Y2, SMALL_K)
+
+BOX_FORMATS = {'cxcywh': BOX_CXCYWH, 'cxcywhd': BOX_CXCYWH, 'x1y1x2y2': BOX_X1Y1X2Y2}
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev(t, dtype, what):
+    if not torch.is_tensor(t):
+        raise TypeError(f'{what}: expected a tensor')
+    if not t.is_cuda:
+        raise _lib.MydetError(f'{what}: expected a CUDA tensor (libmydet has no CPU path)')
+    if t.dtype != dtype:
+        raise TypeError(f'{what}: expected dtype {dtype}, got {t.dtype}')
+    return t
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------------------- levels
+def make_level(raw, stride, anchors_wh=None, conf_key='conf'):
+    """Describe one raw dict of head views (models/rpns.py:29-41, :175-189) as a mydet_level_t.
+
+    raw['bbox'] is (B,nA,nH,nW,P) or (B,nH,nW,P); raw[conf_key] and raw['class'] follow the same
+    layout with a last dim of 1 / C.  No copy is made: pointers and element strides are passed.
+    Returns (Level, keepalive tensors).
+    """
+    bbox = _dev(raw['bbox'], torch.float32, "raw['bbox']")
+    multi = bbox.dim() == 5
+    if bbox.dim() not in (4, 5):
+        raise ValueError("raw['bbox'] must be (B,nA,nH,nW,P) or (B,nH,nW,P)")
+    lv = _lib.Level()
+    sb = bbox.stride()
+    if multi:
+        n_a, n_h, n_w = bbox.shape[1:4]
+        lv.bbox_stride[:] = [sb[0], sb[1], sb[2], sb[3], sb[4]]
+    else:
+        n_a, (n_h, n_w) = 1, bbox.shape[1:3]
+        lv.bbox_stride[:] = [sb[0], 0, sb[1], sb[2], sb[3]]
+    lv.bbox = bbox.data_ptr()
+    keep = [bbox]
+    conf = raw.get(conf_key)
+    if conf is not None:
+        conf = _dev(conf, torch.float32, f"raw['{conf_key}']")
+        sc = conf.stride()
+        lv.conf_stride[:] = [sc[0], sc[1], sc[2], sc[3]] if multi else [sc[0], 0, sc[1], sc[2]]
+        lv.conf = conf.data_ptr()
+        keep.append(conf)
+    cls = raw.get('class')
+    if cls is not None and cls.shape[-1] > 0:
+        cls = _dev(cls, torch.float32, "raw['class']")
+        sk = cls.stride()
+        lv.cls_stride[:] = [sk[0], sk[1], sk[2], sk[3], sk[4]] if multi else [sk[0], 0, sk[1], sk[2], sk[3]]
+        lv.cls = cls.data_ptr()
+        keep.append(cls)
+    lv.n_anchor, lv.n_h, lv.n_w = int(n_a), int(n_h), int(n_w)
+    lv.stride = float(stride)
+    if anchors_wh is not None:
+        aw = [float(a[0]) for a in anchors_wh]
+        ah = [float(a[1]) for a in anchors_wh]
+        if len(aw) != n_a or n_a > _lib.MAX_ANCHORS:
+            raise ValueError(f'{len(aw)} anchors given for {n_a} anchor planes (max {_lib.MAX_ANCHORS})')
+        lv.anchor_w[:n_a] = aw
+        lv.anchor_h[:n_a] = ah
+    return lv, keep
+
+
+class LevelSet:
+    """A host array of mydet_level_t for a fixed set of head tensors (reusable across calls)."""
+
+    def __init__(self, raws, strides, anchors=None, conf_key='conf'):
+        if not 1 <= len(raws) <= _lib.MAX_LEVELS:
+            raise ValueError(f'1..{_lib.MAX_LEVELS} levels supported')
+        self.array = (_lib.Level * len(raws))()
+        self.keep = []
+        self.n_total = 0
+        for i, raw in enumerate(raws):
+            lv, keep = make_level(raw, strides[i], None if anchors is None else anchors[i], conf_key)
+            self.array[i] = lv
+            self.keep += keep
+            self.n_total += lv.n_anchor * lv.n_h * lv.n_w
+        self.n_levels = len(raws)
+        first = raws[0]['bbox']
+        self.batch = int(first.shape[0])
+        self.n_param = int(first.shape[-1])
+        self.device = first.device
+        cls = raws[0].get('class')
+        self.n_cls = 0 if cls is None else int(cls.shape[-1])
+
+
+# --------------------------------------------------------------------------------------- decode
+def decode_dense(kind, levels: LevelSet, img_hw):
+    """All levels -> level-concatenated (bbox (B,N,P) f32, class_idx (B,N) i64, score (B,N) f32)."""
+    B, N, P = levels.batch, levels.n_total, levels.n_param
+    dev = levels.device
+    box = torch.empty(B, N, P, dtype=torch.float32, device=dev)
+    cls = torch.empty(B, N, dtype=torch.int64, device=dev)
+    score = torch.empty(B, N, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().mydet_decode_dense(kind, levels.array, levels.n_levels, B, levels.n_cls, P,
+                                           float(img_hw[0]), float(img_hw[1]), _ptr(box), _ptr(cls), _ptr(score),
+                                           N, _stream())
+    _lib.check(rc, 'mydet_decode_dense')
+    return box, cls, score
+
+
+def decode_compact(kind, levels: LevelSet, img_hw, conf_thres, capacity=None):
+    """Decode fused with `score >= conf_thres` and per-image compaction.
+
+    Returns dict(box (B,cap,P), score (B,cap), cls (B,cap) i32, idx (B,cap) i32, count (B) i32)."""
+    B, N, P = levels.batch, levels.n_total, levels.n_param
+    cap = int(capacity or N)
+    dev = levels.device
+    out = {'box': torch.empty(B, cap, P, dtype=torch.float32, device=dev),
+           'score': torch.empty(B, cap, dtype=torch.float32, device=dev),
+           'cls': torch.empty(B, cap, dtype=torch.int32, device=dev),
+           'idx': torch.empty(B, cap, dtype=torch.int32, device=dev),
+           'count': torch.empty(B, dtype=torch.int32, device=dev)}
+    with torch.cuda.device(dev):
+        rc = _lib.lib().mydet_decode_compact(kind, levels.array, levels.n_levels, B, levels.n_cls, P,
+                                             float(img_hw[0]), float(img_hw[1]), float(conf_thres),
+                                             _ptr(out['box']), _ptr(out['score']), _ptr(out['cls']), _ptr(out['idx']),
+                                             _ptr(out['count']), cap, _stream())
+    _lib.check(rc, 'mydet_decode_compact')
+    return out
+
+
+# --------------------------------------------------------------------------------------- post-process
+def _alloc_dets(B, cap, P, dev):
+    return {'box': torch.empty(B, cap, P, dtype=torch.float32, device=dev),
+            'score': torch.empty(B, cap, dtype=torch.float32, device=dev),
+            'cls': torch.empty(B, cap, dtype=torch.int64, device=dev),
+            'idx': torch.empty(B, cap, dtype=torch.int32, device=dev),
+            'count': torch.empty(B, dtype=torch.int32, device=dev),
+            'status': torch.zeros(B, dtype=torch.int32, device=dev)}
+
+
+def postprocess(boxes, scores, cls, conf_thres, nms_thres, topk=512, box_format='cxcywh', counts=None,
+                src_idx=None, out_cap=None, out=None):
+    """Batched threshold -> top-k -> class-aware NMS.  boxes (B,n,P), scores (B,n), cls (B,n) i32|i64.
+
+    topk=None removes the cap.  Returns dict(box, score, cls (i64), idx (i32), count, status);
+    rows [0, count[b]) of image b are valid and ordered class asc / score desc."""
+    boxes = _dev(boxes, torch.float32, 'boxes')
+    scores = _dev(scores, torch.float32, 'scores')
+    if cls.dtype not in (torch.int32, torch.int64):
+        raise TypeError('cls must be int32 or int64')
+    if not cls.is_cuda:
+        raise _lib.MydetError('cls: expected a CUDA tensor')
+    if boxes.dim() != 3 or scores.dim() != 2 or cls.dim() != 2:
+        raise ValueError('expected boxes (B,n,P), scores (B,n), cls (B,n)')
+    boxes, scores, cls = boxes.contiguous(), scores.contiguous(), cls.contiguous()
+    B, n, P = boxes.shape
+    k = int(topk) if topk else 0
+    eff = min(k, n) if k > 0 else n
+    cap = int(out_cap or max(eff, 1))
+    dev = boxes.device
+    if out is None:
+        out = _alloc_dets(B, cap, P, dev)
+    L = _lib.lib()
+    wbytes = L.mydet_postprocess_workspace_bytes(B, n, k)
+    ws = _workspace(wbytes, dev)
+    with torch.cuda.device(dev):
+        rc = L.mydet_postprocess(_ptr(boxes), _ptr(scores), _ptr(cls), 1 if cls.dtype == torch.int64 else 0,
+                                 _ptr(src_idx), _ptr(counts), B, n, n, P, BOX_FORMATS[box_format],
+                                 float(conf_thres), k, float(nms_thres), _ptr(out['box']), _ptr(out['score']),
+                                 _ptr(out['cls']), _ptr(out['idx']), _ptr(out['count']), _ptr(out['status']), cap,
+                                 _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, 'mydet_postprocess')
+    return out
+
+
+def detect(kind, levels: LevelSet, img_hw, conf_thres, nms_thres, topk=512, out=None, workspace=None):
+    """decode + threshold + top-k + NMS for the whole batch in one C call."""
+    B, N, P = levels.batch, levels.n_total, levels.n_param
+    k = int(topk) if topk else 0
+    cap = min(k, N) if k > 0 else N
+    dev = levels.device
+    if out is None:
+        out = _alloc_dets(B, max(cap, 1), P, dev)
+    L = _lib.lib()
+    if workspace is None:
+        workspace = _workspace(L.mydet_detect_workspace_bytes(B, N, P, k), dev)
+    with torch.cuda.device(dev):
+        rc = L.mydet_detect(kind, levels.array, levels.n_levels, B, levels.n_cls, P, float(img_hw[0]),
+                            float(img_hw[1]), float(conf_thres), k, float(nms_thres), _ptr(out['box']),
+                            _ptr(out['score']), _ptr(out['cls']), _ptr(out['idx']), _ptr(out['count']),
+                            _ptr(out['status']), out['box'].shape[1], _ptr(workspace), workspace.numel(), _stream())
+    _lib.check(rc, 'mydet_detect')
+    return out
+
+
+def detect_workspace(levels: LevelSet, topk=512):
+    k = int(topk) if topk else 0
+    return _workspace(_lib.lib().mydet_detect_workspace_bytes(levels.batch, levels.n_total, levels.n_param, k),
+                      levels.device)
+
+
+# --------------------------------------------------------------------------------------- rotated NMS / IoU
+def nms_rot(boxes, scores, thr, ge=True, counts=None):
+    """Batched single-class rotated NMS.  boxes (B,n,5) degrees, scores (B,n).
+    Returns (keep (B,n) i64, keep_count (B) i32): kept indices per image in descending score."""
+    boxes = _dev(boxes, torch.float32, 'boxes').contiguous()
+    scores = _dev(scores, torch.float32, 'scores').contiguous()
+    if boxes.dim() != 3 or boxes.shape[-1] != 5:
+        raise ValueError('boxes must be (B,n,5)')
+    B, n, _ = boxes.shape
+    dev = boxes.device
+    keep = torch.empty(B, max(n, 1), dtype=torch.int64, device=dev)
+    cnt = torch.zeros(B, dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    ws = _workspace(L.mydet_nms_rot_workspace_bytes(B, n), dev)
+    with torch.cuda.device(dev):
+        rc = L.mydet_nms_rot(_ptr(boxes), _ptr(scores), _ptr(counts), B, n, n, float(thr), 1 if ge else 0,
+                             _ptr(keep), _ptr(cnt), None, _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, 'mydet_nms_rot')
+    return keep, cnt
+
+
+def iou_aabb(a, b, xyxy=False):
+    a = _dev(a, torch.float32, 'bboxes_a').contiguous()
+    b = _dev(b, torch.float32, 'bboxes_b').contiguous()
+    out = torch.empty(a.shape[0], b.shape[0], dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        rc = _lib.lib().mydet_iou_aabb_pairwise(_ptr(a), a.shape[0], _ptr(b), b.shape[0], 1 if xyxy else 0,
+                                                _ptr(out), _stream())
+    _lib.check(rc, 'mydet_iou_aabb_pairwise')
+    return out
+
+
+def iou_rot(a, b):
+    a = _dev(a, torch.float32, 'boxes1').contiguous()
+    b = _dev(b, torch.float32, 'boxes2').contiguous()
+    out = torch.empty(a.shape[0], b.shape[0], dtype=torch.float64, device=a.device)
+    with torch.cuda.device(a.device):
+        rc = _lib.lib().mydet_iou_rot_pairwise(_ptr(a), a.shape[0], _ptr(b), b.shape[0], _ptr(out), _stream())
+    _lib.check(rc, 'mydet_iou_rot_pairwise')
+    return out
+
+
+# --------------------------------------------------------------------------------------- ATSS
+def atss_assign(t_ltrb, level, strides, anchor_sides, img_hw, gt_box, gt_cls, gt_count, topk, ignore_thres, n_cls):
+    """Targets of one level.  t_ltrb (B,nH,nW,4) view; gt_box (B,G,4) f32, gt_cls (B,G) i64,
+    gt_count (B) i32.  Returns dict of PositiveMask/IgnoredMask (bool), TargetLTRB, TargetConf,
+    TargetCls and 'thr' (B,G)."""
+    t = _dev(t_ltrb, torch.float32, 't_ltrb')
+    gt_box = _dev(gt_box, torch.float32, 'gt_box').contiguous()
+    gt_cls = _dev(gt_cls, torch.int64, 'gt_cls').contiguous()
+    gt_count = _dev(gt_count, torch.int32, 'gt_count').contiguous()
+    B, n_h, n_w, _ = t.shape
+    G = gt_box.shape[1]
+    dev = t.device
+    pos = torch.empty(B, n_h, n_w, dtype=torch.uint8, device=dev)
+    ign = torch.empty(B, n_h, n_w, dtype=torch.uint8, device=dev)
+    t_box = torch.empty(B, n_h, n_w, 4, dtype=torch.float32, device=dev)
+    t_conf = torch.empty(B, n_h, n_w, 1, dtype=torch.float32, device=dev)
+    t_cls = torch.empty(B, n_h, n_w, n_cls, dtype=torch.float32, device=dev)
+    thr = torch.full((B, max(G, 1)), float('nan'), dtype=torch.float32, device=dev)
+    L = _lib.lib()
+    ws = _workspace(L.mydet_atss_workspace_bytes(B, G), dev)
+    n_l = len(strides)
+    st = (ctypes.c_int64 * 4)(*t.stride())
+    c_strides = (ctypes.c_int32 * n_l)(*[int(s) for s in strides])
+    c_sides = (ctypes.c_float * n_l)(*[float(s) for s in anchor_sides])
+    with torch.cuda.device(dev):
+        rc = L.mydet_atss_assign(_ptr(t), st, B, int(level), n_l, c_strides, c_sides, int(img_hw[0]), int(img_hw[1]),
+                                 _ptr(gt_box), _ptr(gt_cls), _ptr(gt_count), G, int(topk), float(ignore_thres),
+                                 int(n_cls), _ptr(pos), _ptr(ign), _ptr(t_box), _ptr(t_conf), _ptr(t_cls), _ptr(thr),
+                                 _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, 'mydet_atss_assign')
+    return {'PositiveMask': pos.view(torch.bool), 'IgnoredMask': ign.view(torch.bool), 'TargetLTRB': t_box, 'TargetConf': t_conf,
+            'TargetCls': t_cls, 'thr': thr}

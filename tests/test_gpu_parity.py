@@ -1,0 +1,339 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+
+Bars (BASELINE.json north_star):
+  * integer / index results (class_idx, kept indices, masks) bit-exact, except where a float
+    that feeds a comparison lies inside the stated band of its threshold;
+  * decoded coordinates and scores within 1e-5 relative in fp32.  Box coordinates that are
+    differences of image-scale numbers (FCOS w = x2 - x1 ...) additionally get an absolute floor of
+    2 ulp of the image extent, because a 1-ulp difference between CUDA expf and the CPU's exp is
+    amplified by that cancellation (DESIGN.md "tolerances").
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import T, level_anchors, yolo_views, efdet_views, anchor_views, YOLO_ANCHORS, RAPID_ANCHORS
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def dev():
+    return torch.device('cuda:0')
+
+
+def close(got, ref, extent, what):
+    got, ref = got.detach().cpu().double(), ref.double()
+    atol = 2 * float(np.spacing(np.float32(extent)))
+    err = (got - ref).abs()
+    bad = err > (RTOL * ref.abs() + atol)
+    assert not bad.any(), f'{what}: {int(bad.sum())} of {bad.numel()} outside tolerance, max err {float(err.max()):.3e}'
+
+
+def cls_match(got_cls, raw_cls_logits, ref_cls, what):
+    """class_idx must equal the reference's except where the two best class probabilities are
+    within 1e-6 relative (float32 sigmoid ties)."""
+    got_cls = got_cls.cpu()
+    diff = got_cls != ref_cls
+    if diff.any():
+        p = torch.sigmoid(raw_cls_logits).reshape(-1, raw_cls_logits.shape[-1])
+        top2 = p.topk(2, dim=-1).values
+        band = (top2[:, 0] - top2[:, 1]) <= 1e-6 * top2[:, 0]
+        assert bool(band[diff.reshape(-1)].all()), f'{what}: class_idx differs outside the tie band'
+
+
+def run_dense(kind, raws, strides, anchors, img_hw, conf_key='conf'):
+    from mydetection_b200 import ops
+    d = dev()
+    raws_d = [{k: v.to(d) for k, v in r.items()} for r in raws]
+    # .to(d) of a permuted view keeps the strides: the kernel sees the reference's layout
+    ls = ops.LevelSet(raws_d, strides, anchors, conf_key)
+    out = ops.decode_dense(kind, ls, img_hw)
+    torch.cuda.synchronize()
+    return out
+
+
+# ------------------------------------------------------------------------------------- decode
+def test_decode_yolo_golden(golden):
+    from mydetection_b200 import ops
+    from oracle import decode as od
+    g = golden('decode')
+    raws, refs = [], []
+    for li, s in enumerate((8, 16, 32)):
+        raw = yolo_views(T(g[f'yolo{li}_in']), 3, 4, 5)
+        raws.append(raw)
+        refs.append((T(g[f'yolo{li}_bbox']), T(g[f'yolo{li}_cls']), T(g[f'yolo{li}_score'])))
+    anchors = [level_anchors(YOLO_ANCHORS, li).tolist() for li in range(3)]
+    box, cls, score = run_dense(ops.KIND_YOLO, raws, (8, 16, 32), anchors, (96, 128))
+    rb, rc, rs = od.merge_levels(refs)
+    close(box, rb, 128, 'yolo bbox')
+    close(score, rs, 1, 'yolo score')
+    logits = torch.cat([r['class'].reshape(2, -1, 5) for r in raws], 1)
+    cls_match(cls, logits, rc, 'yolo cls')
+    # zero-class variant, single level
+    raw = yolo_views(T(g['yolo_c0_in']), 3, 4, 0)
+    box, cls, score = run_dense(ops.KIND_YOLO, [raw], (16,), [level_anchors(YOLO_ANCHORS, 1).tolist()], (96, 128))
+    close(box, T(g['yolo_c0_bbox']), 128, 'yolo c0 bbox')
+    close(score, T(g['yolo_c0_score']), 1, 'yolo c0 score')
+    assert int(cls.abs().sum()) == 0
+
+
+def test_decode_rapid_golden(golden):
+    from mydetection_b200 import ops
+    from oracle import decode as od
+    g = golden('decode')
+    for tag, nc in (('rapid_c0', 0), ('rapid_c3', 3)):
+        raws, refs = [], []
+        for li in range(3):
+            raws.append(yolo_views(T(g[f'{tag}_{li}_in']), 3, 5, nc))
+            refs.append((T(g[f'{tag}_{li}_bbox']), T(g[f'{tag}_{li}_cls']), T(g[f'{tag}_{li}_score'])))
+        anchors = [level_anchors(RAPID_ANCHORS, li).tolist() for li in range(3)]
+        box, cls, score = run_dense(ops.KIND_RAPID, raws, (8, 16, 32), anchors, (96, 128))
+        rb, rc, rs = od.merge_levels(refs)
+        close(box[..., :4], rb[..., :4], 128, tag + ' bbox')
+        close(box[..., 4], rb[..., 4], 180, tag + ' angle')
+        close(score, rs, 1, tag + ' score')
+        if nc:
+            cls_match(cls, torch.cat([r['class'].reshape(2, -1, nc) for r in raws], 1), rc, tag + ' cls')
+        else:
+            assert int(cls.abs().sum()) == 0
+
+
+def test_decode_fcos_golden(golden):
+    from mydetection_b200 import ops
+    from oracle import decode as od
+    g = golden('decode')
+    raws, refs = [], []
+    for li in range(5):
+        raws.append(efdet_views(T(g[f'fcos{li}_bbox_in']), T(g[f'fcos{li}_cls_in'])))
+        refs.append((T(g[f'fcos{li}_bbox']), T(g[f'fcos{li}_cls']), T(g[f'fcos{li}_score'])))
+    box, cls, score = run_dense(ops.KIND_FCOS, raws, (8, 16, 32, 64, 128), None, (256, 384))
+    rb, rc, rs = od.merge_levels(refs)
+    close(box, rb, 384, 'fcos bbox')
+    close(score, rs, 1, 'fcos score')
+    cls_match(cls, torch.cat([r['class'].reshape(2, -1, 6) for r in raws], 1), rc, 'fcos cls')
+    # FCOS v1 reads the centerness head under the key 'center'
+    raws1 = [{'bbox': r['bbox'], 'center': r['conf'], 'class': r['class']} for r in raws]
+    box1, cls1, score1 = run_dense(ops.KIND_FCOS, raws1, (8, 16, 32, 64, 128), None, (256, 384), conf_key='center')
+    assert torch.equal(box1, box) and torch.equal(score1, score) and torch.equal(cls1, cls)
+
+
+def test_decode_retina_uv5_golden(golden):
+    from mydetection_b200 import ops
+    g = golden('decode')
+    for tag in ('retina', 'retina_rot'):
+        raw = anchor_views(T(g[f'{tag}_bbox_in']), T(g[f'{tag}_cls_in']), 9)
+        box, cls, score = run_dense(ops.KIND_RETINA, [raw], (16,), [g[f'{tag}_anchors'].tolist()], (96, 128))
+        close(box[..., :4], T(g[f'{tag}_bbox'])[..., :4], 128, tag + ' bbox')
+        if tag == 'retina_rot':
+            close(box[..., 4], T(g[f'{tag}_bbox'])[..., 4], 180, tag + ' angle')
+        close(score, T(g[f'{tag}_score']), 1, tag + ' score')
+        cls_match(cls, raw['class'].reshape(2, -1, 4), T(g[f'{tag}_cls']), tag + ' cls')
+    raw = yolo_views(T(g['uv5_in']), 3, 4, 5)
+    box, cls, score = run_dense(ops.KIND_UV5, [raw], (8,), [level_anchors(YOLO_ANCHORS, 0).tolist()], (96, 128))
+    close(box, T(g['uv5_bbox']), 128, 'uv5 bbox')
+    close(score, T(g['uv5_score']), 1, 'uv5 score')
+    cls_match(cls, raw['class'].reshape(2, -1, 5), T(g['uv5_cls']), 'uv5 cls')
+
+
+def test_decode_generic_strides_and_compact(golden):
+    """A contiguous (B,nH,nW,C) copy (non-planar strides) takes the scalar path and must give the
+    same bits as the planar fast path; the compacting variant must select exactly score >= thr."""
+    from mydetection_b200 import ops
+    g = golden('decode')
+    d = dev()
+    raws = [efdet_views(T(g[f'fcos{li}_bbox_in']), T(g[f'fcos{li}_cls_in'])) for li in range(5)]
+    planar = [{k: v.to(d) for k, v in r.items()} for r in raws]
+    packed = []
+    for r in planar:
+        cc = torch.cat([r['conf'], r['class']], dim=-1).contiguous()      # (B,nH,nW,1+C) channels-last
+        packed.append({'bbox': r['bbox'].contiguous(), 'conf': cc[..., 0:1], 'class': cc[..., 1:]})
+    strides = (8, 16, 32, 64, 128)
+    a = ops.decode_dense(ops.KIND_FCOS, ops.LevelSet(planar, strides), (256, 384))
+    b = ops.decode_dense(ops.KIND_FCOS, ops.LevelSet(packed, strides), (256, 384))
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    box, cls, score = a
+    for thr in (0.005, 0.3, 0.9, 2.0):
+        c = ops.decode_compact(ops.KIND_FCOS, ops.LevelSet(planar, strides), (256, 384), thr)
+        torch.cuda.synchronize()
+        for bi in range(box.shape[0]):
+            n = int(c['count'][bi])
+            want = torch.nonzero(score[bi] >= thr).flatten()
+            assert n == want.numel()
+            order = torch.argsort(c['idx'][bi, :n])
+            idx = c['idx'][bi, :n][order].long()
+            assert torch.equal(idx, want)
+            assert torch.equal(c['box'][bi, :n][order], box[bi][idx])
+            assert torch.equal(c['score'][bi, :n][order], score[bi][idx])
+            assert torch.equal(c['cls'][bi, :n][order].long(), cls[bi][idx])
+
+
+# ------------------------------------------------------------------------------------- post-process
+def gpu_keep(boxes, scores, cats, conf, nms, fmt, topk):
+    from mydetection_b200 import ops
+    d = dev()
+    out = ops.postprocess(boxes[None].to(d), scores[None].to(d), cats[None].to(d), conf, nms, topk=topk, box_format=fmt)
+    torch.cuda.synchronize()
+    n = int(out['count'][0])
+    assert int(out['status'][0]) == 0
+    return out, n
+
+
+@pytest.mark.parametrize('tag,fmt', [('pp_small', 'cxcywh'), ('pp_cap', 'cxcywh'), ('pp_rot', 'cxcywhd'),
+                                     ('pp_empty', 'cxcywh')])
+def test_post_process_golden(golden, tag, fmt):
+    g = golden('postprocess')
+    boxes, scores, cats = T(g[tag + '_boxes']), T(g[tag + '_scores']), T(g[tag + '_cats'])
+    conf, nms = (float(v) for v in g[tag + '_params'])
+    out, n = gpu_keep(boxes, scores, cats, conf, nms, fmt, 512)
+    keep = T(g[tag + '_keep'])
+    assert n == keep.numel()
+    assert torch.equal(out['idx'][0, :n].cpu().long(), keep)           # kept indices, bit-exact, reference order
+    assert torch.equal(out['box'][0, :n].cpu(), boxes[keep])
+    assert torch.equal(out['score'][0, :n].cpu(), scores[keep])
+    assert torch.equal(out['cls'][0, :n].cpu(), cats[keep])
+
+
+def test_nms_direct_large_path_golden(golden):
+    """ImageObjects.nms on 1200 boxes: no cap -> the tiled large-N path."""
+    g = golden('postprocess')
+    boxes, scores, cats = T(g['nms_direct_boxes']), T(g['nms_direct_scores']), T(g['nms_direct_cats'])
+    out, n = gpu_keep(boxes, scores, cats, float('-inf'), float(g['nms_direct_params'][1]), 'cxcywh', None)
+    keep = T(g['nms_direct_keep'])
+    assert n == keep.numel()
+    assert torch.equal(out['idx'][0, :n].cpu().long(), keep)
+
+
+def test_nms_adversarial_golden(golden):
+    g = golden('postprocess')
+    b, s = T(g['adv_boxes']), T(g['adv_scores'])
+    out, n = gpu_keep(b, s, torch.zeros(8, dtype=torch.int64), float('-inf'), float(g['adv_thr'][0]), 'cxcywh', None)
+    assert torch.equal(out['score'][0, :n].cpu(), T(g['adv_keep_scores']))
+
+
+@pytest.mark.parametrize('n,n_cls,topk', [(1, 1, 512), (31, 2, 512), (513, 1, 512), (1024, 3, None), (1025, 3, None),
+                                          (3000, 1, None), (5000, 80, None), (4000, 4, 1000)])
+def test_nms_random_vs_oracle(n, n_cls, topk):
+    from oracle import postprocess as opp
+    gen = torch.Generator().manual_seed(100 + n)
+    boxes = torch.cat([torch.rand(n, 2, generator=gen) * 300, torch.rand(n, 2, generator=gen) * 60 + 2], 1)
+    scores = (torch.rand(n, generator=gen) * 200).round() / 200           # exact score ties on purpose
+    cats = torch.randint(0, n_cls, (n,), generator=gen)
+    want = opp.post_process(boxes, cats, scores, 0.1, 0.5, 'cxcywh', topk)
+    out, cnt = gpu_keep(boxes, scores, cats, 0.1, 0.5, 'cxcywh', topk)
+    assert cnt == want.numel()
+    assert torch.equal(out['idx'][0, :cnt].cpu().long(), want)
+
+
+def test_postprocess_batched_ragged_counts():
+    """Several images of different candidate counts in one launch, including an empty one."""
+    from mydetection_b200 import ops
+    from oracle import postprocess as opp
+    gen = torch.Generator().manual_seed(5)
+    B, n = 5, 900
+    boxes = torch.cat([torch.rand(B, n, 2, generator=gen) * 200, torch.rand(B, n, 2, generator=gen) * 50 + 2], 2)
+    scores = torch.rand(B, n, generator=gen)
+    cats = torch.randint(0, 6, (B, n), generator=gen).int()
+    counts = torch.tensor([900, 0, 1, 513, 37], dtype=torch.int32)
+    d = dev()
+    out = ops.postprocess(boxes.to(d), scores.to(d), cats.to(d), 0.2, 0.45, topk=512, counts=counts.to(d))
+    torch.cuda.synchronize()
+    for b in range(B):
+        c = int(counts[b])
+        want = opp.post_process(boxes[b, :c], cats[b, :c].long(), scores[b, :c], 0.2, 0.45, 'cxcywh', 512)
+        k = int(out['count'][b])
+        assert k == want.numel()
+        assert torch.equal(out['idx'][b, :k].cpu().long(), want)
+
+
+# ------------------------------------------------------------------------------------- whole path
+def test_detect_end_to_end_vs_oracle(golden):
+    """decode + post_process in one C call against the oracle chain on the same logits.  Membership may
+    differ only for candidates whose score is within 1e-5 relative of conf_thres / of the K-th score,
+    or whose IoU with a kept box is within 1e-6 of the NMS threshold; on this input none is."""
+    from mydetection_b200 import ops
+    from oracle import decode as od, postprocess as opp
+    g = golden('decode')
+    raws = [efdet_views(T(g[f'fcos{li}_bbox_in']), T(g[f'fcos{li}_cls_in'])) for li in range(5)]
+    strides = (8, 16, 32, 64, 128)
+    ref = od.merge_levels([od.decode_fcos(r, s, (256, 384)) for r, s in zip(raws, strides)])
+    d = dev()
+    ls = ops.LevelSet([{k: v.to(d) for k, v in r.items()} for r in raws], strides)
+    out = ops.detect(ops.KIND_FCOS, ls, (256, 384), 0.05, 0.5, topk=512)
+    torch.cuda.synchronize()
+    for b in range(2):
+        want = opp.post_process(ref[0][b], ref[1][b], ref[2][b], 0.05, 0.5, 'cxcywh', 512)
+        k = int(out['count'][b])
+        got = out['idx'][b, :k].cpu().long()
+        assert k == want.numel() and torch.equal(got, want)
+        close(out['box'][b, :k], ref[0][b][want], 384, 'e2e box')
+        close(out['score'][b, :k], ref[2][b][want], 1, 'e2e score')
+        assert torch.equal(out['cls'][b, :k].cpu(), ref[1][b][want])
+
+
+# ------------------------------------------------------------------------------------- IoU / rotated
+def test_bboxes_iou_bit_exact(golden):
+    from mydetection_b200 import ops
+    g = golden('iou')
+    d = dev()
+    a, b = T(g['a']).to(d), T(g['b']).to(d)
+    assert torch.equal(ops.iou_aabb(a, b).cpu(), T(g['iou_cxcywh']))
+    from oracle import iou as oi
+    bx = oi.cxcywh_to_x1y1x2y2(T(g['b']))
+    assert torch.equal(ops.iou_aabb(T(g['a_xyxy']).to(d), bx.to(d), xyxy=True).cpu(), T(g['iou_xyxy']))
+    gt = T(g['gt_debug3']).to(d)
+    assert torch.equal(ops.iou_aabb(gt, gt).cpu(), T(g['iou_gt_self']))
+
+
+def test_rot_iou_and_nms_vs_oracle(golden):
+    from mydetection_b200 import ops
+    from oracle import iou as oi
+    g = golden('iou')
+    d = dev()
+    rb, rs = T(g['rot_boxes']), T(g['rot_scores'])
+    got = ops.iou_rot(rb.to(d), rb.to(d)).cpu()
+    want = oi.iou_rot(rb, rb)
+    assert float((got - want).abs().max()) < 1e-9
+    for thr, key in ((0.45, 'rot_keep_045'), (0.2, 'rot_keep_02')):
+        keep, cnt = ops.nms_rot(rb[None].to(d), rs[None].to(d), thr)
+        torch.cuda.synchronize()
+        assert torch.equal(keep[0, :int(cnt[0])].cpu(), T(g[key]))
+    # larger random case, several images, vs the oracle
+    gen = torch.Generator().manual_seed(11)
+    B, n = 3, 2500
+    boxes = torch.empty(B, n, 5)
+    boxes[..., 0:2] = torch.rand(B, n, 2, generator=gen) * 600 + 50
+    boxes[..., 2:4] = torch.rand(B, n, 2, generator=gen) * 90 + 8
+    boxes[..., 4] = torch.rand(B, n, generator=gen) * 360 - 180
+    scores = torch.rand(B, n, generator=gen)
+    keep, cnt = ops.nms_rot(boxes.to(d), scores.to(d), 0.45)
+    torch.cuda.synchronize()
+    for b in range(B):
+        want = oi.nms_rot(boxes[b], scores[b], 0.45)
+        assert torch.equal(keep[b, :int(cnt[b])].cpu(), want)
+
+
+# ------------------------------------------------------------------------------------- ATSS
+def test_atss_golden(golden):
+    from mydetection_b200 import ops
+    g = golden('atss')
+    d = dev()
+    strides, sides = [8, 16, 32, 64, 128], [24, 48, 96, 192, 384]
+    G = 12
+    gt_box = torch.zeros(2, G, 4)
+    gt_cls = torch.zeros(2, G, dtype=torch.int64)
+    cnt = torch.zeros(2, dtype=torch.int32)
+    for b in range(2):
+        bx, ct = T(g[f'gt{b}_boxes']), T(g[f'gt{b}_cats'])
+        gt_box[b, :bx.shape[0]] = bx
+        gt_cls[b, :bx.shape[0]] = ct
+        cnt[b] = bx.shape[0]
+    for li in range(5):
+        t = T(g[f'atss{li}_bbox_in']).to(d).permute(0, 2, 3, 1)
+        out = ops.atss_assign(t, li, strides, sides, (384, 512), gt_box.to(d), gt_cls.to(d), cnt.to(d), 9, 0.7, 6)
+        torch.cuda.synchronize()
+        for k in ('PositiveMask', 'IgnoredMask', 'TargetConf', 'TargetCls'):
+            assert torch.equal(out[k].cpu(), T(g[f'atss{li}_{k}'])), (li, k)
+        close(out['TargetLTRB'], T(g[f'atss{li}_TargetLTRB']), 512, f'atss{li} ltrb')
