@@ -157,6 +157,12 @@ int mydet_iou_aabb_pairwise(const float* a, int64_t n, const float* b, int64_t k
 int mydet_iou_rot_pairwise(const float* a, int64_t n, const float* b, int64_t k, double* out,
                            void* stream);
 
+/* Format helpers of utils/bbox_ops.py, kept because callers outside the path use the names.
+ * cxcywh_to_x1y1x2y2 (:309-316): rows of n_param >= 4 floats, columns 4.. are copied through.
+ * xywha2vertex (:137-172): rows (cx,cy,w,h,RADIANS) with n_param >= 5 -> out (N,4,2) tl,tr,br,bl. */
+int mydet_cxcywh_to_x1y1x2y2(const float* in, int64_t n, int n_param, float* out, void* stream);
+int mydet_xywha2vertex(const float* in, int64_t n, int n_param, float* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * ATSS assignment of one pyramid level.  Replaces the target construction of
  * FCOS_ATSS_Layer.forward (models/detlayers/fcos2.py:253-341) and _get_atss_threshold (:385-405).

@@ -63,7 +63,7 @@ MYDET_API int mydet_postprocess(const float* boxes, const float* scores, const v
     }
     LargeArgs A{boxes, scores, cls, cls_is_i64, src_idx, counts, batch, pitch, n_per_image, n_param, box_format,
                 conf_thres, topk, nms_thres, 0, false, out_box, out_score, reinterpret_cast<long long*>(out_cls),
-                out_idx, out_count, status, out_cap, nullptr};
+                out_idx, out_count, status, out_cap, nullptr, nullptr};
     return run_large(A, workspace, workspace_bytes, st);
 }
 
@@ -128,12 +128,11 @@ MYDET_API int mydet_nms_rot(const float* boxes, const float* scores, const int32
     MYDET_REQUIRE(batch >= 0 && n_per_image >= 0 && pitch >= n_per_image, "bad batch / n_per_image / pitch");
     MYDET_REQUIRE(n_per_image <= MYDET_MAX_CANDIDATES, "more than %d boxes per image", MYDET_MAX_CANDIDATES);
     MYDET_REQUIRE(keep_count, "NULL keep_count");
-    if (votes) { set_error("majority-vote bookkeeping is not implemented yet (SURVEY 8f rank 3)"); return MYDET_ERR_UNSUPPORTED; }
     if (batch == 0) return 0;
     if (n_per_image == 0) { MYDET_CUDA(cudaMemsetAsync(keep_count, 0, sizeof(int32_t) * (size_t)batch, st)); return 0; }
     MYDET_REQUIRE(boxes && scores && keep, "NULL tensor pointer");
     LargeArgs A{boxes, scores, nullptr, 0, nullptr, counts, batch, pitch, n_per_image, 5, MYDET_BOX_CXCYWH,
                 -INFINITY, 0, thr, ge_mode, true, nullptr, nullptr, nullptr, nullptr, keep_count, nullptr, 0,
-                reinterpret_cast<long long*>(keep)};
+                reinterpret_cast<long long*>(keep), votes};
     return run_large(A, workspace, workspace_bytes, st);
 }

@@ -33,6 +33,7 @@ struct LargeArgs {
     int batch; long long pitch; int n, n_param, box_format; float conf_thres; int topk; double thr; int ge; bool rot;
     float* out_box; float* out_score; long long* out_cls; int* out_idx; int* out_count; int* status; int out_cap;
     long long* keep64;
+    int* votes;
 };
 int run_large(const LargeArgs& A, void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t large_workspace_bytes(int batch, int n, bool rot);

@@ -87,9 +87,50 @@ __global__ void __launch_bounds__(kIouCols) iou_rot_kernel(const float* __restri
     }
 }
 
+__global__ void corners_kernel(const float* __restrict__ in, long long n, int n_param, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = in + i * n_param;
+    float* o = out + i * n_param;
+    const float cx = p[0], cy = p[1], hw = __fmul_rn(p[2], 0.5f), hh = __fmul_rn(p[3], 0.5f);
+    o[0] = __fsub_rn(cx, hw); o[1] = __fsub_rn(cy, hh); o[2] = __fadd_rn(cx, hw); o[3] = __fadd_rn(cy, hh);
+    for (int k = 4; k < n_param; ++k) o[k] = p[k];
+}
+
+// xywha2vertex, bbox_ops.py:137-172 (angle already in radians; float32 sinf/cosf like torch.sin/cos)
+__global__ void vertex_kernel(const float* __restrict__ in, long long n, int n_param, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = in + i * n_param;
+    const float s = (float)sin((double)p[4]), c = (float)cos((double)p[4]);
+    const float hh = __fmul_rn(p[3], 0.5f), hw = __fmul_rn(p[2], 0.5f);
+    const float vx = __fmul_rn(hh, s), vy = -__fmul_rn(hh, c), hx = __fmul_rn(hw, c), hy = __fmul_rn(hw, s);
+    float* o = out + i * 8;
+    o[0] = __fsub_rn(__fadd_rn(p[0], vx), hx); o[1] = __fsub_rn(__fadd_rn(p[1], vy), hy);
+    o[2] = __fadd_rn(__fadd_rn(p[0], vx), hx); o[3] = __fadd_rn(__fadd_rn(p[1], vy), hy);
+    o[4] = __fadd_rn(__fsub_rn(p[0], vx), hx); o[5] = __fadd_rn(__fsub_rn(p[1], vy), hy);
+    o[6] = __fsub_rn(__fsub_rn(p[0], vx), hx); o[7] = __fsub_rn(__fsub_rn(p[1], vy), hy);
+}
+
 }  // namespace mydet
 
 using namespace mydet;
+
+MYDET_API int mydet_cxcywh_to_x1y1x2y2(const float* in, int64_t n, int n_param, float* out, void* stream) {
+    MYDET_REQUIRE(n >= 0 && n_param >= 4, "need n >= 0 and at least 4 columns");
+    if (n == 0) return 0;
+    MYDET_REQUIRE(in && out, "NULL tensor pointer");
+    corners_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, n, n_param, out);
+    return launch_status("corners_kernel");
+}
+
+MYDET_API int mydet_xywha2vertex(const float* in, int64_t n, int n_param, float* out, void* stream) {
+    MYDET_REQUIRE(n >= 0 && n_param >= 5, "need n >= 0 and at least 5 columns");
+    if (n == 0) return 0;
+    MYDET_REQUIRE(in && out, "NULL tensor pointer");
+    vertex_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, n, n_param, out);
+    return launch_status("vertex_kernel");
+}
 
 MYDET_API int mydet_iou_aabb_pairwise(const float* a, int64_t n, const float* b, int64_t k, int xyxy, float* out,
                                       void* stream) {

@@ -27,7 +27,8 @@ struct LargeWs {          // carved out of the caller's workspace
     int* cls;                   // B*n
     RotBox* rbox;               // B*n   sorted rotated quads (ROT)
     unsigned long long* mask;   // B*n*words
-    unsigned long long* kept;   // B*words
+    unsigned long long* kept;   // B*words  survivors, bit per sorted row
+    int* rowpos;                // B*n      sorted row -> position in the emitted list (kept rows)
     int words;                  // ceil(n/64)
 };
 
@@ -40,12 +41,14 @@ static size_t carve(LargeWs& w, void* base, int batch, int n, bool rot) {
     const size_t o_box = take(rot ? 0 : bn * 16), o_area = take(rot ? 0 : bn * 4), o_cls = take(rot ? 0 : bn * 4);
     const size_t o_rbox = take(rot ? bn * sizeof(RotBox) : 0);
     const size_t o_mask = take(bn * (size_t)w.words * 8), o_kept = take((size_t)batch * w.words * 8);
+    const size_t o_rowpos = take(rot ? bn * 4 : 0);
     if (base) {
         char* p = static_cast<char*>(base);
         w.keys = (unsigned long long*)(p + o_keys); w.order = (int*)(p + o_order); w.m = (int*)(p + o_m);
         w.box = (float4*)(p + o_box); w.area = (float*)(p + o_area); w.cls = (int*)(p + o_cls);
         w.rbox = (RotBox*)(p + o_rbox);
         w.mask = (unsigned long long*)(p + o_mask); w.kept = (unsigned long long*)(p + o_kept);
+        w.rowpos = (int*)(p + o_rowpos);
     }
     return off;
 }
@@ -233,6 +236,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(LargeWs w, const i
             }
             s_kept = kept;
             keptw[t] = kept;
+            w.kept[(long long)b * w.words + t] = kept;
         }
         __syncthreads();
         const unsigned long long kept = s_kept;
@@ -276,6 +280,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(LargeWs w, const i
             const int i = order[wd * kTile + j];
             if (E.keep64) {
                 E.keep64[(long long)b * E.pitch + pos] = i;
+                w.rowpos[(long long)b * n + wd * kTile + j] = pos;
             } else if (pos < E.out_cap) {
                 const long long orow = (long long)b * E.out_cap + pos;
                 const long long irow = (long long)b * E.pitch + i;
@@ -293,6 +298,41 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(LargeWs w, const i
         if (!E.keep64 && total > E.out_cap) { total = E.out_cap; if (E.status) atomicOr(E.status + b, 2); }
         E.out_count[b] = total;
     }
+}
+
+// ---------------------------------------------------------------------------- majority votes
+// nms_rotbb's vote bookkeeping (utils/bbox_ops.py:291-306): every dropped box votes for the valid
+// box it overlaps most (first maximum over the boxes valid at that time = kept boxes ranked
+// before it); every kept box starts with its own vote.
+__global__ void votes_kernel(LargeWs w, const int* m, int n, int* votes, long long pitch) {
+    const int b = blockIdx.y;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m[b]) return;
+    const long long base = (long long)b * n;
+    const unsigned long long* kept = w.kept + (long long)b * w.words;
+    if ((kept[r >> 6] >> (r & 63)) & 1ull) {
+        atomicAdd(votes + (long long)b * pitch + w.rowpos[base + r], 1);
+        return;
+    }
+    const RotBox me = w.rbox[base + r];
+    double best = -1.0;
+    int best_q = -1;
+    for (int wd = 0; wd <= (r >> 6); ++wd) {
+        unsigned long long kw = kept[wd];
+        if (wd == (r >> 6)) kw &= (1ull << (r & 63)) - 1ull;
+        while (kw) {
+            const int j = __ffsll((long long)kw) - 1;
+            kw &= kw - 1;
+            const int q = wd * kTile + j;
+            const RotBox o = w.rbox[base + q];
+            const double dx = (double)me.cx - (double)o.cx, dy = (double)me.cy - (double)o.cy;
+            const double rr = (double)me.r + (double)o.r + 1e-3;
+            double iou = 0.0;
+            if (dx * dx + dy * dy <= rr * rr) iou = rot_iou_f64(me.x, me.y, o.x, o.y);
+            if (iou > best) { best = iou; best_q = q; }
+        }
+    }
+    if (best_q >= 0) atomicAdd(votes + (long long)b * pitch + w.rowpos[base + best_q], 1);
 }
 
 // ---------------------------------------------------------------------------- host orchestration
@@ -327,6 +367,10 @@ int run_large(const LargeArgs& A, void* workspace, size_t workspace_bytes, cudaS
     MYDET_REQUIRE(smem <= 200 * 1024, "too many candidates per image for the sweep kernel");
     MYDET_CUDA(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem > 48 * 1024 ? (int)smem : 48 * 1024));
     sweep_kernel<<<B, kSweepThreads, smem, st>>>(w, w.m, n, E);
+    if (A.rot && A.votes) {
+        MYDET_CUDA(cudaMemsetAsync(A.votes, 0, sizeof(int) * (size_t)B * (size_t)A.pitch, st));
+        votes_kernel<<<dim3((n + 127) / 128, B), 128, 0, st>>>(w, w.m, n, A.votes, A.pitch);
+    }
     return launch_status("large NMS pipeline");
 }
 

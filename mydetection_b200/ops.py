@@ -217,9 +217,10 @@ def detect_workspace(levels: LevelSet, topk=512):
 
 
 # --------------------------------------------------------------------------------------- rotated NMS / IoU
-def nms_rot(boxes, scores, thr, ge=True, counts=None):
+def nms_rot(boxes, scores, thr, ge=True, counts=None, want_votes=False):
     """Batched single-class rotated NMS.  boxes (B,n,5) degrees, scores (B,n).
-    Returns (keep (B,n) i64, keep_count (B) i32): kept indices per image in descending score."""
+    Returns (keep (B,n) i64, keep_count (B) i32[, votes (B,n) i32]): kept indices per image in
+    descending score; votes[b, p] = 1 + number of dropped boxes whose best overlap was keep[b, p]."""
     boxes = _dev(boxes, torch.float32, 'boxes').contiguous()
     scores = _dev(scores, torch.float32, 'scores').contiguous()
     if boxes.dim() != 3 or boxes.shape[-1] != 5:
@@ -228,13 +229,14 @@ def nms_rot(boxes, scores, thr, ge=True, counts=None):
     dev = boxes.device
     keep = torch.empty(B, max(n, 1), dtype=torch.int64, device=dev)
     cnt = torch.zeros(B, dtype=torch.int32, device=dev)
+    votes = torch.empty(B, max(n, 1), dtype=torch.int32, device=dev) if want_votes else None
     L = _lib.lib()
     ws = _workspace(L.mydet_nms_rot_workspace_bytes(B, n), dev)
     with torch.cuda.device(dev):
         rc = L.mydet_nms_rot(_ptr(boxes), _ptr(scores), _ptr(counts), B, n, n, float(thr), 1 if ge else 0,
-                             _ptr(keep), _ptr(cnt), None, _ptr(ws), ws.numel(), _stream())
+                             _ptr(keep), _ptr(cnt), _ptr(votes), _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, 'mydet_nms_rot')
-    return keep, cnt
+    return (keep, cnt, votes) if want_votes else (keep, cnt)
 
 
 def iou_aabb(a, b, xyxy=False):

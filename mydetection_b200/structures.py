@@ -1,0 +1,164 @@
+"""Host-side mirror of the reference's utils/structures.py::ImageObjects for the hot path.
+
+Same constructor, attributes and method names; `post_process` / `nms` / `non_max_suppression`
+(utils/structures.py:92-173) run in libmydet's CUDA kernels instead of boolean indexing +
+torch.topk + a Python loop over classes around torchvision.ops.nms on the CPU.  Tracklets,
+drawing and mask helpers of the reference file are outside the path and are not mirrored.
+"""
+import torch
+
+from . import _lib, ops
+
+TOPK_CAP = 512  # utils/structures.py:99-101
+
+
+def _cuda_device():
+    if not torch.cuda.is_available():
+        raise _lib.MydetError('mydetection_b200 needs a CUDA device (B200); there is no CPU fallback')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+class ImageObjects():
+    '''
+    A group of image bounding boxes
+
+    Args:
+        bboxes: 2-d tensor, torch.float32
+        cats: 1-d tensor, torch.int64, categories
+        scores (optional): 1-d tensor, torch.float32, scores
+        bb_format (optional): 'cxcywh' | 'x1y1x2y2' | 'cxcywhd' | 'cxcywhr'
+        img_hw: tuple-like, image (height, width)
+    '''
+    def __init__(self, bboxes, cats, masks=None, scores=None, bb_format='cxcywh', img_hw=None):
+        self.bboxes = bboxes
+        self.cats = cats
+        self.masks = masks
+        self.scores = scores
+        self._bb_format = bb_format
+        self.img_hw = img_hw
+        self.sanity_check()
+
+    # ------------------------------------------------------------------ container protocol
+    def __getitem__(self, idx):
+        if isinstance(idx, int):
+            idx = slice(idx, idx + 1)
+        pick = lambda t: None if t is None else t[idx]
+        return ImageObjects(self.bboxes[idx, :], self.cats[idx], pick(self.masks), pick(self.scores),
+                            self._bb_format, self.img_hw)
+
+    def __len__(self):
+        return self.bboxes.shape[0]
+
+    def cpu_(self):
+        '''Move all attributes to CPU in-place'''
+        for name in ('bboxes', 'cats', 'scores', 'masks'):
+            t = getattr(self, name)
+            if t is not None:
+                setattr(self, name, t.cpu())
+
+    def sanity_check(self):
+        '''Integrity check (utils/structures.py:191-213).'''
+        assert self.bboxes.dtype == torch.float and self.bboxes.dim() == 2
+        if self._bb_format in ('cxcywh', 'x1y1x2y2'):
+            assert self.bboxes.shape[1] == 4
+        elif self._bb_format in ('cxcywhd', 'cxcywhr'):
+            assert self.bboxes.shape[1] == 5
+        else:
+            raise NotImplementedError()
+        assert self.cats.dtype == torch.int64, 'Incorrect data type of categories'
+        assert self.cats.dim() == 1 and self.cats.shape[0] == self.bboxes.shape[0]
+        if self.masks is not None:
+            assert self.masks.dtype == torch.bool and self.masks.dim() == 3
+        if self.scores is not None:
+            assert self.scores.shape[0] == self.bboxes.shape[0]
+        assert self.img_hw is None or len(self.img_hw) == 2
+
+    # ------------------------------------------------------------------ the hot path
+    def _run(self, conf_thres, nms_thres, topk):
+        assert self.masks is None, 'nms with masks is not currently supported'
+        assert self.scores is not None
+        if self._bb_format not in ops.BOX_FORMATS:
+            raise NotImplementedError()
+        home = self.bboxes.device
+        dev = home if home.type == 'cuda' else _cuda_device()
+        if len(self) == 0:
+            return self
+        out = ops.postprocess(self.bboxes.detach().to(dev)[None], self.scores.detach().to(dev, torch.float32)[None],
+                              self.cats.to(dev)[None], conf_thres, nms_thres, topk=topk, box_format=self._bb_format)
+        n, status = (int(v) for v in torch.stack([out['count'][0], out['status'][0]]).tolist())  # one D2H sync
+        if status & 1:
+            raise _lib.MydetError(f'category ids must lie in [0, {_lib.MAX_CLASS_ID}]')
+        return ImageObjects(out['box'][0, :n], out['cls'][0, :n], None, out['score'][0, :n], self._bb_format,
+                            img_hw=self.img_hw), out['idx'][0, :n]
+
+    def post_process(self, conf_thres, nms_thres):
+        '''Confidence threshold + top-512 + per-class NMS (utils/structures.py:92-106).
+        Like the reference, the result lives on the CPU.'''
+        res = self._run(conf_thres, nms_thres, TOPK_CAP)
+        if res is self:
+            return self
+        dts, _ = res
+        dts.cpu_()
+        return dts
+
+    def nms(self, nms_thres=0.45):
+        return ImageObjects.non_max_suppression(self, nms_thres)
+
+    @staticmethod
+    def non_max_suppression(dts, nms_thres: float):
+        '''Per-class NMS without threshold or cap (utils/structures.py:111-173); the result stays on
+        the device of the input.'''
+        assert isinstance(dts, ImageObjects)
+        res = dts._run(float('-inf'), nms_thres, None)
+        if res is dts:
+            return dts
+        out, _ = res
+        home = dts.bboxes.device
+        if home.type != 'cuda':
+            out.cpu_()
+        return out
+
+    # ------------------------------------------------------------------ small helpers the API layer calls
+    def bboxes_to_original_(self, pad_info):
+        '''Undo the resize/pad of the input image (utils/structures.py:175-189).'''
+        assert self.masks is None and len(pad_info) == 6
+        ori_w, ori_h, tl_x, tl_y, imw, imh = pad_info
+        self.bboxes[:, 0] = (self.bboxes[:, 0] - tl_x) / imw * ori_w
+        self.bboxes[:, 1] = (self.bboxes[:, 1] - tl_y) / imh * ori_h
+        self.bboxes[:, 2] = self.bboxes[:, 2] / imw * ori_w
+        self.bboxes[:, 3] = self.bboxes[:, 3] / imh * ori_h
+        self.img_hw = (ori_h, ori_w)
+
+    def sort_by_score_(self, descending=True):
+        assert self.scores is not None and self.masks is None
+        order = torch.argsort(self.scores, descending=descending)
+        self.bboxes, self.cats, self.scores = self.bboxes[order, :], self.cats[order], self.scores[order]
+
+    def to_json(self, img_id, eval_type='x1y1wh', catIdx2id=None) -> list:
+        '''COCO-like detection dicts {image_id, category_id, bbox, score} (utils/structures.py:221-259).'''
+        assert self.bboxes.dim() == 2
+        assert self.bboxes.shape[0] == self.cats.shape[0] == self.scores.shape[0]
+        if eval_type == 'x1y1wh':
+            assert self._bb_format == 'cxcywh'
+        elif eval_type == 'cxcywhd':
+            assert self._bb_format == 'cxcywhd'
+        else:
+            raise NotImplementedError()
+        rows = []
+        for bb, c, s in zip(self.bboxes.tolist(), self.cats.tolist(), self.scores.tolist()):
+            if eval_type == 'x1y1wh':
+                cx, cy, w, h = bb
+                bb = [cx - w / 2, cy - h / 2, w, h]
+            cat_id = catIdx2id[c] if catIdx2id is not None else COCO_CATEGORY_IDS[c]
+            rows.append({'image_id': img_id, 'category_id': cat_id, 'bbox': bb, 'score': s})
+        return rows
+
+
+# category index -> COCO 2017 category id (the 'id' fields of the reference's utils/constants.py list)
+# 80 "thing" ids followed by the 53 panoptic "stuff" ids
+COCO_CATEGORY_IDS = ([*range(1, 12), *range(13, 26), 27, 28, *range(31, 45), *range(46, 66), 67, 70,
+                      *range(72, 83), *range(84, 91)] +
+                     [92, 93, 95, 100, 107, 109, 112, 118, 119, 122, 125, 128, 130, 133, 138, 141, 144, 145, 147,
+                      148, 149, 151, 154, 155, 156, 159, 161, 166, 168, 171, *range(175, 179), 180, 181,
+                      *range(184, 201)])
+assert len(COCO_CATEGORY_IDS) == 133

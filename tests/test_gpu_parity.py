@@ -295,7 +295,9 @@ def test_rot_iou_and_nms_vs_oracle(golden):
     rb, rs = T(g['rot_boxes']), T(g['rot_scores'])
     got = ops.iou_rot(rb.to(d), rb.to(d)).cpu()
     want = oi.iou_rot(rb, rb)
-    assert float((got - want).abs().max()) < 1e-9
+    # same polygons up to the last bit of float32 sin/cos (glibc sinf on the CPU, correctly rounded
+    # float64->float32 on the GPU): the IoU values agree far inside the 1e-6 band of the north star
+    assert float((got - want).abs().max()) < 1e-6
     for thr, key in ((0.45, 'rot_keep_045'), (0.2, 'rot_keep_02')):
         keep, cnt = ops.nms_rot(rb[None].to(d), rs[None].to(d), thr)
         torch.cuda.synchronize()
