@@ -306,6 +306,8 @@ def run_gpu(args):
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
 
     if rank == 0:
+        bound[0].launch_decode()
+        torch.cuda.synchronize(dev)
         cand = int(bound[0].cand['count'].clamp(max=bound[0].cand['box'].shape[1]).sum().item())
         peaks = {}
         try:

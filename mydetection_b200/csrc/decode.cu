@@ -16,9 +16,19 @@
 
 namespace mydet {
 
-constexpr int kDecodeWarps = 4;                  // warps per CTA
+// tunables (overridable at build time by scripts/tune_decode.py)
+#ifndef MYDET_DECODE_WARPS
+#define MYDET_DECODE_WARPS 4
+#endif
+#ifndef MYDET_CLS_UNROLL
+#define MYDET_CLS_UNROLL 8
+#endif
+#ifndef MYDET_DECODE_MINBLOCKS
+#define MYDET_DECODE_MINBLOCKS 8
+#endif
+constexpr int kDecodeWarps = MYDET_DECODE_WARPS;   // warps per CTA
 constexpr int kDecodeThreads = kDecodeWarps * 32;
-constexpr int kClsUnroll = 8;                    // class planes in flight per thread
+constexpr int kClsUnroll = MYDET_CLS_UNROLL;       // class planes in flight per thread
 
 struct LevelDev {
     const float* bbox;
@@ -55,16 +65,51 @@ struct DecodeParams {
     int capacity;
 };
 
-// Running "first index of the maximal sigmoid" over class logits.
-// sigmoid is monotone, so comparing logits is enough EXCEPT where float32 sigmoid collapses
-// distinct logits onto one value (gaps below ~1e-3, or the saturated region above ~8): there the
-// reference's torch.max over probabilities keeps the FIRST index, so fall back to comparing the
-// probabilities themselves.  The fallback is a rarely taken, warp-divergent branch.
-__device__ __forceinline__ void class_update(float& best, int& best_c, float v, int c) {
-    if (v > best) {
-        bool take = true;
-        if (__fsub_rn(v, best) < 4e-3f || v > 8.0f) take = sigmoid_f(v) > sigmoid_f(best);
-        if (take) { best = v; best_c = c; }
+// Running arg-max over class logits, plus the runner-up value.
+// The reference takes torch.max over the class PROBABILITIES (first index on ties).  sigmoid is
+// monotone, so the arg-max over logits is the same index EXCEPT where float32 sigmoid collapses two
+// distinct logits onto one probability.  That needs a top-2 gap below ulp(sigma)/sigma'(x):
+// < 2.4e-7 for x <= 0, < 1.3e-6 for x < 3, < 1.8e-4 for x < 8, anything above.  Cells whose top-2
+// gap falls inside a (5-8x wider) guard band are re-scanned on the probabilities (rare, divergent).
+__device__ __forceinline__ void class_update(float& best, float& second, int& best_c, float v, int c) {
+    const bool gt = v > best;
+    second = fmaxf(second, fminf(best, v));
+    best = fmaxf(best, v);
+    best_c = gt ? c : best_c;
+}
+__device__ __forceinline__ bool class_ambiguous(float best, float second) {
+    const float gap = __fsub_rn(best, second);
+    if (best > 8.0f) return second > 8.0f || gap < 1e-3f;   // both saturated, or close
+    return gap < (best < 3.0f ? 1e-5f : 1e-3f);
+}
+
+// Exact restatement of torch.max(sigmoid(logits)) for the cells flagged in `flagged` (one bit per
+// lane): the WHOLE warp re-reads that cell's class logits (lane k takes classes k, k+32, ...),
+// evaluates the probabilities and reduces to the first index of the maximal probability.
+// Must be called by all 32 lanes.  A serial per-thread re-scan here cost a 30 us tail (r1 profile).
+__device__ __forceinline__ void class_rescan_warp(unsigned flagged, const float* pc, long long stride_c, int n_cls,
+                                                  float& best, int& best_c) {
+    const unsigned lane = lane_id();
+    while (flagged) {
+        const int src = __ffs(flagged) - 1;
+        flagged &= flagged - 1;
+        const unsigned long long base = __shfl_sync(0xffffffffu, (unsigned long long)pc, src);
+        const float* q = reinterpret_cast<const float*>(base);
+        float bp = -1.0f, bl = 0.f;
+        int bc = 0x7fffffff;
+        for (int c = (int)lane; c < n_cls; c += 32) {
+            const float v = ld_stream(q + (long long)c * stride_c);
+            const float p = sigmoid_f(v);
+            if (p > bp) { bp = p; bl = v; bc = c; }      // ascending c: keeps the first maximum
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float op = __shfl_xor_sync(0xffffffffu, bp, o);
+            const float ol = __shfl_xor_sync(0xffffffffu, bl, o);
+            const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+            if (op > bp || (op == bp && oc < bc)) { bp = op; bl = ol; bc = oc; }
+        }
+        if ((int)lane == src) { best = bl; best_c = bc; }
     }
 }
 
@@ -146,72 +191,87 @@ __device__ __forceinline__ void decode_unit(const DecodeParams& P, const LevelDe
     const int hw0 = q * VEC;
     const bool active = hw0 < L.n_hw;
     const int n_cls = P.n_cls, n_par = P.n_param;
+    const int h0 = hw0 / L.n_w, w0 = hw0 - h0 * L.n_w;   // VEC == 1: the cell; VEC == 4: first cell
 
-    float t[5][VEC];
-    float conf_logit[VEC];
-    float best[VEC];
+    // ---- class planes first (94 % of the bytes): running arg-max, kClsUnroll loads in flight
+    float best[VEC], second[VEC];
     int best_c[VEC];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) { best[j] = -INFINITY; best_c[j] = 0; conf_logit[j] = 0.f; }
+    for (int j = 0; j < VEC; ++j) { best[j] = -INFINITY; second[j] = -INFINITY; best_c[j] = 0; }
+    if (active && n_cls > 0) {
+        if constexpr (VEC == 4) {
+            const float* pc = L.cls + b * L.ks_b + a * L.ks_a + hw0;   // hw-contiguous planes
+            int c = 0;
+            for (; c + kClsUnroll <= n_cls; c += kClsUnroll) {
+                float4 v[kClsUnroll];
+#pragma unroll
+                for (int u = 0; u < kClsUnroll; ++u) v[u] = ld_stream_v4(pc + (long long)(c + u) * L.ks_c);
+#pragma unroll
+                for (int u = 0; u < kClsUnroll; ++u) {
+                    class_update(best[0], second[0], best_c[0], v[u].x, c + u);
+                    class_update(best[1], second[1], best_c[1], v[u].y, c + u);
+                    class_update(best[2], second[2], best_c[2], v[u].z, c + u);
+                    class_update(best[3], second[3], best_c[3], v[u].w, c + u);
+                }
+            }
+            for (; c < n_cls; ++c) {
+                const float4 v = ld_stream_v4(pc + (long long)c * L.ks_c);
+                class_update(best[0], second[0], best_c[0], v.x, c);
+                class_update(best[1], second[1], best_c[1], v.y, c);
+                class_update(best[2], second[2], best_c[2], v.z, c);
+                class_update(best[3], second[3], best_c[3], v.w, c);
+            }
+        } else {
+            const float* pc = L.cls + b * L.ks_b + a * L.ks_a + h0 * L.ks_h + w0 * L.ks_w;
+            int c = 0;
+            for (; c + kClsUnroll <= n_cls; c += kClsUnroll) {
+                float v[kClsUnroll];
+#pragma unroll
+                for (int u = 0; u < kClsUnroll; ++u) v[u] = ld_stream(pc + (long long)(c + u) * L.ks_c);
+#pragma unroll
+                for (int u = 0; u < kClsUnroll; ++u) class_update(best[0], second[0], best_c[0], v[u], c + u);
+            }
+            for (; c < n_cls; ++c) class_update(best[0], second[0], best_c[0], ld_stream(pc + (long long)c * L.ks_c), c);
+        }
+    }
 
+    if (n_cls > 1) {   // warp-uniform; rare cooperative re-scan of near-tied cells
+        const float* pc0 = (VEC == 4) ? L.cls + b * L.ks_b + a * L.ks_a + hw0
+                                      : L.cls + b * L.ks_b + a * L.ks_a + h0 * L.ks_h + w0 * L.ks_w;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            const unsigned flagged = __ballot_sync(0xffffffffu, active && class_ambiguous(best[j], second[j]));
+            if (flagged) class_rescan_warp(flagged, pc0 + j, L.ks_c, n_cls, best[j], best_c[j]);
+        }
+    }
+
+    // ---- box and objectness planes (6 % of the bytes), loaded after the class loop so that they
+    // do not occupy registers during it
+    float t[5][VEC];
+    float conf_logit[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) conf_logit[j] = 0.f;
     if (active) {
-        if (VEC == 4) {
-            // hw-contiguous planes: plane stride is the "p"/"c" stride, cells are consecutive floats
+        if constexpr (VEC == 4) {
             const float* pb = L.bbox + b * L.bs_b + a * L.bs_a + hw0;
 #pragma unroll
             for (int p = 0; p < 5; ++p) {
                 if (p < n_par) {
-                    float4 v = ld_stream_v4(pb + p * L.bs_p);
-                    t[p][0] = v.x; t[p][1 % VEC] = v.y; t[p][2 % VEC] = v.z; t[p][3 % VEC] = v.w;
+                    const float4 v = ld_stream_v4(pb + p * L.bs_p);
+                    t[p][0] = v.x; t[p][1] = v.y; t[p][2] = v.z; t[p][3] = v.w;
                 }
             }
             if (KIND != MYDET_KIND_RETINA) {
-                float4 v = ld_stream_v4(L.conf + b * L.cs_b + a * L.cs_a + hw0);
-                conf_logit[0] = v.x; conf_logit[1 % VEC] = v.y; conf_logit[2 % VEC] = v.z; conf_logit[3 % VEC] = v.w;
-            }
-            if (n_cls > 0) {
-                const float* pc = L.cls + b * L.ks_b + a * L.ks_a + hw0;
-                int c = 0;
-                for (; c + kClsUnroll <= n_cls; c += kClsUnroll) {
-                    float4 v[kClsUnroll];
-#pragma unroll
-                    for (int u = 0; u < kClsUnroll; ++u) v[u] = ld_stream_v4(pc + (long long)(c + u) * L.ks_c);
-#pragma unroll
-                    for (int u = 0; u < kClsUnroll; ++u) {
-                        class_update(best[0], best_c[0], v[u].x, c + u);
-                        class_update(best[1 % VEC], best_c[1 % VEC], v[u].y, c + u);
-                        class_update(best[2 % VEC], best_c[2 % VEC], v[u].z, c + u);
-                        class_update(best[3 % VEC], best_c[3 % VEC], v[u].w, c + u);
-                    }
-                }
-                for (; c < n_cls; ++c) {
-                    float4 v = ld_stream_v4(pc + (long long)c * L.ks_c);
-                    class_update(best[0], best_c[0], v.x, c);
-                    class_update(best[1 % VEC], best_c[1 % VEC], v.y, c);
-                    class_update(best[2 % VEC], best_c[2 % VEC], v.z, c);
-                    class_update(best[3 % VEC], best_c[3 % VEC], v.w, c);
-                }
+                const float4 v = ld_stream_v4(L.conf + b * L.cs_b + a * L.cs_a + hw0);
+                conf_logit[0] = v.x; conf_logit[1] = v.y; conf_logit[2] = v.z; conf_logit[3] = v.w;
             }
         } else {
-            const int h = hw0 / L.n_w, w = hw0 - h * L.n_w;
-            const float* pb = L.bbox + b * L.bs_b + a * L.bs_a + h * L.bs_h + w * L.bs_w;
+            const float* pb = L.bbox + b * L.bs_b + a * L.bs_a + h0 * L.bs_h + w0 * L.bs_w;
 #pragma unroll
             for (int p = 0; p < 5; ++p)
                 if (p < n_par) t[p][0] = ld_stream(pb + p * L.bs_p);
             if (KIND != MYDET_KIND_RETINA)
-                conf_logit[0] = ld_stream(L.conf + b * L.cs_b + a * L.cs_a + h * L.cs_h + w * L.cs_w);
-            if (n_cls > 0) {
-                const float* pc = L.cls + b * L.ks_b + a * L.ks_a + h * L.ks_h + w * L.ks_w;
-                int c = 0;
-                for (; c + kClsUnroll <= n_cls; c += kClsUnroll) {
-                    float v[kClsUnroll];
-#pragma unroll
-                    for (int u = 0; u < kClsUnroll; ++u) v[u] = ld_stream(pc + (long long)(c + u) * L.ks_c);
-#pragma unroll
-                    for (int u = 0; u < kClsUnroll; ++u) class_update(best[0], best_c[0], v[u], c + u);
-                }
-                for (; c < n_cls; ++c) class_update(best[0], best_c[0], ld_stream(pc + (long long)c * L.ks_c), c);
-            }
+                conf_logit[0] = ld_stream(L.conf + b * L.cs_b + a * L.cs_a + h0 * L.cs_h + w0 * L.cs_w);
         }
     }
 
@@ -299,7 +359,7 @@ __device__ __forceinline__ void decode_unit(const DecodeParams& P, const LevelDe
 }
 
 template <int KIND, bool COMPACT>
-__global__ void __launch_bounds__(kDecodeThreads, 4)
+__global__ void __launch_bounds__(kDecodeThreads, MYDET_DECODE_MINBLOCKS)
 decode_kernel(const __grid_constant__ DecodeParams P) {
     // CTA -> level (levels are laid out back to back in CTA index space)
     int l = 0;

@@ -14,46 +14,67 @@ KINDS = {'YOLO': ops.KIND_YOLO, 'FCOS': ops.KIND_FCOS, 'FCOS2': ops.KIND_FCOS, '
 
 
 class BoundCall:
-    """The pipeline bound to fixed input tensors, outputs and workspace: launch() is one ctypes call."""
+    """The pipeline bound to fixed input tensors, outputs and workspace.
+
+    Every buffer and every ctypes argument is prepared once; launch() / launch_decode() /
+    launch_postprocess() are then single C calls with no Python-side allocation, so the host stays
+    far ahead of the GPU (a step is two kernel launches and one 256-byte memset)."""
 
     def __init__(self, pipe, raws):
         self.pipe = pipe
         self.levels = ops.LevelSet(raws, pipe.strides, pipe.anchors, pipe.conf_key)
-        ls = self.levels
-        k = pipe.topk or 0
+        ls, L, ptr = self.levels, _lib.lib(), ops._ptr
+        dev = ls.device
+        k = int(pipe.topk) if pipe.topk else 0
         cap = min(k, ls.n_total) if k > 0 else ls.n_total
-        self.out = ops._alloc_dets(ls.batch, max(cap, 1), ls.n_param, ls.device)
+        self.out = ops._alloc_dets(ls.batch, max(cap, 1), ls.n_param, dev)
         self.workspace = ops.detect_workspace(ls, pipe.topk)
-        self.cand = None
+        B, N, P = ls.batch, ls.n_total, ls.n_param
+        self.cand = {'box': torch.empty(B, N, P, dtype=torch.float32, device=dev),
+                     'score': torch.empty(B, N, dtype=torch.float32, device=dev),
+                     'cls': torch.empty(B, N, dtype=torch.int32, device=dev),
+                     'idx': torch.empty(B, N, dtype=torch.int32, device=dev),
+                     'count': torch.zeros(B, dtype=torch.int32, device=dev)}
+        self.pp_workspace = ops._workspace(L.mydet_postprocess_workspace_bytes(B, N, k), dev)
+        o, c = self.out, self.cand
+        img_h, img_w = float(pipe.img_hw[0]), float(pipe.img_hw[1])
+        self._L = L
+        self._detect_args = (pipe.kind, ls.array, ls.n_levels, B, ls.n_cls, P, img_h, img_w, pipe.conf_thres, k,
+                             pipe.nms_thres, ptr(o['box']), ptr(o['score']), ptr(o['cls']), ptr(o['idx']),
+                             ptr(o['count']), ptr(o['status']), o['box'].shape[1], ptr(self.workspace),
+                             self.workspace.numel())
+        self._decode_args = (pipe.kind, ls.array, ls.n_levels, B, ls.n_cls, P, img_h, img_w, pipe.conf_thres,
+                             ptr(c['box']), ptr(c['score']), ptr(c['cls']), ptr(c['idx']), ptr(c['count']), N)
+        self._pp_args = (ptr(c['box']), ptr(c['score']), ptr(c['cls']), 0, ptr(c['idx']), ptr(c['count']), B, N, N, P,
+                         ops.BOX_CXCYWH, float('-inf'), k, pipe.nms_thres, ptr(o['box']), ptr(o['score']),
+                         ptr(o['cls']), ptr(o['idx']), ptr(o['count']), ptr(o['status']), o['box'].shape[1],
+                         ptr(self.pp_workspace), self.pp_workspace.numel())
         self.graph = None
 
-    def launch(self):
-        p = self.pipe
-        return ops.detect(p.kind, self.levels, p.img_hw, p.conf_thres, p.nms_thres, p.topk, out=self.out,
-                          workspace=self.workspace)
+    @staticmethod
+    def _stream():
+        return torch.cuda.current_stream().cuda_stream
 
-    # stage-wise entry points (same kernels as launch(); used to time the decode kernel alone)
+    def launch(self):
+        """decode + threshold + top-k + NMS: one C call (mydet_detect), asynchronous."""
+        rc = self._L.mydet_detect(*self._detect_args, self._stream())
+        if rc:
+            _lib.check(rc, 'mydet_detect')
+        return self.out
+
+    # stage-wise entry points: the same two kernels as launch(), exposed so that bench.py can put
+    # CUDA events around the decode kernel
     def launch_decode(self):
-        p = self.pipe
-        self.cand = ops.decode_compact(p.kind, self.levels, p.img_hw, p.conf_thres) if self.cand is None else \
-            self._decode_into(self.cand)
+        rc = self._L.mydet_decode_compact(*self._decode_args, self._stream())
+        if rc:
+            _lib.check(rc, 'mydet_decode_compact')
         return self.cand
 
-    def _decode_into(self, c):
-        p, ls = self.pipe, self.levels
-        with torch.cuda.device(ls.device):
-            rc = _lib.lib().mydet_decode_compact(p.kind, ls.array, ls.n_levels, ls.batch, ls.n_cls, ls.n_param,
-                                                 float(p.img_hw[0]), float(p.img_hw[1]), float(p.conf_thres),
-                                                 ops._ptr(c['box']), ops._ptr(c['score']), ops._ptr(c['cls']),
-                                                 ops._ptr(c['idx']), ops._ptr(c['count']), c['box'].shape[1],
-                                                 ops._stream())
-        _lib.check(rc, 'mydet_decode_compact')
-        return c
-
     def launch_postprocess(self):
-        c, p = self.cand, self.pipe
-        return ops.postprocess(c['box'], c['score'], c['cls'], float('-inf'), p.nms_thres, topk=p.topk,
-                               counts=c['count'], src_idx=c['idx'], out=self.out)
+        rc = self._L.mydet_postprocess(*self._pp_args, self._stream())
+        if rc:
+            _lib.check(rc, 'mydet_postprocess')
+        return self.out
 
     def capture(self):
         """Record launch() into a CUDA graph (fixed shapes, fixed buffers)."""
