@@ -8,30 +8,40 @@
 //   top-k by (score desc, index asc)                (:99-101, torch.topk; tie policy is ours)
 //   per class, visiting order = stable score desc:  suppressed iff (double)iou > nms_thres
 //   output = class ascending, then score descending (:158-171)
+// "index" is the candidate's flat index (src_idx) when the input is a compacted buffer whose slot
+// order is arbitrary, so the result does not depend on the compaction order.
 //
-// Stages: (A) MSB-first 8-bit radix select on the 64-bit key (score, ~index) with early exit,
-// (B) gather + 64-bit bitonic sort on (class, ~score, index), (C) lower-triangular IoU bit matrix
-// in shared memory, same-class pairs only, (D) the greedy sweep evaluated as a parallel fixed
-// point (a serial sweep by one warp was 50 % of this kernel, profiles/r1), (E) ordered compaction.
+// Stages (r1 profile notes in profiles/):
+//  (A0) stage 64-bit select keys (score key, ~index) in shared memory, count threshold survivors
+//  (A)  MSB-first 8-bit radix select of the K-th largest key; per-warp private histograms (scores
+//       cluster in a few digits: one shared histogram serialised 1024 threads on 2-3 addresses);
+//       early exit as soon as the bucket holding the K-th key is taken whole
+//  (B)  gather: one global round trip fetches class, box and source index of every selected
+//       candidate into shared memory; 64-bit bitonic sort on (class, ~score, index) + slot payload
+//  (C)  lower-triangular IoU bit matrix in shared memory, same-class pairs only
+//  (D)  the greedy sweep evaluated as a parallel fixed point (a serial one-warp sweep was 50 % of
+//       the first version of this kernel)
+//  (E)  ordered compaction of the survivors, from shared memory
 #include "internal.cuh"
 
 namespace mydet {
 
 constexpr int kPPThreads = 1024;
+constexpr int kPPWarps = kPPThreads / 32;
 
 __device__ __forceinline__ int load_cls(const void* cls, int is64, long long i) {
     return is64 ? (int)reinterpret_cast<const long long*>(cls)[i] : reinterpret_cast<const int*>(cls)[i];
 }
 
-// key for selection: larger = better.  (score key << 32) | (~index)
-__device__ __forceinline__ unsigned long long select_key(float s, int i) {
-    return ((unsigned long long)float_key(s) << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
-}
-
-// number of candidates whose 32-bit score key is cached in shared memory (the rest is re-read from L2)
+// number of candidates whose select key is cached in shared memory (the rest is re-read from L2)
 __host__ __device__ inline int pp_cache_elems(int n_per_image, int kpad) {
-    const int budget = (kpad <= 512) ? 40960 : 12288;   // floats; keeps the CTA under 227 KB
+    const int budget = (kpad <= 512) ? 16384 : 4096;
     return n_per_image < budget ? n_per_image : budget;
+}
+__host__ __device__ inline size_t pp_mask_bytes(int kpad) {
+    const size_t m = (size_t)kpad * (size_t)(kpad / 32 + 1) * 4;
+    const size_t h = (size_t)kPPWarps * 256 * 4;   // the per-warp histograms alias the mask
+    return m > h ? m : h;
 }
 
 __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const PPParams P) {
@@ -42,15 +52,21 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
     const int W = kpad >> 5;   // mask words per row
     const int Wp = W + 1;      // padded row pitch: conflict-free column walks
 
-    // shared layout
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);           // kpad
-    float4* sbox = reinterpret_cast<float4*>(keys + kpad);                                // kpad
-    float* sarea = reinterpret_cast<float*>(sbox + kpad);                                 // kpad
-    int* scls = reinterpret_cast<int*>(sarea + kpad);                                     // kpad
-    unsigned* mask = reinterpret_cast<unsigned*>(scls + kpad);                            // kpad * Wp
-    unsigned* hist = mask + (size_t)kpad * Wp;                                            // 256
-    unsigned* keptw = hist + 256;                                                         // 2 * 32
-    unsigned* ucache = keptw + 64;                                                        // cache_n
+    // ---- shared layout (16-byte pieces first)
+    unsigned char* sp = smem_raw;
+    float4* gbox = reinterpret_cast<float4*>(sp); sp += (size_t)kpad * 16;                 // by gather slot
+    float4* sbox = reinterpret_cast<float4*>(sp); sp += (size_t)kpad * 16;                 // by sorted rank: corners
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(sp); sp += (size_t)kpad * 8;
+    unsigned* mask = reinterpret_cast<unsigned*>(sp); sp += pp_mask_bytes(kpad);           // kpad * Wp words
+    unsigned* whist = mask;                                                                // 32 x 256, aliases mask
+    float* sarea = reinterpret_cast<float*>(sp); sp += (size_t)kpad * 4;
+    int* scls = reinterpret_cast<int*>(sp); sp += (size_t)kpad * 4;                        // by sorted rank
+    int* gsrc = reinterpret_cast<int*>(sp); sp += (size_t)kpad * 4;                        // by gather slot
+    float* gang = reinterpret_cast<float*>(sp); sp += (size_t)kpad * 4;                    // 5th box column, by slot
+    unsigned* hist = reinterpret_cast<unsigned*>(sp); sp += 256 * 4;
+    unsigned* keptw = reinterpret_cast<unsigned*>(sp); sp += 64 * 4;
+    unsigned long long* ckey = reinterpret_cast<unsigned long long*>(sp); sp += (size_t)pp_cache_elems(P.n_per_image, kpad) * 8;
+    unsigned short* pay = reinterpret_cast<unsigned short*>(sp);                           // slot payload of the sort
     __shared__ unsigned long long s_prefix;
     __shared__ int s_need, s_done, s_nsel, s_total, s_flags;
 
@@ -61,56 +77,58 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
         if (c > n) flags |= 4; else n = c < 0 ? 0 : c;
     }
     const int cache_n = min(n, pp_cache_elems(P.n_per_image, kpad));
-    const float* scores = P.scores + (long long)b * P.pitch;
-    const float* boxes = P.boxes + (long long)b * P.pitch * P.n_param;
-    const long long cls_base = (long long)b * P.pitch;
+    const long long row0 = (long long)b * P.pitch;
+    const float* scores = P.scores + row0;
+    const float* boxes = P.boxes + row0 * P.n_param;
+    const int* src = P.src_idx ? P.src_idx + row0 : nullptr;
     const float thr = P.conf_thres;
     const int K = P.topk;
 
     if (tid == 0) { s_nsel = 0; s_total = 0; s_flags = 0; s_done = 0; s_prefix = 0ull; }
-    for (int i = tid; i < kpad * Wp; i += kPPThreads) mask[i] = 0u;
-    __syncthreads();
 
-    // 32-bit score key of candidate i, 0 when it fails the threshold (or is NaN)
-    auto ukey_global = [&](int i) -> unsigned { const float s = scores[i]; return (s >= thr) ? float_key(s) : 0u; };
-    auto ukey = [&](int i) -> unsigned { return i < cache_n ? ucache[i] : ukey_global(i); };
+    // select key of candidate i: (score key << 32) | ~tie index; 0 when it fails the threshold / is NaN
+    auto key_global = [&](int i) -> unsigned long long {
+        const float s = scores[i];
+        if (!(s >= thr)) return 0ull;
+        const unsigned tie = src ? (unsigned)src[i] : (unsigned)i;
+        return ((unsigned long long)float_key(s) << 32) | (unsigned long long)(0xffffffffu - tie);
+    };
+    auto key_of = [&](int i) -> unsigned long long { return i < cache_n ? ckey[i] : key_global(i); };
 
     // ---- (A0) stage the keys, count the candidates that pass the threshold
     {
         int local = 0;
         for (int i = tid; i < n; i += kPPThreads) {
-            const unsigned u = ukey_global(i);
-            if (i < cache_n) ucache[i] = u;
-            local += u ? 1 : 0;
+            const unsigned long long k = key_global(i);
+            if (i < cache_n) ckey[i] = k;
+            local += k ? 1 : 0;
         }
         local = __reduce_add_sync(0xffffffffu, local);
         if (lane == 0 && local) atomicAdd(&s_total, local);
     }
     __syncthreads();
     const int total = s_total;
-    unsigned long long kth = 1ull;  // select every key >= kth (key 0.. = failed threshold)
+    unsigned long long kth = 1ull;  // select every key >= kth
     if (total > K) {
-        // ---- (A) radix select of the K-th largest 64-bit key (score key, ~index), 8 bits per pass,
-        // MSB first; warp-aggregated histogram (scores cluster in a few digits)
+        // ---- (A) radix select of the K-th largest key
         if (tid == 0) s_need = K;
+        unsigned* myhist = whist + warp * 256;
         for (int pass = 7; pass >= 0; --pass) {
             const int shift = pass * 8;
-            for (int i = tid; i < 256; i += kPPThreads) hist[i] = 0u;
+            for (int i = tid; i < kPPWarps * 256; i += kPPThreads) whist[i] = 0u;
             __syncthreads();
             const unsigned long long prefix = s_prefix;
             const unsigned long long himask = (pass == 7) ? 0ull : (~0ull << (shift + 8));
-            for (int base = 0; base < n; base += kPPThreads) {
-                const int i = base + tid;
-                unsigned digit = 256u;  // "not a candidate"
-                if (i < n) {
-                    const unsigned u = ukey(i);
-                    if (u) {
-                        const unsigned long long k = ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
-                        if ((k & himask) == prefix) digit = (unsigned)(k >> shift) & 255u;
-                    }
-                }
-                const unsigned peers = __match_any_sync(0xffffffffu, digit);
-                if (digit < 256u && lane == __ffs(peers) - 1) atomicAdd(&hist[digit], (unsigned)__popc(peers));
+            for (int i = tid; i < n; i += kPPThreads) {
+                const unsigned long long k = key_of(i);
+                if (k && (k & himask) == prefix) atomicAdd(&myhist[(unsigned)(k >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid < 256) {
+                unsigned sum = 0;
+#pragma unroll 8
+                for (int w = 0; w < kPPWarps; ++w) sum += whist[w * 256 + tid];
+                hist[tid] = sum;
             }
             __syncthreads();
             if (tid < 32) {
@@ -144,33 +162,40 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
         if (kth == 0ull) kth = 1ull;
     }
 
-    // ---- (B) gather the selected candidates as sort keys: class asc, score desc, index asc
-    for (int i = tid; i < kpad; i += kPPThreads) keys[i] = ~0ull;
+    // ---- (B) gather the selected candidates: sort key (class asc, score desc, tie index asc) and,
+    // in the same global round trip, their box / class / source index into shared memory
+    for (int i = tid; i < kpad; i += kPPThreads) { keys[i] = ~0ull; pay[i] = (unsigned short)i; }
+    for (int i = tid; i < kpad * Wp; i += kPPThreads) mask[i] = 0u;   // the histograms are dead now
     __syncthreads();
     for (int base = 0; base < n; base += kPPThreads) {
         const int i = base + tid;
-        unsigned u = 0u;
-        bool take = false;
-        if (i < n) {
-            u = ukey(i);
-            take = u && ((((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (unsigned)i)) >= kth);
-        }
+        unsigned long long k = 0ull;
+        if (i < n) k = key_of(i);
+        const bool take = k >= kth && k != 0ull;
         const unsigned bal = __ballot_sync(0xffffffffu, take);
         int slot0 = 0;
         if (lane == 0 && bal) slot0 = atomicAdd(&s_nsel, __popc(bal));
         slot0 = __shfl_sync(0xffffffffu, slot0, 0);
         if (take) {
-            int c = load_cls(P.cls, P.cls_is_i64, cls_base + i);
-            if (c < 0 || c > MYDET_MAX_CLASS_ID) { atomicOr(&s_flags, 1); c = c < 0 ? 0 : MYDET_MAX_CLASS_ID; }
             const int slot = slot0 + __popc(bal & ((1u << lane) - 1u));
-            if (slot < kpad)
-                keys[slot] = ((unsigned long long)c << 52) | ((unsigned long long)(~u) << 20) | (unsigned long long)i;
+            if (slot < kpad) {
+                int c = load_cls(P.cls, P.cls_is_i64, row0 + i);
+                const float* bx = boxes + (long long)i * P.n_param;
+                gbox[slot] = make_float4(bx[0], bx[1], bx[2], bx[3]);
+                if (P.n_param == 5) gang[slot] = bx[4];
+                if (c < 0 || c > MYDET_MAX_CLASS_ID) { atomicOr(&s_flags, 1); c = c < 0 ? 0 : MYDET_MAX_CLASS_ID; }
+                const unsigned tie = 0xffffffffu - (unsigned)(k & 0xffffffffull);
+                gsrc[slot] = (int)tie;
+                if (tie > 0xfffffu) atomicOr(&s_flags, 8);   // tie index does not fit the 20-bit field
+                keys[slot] = ((unsigned long long)c << 52) | ((unsigned long long)(~(unsigned)(k >> 32)) << 20) |
+                             (unsigned long long)(tie & 0xfffffu);
+            }
         }
     }
     __syncthreads();
     const int m = min(s_nsel, kpad);
 
-    // bitonic sort, ascending
+    // bitonic sort of (key, slot), ascending
     for (int size = 2; size <= kpad; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             for (int t = tid; t < (kpad >> 1); t += kPPThreads) {
@@ -178,7 +203,10 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
                 const int hi = lo + stride;
                 const bool up = (lo & size) == 0;
                 const unsigned long long a = keys[lo], c = keys[hi];
-                if ((a > c) == up) { keys[lo] = c; keys[hi] = a; }
+                if ((a > c) == up) {
+                    keys[lo] = c; keys[hi] = a;
+                    const unsigned short pa = pay[lo]; pay[lo] = pay[hi]; pay[hi] = pa;
+                }
             }
             __syncthreads();
         }
@@ -190,16 +218,13 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
         int c = 0x7fffffff;
         float area = 0.f;
         if (r < m) {
-            const unsigned long long k = keys[r];
-            const int i = (int)(k & 0xfffffu);
-            c = (int)(k >> 52);
-            const float* bx = boxes + (long long)i * P.n_param;
-            const float v0 = bx[0], v1 = bx[1], v2 = bx[2], v3 = bx[3];
+            c = (int)(keys[r] >> 52);
+            const float4 v = gbox[pay[r]];
             if (P.box_format == MYDET_BOX_CXCYWH) {
-                const float hw = __fmul_rn(v2, 0.5f), hh = __fmul_rn(v3, 0.5f);
-                c4 = make_float4(__fsub_rn(v0, hw), __fsub_rn(v1, hh), __fadd_rn(v0, hw), __fadd_rn(v1, hh));
+                const float hw = __fmul_rn(v.z, 0.5f), hh = __fmul_rn(v.w, 0.5f);
+                c4 = make_float4(__fsub_rn(v.x, hw), __fsub_rn(v.y, hh), __fadd_rn(v.x, hw), __fadd_rn(v.y, hh));
             } else {
-                c4 = make_float4(v0, v1, v2, v3);
+                c4 = v;
             }
             area = __fmul_rn(__fsub_rn(c4.z, c4.x), __fsub_rn(c4.w, c4.y));
         }
@@ -210,9 +235,8 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
     // ---- (C) IoU bit matrix, LOWER triangle: mask[r][w] bit j  <=>  box (32w+j) ranks before r,
     // has r's class and iou > thr, i.e. it suppresses r if it is itself kept
     {
-        const int nwarps = kPPThreads >> 5;
         const float thr_f = P.nms_thr_f;
-        for (int r = warp; r < m; r += nwarps) {
+        for (int r = warp; r < m; r += kPPWarps) {
             const float4 a = sbox[r];
             const float aarea = sarea[r];
             const int ac = scls[r];
@@ -222,7 +246,6 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
                 bool hit = false;
                 if (j < r && scls[j] == ac) {
                     const float4 c4 = sbox[j];
-                    // torchvision evaluates the pair from the higher-ranked box: areas (i = j, j = r)
                     hit = iou_corners(c4.x, c4.y, c4.z, c4.w, sarea[j], a.x, a.y, a.z, a.w, aarea) > thr_f;
                 }
                 const unsigned bits = __ballot_sync(0xffffffffu, hit);
@@ -261,24 +284,30 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
     }
     keptw = kept_a;
 
-    // ---- (E) ordered output
+    // ---- (E) ordered output, everything from shared memory
     {
         int nk = 0;
         for (int w = 0; w < W; ++w) nk += __popc(keptw[w]);
-        for (int r = tid; r < m; r += kPPThreads) {
+        const int r = tid;
+        if (r < m) {
             const unsigned wbits = keptw[r >> 5];
             if ((wbits >> (r & 31)) & 1u) {
                 int pos = __popc(wbits & ((1u << (r & 31)) - 1u));
                 for (int w = 0; w < (r >> 5); ++w) pos += __popc(keptw[w]);
                 if (pos < P.out_cap) {
                     const unsigned long long k = keys[r];
-                    const int i = (int)(k & 0xfffffu);
+                    const int slot = pay[r];
                     const long long orow = (long long)b * P.out_cap + pos;
-                    const float* bx = boxes + (long long)i * P.n_param;
-                    for (int p = 0; p < P.n_param; ++p) P.out_box[orow * P.n_param + p] = bx[p];
-                    P.out_score[orow] = scores[i];
-                    P.out_cls[orow] = load_cls(P.cls, P.cls_is_i64, cls_base + i);
-                    P.out_idx[orow] = P.src_idx ? P.src_idx[cls_base + i] : i;
+                    const float4 v = gbox[slot];
+                    if (P.n_param == 4) {
+                        reinterpret_cast<float4*>(P.out_box)[orow] = v;
+                    } else {
+                        float* ob = P.out_box + orow * 5;
+                        ob[0] = v.x; ob[1] = v.y; ob[2] = v.z; ob[3] = v.w; ob[4] = gang[slot];
+                    }
+                    P.out_score[orow] = key_float(~(unsigned)(k >> 20));
+                    P.out_cls[orow] = (long long)(k >> 52);
+                    P.out_idx[orow] = gsrc[slot];
                 }
             }
         }
@@ -291,9 +320,8 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
 }
 
 size_t pp_small_smem_bytes(int kpad, int n_per_image) {
-    const size_t W = (size_t)kpad / 32;
-    return (size_t)kpad * (8 + 16 + 4 + 4) + (size_t)kpad * (W + 1) * 4 + 256 * 4 + 64 * 4 +
-           (size_t)pp_cache_elems(n_per_image, kpad) * 4;
+    return (size_t)kpad * (16 + 16 + 8 + 4 + 4 + 4 + 4 + 2) + pp_mask_bytes(kpad) + 256 * 4 + 64 * 4 +
+           (size_t)pp_cache_elems(n_per_image, kpad) * 8;
 }
 
 int launch_postprocess_small(const PPParams& P, int batch, cudaStream_t st) {

@@ -273,6 +273,35 @@ def test_detect_end_to_end_vs_oracle(golden):
         assert torch.equal(out['cls'][b, :k].cpu(), ref[1][b][want])
 
 
+def test_detect_score_ties_are_broken_by_flat_index(golden):
+    """Coarsely quantised logits give many exactly equal scores.  The compaction order of the fused decode
+    is arbitrary, so the result may only depend on the flat candidate index (the declared tie policy):
+    detect() must equal the oracle post-process applied to the GPU's own dense decode, run after run."""
+    from mydetection_b200 import ops
+    from oracle import postprocess as opp
+    g = golden('decode')
+    d = dev()
+    strides = (8, 16, 32, 64, 128)
+    raws = []
+    for li in range(5):
+        bb = (T(g[f'fcos{li}_bbox_in']) * 2).round() / 2
+        cc = (T(g[f'fcos{li}_cls_in']) * 1).round() / 1
+        raws.append({k: v.to(d) for k, v in efdet_views(bb, cc).items()})
+    ls = ops.LevelSet(raws, strides)
+    box, cls, score = (t.cpu() for t in ops.decode_dense(ops.KIND_FCOS, ls, (256, 384)))
+    assert score[0].unique().numel() < score[0].numel() // 4          # heavy ties
+    first = None
+    for rep in range(3):
+        out = ops.detect(ops.KIND_FCOS, ls, (256, 384), 0.05, 0.5, topk=512)
+        torch.cuda.synchronize()
+        for b in range(2):
+            want = opp.post_process(box[b], cls[b], score[b], 0.05, 0.5, 'cxcywh', 512)
+            k = int(out['count'][b])
+            assert k == want.numel()
+            assert torch.equal(out['idx'][b, :k].cpu().long(), want)
+            assert torch.equal(out['box'][b, :k].cpu(), box[b][want])
+
+
 # ------------------------------------------------------------------------------------- IoU / rotated
 def test_bboxes_iou_bit_exact(golden):
     from mydetection_b200 import ops
