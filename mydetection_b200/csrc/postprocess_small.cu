@@ -29,44 +29,67 @@ namespace mydet {
 constexpr int kPPThreads = 1024;
 constexpr int kPPWarps = kPPThreads / 32;
 
+// developer instrumentation (scripts/pp_phases.py builds with -DMYDET_PP_PROFILE): SM clock at the
+// phase boundaries of CTA 0
+#ifdef MYDET_PP_PROFILE
+__device__ long long g_pp_clock[32];
+#define PP_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_pp_clock[i] = clock64(); } while (0)
+#else
+#define PP_MARK(i) do {} while (0)
+#endif
+
 __device__ __forceinline__ int load_cls(const void* cls, int is64, long long i) {
     return is64 ? (int)reinterpret_cast<const long long*>(cls)[i] : reinterpret_cast<const int*>(cls)[i];
 }
 
 // number of candidates whose select key is cached in shared memory (the rest is re-read from L2)
 __host__ __device__ inline int pp_cache_elems(int n_per_image, int kpad) {
-    const int budget = (kpad <= 512) ? 16384 : 4096;
+    const int budget = (kpad <= 512) ? 16384 : 3072;
     return n_per_image < budget ? n_per_image : budget;
 }
 __host__ __device__ inline size_t pp_mask_bytes(int kpad) {
     const size_t m = (size_t)kpad * (size_t)(kpad / 32 + 1) * 4;
-    const size_t h = (size_t)kPPWarps * 256 * 4;   // the per-warp histograms alias the mask
+    // the mask region first hosts the 32 padded per-warp histograms of the radix select, then the
+    // 4096(+32)+4096 class-sort counters
+    const size_t h = (size_t)kPPWarps * 257 * 4;
     return m > h ? m : h;
 }
+
+constexpr int kClassBins = MYDET_MAX_CLASS_ID + 1;   // 4096
 
 __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const PPParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const int kpad = P.kpad;
     const int W = kpad >> 5;   // mask words per row
     const int Wp = W + 1;      // padded row pitch: conflict-free column walks
 
     // ---- shared layout (16-byte pieces first)
     unsigned char* sp = smem_raw;
-    float4* gbox = reinterpret_cast<float4*>(sp); sp += (size_t)kpad * 16;                 // by gather slot
-    float4* sbox = reinterpret_cast<float4*>(sp); sp += (size_t)kpad * 16;                 // by sorted rank: corners
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(sp); sp += (size_t)kpad * 8;
+    float4* gbox = reinterpret_cast<float4*>(sp); sp += (size_t)kpad * 16;                 // raw box, by gather slot
+    float4* sbox = reinterpret_cast<float4*>(sp); sp += (size_t)kpad * 16;                 // corners, by sorted rank
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(sp); sp += (size_t)kpad * 8;   // sort key by rank
     unsigned* mask = reinterpret_cast<unsigned*>(sp); sp += pp_mask_bytes(kpad);           // kpad * Wp words
-    unsigned* whist = mask;                                                                // 32 x 256, aliases mask
-    float* sarea = reinterpret_cast<float*>(sp); sp += (size_t)kpad * 4;
+    float* sarea = reinterpret_cast<float*>(sp); sp += (size_t)kpad * 4;                   // by sorted rank
     int* scls = reinterpret_cast<int*>(sp); sp += (size_t)kpad * 4;                        // by sorted rank
     int* gsrc = reinterpret_cast<int*>(sp); sp += (size_t)kpad * 4;                        // by gather slot
     float* gang = reinterpret_cast<float*>(sp); sp += (size_t)kpad * 4;                    // 5th box column, by slot
+    int* gcls = reinterpret_cast<int*>(sp); sp += (size_t)kpad * 4;                        // class, by gather slot
+    int* sseg = reinterpret_cast<int*>(sp); sp += (size_t)kpad * 4;                        // first rank of the class, by sorted rank
     unsigned* hist = reinterpret_cast<unsigned*>(sp); sp += 256 * 4;
     unsigned* keptw = reinterpret_cast<unsigned*>(sp); sp += 64 * 4;
+    int* wtot = reinterpret_cast<int*>(sp); sp += 64 * 4;
     unsigned long long* ckey = reinterpret_cast<unsigned long long*>(sp); sp += (size_t)pp_cache_elems(P.n_per_image, kpad) * 8;
-    unsigned short* pay = reinterpret_cast<unsigned short*>(sp);                           // slot payload of the sort
+    unsigned short* pay = reinterpret_cast<unsigned short*>(sp);                           // slot, by sorted rank
+    // regions with two lives
+    unsigned* whist = mask;                                             // radix select: 32 private histograms
+    int* cstart = reinterpret_cast<int*>(mask);                         // class sort: 4096 (+1) segment starts ...
+    int* ccur = cstart + kClassBins + 32;                               // ... and 4096 scatter cursors (both die before (C))
+    unsigned long long* tkey = reinterpret_cast<unsigned long long*>(sbox);               // class-bucketed keys (die before corners)
+    int* sel = reinterpret_cast<int*>(tkey + kpad);                                         // candidate number by slot
+    unsigned short* tslot = reinterpret_cast<unsigned short*>(sel + kpad);                  // class-bucketed slots
     __shared__ unsigned long long s_prefix;
     __shared__ int s_need, s_done, s_nsel, s_total, s_flags;
 
@@ -85,6 +108,7 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
     const int K = P.topk;
 
     if (tid == 0) { s_nsel = 0; s_total = 0; s_flags = 0; s_done = 0; s_prefix = 0ull; }
+    PP_MARK(0);
 
     // select key of candidate i: (score key << 32) | ~tie index; 0 when it fails the threshold / is NaN
     auto key_global = [&](int i) -> unsigned long long {
@@ -95,130 +119,258 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
     };
     auto key_of = [&](int i) -> unsigned long long { return i < cache_n ? ckey[i] : key_global(i); };
 
-    // ---- (A0) stage the keys, count the candidates that pass the threshold
+    // ---- (A0) stage the keys, count the threshold survivors, AND / OR of all keys (common prefix)
+    unsigned long long k_and = ~0ull, k_or = 0ull;
     {
         int local = 0;
-        for (int i = tid; i < n; i += kPPThreads) {
-            const unsigned long long k = key_global(i);
-            if (i < cache_n) ckey[i] = k;
-            local += k ? 1 : 0;
+        constexpr int U = 8;   // independent global loads in flight per thread
+#pragma unroll 1
+        for (int base = 0; base < n; base += U * kPPThreads) {
+            float sv[U];
+            unsigned tv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * kPPThreads + tid;
+                sv[u] = (i < n) ? scores[i] : __int_as_float(0x7fc00000);   // NaN fails the threshold
+                tv[u] = (i < n && src) ? (unsigned)src[i] : (unsigned)i;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * kPPThreads + tid;
+                unsigned long long k = 0ull;
+                if (sv[u] >= thr) {
+                    k = ((unsigned long long)float_key(sv[u]) << 32) | (unsigned long long)(0xffffffffu - tv[u]);
+                    k_and &= k; k_or |= k; ++local;
+                }
+                if (i < cache_n) ckey[i] = k;
+            }
         }
         local = __reduce_add_sync(0xffffffffu, local);
-        if (lane == 0 && local) atomicAdd(&s_total, local);
+        const unsigned a_lo = __reduce_and_sync(0xffffffffu, (unsigned)k_and), a_hi = __reduce_and_sync(0xffffffffu, (unsigned)(k_and >> 32));
+        const unsigned o_lo = __reduce_or_sync(0xffffffffu, (unsigned)k_or), o_hi = __reduce_or_sync(0xffffffffu, (unsigned)(k_or >> 32));
+        if (lane == 0) {
+            if (local) atomicAdd(&s_total, local);
+            hist[2 * warp] = a_lo; hist[2 * warp + 1] = a_hi;          // hist is free until the first pass
+            hist[64 + 2 * warp] = o_lo; hist[64 + 2 * warp + 1] = o_hi;
+        }
     }
     __syncthreads();
     const int total = s_total;
+    PP_MARK(1);
     unsigned long long kth = 1ull;  // select every key >= kth
     if (total > K) {
-        // ---- (A) radix select of the K-th largest key
-        if (tid == 0) s_need = K;
-        unsigned* myhist = whist + warp * 256;
-        for (int pass = 7; pass >= 0; --pass) {
-            const int shift = pass * 8;
-            for (int i = tid; i < kPPWarps * 256; i += kPPThreads) whist[i] = 0u;
-            __syncthreads();
-            const unsigned long long prefix = s_prefix;
-            const unsigned long long himask = (pass == 7) ? 0ull : (~0ull << (shift + 8));
-            for (int i = tid; i < n; i += kPPThreads) {
-                const unsigned long long k = key_of(i);
-                if (k && (k & himask) == prefix) atomicAdd(&myhist[(unsigned)(k >> shift) & 255u], 1u);
+        // ---- (A) radix select of the K-th largest key, 8 bits per pass starting at the first bit
+        // in which the keys differ at all
+        {
+            unsigned long long all_and = ~0ull, all_or = 0ull;
+#pragma unroll 1
+            for (int w = 0; w < kPPWarps; ++w) {
+                all_and &= ((unsigned long long)hist[2 * w + 1] << 32) | hist[2 * w];
+                all_or |= ((unsigned long long)hist[64 + 2 * w + 1] << 32) | hist[64 + 2 * w];
             }
+            const unsigned long long diff = all_and ^ all_or;       // bits that are not common to every key
+            const int top = diff ? 63 - __clzll((long long)diff) : 0;  // highest differing bit
+            if (tid == 0) { s_need = K; s_prefix = (top >= 63) ? 0ull : (all_and & (~0ull << (top + 1))); }
             __syncthreads();
-            if (tid < 256) {
-                unsigned sum = 0;
-#pragma unroll 8
-                for (int w = 0; w < kPPWarps; ++w) sum += whist[w * 256 + tid];
-                hist[tid] = sum;
-            }
-            __syncthreads();
-            if (tid < 32) {
-                // lane l owns digits [8l, 8l+8); find the digit that holds the need-th largest
-                unsigned h[8], mine = 0;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { h[j] = hist[tid * 8 + j]; mine += h[j]; }
-                unsigned above = 0;   // keys in digits above this lane's range
-                for (int l = 31; l >= 0; --l) {
-                    const unsigned v = __shfl_sync(0xffffffffu, mine, l);
-                    if (l > tid) above += v;
-                }
-                const int need = s_need;
-                if ((int)above < need && need <= (int)(above + mine)) {
-                    unsigned acc = above;
-                    for (int j = 7; j >= 0; --j) {
-                        if ((int)acc < need && need <= (int)(acc + h[j])) {
-                            s_prefix = prefix | ((unsigned long long)(tid * 8 + j) << shift);
-                            s_need = need - (int)acc;
-                            if ((int)h[j] == need - (int)acc) s_done = 1;  // the whole bucket is taken
-                            break;
-                        }
-                        acc += h[j];
+            unsigned* myhist = whist + warp * 257;                      // padded: warps hit different banks
+            int hi_bit = top;                                           // digit = bits [hi_bit-7, hi_bit]
+#pragma unroll 1
+            while (true) {
+                const int shift = hi_bit >= 7 ? hi_bit - 7 : 0;
+                const unsigned dmask = (hi_bit >= 7) ? 255u : ((1u << (hi_bit + 1)) - 1u);
+                for (int i = tid; i < kPPWarps * 257; i += kPPThreads) whist[i] = 0u;
+                __syncthreads();
+                const unsigned long long prefix = s_prefix;
+                const unsigned long long himask = (hi_bit >= 63) ? 0ull : (~0ull << (hi_bit + 1));
+#pragma unroll 2
+                for (int base = 0; base < n; base += kPPThreads) {
+                    const int i = base + tid;
+                    unsigned digit = 256u;                              // not a candidate of this pass
+                    if (i < n) {
+                        const unsigned long long k = key_of(i);
+                        if (k && (k & himask) == prefix) digit = (unsigned)(k >> shift) & dmask;
+                    }
+                    // scores cluster: when the whole warp agrees, one lane adds 32
+                    const unsigned first = __shfl_sync(0xffffffffu, digit, 0);
+                    if (__all_sync(0xffffffffu, digit == first)) {
+                        if (lane == 0 && first < 256u) atomicAdd(&myhist[first], 32u);
+                    } else if (digit < 256u) {
+                        atomicAdd(&myhist[digit], 1u);
                     }
                 }
+                __syncthreads();
+                if (tid < 256) {
+                    unsigned sum = 0;
+#pragma unroll 8
+                    for (int w = 0; w < kPPWarps; ++w) sum += whist[w * 257 + tid];
+                    hist[tid] = sum;
+                }
+                __syncthreads();
+                if (tid < 32) {
+                    // lane l owns digits [8l, 8l+8); find the digit that holds the need-th largest
+                    unsigned h[8], mine = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { h[j] = hist[tid * 8 + j]; mine += h[j]; }
+                    unsigned incl = mine;                               // suffix sum over lanes >= tid
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned v = __shfl_down_sync(0xffffffffu, incl, o);
+                        if (tid + o < 32) incl += v;
+                    }
+                    const unsigned above = incl - mine;                 // keys in digits above this lane's range
+                    const int need = s_need;
+                    if ((int)above < need && need <= (int)(above + mine)) {
+                        unsigned acc = above;
+#pragma unroll 1
+                        for (int j = 7; j >= 0; --j) {
+                            if ((int)acc < need && need <= (int)(acc + h[j])) {
+                                s_prefix = prefix | ((unsigned long long)(tid * 8 + j) << shift);
+                                s_need = need - (int)acc;
+                                if ((int)h[j] == need - (int)acc) s_done = 1;  // the whole bucket is taken
+                                break;
+                            }
+                            acc += h[j];
+                        }
+                    }
+                }
+                __syncthreads();
+                if (s_done || shift == 0) break;
+                hi_bit = shift - 1;
             }
-            __syncthreads();
-            if (s_done) break;
         }
         kth = s_prefix;
         if (kth == 0ull) kth = 1ull;
     }
+    PP_MARK(2);
 
-    // ---- (B) gather the selected candidates: sort key (class asc, score desc, tie index asc) and,
-    // in the same global round trip, their box / class / source index into shared memory
-    for (int i = tid; i < kpad; i += kPPThreads) { keys[i] = ~0ull; pay[i] = (unsigned short)i; }
-    for (int i = tid; i < kpad * Wp; i += kPPThreads) mask[i] = 0u;   // the histograms are dead now
-    __syncthreads();
-    for (int base = 0; base < n; base += kPPThreads) {
-        const int i = base + tid;
-        unsigned long long k = 0ull;
-        if (i < n) k = key_of(i);
-        const bool take = k >= kth && k != 0ull;
-        const unsigned bal = __ballot_sync(0xffffffffu, take);
-        int slot0 = 0;
-        if (lane == 0 && bal) slot0 = atomicAdd(&s_nsel, __popc(bal));
-        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-        if (take) {
-            const int slot = slot0 + __popc(bal & ((1u << lane) - 1u));
-            if (slot < kpad) {
-                int c = load_cls(P.cls, P.cls_is_i64, row0 + i);
-                const float* bx = boxes + (long long)i * P.n_param;
-                gbox[slot] = make_float4(bx[0], bx[1], bx[2], bx[3]);
-                if (P.n_param == 5) gang[slot] = bx[4];
-                if (c < 0 || c > MYDET_MAX_CLASS_ID) { atomicOr(&s_flags, 1); c = c < 0 ? 0 : MYDET_MAX_CLASS_ID; }
-                const unsigned tie = 0xffffffffu - (unsigned)(k & 0xffffffffull);
-                gsrc[slot] = (int)tie;
-                if (tie > 0xfffffu) atomicOr(&s_flags, 8);   // tie index does not fit the 20-bit field
-                keys[slot] = ((unsigned long long)c << 52) | ((unsigned long long)(~(unsigned)(k >> 32)) << 20) |
-                             (unsigned long long)(tie & 0xfffffu);
+    // ---- (B1) slots for the selected candidates without atomics: per-warp counts, scan, assign
+    {
+        int mine = 0;
+#pragma unroll 1
+        for (int base = 0; base < n; base += kPPThreads) {
+            const int i = base + tid;
+            const unsigned long long k = (i < n) ? key_of(i) : 0ull;
+            mine += __popc(__ballot_sync(0xffffffffu, k >= kth && k != 0ull));
+        }
+        if (lane == 0) wtot[warp] = mine;
+        for (int i = tid; i < kClassBins + 32; i += kPPThreads) { cstart[i] = 0; }   // class histogram (whist is dead)
+        for (int i = tid; i < kClassBins; i += kPPThreads) { ccur[i] = 0; }
+        __syncthreads();
+        if (warp == 0) {
+            const int v = wtot[lane];
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            wtot[32 + lane] = incl - v;
+            if (lane == 31) s_nsel = incl;
+        }
+        __syncthreads();
+        int running = wtot[32 + warp];
+#pragma unroll 1
+        for (int base = 0; base < n; base += kPPThreads) {
+            const int i = base + tid;
+            const unsigned long long k = (i < n) ? key_of(i) : 0ull;
+            const bool take = k >= kth && k != 0ull;
+            const unsigned bal = __ballot_sync(0xffffffffu, take);
+            if (take) {
+                const int slot = running + __popc(bal & lt_mask);
+                if (slot < kpad) { sel[slot] = i; keys[slot] = k; }
             }
+            running += __popc(bal);
         }
     }
     __syncthreads();
     const int m = min(s_nsel, kpad);
+    PP_MARK(3);
 
-    // bitonic sort of (key, slot), ascending
-    for (int size = 2; size <= kpad; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = tid; t < (kpad >> 1); t += kPPThreads) {
-                const int lo = 2 * t - (t & (stride - 1));
-                const int hi = lo + stride;
-                const bool up = (lo & size) == 0;
-                const unsigned long long a = keys[lo], c = keys[hi];
-                if ((a > c) == up) {
-                    keys[lo] = c; keys[hi] = a;
-                    const unsigned short pa = pay[lo]; pay[lo] = pay[hi]; pay[hi] = pa;
-                }
-            }
-            __syncthreads();
+    // ---- (B2) ONE batch of global loads: class, box, source index of the selected candidates;
+    // histogram of their classes
+#pragma unroll 1
+    for (int slot = tid; slot < m; slot += kPPThreads) {
+        const int i = sel[slot];
+        const unsigned long long k = keys[slot];
+        int c = load_cls(P.cls, P.cls_is_i64, row0 + i);
+        const float* bx = boxes + (long long)i * P.n_param;
+        if (P.n_param == 4) {
+            gbox[slot] = *reinterpret_cast<const float4*>(bx);
+        } else {
+            gbox[slot] = make_float4(bx[0], bx[1], bx[2], bx[3]);
+            gang[slot] = bx[4];
         }
+        if (c < 0 || c > MYDET_MAX_CLASS_ID) { atomicOr(&s_flags, 1); c = c < 0 ? 0 : MYDET_MAX_CLASS_ID; }
+        const unsigned tie = 0xffffffffu - (unsigned)(k & 0xffffffffull);
+        gsrc[slot] = (int)tie;
+        if (tie > 0xfffffu) atomicOr(&s_flags, 8);   // tie index does not fit the 20-bit field
+        gcls[slot] = c;
+        // in-class order: score descending, tie index ascending
+        keys[slot] = ((unsigned long long)(~(unsigned)(k >> 32)) << 20) | (unsigned long long)(tie & 0xfffffu);
+        atomicAdd(&cstart[c], 1);
     }
+    __syncthreads();
+    PP_MARK(4);
+
+    // ---- (B3) sort by (class, key) = counting sort on the class + rank-by-counting inside the class.
+    // (A 45-stage bitonic network is a serial chain of ~300 cycles per stage for one CTA.)
+    {
+        // exclusive scan of the 4096 class counts: 4 bins per thread
+        const int c0 = tid * 4;
+        const int v0 = cstart[c0], v1 = cstart[c0 + 1], v2 = cstart[c0 + 2], v3 = cstart[c0 + 3];
+        const int mine = v0 + v1 + v2 + v3;
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) wtot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int v = wtot[lane];
+            int wi = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+            wtot[32 + lane] = wi - v;
+        }
+        __syncthreads();
+        const int excl = wtot[32 + warp] + incl - mine;
+        cstart[c0] = excl; cstart[c0 + 1] = excl + v0; cstart[c0 + 2] = excl + v0 + v1; cstart[c0 + 3] = excl + v0 + v1 + v2;
+        if (tid == 0) cstart[kClassBins] = m;
+        __syncthreads();
+        // scatter into class buckets (order inside a bucket is arbitrary, fixed by the ranking below)
+#pragma unroll 1
+        for (int slot = tid; slot < m; slot += kPPThreads) {
+            const int c = gcls[slot];
+            const int pos = cstart[c] + atomicAdd(&ccur[c], 1);
+            tkey[pos] = keys[slot];
+            tslot[pos] = (unsigned short)slot;
+        }
+        __syncthreads();
+        // rank inside the bucket; keys are unique, so ranks are a permutation
+#pragma unroll 1
+        for (int p = tid; p < m; p += kPPThreads) {
+            const int slot = tslot[p];
+            const int c = gcls[slot];
+            const int s0 = cstart[c], s1 = cstart[c + 1];
+            const unsigned long long mykey = tkey[p];
+            int rank = 0;
+#pragma unroll 4
+            for (int q = s0; q < s1; ++q) rank += (tkey[q] < mykey) ? 1 : 0;
+            const int r = s0 + rank;
+            keys[r] = ((unsigned long long)c << 52) | mykey;
+            pay[r] = (unsigned short)slot;
+        }
+        __syncthreads();
+    }
+    PP_MARK(5);
 
     // ---- corners and areas exactly as structures.py:128-143 + torchvision: c -/+ w/2, (x2-x1)*(y2-y1)
-    for (int r = tid; r < kpad; r += kPPThreads) {
+    // (cstart is copied out of the mask region first: (C) overwrites it)
+    int seg0 = 0;   // first sorted rank of this thread's class
+    {
+        const int r = tid;
         float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
         int c = 0x7fffffff;
         float area = 0.f;
         if (r < m) {
             c = (int)(keys[r] >> 52);
+            seg0 = cstart[c];
             const float4 v = gbox[pay[r]];
             if (P.box_format == MYDET_BOX_CXCYWH) {
                 const float hw = __fmul_rn(v.z, 0.5f), hh = __fmul_rn(v.w, 0.5f);
@@ -228,31 +380,57 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
             }
             area = __fmul_rn(__fsub_rn(c4.z, c4.x), __fsub_rn(c4.w, c4.y));
         }
-        sbox[r] = c4; sarea[r] = area; scls[r] = c;
+        __syncthreads();          // every thread has read tkey/sel (alias sbox) and cstart (alias mask)
+        if (r < kpad) { sbox[r] = c4; sarea[r] = area; scls[r] = c; sseg[r] = seg0; }
     }
     __syncthreads();
+    PP_MARK(6);
 
     // ---- (C) IoU bit matrix, LOWER triangle: mask[r][w] bit j  <=>  box (32w+j) ranks before r,
-    // has r's class and iou > thr, i.e. it suppresses r if it is itself kept
+    // has r's class and iou > thr, i.e. it suppresses r if it is itself kept.  Row r only needs the
+    // words [seg0>>5, r>>5].  Rows with at most 8 predecessors in their class are done by their own
+    // thread (multi-class case: ~3 IoUs), longer ones by a whole warp, one 32-column word at a time.
+    constexpr int kShortRow = 8;
     {
         const float thr_f = P.nms_thr_f;
-        for (int r = warp; r < m; r += kPPWarps) {
+        const int r = tid;
+        if (r < m && r - seg0 <= kShortRow) {
             const float4 a = sbox[r];
             const float aarea = sarea[r];
-            const int ac = scls[r];
-            for (int w = r >> 5; w >= 0; --w) {
-                if (scls[(w << 5) + 31] < ac) break;    // sorted by class: nothing earlier can match
+            const int w_lo = seg0 >> 5, w_hi = r >> 5;      // at most two words
+            unsigned bits_lo = 0u, bits_hi = 0u;
+#pragma unroll 1
+            for (int j = seg0; j < r; ++j) {
+                const float4 c4 = sbox[j];
+                if (iou_corners(c4.x, c4.y, c4.z, c4.w, sarea[j], a.x, a.y, a.z, a.w, aarea) > thr_f) {
+                    if ((j >> 5) == w_lo) bits_lo |= 1u << (j & 31); else bits_hi |= 1u << (j & 31);
+                }
+            }
+            mask[r * Wp + w_lo] = bits_lo;
+            if (w_hi != w_lo) mask[r * Wp + w_hi] = bits_hi;
+        }
+#pragma unroll 1
+        for (int rr = warp; rr < m; rr += kPPWarps) {
+            const int s0 = sseg[rr];
+            if (rr - s0 <= kShortRow) continue;             // warp-uniform
+            const float4 a = sbox[rr];
+            const float aarea = sarea[rr];
+#pragma unroll 2
+            for (int w = rr >> 5; w >= (s0 >> 5); --w) {
                 const int j = (w << 5) + lane;
                 bool hit = false;
-                if (j < r && scls[j] == ac) {
+                if (j >= s0 && j < rr) {
                     const float4 c4 = sbox[j];
                     hit = iou_corners(c4.x, c4.y, c4.z, c4.w, sarea[j], a.x, a.y, a.z, a.w, aarea) > thr_f;
                 }
                 const unsigned bits = __ballot_sync(0xffffffffu, hit);
-                if (lane == 0) mask[r * Wp + w] = bits;
+                if (lane == 0) mask[rr * Wp + w] = bits;
             }
         }
     }
+    __syncthreads();
+    PP_MARK(7);
+
     // ---- (D) greedy sweep as a fixed point: kept[r] = no kept j < r suppresses r.  The sequential
     // result is the unique fixed point; after t rounds the first t rows are final, in practice a
     // handful of rounds suffice.  Thread r owns row r, warp w's ballot IS word w of the kept vector.
@@ -263,36 +441,40 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
         kept_a[tid] = (lo >= m) ? 0u : ((lo + 32 > m) ? ((1u << (m - lo)) - 1u) : 0xffffffffu);
     }
     __syncthreads();
-    const int my_row = tid;  // kPPThreads == MYDET_SMALL_K >= kpad
-    for (int round = 0; round <= m; ++round) {
-        bool alive = false;
-        if (my_row < m) {
-            unsigned sup = 0u;
-            const int ac = scls[my_row];
-            for (int w = my_row >> 5; w >= 0; --w) {
-                if (scls[(w << 5) + 31] < ac) break;
-                sup |= mask[my_row * Wp + w] & kept_a[w];
+    {
+        const int r = tid;  // kPPThreads == MYDET_SMALL_K >= kpad
+        const int w_lo = seg0 >> 5, w_hi = r >> 5;
+#pragma unroll 1
+        for (int round = 0; round <= m; ++round) {
+            bool alive = false;
+            if (r < m) {
+                unsigned sup = 0u;
+#pragma unroll 1
+                for (int w = w_hi; w >= w_lo; --w) sup |= mask[r * Wp + w] & kept_a[w];
+                alive = (sup == 0u);
             }
-            alive = (sup == 0u);
+            const unsigned word = __ballot_sync(0xffffffffu, alive);
+            bool changed = false;
+            if (lane == 0 && warp < W) { kept_b[warp] = word; changed = (word != kept_a[warp]); }
+            const int any = __syncthreads_or(changed ? 1 : 0);
+            unsigned* t = kept_a; kept_a = kept_b; kept_b = t;
+            if (!any) break;
         }
-        const unsigned word = __ballot_sync(0xffffffffu, alive);
-        bool changed = false;
-        if (lane == 0 && warp < W) { kept_b[warp] = word; changed = (word != kept_a[warp]); }
-        const int any = __syncthreads_or(changed ? 1 : 0);
-        unsigned* t = kept_a; kept_a = kept_b; kept_b = t;
-        if (!any) break;
     }
     keptw = kept_a;
+    PP_MARK(8);
 
     // ---- (E) ordered output, everything from shared memory
     {
         int nk = 0;
+#pragma unroll 1
         for (int w = 0; w < W; ++w) nk += __popc(keptw[w]);
         const int r = tid;
         if (r < m) {
             const unsigned wbits = keptw[r >> 5];
             if ((wbits >> (r & 31)) & 1u) {
                 int pos = __popc(wbits & ((1u << (r & 31)) - 1u));
+#pragma unroll 1
                 for (int w = 0; w < (r >> 5); ++w) pos += __popc(keptw[w]);
                 if (pos < P.out_cap) {
                     const unsigned long long k = keys[r];
@@ -317,10 +499,18 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
             if (P.status) P.status[b] = flags | s_flags;
         }
     }
+    __syncthreads();
+    PP_MARK(9);
 }
 
+#ifdef MYDET_PP_PROFILE
+extern "C" __attribute__((visibility("default"))) int mydet_debug_pp_clocks(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_pp_clock, sizeof(long long) * 32);
+}
+#endif
+
 size_t pp_small_smem_bytes(int kpad, int n_per_image) {
-    return (size_t)kpad * (16 + 16 + 8 + 4 + 4 + 4 + 4 + 2) + pp_mask_bytes(kpad) + 256 * 4 + 64 * 4 +
+    return (size_t)kpad * (16 + 16 + 8 + 4 + 4 + 4 + 4 + 4 + 4 + 2) + pp_mask_bytes(kpad) + 256 * 4 + 64 * 4 + 64 * 4 +
            (size_t)pp_cache_elems(n_per_image, kpad) * 8;
 }
 
