@@ -114,7 +114,8 @@ int mydet_decode_compact(int kind, const mydet_level_t* levels, int n_levels, in
  *            out_idx (B,out_cap) i32, out_count (B) i32; rows ordered class ascending, then score
  *            descending, exactly as the reference concatenates its per-class groups.
  *   status   optional (B) i32 written with a bit mask: 1 = class id out of range, 2 = output
- *            truncated to out_cap, 4 = input count exceeded n_per_image.
+ *            truncated to out_cap, 4 = input count exceeded n_per_image, 8 = a src_idx
+ *            value does not fit 20 bits (tie-break between equal scores then uses its low bits).
  * Workspace: mydet_postprocess_workspace_bytes(...) bytes, 256-byte aligned. */
 size_t mydet_postprocess_workspace_bytes(int batch, int n_per_image, int topk);
 int mydet_postprocess(const float* boxes, const float* scores, const void* cls, int cls_is_i64,

@@ -60,7 +60,7 @@ size_t large_workspace_bytes(int batch, int n, bool rot) {
 
 // ---------------------------------------------------------------------------- keys
 struct KeyParams {
-    const float* scores; const void* cls; const int* counts;
+    const float* scores; const void* cls; const int* counts; const int* src_idx;
     long long pitch; int n, cls_is_i64, use_cls; float thr;
     int* status;
 };
@@ -81,7 +81,11 @@ __global__ void keys_kernel(KeyParams P, unsigned long long* keys, int* m) {
                 c = P.cls_is_i64 ? (int)reinterpret_cast<const long long*>(P.cls)[ci] : reinterpret_cast<const int*>(P.cls)[ci];
                 if (c < 0 || c > MYDET_MAX_CLASS_ID) { if (P.status) atomicOr(P.status + b, 1); c = c < 0 ? 0 : MYDET_MAX_CLASS_ID; }
             }
-            key = ((unsigned long long)c << 52) | ((unsigned long long)(~float_key(s)) << 20) | (unsigned long long)i;
+            // equal scores rank by the candidate's flat index when the input is a compacted buffer
+            // (slot order is arbitrary), else by the slot itself
+            const unsigned tie = P.src_idx ? (unsigned)P.src_idx[(long long)b * P.pitch + i] : (unsigned)i;
+            if (tie > 0xfffffu && P.status) atomicOr(P.status + b, 8);
+            key = ((unsigned long long)c << 52) | ((unsigned long long)(~float_key(s)) << 20) | (unsigned long long)(tie & 0xfffffu);
             valid = true;
         }
     }
@@ -349,7 +353,7 @@ int run_large(const LargeArgs& A, void* workspace, size_t workspace_bytes, cudaS
     const int B = A.batch, n = A.n;
     MYDET_CUDA(cudaMemsetAsync(w.m, 0, sizeof(int) * (size_t)B, st));
     if (A.status) MYDET_CUDA(cudaMemsetAsync(A.status, 0, sizeof(int) * (size_t)B, st));
-    KeyParams K{A.scores, A.cls, A.counts, A.pitch, n, A.cls_is_i64, (A.cls && !A.rot) ? 1 : 0, A.conf_thres, A.status};
+    KeyParams K{A.scores, A.cls, A.counts, A.src_idx, A.pitch, n, A.cls_is_i64, (A.cls && !A.rot) ? 1 : 0, A.conf_thres, A.status};
     keys_kernel<<<dim3((n + 255) / 256, B), 256, 0, st>>>(K, w.keys, w.m);
     rank_kernel<<<dim3((n + kRankThreads - 1) / kRankThreads, B), kRankThreads, 0, st>>>(w.keys, w.order, n);
     GatherParams G{A.boxes, A.pitch, n, A.n_param, A.box_format};

@@ -79,10 +79,10 @@ class ImageObjects():
         assert self.scores is not None
         if self._bb_format not in ops.BOX_FORMATS:
             raise NotImplementedError()
+        if len(self) == 0:
+            return self                      # structures.py:120-121
         home = self.bboxes.device
         dev = home if home.type == 'cuda' else _cuda_device()
-        if len(self) == 0:
-            return self
         out = ops.postprocess(self.bboxes.detach().to(dev)[None], self.scores.detach().to(dev, torch.float32)[None],
                               self.cats.to(dev)[None], conf_thres, nms_thres, topk=topk, box_format=self._bb_format)
         n, status = (int(v) for v in torch.stack([out['count'][0], out['status'][0]]).tolist())  # one D2H sync

@@ -1,0 +1,169 @@
+"""GPU: the host-side mirror of the reference interface (same names / signatures / error behaviour)
+against the golden fixtures produced by the real reference."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import T, level_anchors, yolo_views, efdet_views, YOLO_ANCHORS, RAPID_ANCHORS
+from test_gpu_parity import close, cls_match
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('tag,fmt', [('pp_small', 'cxcywh'), ('pp_cap', 'cxcywh'), ('pp_rot', 'cxcywhd'),
+                                     ('pp_empty', 'cxcywh')])
+def test_image_objects_post_process(golden, tag, fmt):
+    """ImageObjects(...).post_process(conf, nms) exactly as api/detection.py:172 calls it, CPU tensors in."""
+    from mydetection_b200.structures import ImageObjects
+    g = golden('postprocess')
+    boxes, scores, cats = T(g[tag + '_boxes']), T(g[tag + '_scores']), T(g[tag + '_cats'])
+    conf, nms = (float(v) for v in g[tag + '_params'])
+    keep = T(g[tag + '_keep'])
+    dts = ImageObjects(boxes.clone(), cats.clone(), scores=scores.clone(), bb_format=fmt, img_hw=(512, 512))
+    out = dts.post_process(conf, nms)
+    assert isinstance(out, ImageObjects) and out.bboxes.device.type == 'cpu'      # structures.py:97 cpu_()
+    assert torch.equal(out.bboxes, boxes[keep]) and torch.equal(out.scores, scores[keep])
+    assert torch.equal(out.cats, cats[keep]) and out.cats.dtype == torch.int64
+    assert out.img_hw == (512, 512) and out._bb_format == fmt
+
+
+def test_image_objects_nms_direct(golden):
+    from mydetection_b200.structures import ImageObjects
+    g = golden('postprocess')
+    boxes, scores, cats = T(g['nms_direct_boxes']), T(g['nms_direct_scores']), T(g['nms_direct_cats'])
+    keep = T(g['nms_direct_keep'])
+    for device in ('cpu', 'cuda'):
+        dts = ImageObjects(boxes.to(device), cats.to(device), scores=scores.to(device))
+        out = dts.nms(float(g['nms_direct_params'][1]))
+        assert out.bboxes.device.type == device
+        assert torch.equal(out.bboxes.cpu(), boxes[keep]) and torch.equal(out.cats.cpu(), cats[keep])
+    # x1y1x2y2 input format (structures.py:133-136)
+    from oracle import iou as oi, postprocess as opp
+    xy = oi.cxcywh_to_x1y1x2y2(boxes)
+    dts = ImageObjects.__new__(ImageObjects)
+    dts.bboxes, dts.cats, dts.masks, dts.scores, dts._bb_format, dts.img_hw = xy, cats, None, scores, 'x1y1x2y2', None
+    out = ImageObjects.non_max_suppression(dts, 0.3)
+    want = opp.class_nms(xy, scores, cats, 0.3, 'x1y1x2y2')
+    assert torch.equal(out.bboxes, xy[want])
+
+
+def test_bbox_ops_mirror(golden):
+    from mydetection_b200 import bbox_ops
+    g = golden('iou')
+    a, b = T(g['a']), T(g['b'])
+    out = bbox_ops.bboxes_iou(a, b)                                   # CPU in -> CPU out, bit-exact
+    assert out.device.type == 'cpu' and torch.equal(out, T(g['iou_cxcywh']))
+    assert torch.equal(bbox_ops.bboxes_iou(a[0], b), T(g['iou_cxcywh'])[0:1])     # 1-d first argument, :25-26
+    assert torch.equal(bbox_ops.cxcywh_to_x1y1x2y2(a), T(g['a_xyxy']))
+    assert torch.equal(bbox_ops.bboxes_iou(T(g['a_xyxy']), bbox_ops.cxcywh_to_x1y1x2y2(b), xyxy=True), T(g['iou_xyxy']))
+    rb, rs = T(g['rot_boxes']), T(g['rot_scores'])
+    rad = rb.clone()
+    rad[:, 4] = rad[:, 4] * np.pi / 180
+    v = bbox_ops.xywha2vertex(rad, is_degree=False)
+    assert v.shape == (120, 4, 2)
+    close(v, T(g['rot_vertices']), 512, 'xywha2vertex')
+    assert bbox_ops.xywha2vertex(rad, is_degree=False, stack=False).shape == (120, 8)
+    # nms_rotbb incl. majority voting, against the reference's control flow
+    assert torch.equal(bbox_ops.nms_rotbb(rb, rs, 0.45), T(g['rot_keep_045']))
+    assert torch.equal(bbox_ops.nms_rotbb(rb, rs, 0.2), T(g['rot_keep_02']))
+    assert torch.equal(bbox_ops.nms_rotbb(rb, rs, 0.3, majority=2), T(g['rot_keep_maj2']))
+    assert torch.equal(bbox_ops.nms_rotbb(rb.cuda(), rs.cuda(), 0.45).cpu(), T(g['rot_keep_045']))
+    # iou_rle: float64 like the reference (pycocotools returns doubles), numpy in / numpy out
+    rgt = T(g['rot_gt_debug3'])[:40]
+    iou = bbox_ops.iou_rle(rgt, rgt)
+    assert iou.dtype == torch.float64
+    np.testing.assert_allclose(iou.numpy(), g['rot_gt_iou_stub'], rtol=0, atol=2e-6)
+    assert isinstance(bbox_ops.iou_rle(rgt.numpy(), rgt.numpy(), return_numpy=True), np.ndarray)
+    assert bbox_ops.iou_rle(rgt[0], rgt, img_size=1024).shape == (1, 40)
+
+
+def test_det_layers(golden):
+    from mydetection_b200 import detlayers
+    g = golden('decode')
+    # FCOS2 per level through the registry, as OneStageBBox builds it (models/general.py:34-38)
+    cfg = {'model.pred_layer': 'FCOS2', 'model.fcos.anchors': [0, 64, 128, 256, 512, 100000000],
+           'model.fpn.out_strides': [8, 16, 32, 64, 128], 'general.num_class': 6,
+           'model.fcos2.ignored_threshold': 0.7, 'general.pred_bbox_format': 'cxcywh',
+           'model.atss.anchors': [24, 48, 96, 192, 384], 'model.atss.topk_per_level': 9}
+    layer_cls = detlayers.get_det_layer(cfg)
+    for li in range(5):
+        raw = efdet_views(T(g[f'fcos{li}_bbox_in']), T(g[f'fcos{li}_cls_in']))
+        raw = {k: v.cuda() for k, v in raw.items()}
+        preds, loss = layer_cls(level_i=li, cfg=cfg)(raw, (256, 384), None)
+        assert loss is None and set(preds) == {'bbox', 'class_idx', 'score'}
+        assert preds['class_idx'].dtype == torch.int64
+        close(preds['bbox'], T(g[f'fcos{li}_bbox']), 384, 'fcos layer bbox')
+        close(preds['score'], T(g[f'fcos{li}_score']), 1, 'fcos layer score')
+        cls_match(preds['class_idx'], raw['class'].cpu().reshape(2, -1, 6), T(g[f'fcos{li}_cls']), 'fcos layer cls')
+        atss, _ = detlayers.FCOS_ATSS_Layer(li, cfg)(raw, (256, 384))
+        assert torch.equal(atss['bbox'], preds['bbox'])
+        with pytest.raises(NotImplementedError):
+            layer_cls(li, cfg)(raw, (256, 384), labels=[])
+    # YOLO + RAPiD on CPU inputs (the layers stage them on the GPU)
+    ycfg = {'model.yolo.anchors': YOLO_ANCHORS, 'model.yolo.anchor_indices': [[0, 1, 2], [3, 4, 5], [6, 7, 8]],
+            'model.fpn.out_strides': [8, 16, 32], 'general.num_class': 5}
+    preds, _ = detlayers.YOLOLayer(2, ycfg)(yolo_views(T(g['yolo2_in']), 3, 4, 5), (96, 128))
+    close(preds['bbox'], T(g['yolo2_bbox']), 128, 'yolo layer')
+    rcfg = {'model.rapid.anchors': RAPID_ANCHORS, 'model.rapid.anchor_indices': [[0, 1, 2], [3, 4, 5], [6, 7, 8]],
+            'model.fpn.out_strides': [8, 16, 32], 'general.num_class': 0}
+    preds, _ = detlayers.RAPiDLayer(0, rcfg)(yolo_views(T(g['rapid_c0_0_in']), 3, 5, 0), (96, 128))
+    close(preds['bbox'][..., :4], T(g['rapid_c0_0_bbox'])[..., :4], 128, 'rapid layer')
+    assert preds['bbox'].shape[-1] == 5
+
+
+def test_atss_layer_training_forward(golden):
+    """FCOS_ATSS_Layer.forward(raw, img_size, labels): targets from the CUDA kernels, loss as the reference."""
+    import torch.nn.functional as tnf
+    from mydetection_b200 import detlayers
+    from mydetection_b200.structures import ImageObjects
+    from oracle import atss as oa
+    g = golden('atss')
+    strides, sides = [8, 16, 32, 64, 128], [24, 48, 96, 192, 384]
+    cfg = {'model.fpn.out_strides': strides, 'general.num_class': 6, 'model.fcos2.ignored_threshold': 0.7,
+           'model.atss.anchors': sides, 'model.atss.topk_per_level': 9}
+    labels = [ImageObjects(T(g[f'gt{b}_boxes']), T(g[f'gt{b}_cats']), bb_format='cxcywh', img_hw=(384, 512)) for b in range(2)]
+    gts = [(l.bboxes, l.cats) for l in labels]
+    for li in (0, 2, 4):
+        bb, cc = T(g[f'atss{li}_bbox_in']), T(g[f'atss{li}_cls_in'])
+        raw = {k: v.cuda() for k, v in efdet_views(bb, cc).items()}
+        layer = detlayers.FCOS_ATSS_Layer(li, cfg)
+        preds, loss = layer(raw, (384, 512), labels)
+        # reference loss from the oracle's targets (fcos2.py:351-371)
+        tg = oa.assign_level(li, bb.permute(0, 2, 3, 1), gts, (384, 512), strides, sides, 9, 0.7, 6)
+        pos, ign = tg['PositiveMask'], tg['IgnoredMask']
+        t = bb.permute(0, 2, 3, 1)
+        err = (t[pos] - torch.log(tg['TargetLTRB'][pos] / strides[li])).abs()
+        ref = torch.where(err <= 0.2, 0.5 * err.pow(2) / 0.2, err - 0.1).sum()
+        c = cc.permute(0, 2, 3, 1)
+        pen = pos | ~ign
+        ref = ref + tnf.binary_cross_entropy_with_logits(c[..., 0:1][pen], tg['TargetConf'][pen], reduction='sum')
+        ref = ref + tnf.binary_cross_entropy_with_logits(c[..., 1:][pos], tg['TargetCls'][pos], reduction='sum')
+        assert abs(float(loss) - float(ref)) <= 1e-4 * max(1.0, abs(float(ref)))
+        assert layer.loss_str.startswith(f'level_{384 // strides[li]}x{512 // strides[li]}, pos {int(pos.sum())}/')
+
+
+def test_one_stage_forward_flow(golden):
+    """The caller's flow of models/general.py:69-84 + api/detection.py:172 on the mirror: per-level layers,
+    level concat, per-image ImageObjects, post_process -- end to end against the oracle chain."""
+    from mydetection_b200 import detlayers
+    from mydetection_b200.structures import ImageObjects
+    from oracle import decode as od, postprocess as opp
+    g = golden('decode')
+    strides = [8, 16, 32, 64, 128]
+    cfg = {'model.pred_layer': 'FCOS2', 'model.fcos.anchors': [0, 64, 128, 256, 512, 100000000],
+           'model.fpn.out_strides': strides, 'general.num_class': 6, 'model.fcos2.ignored_threshold': 0.7,
+           'general.pred_bbox_format': 'cxcywh'}
+    raws = [efdet_views(T(g[f'fcos{li}_bbox_in']), T(g[f'fcos{li}_cls_in'])) for li in range(5)]
+    layers = [detlayers.get_det_layer(cfg)(level_i=i, cfg=cfg) for i in range(5)]
+    dts_all = [layers[i]({k: v.cuda() for k, v in raws[i].items()}, (256, 384), None)[0] for i in range(5)]
+    bbs = torch.cat([d['bbox'] for d in dts_all], dim=1)
+    cls_idx = torch.cat([d['class_idx'] for d in dts_all], dim=1)
+    scores = torch.cat([d['score'] for d in dts_all], dim=1)
+    ref = od.merge_levels([od.decode_fcos(r, s, (256, 384)) for r, s in zip(raws, strides)])
+    for b in range(2):
+        objs = ImageObjects(bboxes=bbs[b], cats=cls_idx[b], scores=scores[b], bb_format='cxcywh', img_hw=(256, 384))
+        out = objs.post_process(0.05, 0.5)
+        want = opp.post_process(ref[0][b], ref[1][b], ref[2][b], 0.05, 0.5, 'cxcywh', 512)
+        assert len(out) == want.numel()
+        close(out.bboxes, ref[0][b][want], 384, 'flow box')
+        assert torch.equal(out.cats, ref[1][b][want])

@@ -1,0 +1,194 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol include/mydet.h declares,
+argument validation of the entry points (no kernel is launched), the host-side mirror of the
+reference interface, and the multi-rank gather logic over gloo (world size 2)."""
+import ctypes
+import os
+import re
+import socket
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, 'include', 'mydet.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(mydet_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mydetection_b200 import _lib, build
+    build.build()                                   # cross-compiles for sm_100a, no GPU needed
+    names = declared_functions()
+    assert len(names) >= 15
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), f'{n} is declared in include/mydet.h but not exported'
+    assert set(names) == set(_lib.SIGNATURES), 'ctypes binding and header disagree'
+    assert _lib.lib().mydet_version() == 100
+
+
+def test_library_is_sm100a_only():
+    from mydetection_b200 import _lib
+    import subprocess
+    out = subprocess.run(['cuobjdump', '-lelf', _lib.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    archs = set(re.findall(r'sm_\d+a?', out))
+    assert archs == {'sm_100a'}, archs
+
+
+def test_argument_validation_without_launch():
+    """Bad arguments are rejected on the host before any CUDA call."""
+    from mydetection_b200 import _lib
+    L = _lib.lib()
+    lv = (_lib.Level * 1)()
+    rc = L.mydet_decode_dense(99, lv, 1, 1, 80, 4, 640.0, 640.0, None, None, None, 0, None)
+    assert rc == -1 and b'unknown decode kind' in L.mydet_last_error()
+    rc = L.mydet_decode_dense(_lib.KIND_FCOS, lv, 1, 1, 0, 4, 640.0, 640.0, None, None, None, 0, None)
+    assert rc == -1 and b'n_cls > 0' in L.mydet_last_error()        # the reference crashes on C == 0
+    rc = L.mydet_decode_dense(_lib.KIND_RAPID, lv, 1, 1, 0, 4, 640.0, 640.0, None, None, None, 0, None)
+    assert rc == -1 and b'n_param == 5' in L.mydet_last_error()
+    rc = L.mydet_postprocess(None, None, None, 0, None, None, 1, 10, 10, 3, 0, 0.0, 512, 0.5, None, None, None, None,
+                             None, None, 1, None, 0, None)
+    assert rc == -1 and b'n_param' in L.mydet_last_error()
+    rc = L.mydet_iou_aabb_pairwise(None, -1, None, 3, 0, None, None)
+    assert rc == -1
+    with pytest.raises(_lib.MydetError):
+        _lib.check(rc, 'x')
+    # sizes
+    assert L.mydet_postprocess_workspace_bytes(64, 8525, 512) == 256          # fused small path needs none
+    assert L.mydet_postprocess_workspace_bytes(4, 10000, 0) > 4 * 10000 * 157 * 8
+    assert L.mydet_nms_rot_workspace_bytes(1, 10000) > 10000 * 157 * 8
+    assert L.mydet_detect_workspace_bytes(64, 8525, 4, 512) >= 64 * 8525 * 28
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device (this container) the product path must fail loudly, not compute."""
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    from mydetection_b200 import _lib, bbox_ops, structures, ops
+    with pytest.raises(_lib.MydetError):
+        bbox_ops.bboxes_iou(torch.rand(3, 4), torch.rand(2, 4))
+    with pytest.raises(_lib.MydetError):
+        bbox_ops.nms_rotbb(torch.rand(3, 5), torch.rand(3))
+    obj = structures.ImageObjects(torch.rand(5, 4), torch.zeros(5, dtype=torch.int64), scores=torch.rand(5))
+    with pytest.raises(_lib.MydetError):
+        obj.post_process(0.1, 0.5)
+    with pytest.raises(_lib.MydetError):
+        ops.iou_aabb(torch.rand(3, 4), torch.rand(2, 4))
+    from mydetection_b200.detlayers import FCOSLayer
+    cfg = {'model.fcos.anchors': [0, 64, 100000000], 'model.fpn.out_strides': [8], 'general.num_class': 3,
+           'model.fcos2.ignored_threshold': 0.7, 'general.pred_bbox_format': 'cxcywh'}
+    raw = {'bbox': torch.zeros(1, 2, 2, 4), 'conf': torch.zeros(1, 2, 2, 1), 'class': torch.zeros(1, 2, 2, 3)}
+    with pytest.raises(_lib.MydetError):
+        FCOSLayer(0, cfg)(raw, (16, 16))
+
+
+def test_mirror_interface_matches_reference_contract():
+    from mydetection_b200 import bbox_ops, structures, detlayers
+    from mydetection_b200.heads import yolo_head_views, efdet_head_views
+    # bbox_ops: names and error behaviour of utils/bbox_ops.py
+    for name in ('bboxes_iou', 'iou_rle', 'xywha2vertex', 'nms_rotbb', 'cxcywh_to_x1y1x2y2'):
+        assert callable(getattr(bbox_ops, name))
+    with pytest.raises(IndexError):
+        bbox_ops.bboxes_iou(torch.zeros(3, 5), torch.zeros(2, 4))                 # bbox_ops.py:28-29
+    with pytest.raises(NotImplementedError):
+        bbox_ops.nms_rotbb(torch.zeros(3, 5), torch.zeros(3), bb_format='cxcywhr')  # :267-268
+    assert bbox_ops.nms_rotbb(torch.zeros(0, 5), torch.zeros(0)).dtype == torch.int64   # :271-272 empty input
+    # ImageObjects: dtype contract of sanity_check (structures.py:191-213) and container protocol
+    with pytest.raises(AssertionError):
+        structures.ImageObjects(torch.rand(3, 4), torch.zeros(3, dtype=torch.int32))
+    with pytest.raises(NotImplementedError):
+        structures.ImageObjects(torch.rand(3, 4), torch.zeros(3, dtype=torch.int64), bb_format='polygon')
+    obj = structures.ImageObjects(torch.rand(6, 4), torch.arange(6), scores=torch.rand(6), img_hw=(10, 10))
+    assert len(obj) == 6 and len(obj[2]) == 1 and len(obj[torch.tensor([True, False] * 3)]) == 3
+    empty = obj[torch.zeros(6, dtype=torch.bool)]
+    assert len(empty.nms(0.5)) == 0                                              # :120-121 returns itself
+    js = obj.to_json(img_id=7)
+    assert js[0]['image_id'] == 7 and js[3]['category_id'] == 4 and len(js[0]['bbox']) == 4
+    obj.bboxes_to_original_((20, 40, 0, 0, 10, 10))
+    assert obj.img_hw == (40, 20)
+    # registry
+    names = {'YOLO': 'YOLOLayer', 'Ultralytics': 'DetectLayer', 'RetinaNet': 'RetinaLayer', 'FCOS': 'FCOSLayer',
+             'FCOS2': 'FCOSLayer', 'FCOS2_ATSS': 'FCOS_ATSS_Layer', 'RAPiD': 'RAPiDLayer'}
+    for key, cls_name in names.items():
+        assert detlayers.get_det_layer({'model.pred_layer': key}).__name__ == cls_name
+    with pytest.raises(NotImplementedError):
+        detlayers.get_det_layer({'model.pred_layer': 'SSD'})
+    # head views are zero-copy and channel-planar
+    t = torch.zeros(2, 3 * 9, 5, 7)
+    v = yolo_head_views(t, 3, 4, 4)
+    assert v['bbox'].shape == (2, 3, 5, 7, 4) and v['bbox'].stride()[-1] == 35 and v['bbox'].data_ptr() == t.data_ptr()
+    e = efdet_head_views(torch.zeros(2, 4, 5, 7), torch.zeros(2, 1 + 6, 5, 7))
+    assert e['class'].shape == (2, 5, 7, 6) and e['conf'].shape == (2, 5, 7, 1)
+
+
+def test_level_descriptor_consumes_views_in_place():
+    """ops.make_level passes pointers + element strides of the permuted views (needs no GPU compute, but
+    make_level insists on CUDA tensors, so only the stride arithmetic is checked through a fake)."""
+    from mydetection_b200 import _lib
+    lv = _lib.Level()
+    assert ctypes.sizeof(lv) == 3 * 8 + 14 * 8 + 3 * 4 + 4 + 2 * 16 * 4
+    assert _lib.Level.bbox_stride.offset == 24 and _lib.Level.n_anchor.offset == 136
+
+
+def test_dropin_aliases():
+    import importlib
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k.split('.')[0] in ('utils', 'models')}
+    try:
+        from mydetection_b200 import dropin, bbox_ops, structures
+        dropin.install()
+        assert importlib.import_module('utils.bbox_ops') is bbox_ops
+        assert importlib.import_module('utils.structures') is structures
+        fc = importlib.import_module('models.detlayers.fcos2')
+        assert fc.FCOS_ATSS_Layer.__module__ == 'mydetection_b200.detlayers.fcos2'
+    finally:
+        for k in [k for k in sys.modules if k.split('.')[0] in ('utils', 'models')]:
+            del sys.modules[k]
+        sys.modules.update({k: v for k, v in saved.items() if v is not None})
+
+
+def test_shard_range():
+    from mydetection_b200.pipeline import shard_range
+    for n in (0, 1, 7, 64, 256, 257):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(hi - lo for lo, hi in spans) <= (n + world - 1) // world
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _gather_worker(rank, world, port, out_path):
+    import torch.distributed as dist
+    from mydetection_b200 import pipeline as pl
+    dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
+    B, K, P = 3, 8, 4
+    g = torch.Generator().manual_seed(100 + rank)
+    out = {'box': torch.rand(B, K, P, generator=g), 'score': torch.rand(B, K, generator=g),
+           'cls': torch.randint(0, 80, (B, K), generator=g), 'count': torch.tensor([rank + 1, 0, K], dtype=torch.int32)}
+    packed, counts = pl.gather_detections(out)
+    torch.save({'packed': packed, 'counts': counts, 'mine': pl.pack_detections(out)}, f'{out_path}.{rank}')
+    dist.destroy_process_group()
+
+
+def test_gather_detections_gloo_world2(tmp_path):
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    path = str(tmp_path / 'gather')
+    mp.spawn(_gather_worker, args=(world, port, path), nprocs=world, join=True)
+    res = [torch.load(f'{path}.{r}') for r in range(world)]
+    for r in range(world):
+        assert res[r]['packed'].shape == (world * 3, 8, 6)
+        assert torch.equal(res[r]['packed'], res[0]['packed'])            # every rank holds the same gathered set
+        assert torch.equal(res[r]['packed'][3 * r:3 * r + 3], res[r]['mine'])
+        assert res[r]['counts'].tolist() == [1, 0, 8, 2, 0, 8]
