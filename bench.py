@@ -191,6 +191,50 @@ def run_reference(args, budget_s=150.0):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------- rotated NMS
+def rotated_nms_metric(dev, batch=32, n=10000, iters=10):
+    """Second half of BASELINE.json's metric: rotated-NMS us/image at 10 000 boxes (configs[2]: RAPiD
+    @1024, batch 32).  Boxes are the 10 000 best of 64 512 decoded candidates per image; timed with CUDA
+    events; the oracle (exact polygon clipping, nms_rotbb control flow) is timed on one image beside it."""
+    from mydetection_b200 import ops
+    from mydetection_b200.heads import yolo_head_views
+    anchors = [[18.7807, 33.4659], [28.8912, 61.7536], [48.6849, 68.3897], [45.0668, 101.4673], [63.0952, 113.5382],
+               [81.3909, 134.4554], [91.7364, 144.9949], [137.5189, 178.4791], [194.4429, 250.7985]]
+    gen = torch.Generator(device=dev).manual_seed(3003)
+    raws = []
+    for s in (8, 16, 32):
+        m = 1024 // s
+        t = torch.randn(batch, 18, m, m, generator=gen, device=dev) * 0.5
+        v = t.view(batch, 3, 6, m, m)
+        v[:, :, 4] = torch.rand(batch, 3, m, m, generator=gen, device=dev) * 6 - 3
+        v[:, :, 5] = torch.randn(batch, 3, m, m, generator=gen, device=dev) * 1.5 - 1.5
+        raws.append(yolo_head_views(t, 3, 5, 0))
+    ls = ops.LevelSet(raws, (8, 16, 32), [anchors[0:3], anchors[3:6], anchors[6:9]])
+    box, _, score = ops.decode_dense(ops.KIND_RAPID, ls, (1024, 1024))
+    top = score.topk(n, dim=1).indices
+    rb = torch.gather(box, 1, top[..., None].expand(-1, -1, 5)).contiguous()
+    rs = torch.gather(score, 1, top).contiguous()
+    for _ in range(3):
+        keep, cnt = ops.nms_rot(rb, rs, 0.45)
+    torch.cuda.synchronize(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        keep, cnt = ops.nms_rot(rb, rs, 0.45)
+    b.record()
+    torch.cuda.synchronize(dev)
+    us = a.elapsed_time(b) * 1e3 / iters / batch
+    from oracle import iou as oi
+    t0 = time.perf_counter()
+    want = oi.nms_rot(rb[0].cpu(), rs[0].cpu(), 0.45)
+    cpu_us = (time.perf_counter() - t0) * 1e6
+    ok = bool(int(cnt[0]) == want.numel() and torch.equal(keep[0, :int(cnt[0])].cpu(), want))
+    pairs = n * (n - 1) / 2
+    return {'us_per_image': us, 'boxes_per_image': n, 'batch': batch, 'thr': 0.45, 'kept_mean': float(cnt.float().mean()),
+            'algorithmic_pairs_per_s': pairs / (us * 1e-6), 'oracle_cpu_us_per_image': cpu_us, 'matches_oracle': ok,
+            'target_us_per_image': 100.0}
+
+
 # ------------------------------------------------------------------------------------- GPU arm
 def run_gpu(args):
     import torch.distributed as dist
@@ -212,22 +256,71 @@ def run_gpu(args):
     batches = [make_batch(gen, dev) for _ in range(N_ROTATE)]
     bound = [pipe.bind(raws) for _, raws in batches]
     comm = torch.cuda.Stream(dev) if world > 1 else None
-    gathered = None
+    P = 4
+    exchange_mode = 'none'
+    if world > 1:
+        exchange_mode = 'nccl_all_gather'
+        if not args.nccl_exchange:
+            try:   # fused exchange: the post-process kernel stores its rows into every rank's buffer (NVLink)
+                peers = [pl.PeerExchange(BATCH, TOPK, P, dev) for _ in range(N_ROTATE)]
+                for bc, ex in zip(bound, peers):
+                    bc.bind_exchange(ex)
+                exchange_mode = 'p2p_store_fused_in_postprocess'
+            except Exception as e:  # symmetric memory not available on this box: keep the NCCL exchange
+                if rank == 0:
+                    sys.stderr.write(f'[bench] peer-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL\n')
+        ok = torch.tensor([1 if exchange_mode.startswith('p2p') else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            exchange_mode = 'nccl_all_gather'
+        pk = [torch.empty(pl.packed_numel(BATCH, TOPK, P), dtype=torch.float32, device=dev) for _ in range(N_ROTATE)]
+        gathered = [torch.empty(world * pk[0].numel(), dtype=torch.float32, device=dev) for _ in range(N_ROTATE)]
+    fused = exchange_mode.startswith('p2p')
+    done = [torch.cuda.Event() for _ in range(N_ROTATE)]
+    sent = [None] * N_ROTATE     # exchange of buffer j finished (its out/packed buffers may be overwritten)
+
+    def exchange(i):
+        """The path's only exchange: one all-gather of the packed detections, on a side
+        stream behind an event, so that the next batch's decode overlaps it."""
+        j = i % N_ROTATE
+        done[j].record()
+        with torch.cuda.stream(comm):
+            comm.wait_event(done[j])
+            pl.gather_detections(bound[j].out, packed=pk[j], all_packed=gathered[j])
+            sent[j] = torch.cuda.Event()
+            sent[j].record()
+
+    def reuse_guard(i):
+        j = i % N_ROTATE
+        if world > 1 and sent[j] is not None:
+            torch.cuda.current_stream().wait_event(sent[j])
 
     def step(i):
-        nonlocal gathered
         bc = bound[i % N_ROTATE]
+        reuse_guard(i)
         bc.launch_decode()
-        bc.launch_postprocess()
-        if world > 1:
-            # the path's only exchange: final detections of every rank, on a side stream so that the
-            # next batch's decode overlaps it
-            ev = torch.cuda.Event()
-            ev.record()
-            with torch.cuda.stream(comm):
-                comm.wait_event(ev)
-                gathered = pl.gather_detections(bc.out)
+        if fused:
+            bc.launch_postprocess_scatter()
+        else:
+            bc.launch_postprocess()
+            if world > 1:
+                exchange(i)
         return bc
+
+    graphs = None
+    if args.graph and world == 1:
+        # whole step (decode, post-process, pack, all-gather) as one CUDA graph per input batch
+        graphs = []
+        for j in range(N_ROTATE):
+            step_body = (lambda j=j: (bound[j].launch_decode(), bound[j].launch_postprocess(),
+                                      pl.gather_detections(bound[j].out, packed=pk[j], all_packed=gathered[j])
+                                      if world > 1 else None))
+            step_body()
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step_body()
+            graphs.append(g)
 
     def barrier():
         if world > 1:
@@ -245,25 +338,35 @@ def run_gpu(args):
     dec_b = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     t_wall0 = time.perf_counter()
     ev0.record()
-    for i in range(steps):
-        bc = bound[i % N_ROTATE]
-        dec_a[i].record()
-        bc.launch_decode()
-        dec_b[i].record()
-        bc.launch_postprocess()
+    if graphs is not None:
+        for i in range(steps):
+            graphs[i % N_ROTATE].replay()
+    else:
+        for i in range(steps):
+            bc = bound[i % N_ROTATE]
+            reuse_guard(i)
+            dec_a[i].record()
+            bc.launch_decode()
+            dec_b[i].record()
+            if fused:
+                bc.launch_postprocess_scatter()
+            else:
+                bc.launch_postprocess()
+                if world > 1:
+                    exchange(i)
         if world > 1:
-            ev = torch.cuda.Event()
-            ev.record()
-            with torch.cuda.stream(comm):
-                comm.wait_event(ev)
-                gathered = pl.gather_detections(bc.out)
-    if world > 1:
-        torch.cuda.current_stream().wait_stream(comm)
+            torch.cuda.current_stream().wait_stream(comm)
     ev1.record()
     barrier()
     t_wall1 = time.perf_counter()
+    if graphs is not None:
+        # kernel time for the roofline from a short eager pass over the same inputs
+        for i in range(min(steps, 60)):
+            dec_a[i].record(); bound[i % N_ROTATE].launch_decode(); dec_b[i].record(); bound[i % N_ROTATE].launch_postprocess()
+        torch.cuda.synchronize(dev)
+        dec_a, dec_b = dec_a[:min(steps, 60)], dec_b[:min(steps, 60)]
     ms = ev0.elapsed_time(ev1)
-    dec_ms = sum(a.elapsed_time(b) for a, b in zip(dec_a, dec_b)) / steps
+    dec_ms = sum(a.elapsed_time(b) for a, b in zip(dec_a, dec_b)) / len(dec_a)
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -304,6 +407,26 @@ def run_gpu(args):
         e2e_ms = float(t.item())
     e2e_value = world * BATCH * e2e_steps / (e2e_ms * 1e-3)
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    exchange_ok = None
+    if world > 1:
+        # outside the timed region: what the exchange delivered must equal an NCCL all-gather of the
+        # separately packed detections of every rank
+        bc = bound[0]
+        bc.launch_decode()
+        (bc.launch_postprocess_scatter() if fused else bc.launch_postprocess())
+        ref = pl.gather_detections(bc.out)
+        barrier()
+        want_rows, want_counts = pl.unpack_gathered(ref, world, BATCH, TOPK, P)
+        if fused:
+            got_rows, got_counts = bc.exchange.views()
+        else:
+            got_rows, got_counts = want_rows, want_counts
+        live = torch.arange(TOPK, device=dev)[None, :] < want_counts[:, None]
+        good = torch.equal(got_counts, want_counts) and torch.equal(got_rows[live], want_rows[live])
+        flag = torch.tensor([1 if good else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        exchange_ok = bool(flag.item())
+    rot = rotated_nms_metric(dev) if (rank == 0 and not args.no_rot) else None
 
     if rank == 0:
         bound[0].launch_decode()
@@ -332,7 +455,10 @@ def run_gpu(args):
                              else 'fallback 6650 GB/s (B200_PROFILING.md)'},
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                         'steps': e2e_steps, 'ms_per_step': e2e_ms / e2e_steps},
-                'gpu_launches': 2 * steps, 'clocks': clocks}
+                'gpu_launches': (3 if (world > 1 and not fused) else 2) * steps, 'exchange': exchange_mode, 'exchange_verified': exchange_ok, 'launch_mode': 'cuda_graph' if graphs else 'eager',
+                'clocks': clocks}
+        if rot is not None:
+            line['rotated_nms'] = rot
         if world == 1 and not args.no_cpu:
             line['cpu_baseline'] = cpu_baseline()
         print(json.dumps(line))
@@ -347,6 +473,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
+    ap.add_argument('--graph', action='store_true', help='replay each step as one CUDA graph')
+    ap.add_argument('--nccl-exchange', action='store_true', help='N>1: use the NCCL all-gather instead of peer stores')
+    ap.add_argument('--no-rot', action='store_true', help='skip the rotated-NMS side metric')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -125,6 +125,23 @@ int mydet_postprocess(const float* boxes, const float* scores, const void* cls, 
                       int32_t* out_idx, int32_t* out_count, int32_t* status, int out_cap,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* mydet_postprocess fused with the path's only multi-GPU exchange: besides the local
+ * outputs, every surviving detection is stored -- packed as P box floats, score, (float)class -- into the
+ * gathered buffer of EACH of the n_peers GPUs of the node (peer memory mapped into this process, e.g. CUDA
+ * IPC / symmetric memory; the own buffer is one of them), and the per-image count into the int32 tail:
+ *     peer_bufs[q]: float rows[images_total][out_cap][P+2];  int32 counts[images_total];
+ * This rank's images occupy rows [image_offset, image_offset + batch).  Rows beyond an image's count
+ * are not written.  Peer stores are complete when the kernel has completed on `stream`; consumers
+ * on other ranks order themselves with a stream/host barrier.  peer_bufs is a HOST array.
+ * Only the single-kernel path (effective top-k <= MYDET_SMALL_K) supports it. */
+int mydet_postprocess_scatter(const float* boxes, const float* scores, const void* cls, int cls_is_i64,
+                              const int32_t* src_idx, const int32_t* counts, int batch, int64_t pitch,
+                              int n_per_image, int n_param, int box_format, float conf_thres, int topk,
+                              double nms_thres, float* out_box, float* out_score, int64_t* out_cls,
+                              int32_t* out_idx, int32_t* out_count, int32_t* status, int out_cap,
+                              void* workspace, size_t workspace_bytes, void* const* peer_bufs, int n_peers,
+                              int64_t image_offset, int64_t images_total, void* stream);
+
 /* Whole path in one call: decode_compact + postprocess (what api/detection.py:168-172 does per
  * image, here for the batch).  Workspace: mydet_detect_workspace_bytes(...). */
 size_t mydet_detect_workspace_bytes(int batch, int64_t n_total, int n_param, int topk);
@@ -133,6 +150,13 @@ int mydet_detect(int kind, const mydet_level_t* levels, int n_levels, int batch,
                  double nms_thres, float* out_box, float* out_score, int64_t* out_cls,
                  int32_t* out_idx, int32_t* out_count, int32_t* status, int out_cap,
                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Pack the detections of a batch into ONE float32 buffer for the multi-GPU exchange:
+ * packed[(b*out_cap + k)*(P+2) + 0..P-1] = box, [+P] = score, [+P+1] = (float)class, followed by
+ * batch floats holding the bit patterns of the int32 counts.  Size: batch*(out_cap*(P+2) + 1) floats. */
+int mydet_pack_detections(const float* out_box, const float* out_score, const int64_t* out_cls,
+                          const int32_t* out_count, int batch, int out_cap, int n_param, float* packed,
+                          void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Rotated greedy NMS, batched, single class per image.  Replaces nms_rotbb

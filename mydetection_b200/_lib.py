@@ -42,9 +42,13 @@ SIGNATURES = {
     'mydet_postprocess_workspace_bytes': (c_sz, [c_int, c_int, c_int]),
     'mydet_postprocess': (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_f32,
                                   c_int, c_f64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),
+    'mydet_postprocess_scatter': (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_f32,
+                                          c_int, c_f64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_sz,
+                                          ctypes.POINTER(c_vp), c_int, c_i64, c_i64, c_vp]),
     'mydet_detect_workspace_bytes': (c_sz, [c_int, c_i64, c_int, c_int]),
     'mydet_detect': (c_int, [c_int, ctypes.POINTER(Level), c_int, c_int, c_int, c_int, c_f32, c_f32, c_f32, c_int,
                              c_f64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),
+    'mydet_pack_detections': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp]),
     'mydet_nms_rot_workspace_bytes': (c_sz, [c_int, c_int]),
     'mydet_nms_rot': (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_f64, c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     'mydet_iou_aabb_pairwise': (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp]),

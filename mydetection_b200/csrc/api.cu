@@ -31,13 +31,17 @@ MYDET_API size_t mydet_postprocess_workspace_bytes(int batch, int n_per_image, i
     return large_workspace_bytes(batch, n_per_image, false);
 }
 
-MYDET_API int mydet_postprocess(const float* boxes, const float* scores, const void* cls, int cls_is_i64,
-                                const int32_t* src_idx, const int32_t* counts, int batch, int64_t pitch,
-                                int n_per_image, int n_param, int box_format, float conf_thres, int topk,
-                                double nms_thres, float* out_box, float* out_score, int64_t* out_cls,
-                                int32_t* out_idx, int32_t* out_count, int32_t* status, int out_cap,
-                                void* workspace, size_t workspace_bytes, void* stream) {
+static int postprocess_impl(const float* boxes, const float* scores, const void* cls, int cls_is_i64,
+                            const int32_t* src_idx, const int32_t* counts, int batch, int64_t pitch,
+                            int n_per_image, int n_param, int box_format, float conf_thres, int topk,
+                            double nms_thres, float* out_box, float* out_score, int64_t* out_cls,
+                            int32_t* out_idx, int32_t* out_count, int32_t* status, int out_cap,
+                            void* workspace, size_t workspace_bytes, void* const* peers, int n_peers,
+                            int64_t peer_row0, int64_t peer_rows_total, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
+    MYDET_REQUIRE(n_peers >= 0 && n_peers <= 8, "n_peers must be in [0,8]");
+    MYDET_REQUIRE(n_peers == 0 || (peers && peer_row0 >= 0 && peer_row0 + batch <= peer_rows_total),
+                  "bad peer buffer description");
     MYDET_REQUIRE(batch >= 0 && n_per_image >= 0 && pitch >= n_per_image, "bad batch / n_per_image / pitch");
     MYDET_REQUIRE(n_param == 4 || n_param == 5, "n_param must be 4 or 5");
     MYDET_REQUIRE(box_format == MYDET_BOX_CXCYWH || box_format == MYDET_BOX_X1Y1X2Y2, "unknown box format");
@@ -59,12 +63,39 @@ MYDET_API int mydet_postprocess(const float* boxes, const float* scores, const v
         P.nms_thr_f = float_at_or_below(nms_thres); P.kpad = next_pow2_min32(K);
         P.out_box = out_box; P.out_score = out_score; P.out_cls = reinterpret_cast<long long*>(out_cls);
         P.out_idx = out_idx; P.out_count = out_count; P.status = status; P.out_cap = out_cap;
+        P.n_peers = n_peers; P.peer_row0 = peer_row0; P.peer_rows_total = peer_rows_total;
+        for (int q = 0; q < 8; ++q) P.peer[q] = q < n_peers ? static_cast<float*>(peers[q]) : nullptr;
         return launch_postprocess_small(P, batch, st);
     }
+    MYDET_REQUIRE(n_peers == 0, "the fused exchange is implemented for the single-kernel path only (<= %d survivors)", MYDET_SMALL_K);
     LargeArgs A{boxes, scores, cls, cls_is_i64, src_idx, counts, batch, pitch, n_per_image, n_param, box_format,
                 conf_thres, topk, nms_thres, 0, false, out_box, out_score, reinterpret_cast<long long*>(out_cls),
                 out_idx, out_count, status, out_cap, nullptr, nullptr};
     return run_large(A, workspace, workspace_bytes, st);
+}
+
+MYDET_API int mydet_postprocess(const float* boxes, const float* scores, const void* cls, int cls_is_i64,
+                                const int32_t* src_idx, const int32_t* counts, int batch, int64_t pitch,
+                                int n_per_image, int n_param, int box_format, float conf_thres, int topk,
+                                double nms_thres, float* out_box, float* out_score, int64_t* out_cls,
+                                int32_t* out_idx, int32_t* out_count, int32_t* status, int out_cap,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    return postprocess_impl(boxes, scores, cls, cls_is_i64, src_idx, counts, batch, pitch, n_per_image, n_param,
+                            box_format, conf_thres, topk, nms_thres, out_box, out_score, out_cls, out_idx, out_count,
+                            status, out_cap, workspace, workspace_bytes, nullptr, 0, 0, 0, stream);
+}
+
+MYDET_API int mydet_postprocess_scatter(const float* boxes, const float* scores, const void* cls, int cls_is_i64,
+                                        const int32_t* src_idx, const int32_t* counts, int batch, int64_t pitch,
+                                        int n_per_image, int n_param, int box_format, float conf_thres, int topk,
+                                        double nms_thres, float* out_box, float* out_score, int64_t* out_cls,
+                                        int32_t* out_idx, int32_t* out_count, int32_t* status, int out_cap,
+                                        void* workspace, size_t workspace_bytes, void* const* peer_bufs, int n_peers,
+                                        int64_t image_offset, int64_t images_total, void* stream) {
+    return postprocess_impl(boxes, scores, cls, cls_is_i64, src_idx, counts, batch, pitch, n_per_image, n_param,
+                            box_format, conf_thres, topk, nms_thres, out_box, out_score, out_cls, out_idx, out_count,
+                            status, out_cap, workspace, workspace_bytes, peer_bufs, n_peers, image_offset, images_total,
+                            stream);
 }
 
 // ---- whole path: candidate buffers live in the workspace
@@ -114,6 +145,35 @@ MYDET_API int mydet_detect(int kind, const mydet_level_t* levels, int n_levels, 
     return mydet_postprocess(w.box, w.score, w.cls, 0, w.idx, w.count, batch, n_total, (int)n_total, n_param,
                              MYDET_BOX_CXCYWH, -INFINITY, topk, nms_thres, out_box, out_score, out_cls, out_idx,
                              out_count, status, out_cap, w.rest, w.rest_bytes, st);
+}
+
+namespace mydet {
+__global__ void pack_kernel(const float* __restrict__ box, const float* __restrict__ score, const long long* __restrict__ cls,
+                            const int* __restrict__ count, int batch, int cap, int n_param, float* __restrict__ packed) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // detection row
+    const long long rows = (long long)batch * cap;
+    if (i < rows) {
+        float* o = packed + i * (n_param + 2);
+        const int b = (int)(i / cap), k = (int)(i - (long long)b * cap);
+        const bool live = k < count[b];
+        for (int p = 0; p < n_param; ++p) o[p] = live ? box[i * n_param + p] : 0.f;
+        o[n_param] = live ? score[i] : 0.f;
+        o[n_param + 1] = live ? (float)cls[i] : 0.f;
+    }
+    if (i < batch) packed[rows * (n_param + 2) + i] = __int_as_float(count[i]);
+}
+}  // namespace mydet
+
+MYDET_API int mydet_pack_detections(const float* out_box, const float* out_score, const int64_t* out_cls,
+                                    const int32_t* out_count, int batch, int out_cap, int n_param, float* packed,
+                                    void* stream) {
+    MYDET_REQUIRE(batch >= 0 && out_cap > 0 && (n_param == 4 || n_param == 5), "bad batch / out_cap / n_param");
+    if (batch == 0) return 0;
+    MYDET_REQUIRE(out_box && out_score && out_cls && out_count && packed, "NULL tensor pointer");
+    const long long rows = (long long)batch * out_cap;
+    pack_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        out_box, out_score, reinterpret_cast<const long long*>(out_cls), out_count, batch, out_cap, n_param, packed);
+    return launch_status("pack_kernel");
 }
 
 MYDET_API size_t mydet_nms_rot_workspace_bytes(int batch, int n_per_image) {

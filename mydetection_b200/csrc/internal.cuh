@@ -24,6 +24,12 @@ struct PPParams {
     int* out_count;
     int* status;
     int out_cap;
+    // fused exchange (mydet_postprocess_scatter): every detection row is also stored, packed as
+    // (box, score, class) floats, into the gathered buffer of each peer GPU over NVLink
+    float* peer[8];
+    int n_peers;
+    long long peer_row0;        // first image row of this rank inside the gathered buffer
+    long long peer_rows_total;  // images in the gathered buffer (all ranks)
 };
 int launch_postprocess_small(const PPParams& P, int batch, cudaStream_t st);
 

@@ -487,9 +487,25 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
                         float* ob = P.out_box + orow * 5;
                         ob[0] = v.x; ob[1] = v.y; ob[2] = v.z; ob[3] = v.w; ob[4] = gang[slot];
                     }
-                    P.out_score[orow] = key_float(~(unsigned)(k >> 20));
-                    P.out_cls[orow] = (long long)(k >> 52);
+                    const float sc = key_float(~(unsigned)(k >> 20));
+                    const long long cl = (long long)(k >> 52);
+                    P.out_score[orow] = sc;
+                    P.out_cls[orow] = cl;
                     P.out_idx[orow] = gsrc[slot];
+                    if (P.n_peers > 0) {
+                        // the path's only exchange, fused: this row goes straight into every rank's
+                        // gathered buffer (peer stores over NVLink / NVSwitch; own copy included)
+                        const int np2 = P.n_param + 2;
+                        const long long grow = ((P.peer_row0 + b) * P.out_cap + pos) * np2;
+                        const float ang = (P.n_param == 5) ? gang[slot] : 0.f;
+#pragma unroll 1
+                        for (int q = 0; q < P.n_peers; ++q) {
+                            float* o = P.peer[q] + grow;
+                            o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+                            if (P.n_param == 5) { o[4] = ang; o[5] = sc; o[6] = (float)cl; }
+                            else { o[4] = sc; o[5] = (float)cl; }
+                        }
+                    }
                 }
             }
         }
@@ -497,6 +513,10 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
             if (nk > P.out_cap) { nk = P.out_cap; flags |= 2; }
             P.out_count[b] = nk;
             if (P.status) P.status[b] = flags | s_flags;
+            for (int q = 0; q < P.n_peers; ++q) {
+                int* counts_q = reinterpret_cast<int*>(P.peer[q] + P.peer_rows_total * P.out_cap * (P.n_param + 2));
+                counts_q[P.peer_row0 + b] = nk;
+            }
         }
     }
     __syncthreads();

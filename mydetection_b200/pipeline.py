@@ -76,6 +76,24 @@ class BoundCall:
             _lib.check(rc, 'mydet_postprocess')
         return self.out
 
+    def bind_exchange(self, exchange):
+        """Fuse the multi-GPU exchange into the post-process kernel: detections are stored straight
+        into every rank's gathered buffer (peer memory) by the kernel's output stage."""
+        o = self.out
+        B, K, P = o['box'].shape
+        if exchange.batch != B or exchange.cap != K or exchange.n_param != P:
+            raise ValueError('exchange buffer geometry does not match the bound call')
+        self._scatter_args = self._pp_args + (exchange.peer_array, exchange.world, exchange.rank * B,
+                                              exchange.world * B)
+        self.exchange = exchange
+        return self
+
+    def launch_postprocess_scatter(self):
+        rc = self._L.mydet_postprocess_scatter(*self._scatter_args, self._stream())
+        if rc:
+            _lib.check(rc, 'mydet_postprocess_scatter')
+        return self.out
+
     def capture(self):
         """Record launch() into a CUDA graph (fixed shapes, fixed buffers)."""
         self.launch()                      # warm-up outside capture (lazy module load, attributes)
@@ -123,6 +141,43 @@ def unpack(out, to_cpu=True):
 
 
 # --------------------------------------------------------------------------------------- multi-GPU
+class PeerExchange:
+    """Gathered-detections buffer of every rank, mapped into this process (torch symmetric memory over
+    CUDA IPC / NVLink), for the fused exchange of mydet_postprocess_scatter.
+
+    Layout per rank: float32 rows[world*batch][cap][P+2] followed by int32 counts[world*batch].
+    `peers` may be given explicitly (a list of device pointers) -- with a single entry pointing at a local
+    tensor this degenerates to "pack into one buffer" and is how the layout is unit-tested on one GPU."""
+
+    def __init__(self, batch, cap, n_param, device, group=None, local_only=False):
+        import ctypes
+        self.batch, self.cap, self.n_param = batch, cap, n_param
+        if local_only:
+            self.world, self.rank = 1, 0
+            self.buffer = torch.zeros(self.numel(1), dtype=torch.float32, device=device)
+            ptrs = [self.buffer.data_ptr()]
+            self.handle = None
+        else:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+            self.buffer = symm.empty(self.numel(self.world), dtype=torch.float32, device=device)
+            self.buffer.zero_()
+            self.handle = symm.rendezvous(self.buffer, group if group is not None else dist.group.WORLD)
+            ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.peer_array = (ctypes.c_void_p * len(ptrs))(*ptrs)
+
+    def numel(self, world):
+        return world * self.batch * (self.cap * (self.n_param + 2) + 1)
+
+    def views(self):
+        """(rows (world*batch, cap, P+2) f32, counts (world*batch,) i32) views of the local gathered buffer."""
+        n_img = self.world * self.batch
+        n_rows = n_img * self.cap * (self.n_param + 2)
+        rows = self.buffer[:n_rows].view(n_img, self.cap, self.n_param + 2)
+        counts = self.buffer[n_rows:n_rows + n_img].view(torch.int32)
+        return rows, counts
+
 def shard_range(n_images, rank, world):
     """Contiguous block of ceil(n/world) images per rank."""
     per = (n_images + world - 1) // world
@@ -130,26 +185,49 @@ def shard_range(n_images, rank, world):
     return lo, min(lo + per, n_images)
 
 
-def pack_detections(out):
-    """(B,K,P) boxes + scores + classes -> one (B,K,P+2) float32 tensor for the exchange.
-    Class ids < 2^24 are exact in float32."""
-    return torch.cat([out['box'], out['score'].unsqueeze(-1), out['cls'].to(torch.float32).unsqueeze(-1)], dim=-1)
+def packed_numel(batch, cap, n_param):
+    return batch * (cap * (n_param + 2) + 1)
 
 
-def gather_detections(out, group=None):
+def pack_detections(out, packed=None):
+    """Detections dict -> ONE float32 buffer (mydet_pack_detections): rows of (box, score, class) followed
+    by the bit patterns of the per-image counts, so the exchange is a single collective."""
+    B, K, P = out['box'].shape
+    if packed is None:
+        packed = torch.empty(packed_numel(B, K, P), dtype=torch.float32, device=out['box'].device)
+    if out['box'].is_cuda:
+        rc = _lib.lib().mydet_pack_detections(ops._ptr(out['box']), ops._ptr(out['score']), ops._ptr(out['cls']),
+                                              ops._ptr(out['count']), B, K, P, ops._ptr(packed),
+                                              torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, 'mydet_pack_detections')
+    else:   # host-side restatement, used by the gloo tests of the exchange logic only
+        live = (torch.arange(K)[None, :] < out['count'][:, None]).unsqueeze(-1)
+        rows = torch.cat([out['box'], out['score'].unsqueeze(-1), out['cls'].to(torch.float32).unsqueeze(-1)], dim=-1)
+        packed[:B * K * (P + 2)] = (rows * live).reshape(-1)
+        packed[B * K * (P + 2):] = out['count'].to(torch.int32).view(torch.float32)
+    return packed
+
+
+def unpack_gathered(all_packed, world, batch, cap, n_param):
+    """(world * packed_numel,) -> (rows (world*batch, cap, P+2) f32, counts (world*batch,) i32)."""
+    per = packed_numel(batch, cap, n_param)
+    chunks = all_packed.view(world, per)
+    rows = chunks[:, :batch * cap * (n_param + 2)].reshape(world * batch, cap, n_param + 2)
+    counts = chunks[:, batch * cap * (n_param + 2):].contiguous().view(torch.int32).reshape(world * batch)
+    return rows, counts
+
+
+def gather_detections(out, group=None, packed=None, all_packed=None):
     """The path's only exchange: every rank receives every rank's final detections.
-    Two collectives on fixed-capacity buffers (counts, padded detections), no host sync.
-    Returns (packed (world*B, K, P+2), counts (world*B,))."""
+    One collective on one fixed-capacity buffer, no host sync.  Returns the gathered flat buffer;
+    unpack_gathered() gives (rows, counts) views."""
     import torch.distributed as dist
-    packed = pack_detections(out).contiguous()
-    counts = out['count'].contiguous()
+    packed = pack_detections(out, packed)
     world = dist.get_world_size(group)
-    all_packed = packed.new_empty((world * packed.shape[0],) + tuple(packed.shape[1:]))
-    all_counts = counts.new_empty(world * counts.shape[0])
+    if all_packed is None:
+        all_packed = packed.new_empty(world * packed.numel())
     if dist.get_backend(group) == 'nccl':
-        dist.all_gather_into_tensor(all_counts, counts, group=group)
         dist.all_gather_into_tensor(all_packed, packed, group=group)
     else:  # gloo (CPU tests of the host logic)
-        dist.all_gather(list(all_counts.chunk(world)), counts, group=group)
         dist.all_gather(list(all_packed.chunk(world)), packed, group=group)
-    return all_packed, all_counts
+    return all_packed

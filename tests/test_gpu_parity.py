@@ -302,6 +302,29 @@ def test_detect_score_ties_are_broken_by_flat_index(golden):
             assert torch.equal(out['box'][b, :k].cpu(), box[b][want])
 
 
+def test_fused_exchange_layout_single_gpu(golden):
+    """mydet_postprocess_scatter with ONE peer (a local buffer): the rows the kernel's output stage stores
+    into the gathered buffer must equal the separately packed detections, counts in the int32 tail."""
+    from mydetection_b200 import ops, pipeline as pl
+    g = golden('decode')
+    d = dev()
+    strides = (8, 16, 32, 64, 128)
+    raws = [{k: v.to(d) for k, v in efdet_views(T(g[f'fcos{li}_bbox_in']), T(g[f'fcos{li}_cls_in'])).items()} for li in range(5)]
+    pipe = pl.DetectionPipeline('FCOS2', strides, 6, (256, 384), 0.05, 0.5, 512)
+    bc = pipe.bind(raws)
+    ex = pl.PeerExchange(2, 512, 4, d, local_only=True)
+    bc.bind_exchange(ex)
+    bc.launch_decode()
+    out = bc.launch_postprocess_scatter()
+    torch.cuda.synchronize()
+    rows, counts = ex.views()
+    want_rows, want_counts = pl.unpack_gathered(pl.pack_detections(out), 1, 2, 512, 4)
+    assert torch.equal(counts, out['count']) and torch.equal(counts, want_counts)
+    for b in range(2):
+        n = int(counts[b])
+        assert n > 0 and torch.equal(rows[b, :n], want_rows[b, :n])
+
+
 # ------------------------------------------------------------------------------------- IoU / rotated
 def test_bboxes_iou_bit_exact(golden):
     from mydetection_b200 import ops

@@ -176,8 +176,10 @@ def _gather_worker(rank, world, port, out_path):
     g = torch.Generator().manual_seed(100 + rank)
     out = {'box': torch.rand(B, K, P, generator=g), 'score': torch.rand(B, K, generator=g),
            'cls': torch.randint(0, 80, (B, K), generator=g), 'count': torch.tensor([rank + 1, 0, K], dtype=torch.int32)}
-    packed, counts = pl.gather_detections(out)
-    torch.save({'packed': packed, 'counts': counts, 'mine': pl.pack_detections(out)}, f'{out_path}.{rank}')
+    flat = pl.gather_detections(out)
+    packed, counts = pl.unpack_gathered(flat, world, B, K, P)
+    mine, _ = pl.unpack_gathered(pl.pack_detections(out), 1, B, K, P)
+    torch.save({'packed': packed, 'counts': counts, 'mine': mine, 'box': out['box'], 'count': out['count']}, f'{out_path}.{rank}')
     dist.destroy_process_group()
 
 
@@ -192,3 +194,6 @@ def test_gather_detections_gloo_world2(tmp_path):
         assert torch.equal(res[r]['packed'], res[0]['packed'])            # every rank holds the same gathered set
         assert torch.equal(res[r]['packed'][3 * r:3 * r + 3], res[r]['mine'])
         assert res[r]['counts'].tolist() == [1, 0, 8, 2, 0, 8]
+        # live rows carry the boxes, rows beyond the count are zeroed
+        assert torch.equal(res[r]['mine'][0, :r + 1, :4], res[r]['box'][0, :r + 1])
+        assert float(res[r]['mine'][1].abs().sum()) == 0.0
