@@ -114,6 +114,40 @@ __global__ void __launch_bounds__(kRankThreads) rank_kernel(const unsigned long 
     if (i < n && mine != ~0ull) order[(long long)b * n + rank] = i;
 }
 
+// Sort for images of at most 16 384 candidates: one CTA per image, bitonic network over (key, slot) held
+// entirely in shared memory (192 KB).  32 images sort concurrently on 32 SMs in ~50 us, where the
+// all-pairs rank kernel above needs 545 us for the same batch.
+constexpr int kSortThreads = 1024;
+constexpr int kSortMaxN = 16384;
+__global__ void __launch_bounds__(kSortThreads, 1) sort_smem_kernel(const unsigned long long* keys, int* order, int n, int npad) {
+    extern __shared__ unsigned long long skeys[];
+    int* spay = reinterpret_cast<int*>(skeys + npad);
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const unsigned long long* kb = keys + (long long)b * n;
+    for (int i = tid; i < npad; i += kSortThreads) { skeys[i] = (i < n) ? kb[i] : ~0ull; spay[i] = i; }
+    __syncthreads();
+#pragma unroll 1
+    for (int size = 2; size <= npad; size <<= 1) {
+#pragma unroll 1
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll 4
+            for (int t = tid; t < (npad >> 1); t += kSortThreads) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const unsigned long long a = skeys[lo], c = skeys[hi];
+                if ((a > c) == up) {
+                    skeys[lo] = c; skeys[hi] = a;
+                    const int pa = spay[lo]; spay[lo] = spay[hi]; spay[hi] = pa;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < n; i += kSortThreads)
+        if (skeys[i] != ~0ull) order[(long long)b * n + i] = spay[i];
+}
+
 // ---------------------------------------------------------------------------- gather
 struct GatherParams {
     const float* boxes; long long pitch; int n, n_param, box_format;
@@ -132,6 +166,7 @@ __global__ void gather_kernel(GatherParams P, const unsigned long long* keys, co
         make_rot_box(v, q.x, q.y, q.r);
         q.cx = v[0]; q.cy = v[1];
         q.area2 = (float)signed_area2_f64(q.x, q.y);
+        rot_box_hull(q);
         w.rbox[row] = q;
     } else {
         const float v0 = bx[0], v1 = bx[1], v2 = bx[2], v3 = bx[3];
@@ -149,11 +184,17 @@ __global__ void gather_kernel(GatherParams P, const unsigned long long* keys, co
 }
 
 // ---------------------------------------------------------------------------- mask
-// grid (col_tile, row_tile, image); 64 threads; thread t owns row row_tile*64+t.
+// grid (upper-triangular tile pair, image); 64 threads; thread t owns row row_tile*64+t.
 template <bool ROT>
 __global__ void __launch_bounds__(kTile) mask_kernel(LargeWs w, const int* m, int n, float thr_f, double thr_d, int ge) {
-    const int ct = blockIdx.x, rt = blockIdx.y, b = blockIdx.z;
-    if (ct < rt) return;
+    // blockIdx.x enumerates the upper-triangular tile pairs (rt <= ct) row by row
+    const int T = (n + kTile - 1) / kTile;
+    const int b = blockIdx.y;
+    int rt = (int)((2.0f * T + 1.0f - sqrtf((2.0f * T + 1.0f) * (2.0f * T + 1.0f) - 8.0f * (float)blockIdx.x)) * 0.5f);
+    rt = max(0, min(rt, T - 1));
+    while (rt > 0 && (long long)rt * T - (long long)rt * (rt - 1) / 2 > (long long)blockIdx.x) --rt;
+    while ((long long)(rt + 1) * T - (long long)(rt + 1) * rt / 2 <= (long long)blockIdx.x) ++rt;
+    const int ct = rt + (int)((long long)blockIdx.x - ((long long)rt * T - (long long)rt * (rt - 1) / 2));
     const int mb = m[b];
     if (rt * kTile >= mb || ct * kTile >= mb) return;
     const long long base = (long long)b * n;
@@ -162,14 +203,75 @@ __global__ void __launch_bounds__(kTile) mask_kernel(LargeWs w, const int* m, in
     const int c0 = ct * kTile;
     unsigned long long bits = 0ull;
     if (ROT) {
+        // Two phases, so that the expensive polygon clipping runs with every lane busy:
+        //  (1) each thread culls its row against the 64 columns (circumscribed circles, area ratio) and
+        //      appends the surviving (row, col) pairs to a queue in shared memory;
+        //  (2) the 64 threads drain the queue, one pair per thread and round, and set bits in shared memory.
+        // (Clipping inside the per-row loop left ~1 of 32 lanes active: 585 us per 10 k-box image.)
         __shared__ RotBox cols[kTile];
-        if (c0 + t < mb) cols[t] = w.rbox[base + c0 + t];
+        __shared__ RotBox rows[kTile];
+        __shared__ float4 ccull[kTile];                 // cx, cy, r, area of the column boxes: one LDS.128 per pair
+        __shared__ unsigned short queue[kTile * kTile];
+        __shared__ unsigned bits32[kTile][2];
+        __shared__ int qn;
+        if (c0 + t < mb) {
+            const RotBox q = w.rbox[base + c0 + t];
+            cols[t] = q;
+            ccull[t] = make_float4(q.cx, q.cy, q.r, 0.5f * fabsf(q.area2));
+        } else {
+            ccull[t] = make_float4(3.0e18f, 3.0e18f, 0.f, 0.f);   // never passes the circle test
+        }
+        if (r < mb) rows[t] = w.rbox[base + r];
+        bits32[t][0] = 0u; bits32[t][1] = 0u;
+        if (t == 0) qn = 0;
         __syncthreads();
+        const int lim = min(kTile, mb - c0);
+        const bool ge_mode = ge != 0;
         if (r < mb) {
-            const RotBox me = w.rbox[base + r];
-            const int lim = min(kTile, mb - c0);
-            for (int j = 0; j < lim; ++j)
-                if (c0 + j > r && rot_overlaps(me, cols[j], thr_d, ge != 0)) bits |= 1ull << j;
+            const float mcx = rows[t].cx, mcy = rows[t].cy, mr = rows[t].r * 1.00001f + 1e-3f;
+            const float ma = 0.5f * fabsf(rows[t].area2);
+            const float mx0 = rows[t].x0, my0 = rows[t].y0, mx1 = rows[t].x1, my1 = rows[t].y1;
+            const float thr_f = (float)thr_d;
+            // (1a) branch-free circle test against all 64 columns -> candidate bit set
+            unsigned long long cand = 0ull;
+#pragma unroll 16
+            for (int j = 0; j < kTile; ++j) {
+                const float4 c = ccull[j];
+                const float dx = mcx - c.x, dy = mcy - c.y, rr = fmaf(c.z, 1.00001f, mr);
+                const bool pass = fmaf(dx, dx, dy * dy) <= rr * rr;
+                cand |= (unsigned long long)pass << j;
+            }
+            // only columns that rank after this row
+            const int first = r + 1 - c0;                              // first admissible column
+            if (first >= kTile) cand = 0ull; else if (first > 0) cand &= ~0ull << first;
+            // (1b) area-ratio and hull bounds on the few survivors, then queue them for clipping
+            while (cand) {
+                const int j = __ffsll((long long)cand) - 1;
+                cand &= cand - 1;
+                const float oa = ccull[j].w;
+                const float lo = fminf(ma, oa), hi = fmaxf(ma, oa);
+                if (lo * 1.0001f < thr_f * hi) continue;                         // IoU <= lo/hi < thr
+                // the intersection lies inside the intersection of the two axis-aligned hulls
+                const float ix = fminf(mx1, cols[j].x1) - fmaxf(mx0, cols[j].x0);
+                const float iy = fminf(my1, cols[j].y1) - fmaxf(my0, cols[j].y0);
+                if (!(ix > -1e-3f && iy > -1e-3f)) continue;                     // hulls apart: IoU == 0
+                const float ub = (ix + 2e-3f) * (iy + 2e-3f);
+                if (ub * 1.0001f < thr_f * (ma + oa - ub)) continue;             // IoU <= ub/(a+b-ub) < thr
+                queue[atomicAdd(&qn, 1)] = (unsigned short)((t << 6) | j);
+            }
+        }
+        __syncthreads();
+        const int total = qn;
+        for (int e = t; e < total; e += kTile) {
+            const int code = queue[e], rt_ = code >> 6, j = code & 63;
+            if (rot_overlaps(rows[rt_], cols[j], thr_d, ge_mode)) atomicOr(&bits32[rt_][j >> 5], 1u << (j & 31));
+        }
+        __syncthreads();
+        bits = ((unsigned long long)bits32[t][1] << 32) | bits32[t][0];
+        if (thr_d <= 0.0 && ge_mode && r < mb) {
+            // degenerate threshold: every later box is suppressed (IoU >= thr always holds)
+            bits = 0ull;
+            for (int j = 0; j < lim; ++j) if (c0 + j > r) bits |= 1ull << j;
         }
     } else {
         __shared__ float4 cbox[kTile];
@@ -196,8 +298,96 @@ __global__ void __launch_bounds__(kTile) mask_kernel(LargeWs w, const int* m, in
     if (r < mb) w.mask[(base + r) * w.words + ct] = bits;
 }
 
+// Rotated mask, v3: one CTA owns a row tile and walks kColChunk consecutive column tiles, so the per-tile
+// cost is one coalesced 1 KB load of cull records + 64 branch-free circle tests per thread.  (One CTA per
+// 64x64 tile spent most of its 6 ms on set-up: index mapping, two 4 KB structure loads, barriers.)
+constexpr int kColChunk = 8;
+__global__ void __launch_bounds__(kTile) mask_rot_kernel(LargeWs w, const int* m, int n, double thr_d, int ge) {
+    const int rt = blockIdx.x, cc = blockIdx.y, b = blockIdx.z;
+    const int T = (n + kTile - 1) / kTile;
+    const int ct_lo = max(rt, cc * kColChunk), ct_hi = min(T, (cc + 1) * kColChunk);
+    if (ct_lo >= ct_hi) return;
+    const int mb = m[b];
+    if (rt * kTile >= mb || ct_lo * kTile >= mb) return;
+    const long long base = (long long)b * n;
+    const int t = threadIdx.x;
+    const int r = rt * kTile + t;
+    __shared__ float4 ccull[kTile];
+    __shared__ unsigned short queue[kTile * kTile];
+    __shared__ unsigned bits32[kTile][2];
+    __shared__ int qn;
+    const bool ge_mode = ge != 0;
+    const float thr_f = (float)thr_d;
+    float mcx = 3.0e18f, mcy = 3.0e18f, mr = 0.f, ma = 0.f, mx0 = 0.f, my0 = 0.f, mx1 = 0.f, my1 = 0.f;
+    if (r < mb) {
+        const RotBox q = w.rbox[base + r];
+        mcx = q.cx; mcy = q.cy; mr = q.r * 1.00001f + 1e-3f; ma = 0.5f * fabsf(q.area2);
+        mx0 = q.x0; my0 = q.y0; mx1 = q.x1; my1 = q.y1;
+    }
+#pragma unroll 1
+    for (int ct = ct_lo; ct < ct_hi; ++ct) {
+        const int c0 = ct * kTile;
+        if (c0 >= mb) break;
+        {
+            float4 c = make_float4(-3.0e18f, -3.0e18f, 0.f, 0.f);              // never passes the circle test
+            if (c0 + t < mb) {
+                const RotBox& q = w.rbox[base + c0 + t];
+                c = make_float4(q.cx, q.cy, q.r, 0.5f * fabsf(q.area2));
+            }
+            ccull[t] = c;
+            bits32[t][0] = 0u; bits32[t][1] = 0u;
+            if (t == 0) qn = 0;
+        }
+        __syncthreads();
+        if (r < mb) {
+            unsigned long long cand = 0ull;
+#pragma unroll 16
+            for (int j = 0; j < kTile; ++j) {
+                const float4 c = ccull[j];
+                const float dx = mcx - c.x, dy = mcy - c.y, rr = fmaf(c.z, 1.00001f, mr);
+                const bool pass = fmaf(dx, dx, dy * dy) <= rr * rr;
+                cand |= (unsigned long long)pass << j;
+            }
+            const int first = r + 1 - c0;                                       // only columns ranked after the row
+            if (first >= kTile) cand = 0ull; else if (first > 0) cand &= ~0ull << first;
+            while (cand) {
+                const int j = __ffsll((long long)cand) - 1;
+                cand &= cand - 1;
+                const float oa = ccull[j].w;
+                const float lo = fminf(ma, oa), hi = fmaxf(ma, oa);
+                if (lo * 1.0001f < thr_f * hi) continue;                         // IoU <= lo/hi < thr
+                const RotBox& q = w.rbox[base + c0 + j];
+                const float ix = fminf(mx1, q.x1) - fmaxf(mx0, q.x0);
+                const float iy = fminf(my1, q.y1) - fmaxf(my0, q.y0);
+                if (!(ix > -1e-3f && iy > -1e-3f)) continue;                     // hulls apart: IoU == 0
+                const float ub = (ix + 2e-3f) * (iy + 2e-3f);
+                if (ub * 1.0001f < thr_f * (ma + oa - ub)) continue;             // IoU <= ub/(a+b-ub) < thr
+                queue[atomicAdd(&qn, 1)] = (unsigned short)((t << 6) | j);
+            }
+        }
+        __syncthreads();
+        const int total = qn;
+        for (int e = t; e < total; e += kTile) {
+            const int code = queue[e], rt_ = code >> 6, j = code & 63;
+            const RotBox A = w.rbox[base + rt * kTile + rt_];
+            const RotBox B = w.rbox[base + c0 + j];
+            if (rot_overlaps(A, B, thr_d, ge_mode)) atomicOr(&bits32[rt_][j >> 5], 1u << (j & 31));
+        }
+        __syncthreads();
+        if (r < mb) {
+            unsigned long long bits = ((unsigned long long)bits32[t][1] << 32) | bits32[t][0];
+            if (thr_d <= 0.0 && ge_mode) {           // degenerate threshold: every later box is suppressed
+                bits = 0ull;
+                const int lim = min(kTile, mb - c0);
+                for (int j = 0; j < lim; ++j) if (c0 + j > r) bits |= 1ull << j;
+            }
+            w.mask[(base + r) * w.words + ct] = bits;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------- sweep + emit
-constexpr int kSweepThreads = 256;
+constexpr int kSweepThreads = 512;
 
 struct EmitParams {
     const float* boxes; const float* scores; const void* cls; const int* src_idx;
@@ -215,6 +405,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(LargeWs w, const i
     unsigned long long* keptw = sm + w.words;            // w.words
     unsigned long long* diag = keptw + w.words;          // 64
     __shared__ unsigned long long s_kept;
+    __shared__ int klist[kTile];
     __shared__ int s_prefix_total;
     const unsigned long long* mask = w.mask + (long long)b * n * w.words;
 
@@ -244,16 +435,36 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(LargeWs w, const i
         }
         __syncthreads();
         const unsigned long long kept = s_kept;
-        // OR the kept rows of this block into the removed words that are still ahead
-        for (int wd = t + 1 + tid; wd < words; wd += kSweepThreads) {
-            unsigned long long acc = 0ull;
-            unsigned long long k = kept;
-            while (k) {
-                const int j = __ffsll((long long)k) - 1;
-                k &= k - 1;
-                acc |= mask[(long long)(r0 + j) * w.words + wd];
+        // OR the kept rows of this block into the removed words that are still ahead.  (kept row, word)
+        // pairs are spread over all threads, four independent loads in flight each: a per-word loop over
+        // the kept rows issued one dependent load after the other, 24 us per block.
+        if (tid < kTile) {
+            if ((kept >> tid) & 1ull) klist[__popcll(kept & ((1ull << tid) - 1ull))] = tid;
+        }
+        __syncthreads();
+        {
+            const int nk = __popcll(kept), nw = words - (t + 1);
+            const int work = nk * nw;
+            unsigned* removed32 = reinterpret_cast<unsigned*>(removed);
+            for (int base_i = tid; base_i < work; base_i += 4 * kSweepThreads) {
+                unsigned long long v[4];
+                int wdv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int idx = base_i + u * kSweepThreads;
+                    v[u] = 0ull; wdv[u] = 0;
+                    if (idx < work) {
+                        const int kr = idx / nw, wd = t + 1 + (idx - kr * nw);
+                        wdv[u] = wd;
+                        v[u] = mask[(long long)(r0 + klist[kr]) * w.words + wd];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if ((unsigned)v[u]) atomicOr(&removed32[2 * wdv[u]], (unsigned)v[u]);
+                    if ((unsigned)(v[u] >> 32)) atomicOr(&removed32[2 * wdv[u] + 1], (unsigned)(v[u] >> 32));
+                }
             }
-            removed[wd] |= acc;
         }
         __syncthreads();
     }
@@ -355,15 +566,23 @@ int run_large(const LargeArgs& A, void* workspace, size_t workspace_bytes, cudaS
     if (A.status) MYDET_CUDA(cudaMemsetAsync(A.status, 0, sizeof(int) * (size_t)B, st));
     KeyParams K{A.scores, A.cls, A.counts, A.src_idx, A.pitch, n, A.cls_is_i64, (A.cls && !A.rot) ? 1 : 0, A.conf_thres, A.status};
     keys_kernel<<<dim3((n + 255) / 256, B), 256, 0, st>>>(K, w.keys, w.m);
-    rank_kernel<<<dim3((n + kRankThreads - 1) / kRankThreads, B), kRankThreads, 0, st>>>(w.keys, w.order, n);
+    if (n <= kSortMaxN) {
+        int npad = 64;
+        while (npad < n) npad <<= 1;
+        const size_t sort_smem = (size_t)npad * 12;
+        MYDET_CUDA(cudaFuncSetAttribute(sort_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortMaxN * 12)));
+        sort_smem_kernel<<<B, kSortThreads, sort_smem, st>>>(w.keys, w.order, n, npad);
+    } else {
+        rank_kernel<<<dim3((n + kRankThreads - 1) / kRankThreads, B), kRankThreads, 0, st>>>(w.keys, w.order, n);
+    }
     GatherParams G{A.boxes, A.pitch, n, A.n_param, A.box_format};
     const int tiles = (n + kTile - 1) / kTile;
     if (A.rot) {
         gather_kernel<true><<<dim3((n + 255) / 256, B), 256, 0, st>>>(G, w.keys, w.order, w.m, w);
-        mask_kernel<true><<<dim3(tiles, tiles, B), kTile, 0, st>>>(w, w.m, n, 0.f, A.thr, A.ge);
+        mask_rot_kernel<<<dim3(tiles, (tiles + kColChunk - 1) / kColChunk, B), kTile, 0, st>>>(w, w.m, n, A.thr, A.ge);
     } else {
         gather_kernel<false><<<dim3((n + 255) / 256, B), 256, 0, st>>>(G, w.keys, w.order, w.m, w);
-        mask_kernel<false><<<dim3(tiles, tiles, B), kTile, 0, st>>>(w, w.m, n, float_at_or_below(A.thr), A.thr, 0);
+        mask_kernel<false><<<dim3(tiles * (tiles + 1) / 2, B), kTile, 0, st>>>(w, w.m, n, float_at_or_below(A.thr), A.thr, 0);
     }
     EmitParams E{A.boxes, A.scores, A.cls, A.src_idx, A.pitch, n, A.n_param, A.cls_is_i64,
                  A.out_box, A.out_score, A.out_cls, A.out_idx, A.out_count, A.status, A.out_cap, A.keep64};

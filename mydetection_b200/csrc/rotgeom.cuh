@@ -10,12 +10,19 @@
 
 namespace mydet {
 
-struct RotBox {       // 12 floats, one per box, precomputed once
+struct __align__(16) RotBox {       // 16 floats, one per box, precomputed once
     float x[4], y[4]; // corners tl,tr,br,bl in float32, as the reference computes them
     float cx, cy;     // centre
     float r;          // circumscribed radius (cull)
     float area2;      // signed 2*area of the corner polygon (shoelace), float64-rounded to float32
+    float x0, y0, x1, y1;   // axis-aligned hull of the corners (cull)
 };
+__device__ __forceinline__ void rot_box_hull(RotBox& q) {
+    q.x0 = fminf(fminf(q.x[0], q.x[1]), fminf(q.x[2], q.x[3]));
+    q.x1 = fmaxf(fmaxf(q.x[0], q.x[1]), fmaxf(q.x[2], q.x[3]));
+    q.y0 = fminf(fminf(q.y[0], q.y[1]), fminf(q.y[2], q.y[3]));
+    q.y1 = fmaxf(fmaxf(q.y[0], q.y[1]), fmaxf(q.y[2], q.y[3]));
+}
 
 __device__ __forceinline__ void make_rot_box(const float* b, float* x, float* y, float& r) {
     // degrees -> radians: a * pi / 180 in float32 (bbox_ops.py:88-89).  sin/cos are evaluated in

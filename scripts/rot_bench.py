@@ -1,0 +1,11 @@
+"""Developer tool: rotated-NMS us/image at 10 000 boxes (bench.py's side metric) on its own."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import bench
+
+print(json.dumps(bench.rotated_nms_metric(torch.device('cuda', 0))))

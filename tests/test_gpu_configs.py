@@ -236,3 +236,31 @@ def test_cfg5_dense_scene_uncapped(img, batch):
         k = int(out['count'][bb])
         s = out['score'][bb, :k]
         assert bool((s[1:] <= s[:-1]).all()) and k > 1000
+
+
+# ---------------------------------------------------------------------------------------------- repeatability
+def test_large_paths_repeatable():
+    """compute-sanitizer is closed on this pool, so races are hunted the blunt way: the tiled large-N paths
+    (sort, mask queues with shared-memory atomics, sweep with atomicOr) must give bit-identical results over
+    many repetitions on the same input."""
+    from mydetection_b200 import ops
+    gen = torch.Generator().manual_seed(77)
+    B, n = 4, 6000
+    xy = torch.rand(B, n, 2, generator=gen) * 700 + 50
+    wh = torch.rand(B, n, 2, generator=gen) * 90 + 8
+    ang = torch.rand(B, n, 1, generator=gen) * 360 - 180
+    rb = torch.cat([xy, wh, ang], 2).to(DEV)
+    scores = torch.rand(B, n, generator=gen).to(DEV)
+    cls = torch.randint(0, 3, (B, n), generator=gen).to(DEV)
+    first = None
+    for rep in range(12):
+        keep, cnt, votes = ops.nms_rot(rb, scores, 0.4, want_votes=True)
+        out = ops.postprocess(rb[..., :4].contiguous(), scores, cls, 0.05, 0.5, topk=None)
+        torch.cuda.synchronize()
+        snap = [cnt.clone(), out['count'].clone()]
+        for b in range(B):
+            snap += [keep[b, :int(cnt[b])].clone(), votes[b, :int(cnt[b])].clone(), out['idx'][b, :int(out['count'][b])].clone()]
+        if first is None:
+            first = snap
+        else:
+            assert all(torch.equal(a, c) for a, c in zip(first, snap)), f'repetition {rep} differs'
