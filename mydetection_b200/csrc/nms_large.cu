@@ -29,6 +29,14 @@ struct LargeWs {          // carved out of the caller's workspace
     unsigned long long* mask;   // B*n*words
     unsigned long long* kept;   // B*words  survivors, bit per sorted row
     int* rowpos;                // B*n      sorted row -> position in the emitted list (kept rows)
+    // spatially ordered variant (rotated path, n <= 16384): boxes live in Morton order of their centres
+    unsigned long long* skeys;  // B*n      (morton << 20 | score rank), indexed by score rank
+    int* rank_of_spos;          // B*n      spatial position -> score rank
+    int* spos_of_rank;          // B*n      score rank -> spatial position
+    float4* tile_hull;          // B*tiles  hull of the 64 boxes of a spatial tile
+    unsigned long long* diag_all; // B*tiles*64  per score block, TRANSPOSED: entry c, bit a = "a suppresses c" (both of the block)
+    unsigned long long* adj_blk;  // B*tiles*64*4  per score block row: the tile_adj words of that row's spatial tile
+    unsigned long long* tile_adj; // B*tiles*4  bit j of tile i: some row of tile i has a nonzero mask word j (tiles <= 256)
     int words;                  // ceil(n/64)
 };
 
@@ -42,6 +50,11 @@ static size_t carve(LargeWs& w, void* base, int batch, int n, bool rot) {
     const size_t o_rbox = take(rot ? bn * sizeof(RotBox) : 0);
     const size_t o_mask = take(bn * (size_t)w.words * 8), o_kept = take((size_t)batch * w.words * 8);
     const size_t o_rowpos = take(rot ? bn * 4 : 0);
+    const size_t o_skeys = take(rot ? bn * 8 : 0), o_ros = take(rot ? bn * 4 : 0), o_sor = take(rot ? bn * 4 : 0);
+    const size_t o_hull = take(rot ? (size_t)batch * w.words * 16 : 0);
+    const size_t o_adj = take(rot ? (size_t)batch * w.words * 32 : 0);
+    const size_t o_diag = take(rot ? (size_t)batch * w.words * kTile * 8 : 0);
+    const size_t o_adjb = take(rot ? (size_t)batch * w.words * kTile * 32 : 0);
     if (base) {
         char* p = static_cast<char*>(base);
         w.keys = (unsigned long long*)(p + o_keys); w.order = (int*)(p + o_order); w.m = (int*)(p + o_m);
@@ -49,6 +62,11 @@ static size_t carve(LargeWs& w, void* base, int batch, int n, bool rot) {
         w.rbox = (RotBox*)(p + o_rbox);
         w.mask = (unsigned long long*)(p + o_mask); w.kept = (unsigned long long*)(p + o_kept);
         w.rowpos = (int*)(p + o_rowpos);
+        w.skeys = (unsigned long long*)(p + o_skeys); w.rank_of_spos = (int*)(p + o_ros); w.spos_of_rank = (int*)(p + o_sor);
+        w.tile_hull = (float4*)(p + o_hull);
+        w.tile_adj = (unsigned long long*)(p + o_adj);
+        w.diag_all = (unsigned long long*)(p + o_diag);
+        w.adj_blk = (unsigned long long*)(p + o_adjb);
     }
     return off;
 }
@@ -298,10 +316,17 @@ __global__ void __launch_bounds__(kTile) mask_kernel(LargeWs w, const int* m, in
     if (r < mb) w.mask[(base + r) * w.words + ct] = bits;
 }
 
-// Rotated mask, v3: one CTA owns a row tile and walks kColChunk consecutive column tiles, so the per-tile
-// cost is one coalesced 1 KB load of cull records + 64 branch-free circle tests per thread.  (One CTA per
-// 64x64 tile spent most of its 6 ms on set-up: index mapping, two 4 KB structure loads, barriers.)
+// Rotated mask: one CTA owns a row tile and walks kColChunk consecutive column tiles.
+//  (1) per column tile: one coalesced 1 KB load of cull records, then every thread runs 64 branch-free
+//      circumscribed-circle tests for its row; the few survivors pass the area-ratio and hull bounds and
+//      are appended to a queue in shared memory;
+//  (2) the queue is drained once it holds at least one entry per thread (or at the end of the chunk):
+//      one pair per thread, polygon clipping with every lane busy.
+// History (profiles/r1_history.md): clipping inside the per-row loop ran with ~1 of 32 lanes active
+// (585 us per 10 k-box image); one CTA per 64x64 tile spent its time on set-up and barriers (209 us);
+// draining after every tile clipped ~10 pairs with 64 threads (136 us).
 constexpr int kColChunk = 8;
+constexpr int kQueueCap = kTile * kTile + kTile;
 __global__ void __launch_bounds__(kTile) mask_rot_kernel(LargeWs w, const int* m, int n, double thr_d, int ge) {
     const int rt = blockIdx.x, cc = blockIdx.y, b = blockIdx.z;
     const int T = (n + kTile - 1) / kTile;
@@ -312,9 +337,9 @@ __global__ void __launch_bounds__(kTile) mask_rot_kernel(LargeWs w, const int* m
     const long long base = (long long)b * n;
     const int t = threadIdx.x;
     const int r = rt * kTile + t;
-    __shared__ float4 ccull[kTile];
-    __shared__ unsigned short queue[kTile * kTile];
-    __shared__ unsigned bits32[kTile][2];
+    __shared__ float4 ccull[2][kTile];
+    __shared__ unsigned short queue[kQueueCap];          // (tile in chunk) << 12 | row << 6 | col
+    __shared__ unsigned bits32[kColChunk][kTile][2];
     __shared__ int qn;
     const bool ge_mode = ge != 0;
     const float thr_f = (float)thr_d;
@@ -324,8 +349,22 @@ __global__ void __launch_bounds__(kTile) mask_rot_kernel(LargeWs w, const int* m
         mcx = q.cx; mcy = q.cy; mr = q.r * 1.00001f + 1e-3f; ma = 0.5f * fabsf(q.area2);
         mx0 = q.x0; my0 = q.y0; mx1 = q.x1; my1 = q.y1;
     }
+#pragma unroll
+    for (int k = 0; k < kColChunk; ++k) { bits32[k][t][0] = 0u; bits32[k][t][1] = 0u; }
+    if (t == 0) qn = 0;
+
+    auto drain = [&](int total) {
+        for (int e = t; e < total; e += kTile) {
+            const int code = queue[e], k = code >> 12, rt_ = (code >> 6) & 63, j = code & 63;
+            const RotBox A = w.rbox[base + rt * kTile + rt_];
+            const RotBox B = w.rbox[base + (ct_lo + k) * kTile + j];
+            if (rot_overlaps(A, B, thr_d, ge_mode)) atomicOr(&bits32[k][rt_][j >> 5], 1u << (j & 31));
+        }
+    };
+
+    int buf = 0;
 #pragma unroll 1
-    for (int ct = ct_lo; ct < ct_hi; ++ct) {
+    for (int ct = ct_lo; ct < ct_hi; ++ct, buf ^= 1) {
         const int c0 = ct * kTile;
         if (c0 >= mb) break;
         {
@@ -334,26 +373,37 @@ __global__ void __launch_bounds__(kTile) mask_rot_kernel(LargeWs w, const int* m
                 const RotBox& q = w.rbox[base + c0 + t];
                 c = make_float4(q.cx, q.cy, q.r, 0.5f * fabsf(q.area2));
             }
-            ccull[t] = c;
-            bits32[t][0] = 0u; bits32[t][1] = 0u;
-            if (t == 0) qn = 0;
+            ccull[buf][t] = c;
         }
-        __syncthreads();
+        __syncthreads();                       // cull records visible; the previous tile's pushes are complete
+        const int pending = qn;
+        if (pending >= kTile) {                // uniform
+            drain(pending);
+            __syncthreads();
+            if (t == 0) qn = 0;
+            __syncthreads();
+        }
         if (r < mb) {
-            unsigned long long cand = 0ull;
-#pragma unroll 16
-            for (int j = 0; j < kTile; ++j) {
-                const float4 c = ccull[j];
+            unsigned cand_lo = 0u, cand_hi = 0u;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float4 c = ccull[buf][j];
                 const float dx = mcx - c.x, dy = mcy - c.y, rr = fmaf(c.z, 1.00001f, mr);
-                const bool pass = fmaf(dx, dx, dy * dy) <= rr * rr;
-                cand |= (unsigned long long)pass << j;
+                if (fmaf(dx, dx, dy * dy) <= rr * rr) cand_lo |= 1u << j;
             }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float4 c = ccull[buf][32 + j];
+                const float dx = mcx - c.x, dy = mcy - c.y, rr = fmaf(c.z, 1.00001f, mr);
+                if (fmaf(dx, dx, dy * dy) <= rr * rr) cand_hi |= 1u << j;
+            }
+            unsigned long long cand = ((unsigned long long)cand_hi << 32) | cand_lo;
             const int first = r + 1 - c0;                                       // only columns ranked after the row
             if (first >= kTile) cand = 0ull; else if (first > 0) cand &= ~0ull << first;
             while (cand) {
                 const int j = __ffsll((long long)cand) - 1;
                 cand &= cand - 1;
-                const float oa = ccull[j].w;
+                const float oa = ccull[buf][j].w;
                 const float lo = fminf(ma, oa), hi = fmaxf(ma, oa);
                 if (lo * 1.0001f < thr_f * hi) continue;                         // IoU <= lo/hi < thr
                 const RotBox& q = w.rbox[base + c0 + j];
@@ -362,20 +412,19 @@ __global__ void __launch_bounds__(kTile) mask_rot_kernel(LargeWs w, const int* m
                 if (!(ix > -1e-3f && iy > -1e-3f)) continue;                     // hulls apart: IoU == 0
                 const float ub = (ix + 2e-3f) * (iy + 2e-3f);
                 if (ub * 1.0001f < thr_f * (ma + oa - ub)) continue;             // IoU <= ub/(a+b-ub) < thr
-                queue[atomicAdd(&qn, 1)] = (unsigned short)((t << 6) | j);
+                queue[atomicAdd(&qn, 1)] = (unsigned short)(((ct - ct_lo) << 12) | (t << 6) | j);
             }
         }
-        __syncthreads();
-        const int total = qn;
-        for (int e = t; e < total; e += kTile) {
-            const int code = queue[e], rt_ = code >> 6, j = code & 63;
-            const RotBox A = w.rbox[base + rt * kTile + rt_];
-            const RotBox B = w.rbox[base + c0 + j];
-            if (rot_overlaps(A, B, thr_d, ge_mode)) atomicOr(&bits32[rt_][j >> 5], 1u << (j & 31));
-        }
-        __syncthreads();
-        if (r < mb) {
-            unsigned long long bits = ((unsigned long long)bits32[t][1] << 32) | bits32[t][0];
+    }
+    __syncthreads();
+    drain(qn);
+    __syncthreads();
+    if (r < mb) {
+#pragma unroll 1
+        for (int ct = ct_lo; ct < ct_hi; ++ct) {
+            const int c0 = ct * kTile;
+            if (c0 >= mb) break;
+            unsigned long long bits = ((unsigned long long)bits32[ct - ct_lo][t][1] << 32) | bits32[ct - ct_lo][t][0];
             if (thr_d <= 0.0 && ge_mode) {           // degenerate threshold: every later box is suppressed
                 bits = 0ull;
                 const int lim = min(kTile, mb - c0);
@@ -384,6 +433,219 @@ __global__ void __launch_bounds__(kTile) mask_rot_kernel(LargeWs w, const int* m
             w.mask[(base + r) * w.words + ct] = bits;
         }
     }
+}
+
+// ---------------------------------------------------------------------------- spatially ordered rotated NMS
+// With boxes in score order a 64-box tile is spread over the whole image, so every tile pair has to be
+// culled pair by pair: 5e7 circle tests per 10 k-box image, 2.9 ms per 32-image batch even at 9 instructions
+// per test.  Here the MASK lives in Morton order of the box centres: a tile is a compact patch, tile pairs
+// whose hulls are disjoint are skipped outright (~90 % of them), and the bit for an overlapping pair is set
+// in the row of the higher-scored box (rank comparison) instead of being implied by the tile position.
+// The sweep still visits boxes in score order and gathers the bits it needs through the rank<->position maps.
+__device__ __forceinline__ unsigned part1by1(unsigned v) {      // spread the low 16 bits to the even positions
+    v &= 0x0000ffffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+
+__global__ void spatial_keys_kernel(GatherParams P, const int* order, const int* m, unsigned long long* skeys) {
+    const int b = blockIdx.y;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= P.n) return;
+    unsigned long long key = ~0ull;
+    if (r < m[b]) {
+        const int i = order[(long long)b * P.n + r];
+        const float* bx = P.boxes + ((long long)b * P.pitch + i) * P.n_param;
+        const unsigned qx = (unsigned)fminf(fmaxf(bx[0], 0.f), 65535.f), qy = (unsigned)fminf(fmaxf(bx[1], 0.f), 65535.f);
+        const unsigned morton = part1by1(qx) | (part1by1(qy) << 1);
+        key = ((unsigned long long)morton << 20) | (unsigned long long)r;
+    }
+    skeys[(long long)b * P.n + r] = key;
+}
+
+// after sorting skeys: rank_of_spos[spos] = score rank (the sort's payload).  Build the quads in spatial
+// order, the inverse map, and the hull of every 64-box tile (one warp pair per tile).
+__global__ void __launch_bounds__(kTile) spatial_gather_kernel(GatherParams P, const int* order, const int* m, LargeWs w) {
+    const int tile = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
+    const int mb = m[b];
+    const int spos = tile * kTile + t;
+    __shared__ float4 part[2];
+    float x0 = 3.0e18f, y0 = 3.0e18f, x1 = -3.0e18f, y1 = -3.0e18f;
+    if (spos < mb) {
+        const long long row = (long long)b * P.n + spos;
+        const int r = w.rank_of_spos[row];
+        const int i = order[(long long)b * P.n + r];
+        const float* bx = P.boxes + ((long long)b * P.pitch + i) * P.n_param;
+        float v[5] = {bx[0], bx[1], bx[2], bx[3], bx[4]};
+        RotBox q;
+        make_rot_box(v, q.x, q.y, q.r);
+        q.cx = v[0]; q.cy = v[1];
+        q.area2 = (float)signed_area2_f64(q.x, q.y);
+        rot_box_hull(q);
+        w.rbox[row] = q;
+        w.spos_of_rank[(long long)b * P.n + r] = spos;
+        x0 = q.x0; y0 = q.y0; x1 = q.x1; y1 = q.y1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+        x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    }
+    if ((t & 31) == 0) part[t >> 5] = make_float4(x0, y0, x1, y1);
+    __syncthreads();
+    if (t == 0 && tile * kTile < mb)
+        w.tile_hull[(long long)b * w.words + tile] = make_float4(fminf(part[0].x, part[1].x) - 1e-2f, fminf(part[0].y, part[1].y) - 1e-2f,
+                                                                 fmaxf(part[0].z, part[1].z) + 1e-2f, fmaxf(part[0].w, part[1].w) + 1e-2f);
+}
+
+// grid (row tile ti, chunk of column tiles, image).  Unordered tile pairs ti <= tj are visited once; a hit
+// sets the bit in the row of the higher-scored box with a global atomicOr (hits are rare); the mask is
+// zeroed beforehand.  Cull / queue / drain exactly as mask_rot_kernel.
+__global__ void __launch_bounds__(kTile) mask_rot_spatial_kernel(LargeWs w, const int* m, int n, double thr_d, int ge) {
+    const int ti = blockIdx.x, cc = blockIdx.y, b = blockIdx.z;
+    const int T = (n + kTile - 1) / kTile;
+    const int tj_lo = max(ti, cc * kColChunk), tj_hi = min(T, (cc + 1) * kColChunk);
+    if (tj_lo >= tj_hi) return;
+    const int mb = m[b];
+    if (ti * kTile >= mb || tj_lo * kTile >= mb) return;
+    const long long base = (long long)b * n;
+    const int t = threadIdx.x;
+    const int r = ti * kTile + t;
+    __shared__ float4 ccull[2][kTile];
+    __shared__ unsigned short queue[kQueueCap];
+    __shared__ int qn;
+    const bool ge_mode = ge != 0;
+    const float thr_f = (float)thr_d;
+    const float4 my_hull = w.tile_hull[(long long)b * w.words + ti];
+    float mcx = 3.0e18f, mcy = 3.0e18f, mr = 0.f, ma = 0.f, mx0 = 0.f, my0 = 0.f, mx1 = 0.f, my1 = 0.f;
+    if (r < mb) {
+        const RotBox q = w.rbox[base + r];
+        mcx = q.cx; mcy = q.cy; mr = q.r * 1.00001f + 1e-3f; ma = 0.5f * fabsf(q.area2);
+        mx0 = q.x0; my0 = q.y0; mx1 = q.x1; my1 = q.y1;
+    }
+    if (t == 0) qn = 0;
+    unsigned* mask32 = reinterpret_cast<unsigned*>(w.mask);
+
+    auto drain = [&](int total) {
+        for (int e = t; e < total; e += kTile) {
+            const int code = queue[e], k = code >> 12, rt_ = (code >> 6) & 63, j = code & 63;
+            const int pa = ti * kTile + rt_, pb = (tj_lo + k) * kTile + j;            // spatial positions
+            const RotBox A = w.rbox[base + pa];
+            const RotBox B = w.rbox[base + pb];
+            if (rot_overlaps(A, B, thr_d, ge_mode)) {
+                const bool a_first = w.rank_of_spos[base + pa] < w.rank_of_spos[base + pb];
+                const int row = a_first ? pa : pb, col = a_first ? pb : pa;           // the higher-scored box suppresses
+                atomicOr(&mask32[((base + row) * w.words + (col >> 6)) * 2 + ((col >> 5) & 1)], 1u << (col & 31));
+                const int trow = row >> 6, tcol = col >> 6;
+                atomicOr(&w.tile_adj[((long long)b * w.words + trow) * 4 + (tcol >> 6)], 1ull << (tcol & 63));
+            }
+        }
+    };
+
+    int buf = 0;
+#pragma unroll 1
+    for (int tj = tj_lo; tj < tj_hi; ++tj) {
+        const int c0 = tj * kTile;
+        if (c0 >= mb) break;
+        const float4 oh = w.tile_hull[(long long)b * w.words + tj];
+        if (oh.x > my_hull.z || my_hull.x > oh.z || oh.y > my_hull.w || my_hull.y > oh.w) continue;   // patches apart
+        {
+            float4 c = make_float4(-3.0e18f, -3.0e18f, 0.f, 0.f);
+            if (c0 + t < mb) {
+                const RotBox& q = w.rbox[base + c0 + t];
+                c = make_float4(q.cx, q.cy, q.r, 0.5f * fabsf(q.area2));
+            }
+            ccull[buf][t] = c;
+        }
+        __syncthreads();
+        const int pending = qn;
+        if (pending >= kTile) {
+            drain(pending);
+            __syncthreads();
+            if (t == 0) qn = 0;
+            __syncthreads();
+        }
+        if (r < mb) {
+            unsigned cand_lo = 0u, cand_hi = 0u;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float4 c = ccull[buf][j];
+                const float dx = mcx - c.x, dy = mcy - c.y, rr = fmaf(c.z, 1.00001f, mr);
+                if (fmaf(dx, dx, dy * dy) <= rr * rr) cand_lo |= 1u << j;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float4 c = ccull[buf][32 + j];
+                const float dx = mcx - c.x, dy = mcy - c.y, rr = fmaf(c.z, 1.00001f, mr);
+                if (fmaf(dx, dx, dy * dy) <= rr * rr) cand_hi |= 1u << j;
+            }
+            unsigned long long cand = ((unsigned long long)cand_hi << 32) | cand_lo;
+            if (tj == ti) cand = (t >= kTile - 1) ? 0ull : (cand & (~0ull << (t + 1)));   // each unordered pair once
+            while (cand) {
+                const int j = __ffsll((long long)cand) - 1;
+                cand &= cand - 1;
+                const float oa = ccull[buf][j].w;
+                const float lo = fminf(ma, oa), hi = fmaxf(ma, oa);
+                if (lo * 1.0001f < thr_f * hi) continue;
+                const RotBox& q = w.rbox[base + c0 + j];
+                const float ix = fminf(mx1, q.x1) - fmaxf(mx0, q.x0);
+                const float iy = fminf(my1, q.y1) - fmaxf(my0, q.y0);
+                if (!(ix > -1e-3f && iy > -1e-3f)) continue;
+                const float ub = (ix + 2e-3f) * (iy + 2e-3f);
+                if (ub * 1.0001f < thr_f * (ma + oa - ub)) continue;
+                queue[atomicAdd(&qn, 1)] = (unsigned short)(((tj - tj_lo) << 12) | (t << 6) | j);
+            }
+        }
+        buf ^= 1;
+    }
+    __syncthreads();
+    drain(qn);
+}
+
+// The 64 boxes of a score block sit at arbitrary spatial positions: gather their mutual suppression bits
+// (row of a, bit of c) for EVERY block in parallel, so that the serial sweep only reads 64 words per block.
+__global__ void __launch_bounds__(512) spatial_diag_kernel(LargeWs w, const int* m, int n) {
+    const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int mb = m[b];
+    const int r0 = t * kTile;
+    if (r0 >= mb) return;
+    const int rows = min(kTile, mb - r0);
+    const long long base_n = (long long)b * n;
+    const unsigned long long* mask = w.mask + base_n * w.words;
+    __shared__ int s_sp[kTile];
+    __shared__ unsigned long long s_adj[kTile][4];
+    __shared__ unsigned long long s_d[kTile];
+    if (tid < kTile) { s_sp[tid] = (tid < rows) ? w.spos_of_rank[base_n + r0 + tid] : 0; s_d[tid] = 0ull; }
+    __syncthreads();
+    if (tid < kTile * 4) {
+        const int a = tid >> 2, q = tid & 3;
+        const unsigned long long v = (a < rows) ? w.tile_adj[((long long)b * w.words + (s_sp[a] >> 6)) * 4 + q] : 0ull;
+        s_adj[a][q] = v;
+        w.adj_blk[((long long)b * w.words + t) * (kTile * 4) + tid] = v;      // staged per block for the sweep
+    }
+    __syncthreads();
+    const int a = tid & (kTile - 1), cg = tid >> 6;              // 64 rows x 8 column groups
+    unsigned long long d = 0ull;
+    if (a < rows) {
+        const unsigned long long* rowp = mask + (long long)s_sp[a] * w.words;
+        unsigned long long wv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = cg * 8 + u, wc = s_sp[c] >> 6;
+            wv[u] = (c < rows && ((s_adj[a][wc >> 6] >> (wc & 63)) & 1ull)) ? rowp[wc] : 0ull;   // provably empty words are skipped
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = cg * 8 + u;
+            if ((wv[u] >> (s_sp[c] & 63)) & 1ull) atomicOr(&s_d[c], 1ull << a);       // transposed: column c collects its suppressors
+        }
+    }
+    (void)d;
+    __syncthreads();
+    if (tid < kTile) w.diag_all[((long long)b * w.words + t) * kTile + tid] = s_d[tid];
 }
 
 // ---------------------------------------------------------------------------- sweep + emit
@@ -396,38 +658,143 @@ struct EmitParams {
     long long* keep64;   // rotated API: kept candidate indices as int64 (B, pitch)
 };
 
+template <bool SPATIAL>
 __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(LargeWs w, const int* m, int n, EmitParams E) {
     extern __shared__ unsigned long long sm[];
     const int b = blockIdx.x, tid = threadIdx.x;
     const int mb = m[b];
     const int words = (mb + 63) / 64;
-    unsigned long long* removed = sm;                    // w.words
-    unsigned long long* keptw = sm + w.words;            // w.words
+    unsigned long long* removed = sm;                    // w.words   (indexed by rank, or by spatial position)
+    unsigned long long* keptw = sm + w.words;            // w.words   (indexed by rank)
     unsigned long long* diag = keptw + w.words;          // 64
     __shared__ unsigned long long s_kept;
     __shared__ int klist[kTile];
+    __shared__ int kslot[kTile];                     // block-local row number of the kept-list entries
+    __shared__ unsigned s_remw[2];
     __shared__ int s_prefix_total;
-    const unsigned long long* mask = w.mask + (long long)b * n * w.words;
+    const long long base_n = (long long)b * n;
+    const unsigned long long* mask = w.mask + base_n * w.words;
 
     for (int i = tid; i < w.words; i += kSweepThreads) { removed[i] = 0ull; keptw[i] = 0ull; }
     __syncthreads();
 
+    if (SPATIAL) {
+        // Software-pipelined: the data of block t+1 (positions, adjacency rows, gathered diagonal words) does
+        // not depend on the removed vector, so it is loaded while thread 0 resolves block t.
+        __shared__ int sp2[2][kTile];
+        __shared__ unsigned long long adj2[2][kTile][4];
+        __shared__ unsigned long long dg2[2][kTile];
+        auto fetch = [&](int t, int& v_sp, unsigned long long& v_dg, unsigned long long& v_adj) {
+            v_sp = 0; v_dg = 0ull; v_adj = 0ull;
+            if (t >= words) return;
+            const int r0 = t * kTile, rows = min(kTile, mb - r0);
+            if (tid < kTile && tid < rows) {
+                v_sp = w.spos_of_rank[base_n + r0 + tid];
+                v_dg = w.diag_all[((long long)b * w.words + t) * kTile + tid];
+            }
+            if (tid < kTile * 4) v_adj = w.adj_blk[((long long)b * w.words + t) * (kTile * 4) + tid];
+        };
+        auto stash = [&](int buf, int v_sp, unsigned long long v_dg, unsigned long long v_adj) {
+            if (tid < kTile) { sp2[buf][tid] = v_sp; dg2[buf][tid] = v_dg; }
+            if (tid < kTile * 4) adj2[buf][tid >> 2][tid & 3] = v_adj;
+        };
+        int v_sp; unsigned long long v_dg, v_adj;
+        fetch(0, v_sp, v_dg, v_adj);
+        stash(0, v_sp, v_dg, v_adj);
+        fetch(1, v_sp, v_dg, v_adj);              // two blocks of look-ahead: a full iteration to land
+        int buf = 0;
+#ifdef MYDET_SWEEP_PROFILE
+        long long c_a = 0, c_b = 0, c_c = 0, c_d = 0, tk;
+#define SW_T(x) do { if (tid == 0) { long long now = clock64(); x += now - tk; tk = now; } } while (0)
+        tk = clock64();
+#else
+#define SW_T(x) do {} while (0)
+#endif
+        for (int t = 0; t < words; ++t, buf ^= 1) {
+            const int r0 = t * kTile;
+            const int rows = min(kTile, mb - r0);
+            __syncthreads();                       // block t staged, removed vector up to date
+            SW_T(c_d);
+            if (tid < 32) {
+                // Resolve the 64 boxes of the block with ONE warp, as a fixed point: lane l owns boxes l and
+                // l+32; a box is kept iff it is not removed yet and no KEPT box of the block suppresses it
+                // (dg2 holds, per box, the set of block-mates that would).  The greedy result is the unique
+                // fixed point; every round settles at least the next undecided box, typically 2-4 rounds.
+                // (A 64-step serial chain in one thread cost 3.6 k cycles per block.)
+                const int c0 = tid, c1 = tid + 32;
+                bool a0 = false, a1 = false;
+                if (c0 < rows) { const int sa = sp2[buf][c0]; a0 = !((removed[sa >> 6] >> (sa & 63)) & 1ull); }
+                if (c1 < rows) { const int sa = sp2[buf][c1]; a1 = !((removed[sa >> 6] >> (sa & 63)) & 1ull); }
+                const unsigned long long s0 = dg2[buf][c0], s1 = dg2[buf][c1];
+                unsigned long long kept = ((unsigned long long)__ballot_sync(0xffffffffu, a1) << 32) | __ballot_sync(0xffffffffu, a0);
+#pragma unroll 1
+                for (int round = 0; round < kTile; ++round) {
+                    const bool k0 = a0 && !(s0 & kept), k1 = a1 && !(s1 & kept);
+                    const unsigned long long next = ((unsigned long long)__ballot_sync(0xffffffffu, k1) << 32) | __ballot_sync(0xffffffffu, k0);
+                    if (next == kept) break;
+                    kept = next;
+                }
+                if (tid == 0) {
+                    s_kept = kept;
+                    keptw[t] = kept;
+                    w.kept[(long long)b * w.words + t] = kept;
+                }
+            }
+            __syncthreads();
+            SW_T(c_b);
+            const unsigned long long kept = s_kept;
+            if (tid < kTile && ((kept >> tid) & 1ull)) {
+                const int kpos = __popcll(kept & ((1ull << tid) - 1ull));
+                klist[kpos] = sp2[buf][tid];
+                kslot[kpos] = tid;
+            }
+            stash(buf ^ 1, v_sp, v_dg, v_adj);     // block t+1, fetched one iteration ago
+            fetch(t + 2, v_sp, v_dg, v_adj);
+            __syncthreads();
+            SW_T(c_c);
+            {
+                // OR the kept rows into the removed vector: one warp per kept row, lanes over its words, and only
+                // the words the adjacency map marks non-empty are loaded
+                const int nk = __popcll(kept);
+                unsigned* removed32 = reinterpret_cast<unsigned*>(removed);
+                const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll 1
+                for (int kr = warp; kr < nk; kr += kSweepThreads / 32) {
+                    const unsigned long long* rowp = mask + (long long)klist[kr] * w.words;
+                    const unsigned long long* adj = adj2[buf][kslot[kr]];
+                    unsigned long long v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {                       // up to 256 words (n <= 16384)
+                        const int wd = lane + 32 * u;
+                        v[u] = (wd < words && ((adj[wd >> 6] >> (wd & 63)) & 1ull)) ? rowp[wd] : 0ull;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int wd = lane + 32 * u;
+                        if ((unsigned)v[u]) atomicOr(&removed32[2 * wd], (unsigned)v[u]);
+                        if ((unsigned)(v[u] >> 32)) atomicOr(&removed32[2 * wd + 1], (unsigned)(v[u] >> 32));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+#ifdef MYDET_SWEEP_PROFILE
+        if (tid == 0 && b == 0) printf("sweep phases (cycles, %d blocks): rem-bits %lld  chain %lld  klist+stash %lld  OR %lld\n", words, c_a, c_b, c_c, c_d);
+#endif
+    } else {
     for (int t = 0; t < words; ++t) {
         const int r0 = t * kTile;
         const int rows = min(kTile, mb - r0);
         if (tid < kTile) diag[tid] = (tid < rows) ? mask[(long long)(r0 + tid) * w.words + t] : 0ull;
         __syncthreads();
         if (tid == 0) {
-            unsigned long long d[kTile];
-#pragma unroll
-            for (int j = 0; j < kTile; ++j) d[j] = diag[j];
             unsigned long long cur = removed[t];
             if (rows < kTile) cur |= ~0ull << rows;
             unsigned long long kept = 0ull;
 #pragma unroll
             for (int j = 0; j < kTile; ++j) {
                 const bool alive = !((cur >> j) & 1ull);
-                if (alive) { kept |= 1ull << j; cur |= d[j]; }
+                if (alive) { kept |= 1ull << j; cur |= diag[j]; }
             }
             s_kept = kept;
             keptw[t] = kept;
@@ -438,9 +805,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(LargeWs w, const i
         // OR the kept rows of this block into the removed words that are still ahead.  (kept row, word)
         // pairs are spread over all threads, four independent loads in flight each: a per-word loop over
         // the kept rows issued one dependent load after the other, 24 us per block.
-        if (tid < kTile) {
-            if ((kept >> tid) & 1ull) klist[__popcll(kept & ((1ull << tid) - 1ull))] = tid;
-        }
+        if (tid < kTile && ((kept >> tid) & 1ull)) klist[__popcll(kept & ((1ull << tid) - 1ull))] = r0 + tid;
         __syncthreads();
         {
             const int nk = __popcll(kept), nw = words - (t + 1);
@@ -456,7 +821,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(LargeWs w, const i
                     if (idx < work) {
                         const int kr = idx / nw, wd = t + 1 + (idx - kr * nw);
                         wdv[u] = wd;
-                        v[u] = mask[(long long)(r0 + klist[kr]) * w.words + wd];
+                        v[u] = mask[(long long)klist[kr] * w.words + wd];
                     }
                 }
 #pragma unroll
@@ -467,6 +832,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(LargeWs w, const i
             }
         }
         __syncthreads();
+    }
     }
 
     // ---- emit survivors in sorted order
@@ -519,7 +885,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(LargeWs w, const i
 // nms_rotbb's vote bookkeeping (utils/bbox_ops.py:291-306): every dropped box votes for the valid
 // box it overlaps most (first maximum over the boxes valid at that time = kept boxes ranked
 // before it); every kept box starts with its own vote.
-__global__ void votes_kernel(LargeWs w, const int* m, int n, int* votes, long long pitch) {
+__global__ void votes_kernel(LargeWs w, const int* m, int n, int* votes, long long pitch, int spatial) {
     const int b = blockIdx.y;
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= m[b]) return;
@@ -529,7 +895,8 @@ __global__ void votes_kernel(LargeWs w, const int* m, int n, int* votes, long lo
         atomicAdd(votes + (long long)b * pitch + w.rowpos[base + r], 1);
         return;
     }
-    const RotBox me = w.rbox[base + r];
+    // the quads are stored by score rank, or by spatial position (then reached through spos_of_rank)
+    const RotBox me = w.rbox[base + (spatial ? w.spos_of_rank[base + r] : r)];
     double best = -1.0;
     int best_q = -1;
     for (int wd = 0; wd <= (r >> 6); ++wd) {
@@ -539,7 +906,7 @@ __global__ void votes_kernel(LargeWs w, const int* m, int n, int* votes, long lo
             const int j = __ffsll((long long)kw) - 1;
             kw &= kw - 1;
             const int q = wd * kTile + j;
-            const RotBox o = w.rbox[base + q];
+            const RotBox o = w.rbox[base + (spatial ? w.spos_of_rank[base + q] : q)];
             const double dx = (double)me.cx - (double)o.cx, dy = (double)me.cy - (double)o.cy;
             const double rr = (double)me.r + (double)o.r + 1e-3;
             double iou = 0.0;
@@ -577,22 +944,40 @@ int run_large(const LargeArgs& A, void* workspace, size_t workspace_bytes, cudaS
     }
     GatherParams G{A.boxes, A.pitch, n, A.n_param, A.box_format};
     const int tiles = (n + kTile - 1) / kTile;
-    if (A.rot) {
-        gather_kernel<true><<<dim3((n + 255) / 256, B), 256, 0, st>>>(G, w.keys, w.order, w.m, w);
-        mask_rot_kernel<<<dim3(tiles, (tiles + kColChunk - 1) / kColChunk, B), kTile, 0, st>>>(w, w.m, n, A.thr, A.ge);
-    } else {
-        gather_kernel<false><<<dim3((n + 255) / 256, B), 256, 0, st>>>(G, w.keys, w.order, w.m, w);
-        mask_kernel<false><<<dim3(tiles * (tiles + 1) / 2, B), kTile, 0, st>>>(w, w.m, n, float_at_or_below(A.thr), A.thr, 0);
-    }
     EmitParams E{A.boxes, A.scores, A.cls, A.src_idx, A.pitch, n, A.n_param, A.cls_is_i64,
                  A.out_box, A.out_score, A.out_cls, A.out_idx, A.out_count, A.status, A.out_cap, A.keep64};
     const size_t smem = ((size_t)w.words * 2 + kTile) * sizeof(unsigned long long);
     MYDET_REQUIRE(smem <= 200 * 1024, "too many candidates per image for the sweep kernel");
-    MYDET_CUDA(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem > 48 * 1024 ? (int)smem : 48 * 1024));
-    sweep_kernel<<<B, kSweepThreads, smem, st>>>(w, w.m, n, E);
+    const int smem_attr = (int)smem > 48 * 1024 ? (int)smem : 48 * 1024;
+    // Morton-ordered mask for rotated boxes (the degenerate "IoU >= 0" threshold suppresses disjoint
+    // boxes too, which patch culling would miss: it keeps the score-ordered kernel)
+    const bool spatial = A.rot && n <= kSortMaxN && !(A.ge && A.thr <= 0.0);
+    if (spatial) {
+        int npad = 64;
+        while (npad < n) npad <<= 1;
+        spatial_keys_kernel<<<dim3((n + 255) / 256, B), 256, 0, st>>>(G, w.order, w.m, w.skeys);
+        sort_smem_kernel<<<B, kSortThreads, (size_t)npad * 12, st>>>(w.skeys, w.rank_of_spos, n, npad);
+        MYDET_CUDA(cudaMemsetAsync(w.mask, 0, (size_t)B * n * w.words * sizeof(unsigned long long), st));
+        MYDET_CUDA(cudaMemsetAsync(w.tile_adj, 0, (size_t)B * w.words * 32, st));
+        spatial_gather_kernel<<<dim3(tiles, B), kTile, 0, st>>>(G, w.order, w.m, w);
+        mask_rot_spatial_kernel<<<dim3(tiles, (tiles + kColChunk - 1) / kColChunk, B), kTile, 0, st>>>(w, w.m, n, A.thr, A.ge);
+        spatial_diag_kernel<<<dim3(w.words, B), 512, 0, st>>>(w, w.m, n);
+        MYDET_CUDA(cudaFuncSetAttribute(sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr));
+        sweep_kernel<true><<<B, kSweepThreads, smem, st>>>(w, w.m, n, E);
+    } else {
+        if (A.rot) {
+            gather_kernel<true><<<dim3((n + 255) / 256, B), 256, 0, st>>>(G, w.keys, w.order, w.m, w);
+            mask_rot_kernel<<<dim3(tiles, (tiles + kColChunk - 1) / kColChunk, B), kTile, 0, st>>>(w, w.m, n, A.thr, A.ge);
+        } else {
+            gather_kernel<false><<<dim3((n + 255) / 256, B), 256, 0, st>>>(G, w.keys, w.order, w.m, w);
+            mask_kernel<false><<<dim3(tiles * (tiles + 1) / 2, B), kTile, 0, st>>>(w, w.m, n, float_at_or_below(A.thr), A.thr, 0);
+        }
+        MYDET_CUDA(cudaFuncSetAttribute(sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr));
+        sweep_kernel<false><<<B, kSweepThreads, smem, st>>>(w, w.m, n, E);
+    }
     if (A.rot && A.votes) {
         MYDET_CUDA(cudaMemsetAsync(A.votes, 0, sizeof(int) * (size_t)B * (size_t)A.pitch, st));
-        votes_kernel<<<dim3((n + 127) / 128, B), 128, 0, st>>>(w, w.m, n, A.votes, A.pitch);
+        votes_kernel<<<dim3((n + 127) / 128, B), 128, 0, st>>>(w, w.m, n, A.votes, A.pitch, spatial ? 1 : 0);
     }
     return launch_status("large NMS pipeline");
 }
