@@ -308,7 +308,7 @@ def run_gpu(args):
         return bc
 
     graphs = None
-    if args.graph and world == 1:
+    if args.launch == 'graph' and world == 1:
         # whole step (decode, post-process, pack, all-gather) as one CUDA graph per input batch
         graphs = []
         for j in range(N_ROTATE):
@@ -321,6 +321,35 @@ def run_gpu(args):
             with torch.cuda.graph(g):
                 step_body()
             graphs.append(g)
+
+    pipe_graph, PIPE_STEPS = None, max(N_ROTATE, args.pipe_steps // N_ROTATE * N_ROTATE)
+    if args.launch == 'pipelined' and (world == 1 or fused):
+        # one CUDA graph spanning PIPE_STEPS steps with a fork: decode(k+1) runs on the capture stream while
+        # post-process(k) runs on a second, higher-priority stream (only the candidate-buffer reuse and the
+        # final join order them)
+        pp_launch = (lambda bc: bc.launch_postprocess_scatter()) if fused else (lambda bc: bc.launch_postprocess())
+        for bc in bound:
+            bc.launch_decode(); pp_launch(bc)
+        barrier_early = dist.barrier if world > 1 else (lambda: None)
+        torch.cuda.synchronize(dev); barrier_early()
+        s_cap, s_pp = torch.cuda.Stream(dev), torch.cuda.Stream(dev, priority=-1)
+        pipe_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(pipe_graph, stream=s_cap):
+            pp_ev = []
+            for k in range(PIPE_STEPS):
+                j = k % N_ROTATE
+                if k >= N_ROTATE:
+                    s_cap.wait_event(pp_ev[k - N_ROTATE])
+                bound[j].launch_decode()
+                ev = torch.cuda.Event()
+                ev.record(s_cap)
+                with torch.cuda.stream(s_pp):
+                    s_pp.wait_event(ev)
+                    pp_launch(bound[j])
+                    e2 = torch.cuda.Event()
+                    e2.record(s_pp)
+                    pp_ev.append(e2)
+            s_cap.wait_stream(s_pp)
 
     def barrier():
         if world > 1:
@@ -338,9 +367,38 @@ def run_gpu(args):
     dec_b = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     t_wall0 = time.perf_counter()
     ev0.record()
-    if graphs is not None:
+    if pipe_graph is not None:
+        for i in range(steps // PIPE_STEPS):
+            pipe_graph.replay()
+        for i in range(steps - steps % PIPE_STEPS, steps):
+            step(i)
+    elif graphs is not None:
         for i in range(steps):
             graphs[i % N_ROTATE].replay()
+    elif args.launch == 'two-streams' and world == 1:
+        # decode(i+1) on one stream, post-process(i) on a second, higher-priority stream: the 64 one-CTA-per-
+        # image post-process blocks take their SMs first, the bandwidth-bound decode fills the rest
+        s_dec, s_pp = torch.cuda.Stream(dev), torch.cuda.Stream(dev, priority=-1)
+        main = torch.cuda.current_stream()
+        dec_done = [torch.cuda.Event() for _ in range(steps)]
+        pp_done = [None] * N_ROTATE
+        s_dec.wait_stream(main); s_pp.wait_stream(main)
+        for i in range(steps):
+            j = i % N_ROTATE
+            bc = bound[j]
+            with torch.cuda.stream(s_dec):
+                if pp_done[j] is not None:
+                    s_dec.wait_event(pp_done[j])          # candidate buffers of batch j are free again
+                dec_a[i].record()
+                bc.launch_decode()
+                dec_b[i].record()
+                dec_done[i].record()
+            with torch.cuda.stream(s_pp):
+                s_pp.wait_event(dec_done[i])
+                bc.launch_postprocess()
+                pp_done[j] = torch.cuda.Event()
+                pp_done[j].record()
+        main.wait_stream(s_dec); main.wait_stream(s_pp)
     else:
         for i in range(steps):
             bc = bound[i % N_ROTATE]
@@ -359,7 +417,7 @@ def run_gpu(args):
     ev1.record()
     barrier()
     t_wall1 = time.perf_counter()
-    if graphs is not None:
+    if graphs is not None or pipe_graph is not None:
         # kernel time for the roofline from a short eager pass over the same inputs
         for i in range(min(steps, 60)):
             dec_a[i].record(); bound[i % N_ROTATE].launch_decode(); dec_b[i].record(); bound[i % N_ROTATE].launch_postprocess()
@@ -455,7 +513,7 @@ def run_gpu(args):
                              else 'fallback 6650 GB/s (B200_PROFILING.md)'},
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                         'steps': e2e_steps, 'ms_per_step': e2e_ms / e2e_steps},
-                'gpu_launches': (3 if (world > 1 and not fused) else 2) * steps, 'exchange': exchange_mode, 'exchange_verified': exchange_ok, 'launch_mode': 'cuda_graph' if graphs else 'eager',
+                'gpu_launches': (3 if (world > 1 and not fused) else 2) * steps, 'exchange': exchange_mode, 'exchange_verified': exchange_ok, 'launch_mode': 'cuda_graph_pipelined' if pipe_graph else 'cuda_graph' if graphs else ('eager_two_streams' if (args.launch == 'two-streams' and world == 1) else 'eager'),
                 'clocks': clocks}
         if rot is not None:
             line['rotated_nms'] = rot
@@ -473,7 +531,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
-    ap.add_argument('--graph', action='store_true', help='replay each step as one CUDA graph')
+    ap.add_argument('--launch', default='pipelined', choices=['pipelined', 'graph', 'eager', 'two-streams'],
+                    help='pipelined: multi-step CUDA graph with decode(k+1) || post-process(k) [default]')
+    ap.add_argument('--pipe-steps', type=int, default=24, help='steps per pipelined CUDA graph')
     ap.add_argument('--nccl-exchange', action='store_true', help='N>1: use the NCCL all-gather instead of peer stores')
     ap.add_argument('--no-rot', action='store_true', help='skip the rotated-NMS side metric')
     args = ap.parse_args()
