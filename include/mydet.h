@@ -197,15 +197,19 @@ int mydet_xywha2vertex(const float* in, int64_t n, int n_param, float* out, void
  *                           'model.atss.anchors'); level = index of this level
  *   outputs     positive, ignored (B,nH,nW) u8; target_ltrb (B,nH,nW,4), target_conf (B,nH,nW),
  *               target_cls (B,nH,nW,C) f32 -- all fully written by the call
- *   thr_out     optional (B, max_gt) f32: the adaptive threshold of every GT (mean + std) */
+ *   thr_out     optional (B, max_gt) f32: the adaptive threshold of every GT (mean + std), in the caller's
+ *               GT order.  The threshold of a GT does not depend on the level, but the reference
+ *               recomputes it in every level's forward (fcos2.py:262-264 admits the waste): with
+ *               thr_is_input != 0 the thresholds are READ from thr_out (as written by an earlier level's
+ *               call for the same GT) and the nearest-anchor search is skipped. */
 size_t mydet_atss_workspace_bytes(int batch, int max_gt);
 int mydet_atss_assign(const float* t_ltrb, const int64_t t_stride[4], int batch, int level,
                       int n_levels, const int32_t* strides, const float* anchor_sides, int img_h,
                       int img_w, const float* gt_box, const int64_t* gt_cls,
                       const int32_t* gt_count, int max_gt, int topk, float ignore_thres, int n_cls,
                       uint8_t* positive, uint8_t* ignored, float* target_ltrb, float* target_conf,
-                      float* target_cls, float* thr_out, void* workspace, size_t workspace_bytes,
-                      void* stream);
+                      float* target_cls, float* thr_out, int thr_is_input, void* workspace,
+                      size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

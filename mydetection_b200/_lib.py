@@ -58,7 +58,7 @@ SIGNATURES = {
     'mydet_atss_workspace_bytes': (c_sz, [c_int, c_int]),
     'mydet_atss_assign': (c_int, [c_vp, ctypes.POINTER(c_i64), c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int32),
                                   ctypes.POINTER(c_f32), c_int, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_f32, c_int,
-                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),
 }
 
 _LIB = None

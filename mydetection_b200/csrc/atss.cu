@@ -132,6 +132,14 @@ __global__ void atss_threshold_kernel(AtssGeom G, const int* gt_count, int max_g
     }
 }
 
+// thresholds computed by an earlier level's call (caller's GT order) -> area-sorted order
+__global__ void atss_load_thr_kernel(const int* gt_count, int max_gt, AtssWs w, const float* thr_user) {
+    const int b = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= min(max(gt_count[b], 0), max_gt)) return;
+    const long long o = (long long)b * max_gt + g;
+    w.thr[o] = thr_user[(long long)b * max_gt + w.src_sorted[o]];
+}
+
 struct AssignParams {
     const float* t; long long ts_b, ts_h, ts_w, ts_p;
     int n_h, n_w, n_cls, max_gt;
@@ -218,7 +226,7 @@ MYDET_API int mydet_atss_assign(const float* t_ltrb, const int64_t t_stride[4], 
                                 const float* gt_box, const int64_t* gt_cls, const int32_t* gt_count, int max_gt,
                                 int topk, float ignore_thres, int n_cls, uint8_t* positive, uint8_t* ignored,
                                 float* target_ltrb, float* target_conf, float* target_cls, float* thr_out,
-                                void* workspace, size_t workspace_bytes, void* stream) {
+                                int thr_is_input, void* workspace, size_t workspace_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     MYDET_REQUIRE(n_levels >= 1 && n_levels <= MYDET_MAX_LEVELS && level >= 0 && level < n_levels, "bad level / n_levels");
     MYDET_REQUIRE(strides && anchor_sides && t_stride, "NULL host array");
@@ -246,7 +254,12 @@ MYDET_API int mydet_atss_assign(const float* t_ltrb, const int64_t t_stride[4], 
     }
     if (max_gt > 0) {
         atss_prepare_kernel<<<batch, 128, sizeof(float) * max_gt, st>>>(gt_box, reinterpret_cast<const long long*>(gt_cls), gt_count, max_gt, w);
-        atss_threshold_kernel<<<dim3(max_gt, batch), 32 * n_levels, 0, st>>>(G, gt_count, max_gt, w, thr_out);
+        if (thr_is_input) {
+            MYDET_REQUIRE(thr_out, "thr_is_input needs the thresholds in thr_out");
+            atss_load_thr_kernel<<<dim3((max_gt + 127) / 128, batch), 128, 0, st>>>(gt_count, max_gt, w, thr_out);
+        } else {
+            atss_threshold_kernel<<<dim3(max_gt, batch), 32 * n_levels, 0, st>>>(G, gt_count, max_gt, w, thr_out);
+        }
     }
     AssignParams P;
     P.t = t_ltrb; P.ts_b = t_stride[0]; P.ts_h = t_stride[1]; P.ts_w = t_stride[2]; P.ts_p = t_stride[3];

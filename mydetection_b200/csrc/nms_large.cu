@@ -202,9 +202,8 @@ __global__ void gather_kernel(GatherParams P, const unsigned long long* keys, co
 }
 
 // ---------------------------------------------------------------------------- mask
-// grid (upper-triangular tile pair, image); 64 threads; thread t owns row row_tile*64+t.
-template <bool ROT>
-__global__ void __launch_bounds__(kTile) mask_kernel(LargeWs w, const int* m, int n, float thr_f, double thr_d, int ge) {
+// Axis-aligned mask.  grid (upper-triangular tile pair, image); 64 threads; thread t owns row row_tile*64+t.
+__global__ void __launch_bounds__(kTile) mask_kernel(LargeWs w, const int* m, int n, float thr_f) {
     // blockIdx.x enumerates the upper-triangular tile pairs (rt <= ct) row by row
     const int T = (n + kTile - 1) / kTile;
     const int b = blockIdx.y;
@@ -220,78 +219,7 @@ __global__ void __launch_bounds__(kTile) mask_kernel(LargeWs w, const int* m, in
     const int r = rt * kTile + t;
     const int c0 = ct * kTile;
     unsigned long long bits = 0ull;
-    if (ROT) {
-        // Two phases, so that the expensive polygon clipping runs with every lane busy:
-        //  (1) each thread culls its row against the 64 columns (circumscribed circles, area ratio) and
-        //      appends the surviving (row, col) pairs to a queue in shared memory;
-        //  (2) the 64 threads drain the queue, one pair per thread and round, and set bits in shared memory.
-        // (Clipping inside the per-row loop left ~1 of 32 lanes active: 585 us per 10 k-box image.)
-        __shared__ RotBox cols[kTile];
-        __shared__ RotBox rows[kTile];
-        __shared__ float4 ccull[kTile];                 // cx, cy, r, area of the column boxes: one LDS.128 per pair
-        __shared__ unsigned short queue[kTile * kTile];
-        __shared__ unsigned bits32[kTile][2];
-        __shared__ int qn;
-        if (c0 + t < mb) {
-            const RotBox q = w.rbox[base + c0 + t];
-            cols[t] = q;
-            ccull[t] = make_float4(q.cx, q.cy, q.r, 0.5f * fabsf(q.area2));
-        } else {
-            ccull[t] = make_float4(3.0e18f, 3.0e18f, 0.f, 0.f);   // never passes the circle test
-        }
-        if (r < mb) rows[t] = w.rbox[base + r];
-        bits32[t][0] = 0u; bits32[t][1] = 0u;
-        if (t == 0) qn = 0;
-        __syncthreads();
-        const int lim = min(kTile, mb - c0);
-        const bool ge_mode = ge != 0;
-        if (r < mb) {
-            const float mcx = rows[t].cx, mcy = rows[t].cy, mr = rows[t].r * 1.00001f + 1e-3f;
-            const float ma = 0.5f * fabsf(rows[t].area2);
-            const float mx0 = rows[t].x0, my0 = rows[t].y0, mx1 = rows[t].x1, my1 = rows[t].y1;
-            const float thr_f = (float)thr_d;
-            // (1a) branch-free circle test against all 64 columns -> candidate bit set
-            unsigned long long cand = 0ull;
-#pragma unroll 16
-            for (int j = 0; j < kTile; ++j) {
-                const float4 c = ccull[j];
-                const float dx = mcx - c.x, dy = mcy - c.y, rr = fmaf(c.z, 1.00001f, mr);
-                const bool pass = fmaf(dx, dx, dy * dy) <= rr * rr;
-                cand |= (unsigned long long)pass << j;
-            }
-            // only columns that rank after this row
-            const int first = r + 1 - c0;                              // first admissible column
-            if (first >= kTile) cand = 0ull; else if (first > 0) cand &= ~0ull << first;
-            // (1b) area-ratio and hull bounds on the few survivors, then queue them for clipping
-            while (cand) {
-                const int j = __ffsll((long long)cand) - 1;
-                cand &= cand - 1;
-                const float oa = ccull[j].w;
-                const float lo = fminf(ma, oa), hi = fmaxf(ma, oa);
-                if (lo * 1.0001f < thr_f * hi) continue;                         // IoU <= lo/hi < thr
-                // the intersection lies inside the intersection of the two axis-aligned hulls
-                const float ix = fminf(mx1, cols[j].x1) - fmaxf(mx0, cols[j].x0);
-                const float iy = fminf(my1, cols[j].y1) - fmaxf(my0, cols[j].y0);
-                if (!(ix > -1e-3f && iy > -1e-3f)) continue;                     // hulls apart: IoU == 0
-                const float ub = (ix + 2e-3f) * (iy + 2e-3f);
-                if (ub * 1.0001f < thr_f * (ma + oa - ub)) continue;             // IoU <= ub/(a+b-ub) < thr
-                queue[atomicAdd(&qn, 1)] = (unsigned short)((t << 6) | j);
-            }
-        }
-        __syncthreads();
-        const int total = qn;
-        for (int e = t; e < total; e += kTile) {
-            const int code = queue[e], rt_ = code >> 6, j = code & 63;
-            if (rot_overlaps(rows[rt_], cols[j], thr_d, ge_mode)) atomicOr(&bits32[rt_][j >> 5], 1u << (j & 31));
-        }
-        __syncthreads();
-        bits = ((unsigned long long)bits32[t][1] << 32) | bits32[t][0];
-        if (thr_d <= 0.0 && ge_mode && r < mb) {
-            // degenerate threshold: every later box is suppressed (IoU >= thr always holds)
-            bits = 0ull;
-            for (int j = 0; j < lim; ++j) if (c0 + j > r) bits |= 1ull << j;
-        }
-    } else {
+    {
         __shared__ float4 cbox[kTile];
         __shared__ float carea[kTile];
         __shared__ int ccls[kTile];
@@ -970,7 +898,7 @@ int run_large(const LargeArgs& A, void* workspace, size_t workspace_bytes, cudaS
             mask_rot_kernel<<<dim3(tiles, (tiles + kColChunk - 1) / kColChunk, B), kTile, 0, st>>>(w, w.m, n, A.thr, A.ge);
         } else {
             gather_kernel<false><<<dim3((n + 255) / 256, B), 256, 0, st>>>(G, w.keys, w.order, w.m, w);
-            mask_kernel<false><<<dim3(tiles * (tiles + 1) / 2, B), kTile, 0, st>>>(w, w.m, n, float_at_or_below(A.thr), A.thr, 0);
+            mask_kernel<<<dim3(tiles * (tiles + 1) / 2, B), kTile, 0, st>>>(w, w.m, n, float_at_or_below(A.thr));
         }
         MYDET_CUDA(cudaFuncSetAttribute(sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr));
         sweep_kernel<false><<<B, kSweepThreads, smem, st>>>(w, w.m, n, E);

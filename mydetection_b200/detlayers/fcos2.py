@@ -5,6 +5,9 @@ from .. import ops
 from ._base import decode_level, no_training, stage_raw
 
 
+_THR_CACHE = {}   # (id(labels), img_size, batch, max_gt) -> thresholds of the forward pass in progress
+
+
 def _check_shapes(raw, img_size, stride, n_cls):
     img_h, img_w = img_size
     n_h, n_w = int(img_h / stride), int(img_w / stride)
@@ -65,9 +68,17 @@ class FCOS_ATSS_Layer(torch.nn.Module):
                 gt_box[b, :n] = l.bboxes.detach().cpu()
                 gt_cls[b, :n] = l.cats.detach().cpu()
             counts[b] = n
-        return ops.atss_assign(t_ltrb, self.level_i, self.strides_all, self.anchors_all, img_size,
-                               gt_box.to(dev), gt_cls.to(dev), counts.to(dev), self.topk, self.ignore_thre,
-                               self.n_cls)
+        # the adaptive threshold of a GT is level independent: the first level's call computes it, the
+        # other levels of the same forward pass (same labels list) reuse it
+        key = (id(labels), tuple(img_size), n_b, max_gt)
+        thr = _THR_CACHE.get(key)
+        out = ops.atss_assign(t_ltrb, self.level_i, self.strides_all, self.anchors_all, img_size,
+                              gt_box.to(dev), gt_cls.to(dev), counts.to(dev), self.topk, self.ignore_thre,
+                              self.n_cls, thr=thr)
+        _THR_CACHE.clear()
+        if self.level_i + 1 < len(self.strides_all):
+            _THR_CACHE[key] = out['thr']
+        return out
 
     def forward(self, raw, img_size, labels=None):
         assert isinstance(raw, dict)

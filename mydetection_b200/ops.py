@@ -261,10 +261,12 @@ def iou_rot(a, b):
 
 
 # --------------------------------------------------------------------------------------- ATSS
-def atss_assign(t_ltrb, level, strides, anchor_sides, img_hw, gt_box, gt_cls, gt_count, topk, ignore_thres, n_cls):
+def atss_assign(t_ltrb, level, strides, anchor_sides, img_hw, gt_box, gt_cls, gt_count, topk, ignore_thres, n_cls,
+                thr=None):
     """Targets of one level.  t_ltrb (B,nH,nW,4) view; gt_box (B,G,4) f32, gt_cls (B,G) i64,
     gt_count (B) i32.  Returns dict of PositiveMask/IgnoredMask (bool), TargetLTRB, TargetConf,
-    TargetCls and 'thr' (B,G)."""
+    TargetCls and 'thr' (B,G).  Pass the 'thr' of an earlier level's call (same GT) as `thr` to skip the
+    per-GT nearest-anchor search, which does not depend on the level."""
     t = _dev(t_ltrb, torch.float32, 't_ltrb')
     gt_box = _dev(gt_box, torch.float32, 'gt_box').contiguous()
     gt_cls = _dev(gt_cls, torch.int64, 'gt_cls').contiguous()
@@ -277,7 +279,11 @@ def atss_assign(t_ltrb, level, strides, anchor_sides, img_hw, gt_box, gt_cls, gt
     t_box = torch.empty(B, n_h, n_w, 4, dtype=torch.float32, device=dev)
     t_conf = torch.empty(B, n_h, n_w, 1, dtype=torch.float32, device=dev)
     t_cls = torch.empty(B, n_h, n_w, n_cls, dtype=torch.float32, device=dev)
-    thr = torch.full((B, max(G, 1)), float('nan'), dtype=torch.float32, device=dev)
+    thr_is_input = thr is not None
+    if thr is None:
+        thr = torch.full((B, max(G, 1)), float('nan'), dtype=torch.float32, device=dev)
+    else:
+        thr = _dev(thr, torch.float32, 'thr').contiguous()
     L = _lib.lib()
     ws = _workspace(L.mydet_atss_workspace_bytes(B, G), dev)
     n_l = len(strides)
@@ -288,7 +294,7 @@ def atss_assign(t_ltrb, level, strides, anchor_sides, img_hw, gt_box, gt_cls, gt
         rc = L.mydet_atss_assign(_ptr(t), st, B, int(level), n_l, c_strides, c_sides, int(img_hw[0]), int(img_hw[1]),
                                  _ptr(gt_box), _ptr(gt_cls), _ptr(gt_count), G, int(topk), float(ignore_thres),
                                  int(n_cls), _ptr(pos), _ptr(ign), _ptr(t_box), _ptr(t_conf), _ptr(t_cls), _ptr(thr),
-                                 _ptr(ws), ws.numel(), _stream())
+                                 1 if thr_is_input else 0, _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, 'mydet_atss_assign')
     return {'PositiveMask': pos.view(torch.bool), 'IgnoredMask': ign.view(torch.bool), 'TargetLTRB': t_box, 'TargetConf': t_conf,
             'TargetCls': t_cls, 'thr': thr}

@@ -391,3 +391,8 @@ def test_atss_golden(golden):
         for k in ('PositiveMask', 'IgnoredMask', 'TargetConf', 'TargetCls'):
             assert torch.equal(out[k].cpu(), T(g[f'atss{li}_{k}'])), (li, k)
         close(out['TargetLTRB'], T(g[f'atss{li}_TargetLTRB']), 512, f'atss{li} ltrb')
+        # thresholds handed over from another level's call give the same maps (they are level independent)
+        again = ops.atss_assign(t, li, strides, sides, (384, 512), gt_box.to(d), gt_cls.to(d), cnt.to(d), 9, 0.7, 6,
+                                thr=out['thr'])
+        for k in ('PositiveMask', 'IgnoredMask', 'TargetConf', 'TargetCls', 'TargetLTRB'):
+            assert torch.equal(again[k], out[k]), (li, k)
