@@ -556,7 +556,6 @@ __global__ void __launch_bounds__(512) spatial_diag_kernel(LargeWs w, const int*
     }
     __syncthreads();
     const int a = tid & (kTile - 1), cg = tid >> 6;              // 64 rows x 8 column groups
-    unsigned long long d = 0ull;
     if (a < rows) {
         const unsigned long long* rowp = mask + (long long)s_sp[a] * w.words;
         unsigned long long wv[8];
@@ -571,7 +570,6 @@ __global__ void __launch_bounds__(512) spatial_diag_kernel(LargeWs w, const int*
             if ((wv[u] >> (s_sp[c] & 63)) & 1ull) atomicOr(&s_d[c], 1ull << a);       // transposed: column c collects its suppressors
         }
     }
-    (void)d;
     __syncthreads();
     if (tid < kTile) w.diag_all[((long long)b * w.words + t) * kTile + tid] = s_d[tid];
 }
@@ -598,7 +596,6 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(LargeWs w, const i
     __shared__ unsigned long long s_kept;
     __shared__ int klist[kTile];
     __shared__ int kslot[kTile];                     // block-local row number of the kept-list entries
-    __shared__ unsigned s_remw[2];
     __shared__ int s_prefix_total;
     const long long base_n = (long long)b * n;
     const unsigned long long* mask = w.mask + base_n * w.words;

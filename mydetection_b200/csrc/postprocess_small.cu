@@ -90,8 +90,10 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
     unsigned long long* tkey = reinterpret_cast<unsigned long long*>(sbox);               // class-bucketed keys (die before corners)
     int* sel = reinterpret_cast<int*>(tkey + kpad);                                         // candidate number by slot
     unsigned short* tslot = reinterpret_cast<unsigned short*>(sel + kpad);                  // class-bucketed slots
+    unsigned long long* ukey = reinterpret_cast<unsigned long long*>(gbox);                 // undecided bucket of the select: keys ...
+    int* uidx = reinterpret_cast<int*>(sarea);                                              // ... and candidate numbers (both die before (B2))
     __shared__ unsigned long long s_prefix;
-    __shared__ int s_need, s_done, s_nsel, s_total, s_flags;
+    __shared__ int s_need, s_done, s_nsel, s_total, s_flags, s_bucket, s_ucount, s_top;
 
     int n = P.n_per_image;
     int flags = 0;
@@ -158,36 +160,47 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
     const int total = s_total;
     PP_MARK(1);
     unsigned long long kth = 1ull;  // select every key >= kth
+    bool use_list = false;                       // block-uniform
+    unsigned long long list_bucket = 0ull, list_mask = 0ull;
     if (total > K) {
-        // ---- (A) radix select of the K-th largest key, 8 bits per pass starting at the first bit
-        // in which the keys differ at all
+        // ---- (A) radix select of the K-th largest key, 8 bits per pass starting at the first bit in which
+        // the keys differ at all.  Only the FIRST pass scans all n keys: the keys of the bucket that holds the
+        // K-th key ("undecided", usually a few dozen) are then copied to a short list and the remaining passes
+        // run on that list.  (Four full passes + two slot-assignment passes were 21 k of the kernel's 42 k cycles.)
         {
-            unsigned long long all_and = ~0ull, all_or = 0ull;
-#pragma unroll 1
-            for (int w = 0; w < kPPWarps; ++w) {
-                all_and &= ((unsigned long long)hist[2 * w + 1] << 32) | hist[2 * w];
-                all_or |= ((unsigned long long)hist[64 + 2 * w + 1] << 32) | hist[64 + 2 * w];
+            if (warp == 0) {
+                // combine the per-warp AND / OR of the keys: lane w holds warp w's pair
+                unsigned a_lo = hist[2 * lane], a_hi = hist[2 * lane + 1], o_lo = hist[64 + 2 * lane], o_hi = hist[64 + 2 * lane + 1];
+                a_lo = __reduce_and_sync(0xffffffffu, a_lo); a_hi = __reduce_and_sync(0xffffffffu, a_hi);
+                o_lo = __reduce_or_sync(0xffffffffu, o_lo); o_hi = __reduce_or_sync(0xffffffffu, o_hi);
+                if (lane == 0) {
+                    const unsigned long long all_and = ((unsigned long long)a_hi << 32) | a_lo, all_or = ((unsigned long long)o_hi << 32) | o_lo;
+                    const unsigned long long diff = all_and ^ all_or;           // bits that are not common to every key
+                    const int top = diff ? 63 - __clzll((long long)diff) : 0;   // highest differing bit
+                    s_top = top;
+                    s_need = K; s_prefix = (top >= 63) ? 0ull : (all_and & (~0ull << (top + 1))); s_ucount = 0;
+                }
             }
-            const unsigned long long diff = all_and ^ all_or;       // bits that are not common to every key
-            const int top = diff ? 63 - __clzll((long long)diff) : 0;  // highest differing bit
-            if (tid == 0) { s_need = K; s_prefix = (top >= 63) ? 0ull : (all_and & (~0ull << (top + 1))); }
             __syncthreads();
-            unsigned* myhist = whist + warp * 257;                      // padded: warps hit different banks
-            int hi_bit = top;                                           // digit = bits [hi_bit-7, hi_bit]
-#pragma unroll 1
-            while (true) {
+            const int top = s_top;
+
+            // one histogram pass over `cnt` keys delivered by key_at(i); digit = bits [hi_bit-7, hi_bit]
+            auto pass = [&](auto key_at, int cnt, int hi_bit, bool priv) -> int {
+                // priv: 32 padded per-warp histograms (all n keys: the digits cluster); else one shared one (short list)
                 const int shift = hi_bit >= 7 ? hi_bit - 7 : 0;
                 const unsigned dmask = (hi_bit >= 7) ? 255u : ((1u << (hi_bit + 1)) - 1u);
-                for (int i = tid; i < kPPWarps * 257; i += kPPThreads) whist[i] = 0u;
+                if (priv) { for (int i = tid; i < kPPWarps * 257; i += kPPThreads) whist[i] = 0u; }
+                else if (tid < 256) hist[tid] = 0u;
+                unsigned* myhist = priv ? whist + warp * 257 : hist;
                 __syncthreads();
                 const unsigned long long prefix = s_prefix;
                 const unsigned long long himask = (hi_bit >= 63) ? 0ull : (~0ull << (hi_bit + 1));
 #pragma unroll 2
-                for (int base = 0; base < n; base += kPPThreads) {
+                for (int base = 0; base < cnt; base += kPPThreads) {
                     const int i = base + tid;
                     unsigned digit = 256u;                              // not a candidate of this pass
-                    if (i < n) {
-                        const unsigned long long k = key_of(i);
+                    if (i < cnt) {
+                        const unsigned long long k = key_at(i);
                         if (k && (k & himask) == prefix) digit = (unsigned)(k >> shift) & dmask;
                     }
                     // scores cluster: when the whole warp agrees, one lane adds 32
@@ -199,13 +212,15 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
                     }
                 }
                 __syncthreads();
-                if (tid < 256) {
-                    unsigned sum = 0;
+                if (priv) {
+                    if (tid < 256) {
+                        unsigned sum = 0;
 #pragma unroll 8
-                    for (int w = 0; w < kPPWarps; ++w) sum += whist[w * 257 + tid];
-                    hist[tid] = sum;
+                        for (int w = 0; w < kPPWarps; ++w) sum += whist[w * 257 + tid];
+                        hist[tid] = sum;
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
                 if (tid < 32) {
                     // lane l owns digits [8l, 8l+8); find the digit that holds the need-th largest
                     unsigned h[8], mine = 0;
@@ -226,6 +241,7 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
                             if ((int)acc < need && need <= (int)(acc + h[j])) {
                                 s_prefix = prefix | ((unsigned long long)(tid * 8 + j) << shift);
                                 s_need = need - (int)acc;
+                                s_bucket = (int)h[j];
                                 if ((int)h[j] == need - (int)acc) s_done = 1;  // the whole bucket is taken
                                 break;
                             }
@@ -234,8 +250,51 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
                     }
                 }
                 __syncthreads();
-                if (s_done || shift == 0) break;
-                hi_bit = shift - 1;
+                return shift;
+            };
+
+            PP_MARK(16);
+            int shift = pass(key_of, n, top, true);                           // the only pass over all n keys
+            PP_MARK(17);
+            bool done = s_done || shift == 0;
+            if (!done && s_bucket <= kpad) {
+                // copy the undecided bucket (key + candidate number) to the short list; count, per warp, the
+                // keys ABOVE the bucket: they are selected whatever happens next
+                const unsigned long long bucket = s_prefix, bmask = ~0ull << shift;
+                int sure = 0;
+#pragma unroll 1
+                for (int base = 0; base < n; base += kPPThreads) {
+                    const int i = base + tid;
+                    const unsigned long long k = (i < n) ? key_of(i) : 0ull;
+                    const unsigned long long kb = k & bmask;
+                    sure += __popc(__ballot_sync(0xffffffffu, k != 0ull && kb > bucket));
+                    const bool inb = k != 0ull && kb == bucket;
+                    const unsigned bal = __ballot_sync(0xffffffffu, inb);
+                    if (bal) {
+                        int base_u = 0;
+                        if (lane == 0) base_u = atomicAdd(&s_ucount, __popc(bal));
+                        base_u = __shfl_sync(0xffffffffu, base_u, 0);
+                        if (inb) { const int u = base_u + __popc(bal & lt_mask); ukey[u] = k; uidx[u] = i; }
+                    }
+                }
+                if (lane == 0) wtot[warp] = sure;
+                __syncthreads();
+                PP_MARK(18);
+                use_list = true;
+                list_bucket = bucket; list_mask = bmask;
+                const int ucount = s_ucount;
+                auto key_list = [&](int i) -> unsigned long long { return ukey[i]; };
+                int np_ = 0;
+                while (!done) {
+                    shift = pass(key_list, ucount, shift - 1, false);
+                    done = s_done || shift == 0;
+                    PP_MARK(19 + np_); ++np_;
+                }
+            } else {
+                while (!done) {                                         // heavy ties: keep scanning all keys
+                    shift = pass(key_of, n, shift - 1, true);
+                    done = s_done || shift == 0;
+                }
             }
         }
         kth = s_prefix;
@@ -243,8 +302,10 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
     }
     PP_MARK(2);
 
-    // ---- (B1) slots for the selected candidates without atomics: per-warp counts, scan, assign
-    {
+    // ---- (B1) slots for the selected candidates without contended atomics: per-warp counts, scan, assign
+    for (int i = tid; i < kClassBins + 32; i += kPPThreads) { cstart[i] = 0; }   // class histogram (whist is dead)
+    for (int i = tid; i < kClassBins; i += kPPThreads) { ccur[i] = 0; }
+    if (!use_list) {
         int mine = 0;
 #pragma unroll 1
         for (int base = 0; base < n; base += kPPThreads) {
@@ -253,24 +314,24 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
             mine += __popc(__ballot_sync(0xffffffffu, k >= kth && k != 0ull));
         }
         if (lane == 0) wtot[warp] = mine;
-        for (int i = tid; i < kClassBins + 32; i += kPPThreads) { cstart[i] = 0; }   // class histogram (whist is dead)
-        for (int i = tid; i < kClassBins; i += kPPThreads) { ccur[i] = 0; }
-        __syncthreads();
-        if (warp == 0) {
-            const int v = wtot[lane];
-            int incl = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const int v = wtot[lane];
+        int incl = v;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-            wtot[32 + lane] = incl - v;
-            if (lane == 31) s_nsel = incl;
-        }
-        __syncthreads();
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        wtot[32 + lane] = incl - v;
+        if (lane == 31) s_nsel = incl;
+    }
+    __syncthreads();
+    {
         int running = wtot[32 + warp];
 #pragma unroll 1
         for (int base = 0; base < n; base += kPPThreads) {
             const int i = base + tid;
             const unsigned long long k = (i < n) ? key_of(i) : 0ull;
-            const bool take = k >= kth && k != 0ull;
+            const bool take = use_list ? (k != 0ull && (k & list_mask) > list_bucket) : (k >= kth && k != 0ull);
             const unsigned bal = __ballot_sync(0xffffffffu, take);
             if (take) {
                 const int slot = running + __popc(bal & lt_mask);
@@ -280,6 +341,25 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
         }
     }
     __syncthreads();
+    if (use_list) {
+        // the undecided keys at or above the K-th key take the slots after the sure ones
+        const int ucount = s_ucount;
+        for (int base = 0; base < ucount; base += kPPThreads) {
+            const int u = base + tid;
+            const bool take = u < ucount && ukey[u] >= kth;
+            const unsigned bal = __ballot_sync(0xffffffffu, take);
+            if (bal) {
+                int slot0 = 0;
+                if (lane == 0) slot0 = atomicAdd(&s_nsel, __popc(bal));
+                slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                if (take) {
+                    const int slot = slot0 + __popc(bal & lt_mask);
+                    if (slot < kpad) { sel[slot] = uidx[u]; keys[slot] = ukey[u]; }
+                }
+            }
+        }
+        __syncthreads();
+    }
     const int m = min(s_nsel, kpad);
     PP_MARK(3);
 

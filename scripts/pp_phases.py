@@ -35,3 +35,4 @@ else:
     for i, nm in enumerate(NAMES):
         print(f'{nm:18s} {t[i + 1] - t[i]:8d} cycles')
     print(f'{"total":18s} {t[9] - t[0]:8d} cycles')
+    print('select detail: prefix', t[16]-t[1], 'pass1', t[17]-t[16], 'build', t[18]-t[17], 'list passes', [t[19+i]-t[18+i] for i in range(6) if t[19+i] > t[18+i]])
