@@ -4,7 +4,7 @@
 // Replaces ImageObjects.non_max_suppression (utils/structures.py:111-173, via torchvision.ops.nms)
 // and nms_rotbb (utils/bbox_ops.py:250-306).  Pipeline, all stream-ordered, no host round trip:
 //   keys   : 64-bit sort key per candidate (class asc, score desc, index asc); failed threshold = ~0
-//   rank   : rank[i] = #{j : key[j] < key[i]}  (tiled all-pairs count; keys are unique) -> order
+//   sort   : bitonic sort of (key, slot) in shared memory (<= 16 384 keys per image) or split over CTAs -> order
 //   gather : sorted corner boxes / rotated quads
 //   mask   : upper-triangular 64x64-tile IoU bit matrix, column tile staged in shared memory,
 //            one row per thread; rotated boxes use the cull + polygon clipping of rotgeom.cuh
@@ -30,6 +30,8 @@ struct LargeWs {          // carved out of the caller's workspace
     unsigned long long* kept;   // B*words  survivors, bit per sorted row
     int* rowpos;                // B*n      sorted row -> position in the emitted list (kept rows)
     // spatially ordered variant (rotated path, n <= 16384): boxes live in Morton order of their centres
+    unsigned long long* bk;     // B*npad   big sort (n > 16384): keys ...
+    int* bp;                    // B*npad   ... and payload
     unsigned long long* skeys;  // B*n      (morton << 20 | score rank), indexed by score rank
     int* rank_of_spos;          // B*n      spatial position -> score rank
     int* spos_of_rank;          // B*n      score rank -> spatial position
@@ -50,6 +52,9 @@ static size_t carve(LargeWs& w, void* base, int batch, int n, bool rot) {
     const size_t o_rbox = take(rot ? bn * sizeof(RotBox) : 0);
     const size_t o_mask = take(bn * (size_t)w.words * 8), o_kept = take((size_t)batch * w.words * 8);
     const size_t o_rowpos = take(rot ? bn * 4 : 0);
+    size_t npad_big = 0;
+    if (n > 16384) { npad_big = 32768; while (npad_big < (size_t)n) npad_big <<= 1; }
+    const size_t o_bk = take((size_t)batch * npad_big * 8), o_bp = take((size_t)batch * npad_big * 4);
     const size_t o_skeys = take(rot ? bn * 8 : 0), o_ros = take(rot ? bn * 4 : 0), o_sor = take(rot ? bn * 4 : 0);
     const size_t o_hull = take(rot ? (size_t)batch * w.words * 16 : 0);
     const size_t o_adj = take(rot ? (size_t)batch * w.words * 32 : 0);
@@ -62,6 +67,7 @@ static size_t carve(LargeWs& w, void* base, int batch, int n, bool rot) {
         w.rbox = (RotBox*)(p + o_rbox);
         w.mask = (unsigned long long*)(p + o_mask); w.kept = (unsigned long long*)(p + o_kept);
         w.rowpos = (int*)(p + o_rowpos);
+        w.bk = (unsigned long long*)(p + o_bk); w.bp = (int*)(p + o_bp);
         w.skeys = (unsigned long long*)(p + o_skeys); w.rank_of_spos = (int*)(p + o_ros); w.spos_of_rank = (int*)(p + o_sor);
         w.tile_hull = (float4*)(p + o_hull);
         w.tile_adj = (unsigned long long*)(p + o_adj);
@@ -112,29 +118,10 @@ __global__ void keys_kernel(KeyParams P, unsigned long long* keys, int* m) {
     if ((threadIdx.x & 31) == 0 && bal) atomicAdd(m + b, __popc(bal));
 }
 
-// ---------------------------------------------------------------------------- rank (sort)
-constexpr int kRankThreads = 256;
-__global__ void __launch_bounds__(kRankThreads) rank_kernel(const unsigned long long* keys, int* order, int n) {
-    __shared__ unsigned long long tile[kRankThreads];
-    const int b = blockIdx.y;
-    const int i = blockIdx.x * kRankThreads + threadIdx.x;
-    const unsigned long long* kb = keys + (long long)b * n;
-    const unsigned long long mine = (i < n) ? kb[i] : ~0ull;
-    int rank = 0;
-    for (int base = 0; base < n; base += kRankThreads) {
-        const int j = base + threadIdx.x;
-        tile[threadIdx.x] = (j < n) ? kb[j] : ~0ull;
-        __syncthreads();
-#pragma unroll 8
-        for (int t = 0; t < kRankThreads; ++t) rank += (tile[t] < mine) ? 1 : 0;
-        __syncthreads();
-    }
-    if (i < n && mine != ~0ull) order[(long long)b * n + rank] = i;
-}
-
+// ---------------------------------------------------------------------------- sort
 // Sort for images of at most 16 384 candidates: one CTA per image, bitonic network over (key, slot) held
-// entirely in shared memory (192 KB).  32 images sort concurrently on 32 SMs in ~50 us, where the
-// all-pairs rank kernel above needs 545 us for the same batch.
+// entirely in shared memory (192 KB).  32 images sort concurrently on 32 SMs in ~230 us, where an
+// all-pairs rank kernel (rank = number of smaller keys) needed 545 us for the same batch.
 constexpr int kSortThreads = 1024;
 constexpr int kSortMaxN = 16384;
 __global__ void __launch_bounds__(kSortThreads, 1) sort_smem_kernel(const unsigned long long* keys, int* order, int n, int npad) {
@@ -164,6 +151,88 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_smem_kernel(const unsign
     }
     for (int i = tid; i < n; i += kSortThreads)
         if (skeys[i] != ~0ull) order[(long long)b * n + i] = spay[i];
+}
+
+// Sort for larger images (16 384 < n <= 2^20): the same bitonic network split over CTAs.  16 384-key chunks
+// are sorted / merged in shared memory (strides < 16 384), the few stages with longer strides are
+// compare-exchanges in global memory.  Replaces the O(n^2) all-pairs rank kernel (2.3e9 compares at 48 k).
+constexpr int kChunk = kSortMaxN;
+__global__ void sort_big_load_kernel(const unsigned long long* keys, unsigned long long* bk, int* bp, int n, int npad) {
+    const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npad) return;
+    bk[(long long)b * npad + i] = (i < n) ? keys[(long long)b * n + i] : ~0ull;
+    bp[(long long)b * npad + i] = i;
+}
+// first != 0: full network for sizes 2..kChunk; else: the strides kChunk/2..1 of the merge step `size`
+__global__ void __launch_bounds__(kSortThreads, 1) sort_big_chunk_kernel(unsigned long long* bk, int* bp, int npad, int size_arg, int first) {
+    extern __shared__ unsigned long long skeys[];
+    int* spay = reinterpret_cast<int*>(skeys + kChunk);
+    const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    unsigned long long* gk = bk + (long long)b * npad + (long long)c * kChunk;
+    int* gp = bp + (long long)b * npad + (long long)c * kChunk;
+    for (int i = tid; i < kChunk; i += kSortThreads) { skeys[i] = gk[i]; spay[i] = gp[i]; }
+    __syncthreads();
+    const int gbase = c * kChunk;
+#pragma unroll 1
+    for (int size = first ? 2 : size_arg; size <= (first ? kChunk : size_arg); size <<= 1) {
+#pragma unroll 1
+        for (int stride = min(size >> 1, kChunk >> 1); stride > 0; stride >>= 1) {
+#pragma unroll 4
+            for (int t = tid; t < (kChunk >> 1); t += kSortThreads) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = ((gbase + lo) & size) == 0;
+                const unsigned long long a = skeys[lo], d = skeys[hi];
+                if ((a > d) == up) {
+                    skeys[lo] = d; skeys[hi] = a;
+                    const int pa = spay[lo]; spay[lo] = spay[hi]; spay[hi] = pa;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < kChunk; i += kSortThreads) { gk[i] = skeys[i]; gp[i] = spay[i]; }
+}
+__global__ void sort_big_global_kernel(unsigned long long* bk, int* bp, int npad, int size, int stride) {
+    const int b = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (npad >> 1)) return;
+    const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+    const bool up = (lo & size) == 0;
+    unsigned long long* gk = bk + (long long)b * npad;
+    int* gp = bp + (long long)b * npad;
+    const unsigned long long a = gk[lo], d = gk[hi];
+    if ((a > d) == up) {
+        gk[lo] = d; gk[hi] = a;
+        const int pa = gp[lo]; gp[lo] = gp[hi]; gp[hi] = pa;
+    }
+}
+__global__ void sort_big_store_kernel(const unsigned long long* bk, const int* bp, int* order, int n, int npad) {
+    const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && bk[(long long)b * npad + i] != ~0ull) order[(long long)b * n + i] = bp[(long long)b * npad + i];
+}
+
+// order[b][rank] = index of the rank-th smallest key of image b (invalid keys ~0 are left out)
+static int sort_keys(const unsigned long long* keys, int* order, int n, int B, LargeWs& w, cudaStream_t st) {
+    if (n <= kSortMaxN) {
+        int npad = 64;
+        while (npad < n) npad <<= 1;
+        MYDET_CUDA(cudaFuncSetAttribute(sort_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortMaxN * 12)));
+        sort_smem_kernel<<<B, kSortThreads, (size_t)npad * 12, st>>>(keys, order, n, npad);
+        return launch_status("sort_smem_kernel");
+    }
+    int npad = 2 * kChunk;
+    while (npad < n) npad <<= 1;
+    const int chunks = npad / kChunk;
+    MYDET_CUDA(cudaFuncSetAttribute(sort_big_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kChunk * 12)));
+    sort_big_load_kernel<<<dim3((npad + 255) / 256, B), 256, 0, st>>>(keys, w.bk, w.bp, n, npad);
+    sort_big_chunk_kernel<<<dim3(chunks, B), kSortThreads, (size_t)kChunk * 12, st>>>(w.bk, w.bp, npad, 0, 1);
+    for (int size = 2 * kChunk; size <= npad; size <<= 1) {
+        for (int stride = size >> 1; stride >= kChunk; stride >>= 1)
+            sort_big_global_kernel<<<dim3((npad / 2 + 255) / 256, B), 256, 0, st>>>(w.bk, w.bp, npad, size, stride);
+        sort_big_chunk_kernel<<<dim3(chunks, B), kSortThreads, (size_t)kChunk * 12, st>>>(w.bk, w.bp, npad, size, 0);
+    }
+    sort_big_store_kernel<<<dim3((n + 255) / 256, B), 256, 0, st>>>(w.bk, w.bp, order, n, npad);
+    return launch_status("sort_big kernels");
 }
 
 // ---------------------------------------------------------------------------- gather
@@ -858,14 +927,9 @@ int run_large(const LargeArgs& A, void* workspace, size_t workspace_bytes, cudaS
     if (A.status) MYDET_CUDA(cudaMemsetAsync(A.status, 0, sizeof(int) * (size_t)B, st));
     KeyParams K{A.scores, A.cls, A.counts, A.src_idx, A.pitch, n, A.cls_is_i64, (A.cls && !A.rot) ? 1 : 0, A.conf_thres, A.status};
     keys_kernel<<<dim3((n + 255) / 256, B), 256, 0, st>>>(K, w.keys, w.m);
-    if (n <= kSortMaxN) {
-        int npad = 64;
-        while (npad < n) npad <<= 1;
-        const size_t sort_smem = (size_t)npad * 12;
-        MYDET_CUDA(cudaFuncSetAttribute(sort_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortMaxN * 12)));
-        sort_smem_kernel<<<B, kSortThreads, sort_smem, st>>>(w.keys, w.order, n, npad);
-    } else {
-        rank_kernel<<<dim3((n + kRankThreads - 1) / kRankThreads, B), kRankThreads, 0, st>>>(w.keys, w.order, n);
+    {
+        const int rc = sort_keys(w.keys, w.order, n, B, w, st);
+        if (rc) return rc;
     }
     GatherParams G{A.boxes, A.pitch, n, A.n_param, A.box_format};
     const int tiles = (n + kTile - 1) / kTile;

@@ -167,3 +167,25 @@ def test_one_stage_forward_flow(golden):
         assert len(out) == want.numel()
         close(out.bboxes, ref[0][b][want], 384, 'flow box')
         assert torch.equal(out.cats, ref[1][b][want])
+
+
+def test_cepdof_matching_iou(golden):
+    """CEPDOFeval.computeIoU (dt x gt rotated IoU, stable score order, maxDets cap)."""
+    from mydetection_b200 import evaluation
+    from oracle import iou as oi
+    g = golden('iou')
+    rgt = T(g['rot_gt_debug3'])
+    gts = [{'bbox': b.tolist()} for b in rgt[:30]]
+    gen = torch.Generator().manual_seed(5)
+    dt_boxes = rgt[:60].clone()
+    dt_boxes[:, :2] += torch.randn(60, 2, generator=gen) * 6
+    dt_boxes[:, 4] += torch.randn(60, generator=gen) * 10
+    scores = (torch.rand(60, generator=gen) * 20).round() / 20            # ties: the sort must be stable
+    dts = [{'bbox': b.tolist(), 'score': float(s)} for b, s in zip(dt_boxes, scores)]
+    ious, order = evaluation.compute_iou(dts, gts, max_dets=40)
+    want_order = np.argsort([-d['score'] for d in dts], kind='mergesort')[:40]
+    assert np.array_equal(order, want_order) and ious.shape == (40, 30) and ious.dtype == np.float64
+    want = oi.iou_rot(dt_boxes[want_order], rgt[:30]).numpy()
+    np.testing.assert_allclose(ious, want, rtol=0, atol=1e-6)
+    assert evaluation.iou_rle([], [[1, 2, 3, 4, 5]]).shape == (0, 1)
+    assert evaluation.compute_iou([], [])[0] == []
