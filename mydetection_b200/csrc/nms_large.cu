@@ -17,6 +17,8 @@
 namespace mydet {
 
 constexpr int kTile = 64;
+constexpr int kAdjMax = 16;            // adjacency words per tile: tiles <= 1024, i.e. n <= 65 536 in the spatial path
+constexpr int kSpatialMaxN = kAdjMax * 64 * kTile;
 
 struct LargeWs {          // carved out of the caller's workspace
     unsigned long long* keys;   // B*n
@@ -37,8 +39,10 @@ struct LargeWs {          // carved out of the caller's workspace
     int* spos_of_rank;          // B*n      score rank -> spatial position
     float4* tile_hull;          // B*tiles  hull of the 64 boxes of a spatial tile
     unsigned long long* diag_all; // B*tiles*64  per score block, TRANSPOSED: entry c, bit a = "a suppresses c" (both of the block)
-    unsigned long long* adj_blk;  // B*tiles*64*4  per score block row: the tile_adj words of that row's spatial tile
-    unsigned long long* tile_adj; // B*tiles*4  bit j of tile i: some row of tile i has a nonzero mask word j (tiles <= 256)
+    unsigned long long* adj_blk;  // B*tiles*64*aw  per score block row: the tile_adj words of that row's spatial tile
+    unsigned long long* tile_adj; // B*tiles*aw  bit j of tile i: some row of tile i has a nonzero mask word j
+    int2* tile_cls;               // B*tiles     class range of a spatial tile (axis-aligned path)
+    int aw;                       // adjacency words per tile = ceil(tiles / 64)
     int words;                  // ceil(n/64)
 };
 
@@ -55,11 +59,14 @@ static size_t carve(LargeWs& w, void* base, int batch, int n, bool rot) {
     size_t npad_big = 0;
     if (n > 16384) { npad_big = 32768; while (npad_big < (size_t)n) npad_big <<= 1; }
     const size_t o_bk = take((size_t)batch * npad_big * 8), o_bp = take((size_t)batch * npad_big * 4);
-    const size_t o_skeys = take(rot ? bn * 8 : 0), o_ros = take(rot ? bn * 4 : 0), o_sor = take(rot ? bn * 4 : 0);
-    const size_t o_hull = take(rot ? (size_t)batch * w.words * 16 : 0);
-    const size_t o_adj = take(rot ? (size_t)batch * w.words * 32 : 0);
-    const size_t o_diag = take(rot ? (size_t)batch * w.words * kTile * 8 : 0);
-    const size_t o_adjb = take(rot ? (size_t)batch * w.words * kTile * 32 : 0);
+    const bool sp = n <= kSpatialMaxN;            // buffers of the spatially ordered path
+    w.aw = (w.words + 63) / 64;
+    const size_t o_skeys = take(sp ? bn * 8 : 0), o_ros = take(sp ? bn * 4 : 0), o_sor = take(sp ? bn * 4 : 0);
+    const size_t o_hull = take(sp ? (size_t)batch * w.words * 16 : 0);
+    const size_t o_tcls = take(sp ? (size_t)batch * w.words * 8 : 0);
+    const size_t o_adj = take(sp ? (size_t)batch * w.words * w.aw * 8 : 0);
+    const size_t o_diag = take(sp ? (size_t)batch * w.words * kTile * 8 : 0);
+    const size_t o_adjb = take(sp ? (size_t)batch * w.words * kTile * w.aw * 8 : 0);
     if (base) {
         char* p = static_cast<char*>(base);
         w.keys = (unsigned long long*)(p + o_keys); w.order = (int*)(p + o_order); w.m = (int*)(p + o_m);
@@ -70,6 +77,7 @@ static size_t carve(LargeWs& w, void* base, int batch, int n, bool rot) {
         w.bk = (unsigned long long*)(p + o_bk); w.bp = (int*)(p + o_bp);
         w.skeys = (unsigned long long*)(p + o_skeys); w.rank_of_spos = (int*)(p + o_ros); w.spos_of_rank = (int*)(p + o_sor);
         w.tile_hull = (float4*)(p + o_hull);
+        w.tile_cls = (int2*)(p + o_tcls);
         w.tile_adj = (unsigned long long*)(p + o_adj);
         w.diag_all = (unsigned long long*)(p + o_diag);
         w.adj_blk = (unsigned long long*)(p + o_adjb);
@@ -448,7 +456,8 @@ __device__ __forceinline__ unsigned part1by1(unsigned v) {      // spread the lo
     return v;
 }
 
-__global__ void spatial_keys_kernel(GatherParams P, const int* order, const int* m, unsigned long long* skeys) {
+__global__ void spatial_keys_kernel(GatherParams P, const unsigned long long* keys, const int* order, const int* m,
+                                    unsigned long long* skeys) {
     const int b = blockIdx.y;
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= P.n) return;
@@ -456,46 +465,133 @@ __global__ void spatial_keys_kernel(GatherParams P, const int* order, const int*
     if (r < m[b]) {
         const int i = order[(long long)b * P.n + r];
         const float* bx = P.boxes + ((long long)b * P.pitch + i) * P.n_param;
-        const unsigned qx = (unsigned)fminf(fmaxf(bx[0], 0.f), 65535.f), qy = (unsigned)fminf(fmaxf(bx[1], 0.f), 65535.f);
+        float cx = bx[0], cy = bx[1];
+        if (P.box_format == MYDET_BOX_X1Y1X2Y2) { cx = 0.5f * (bx[0] + bx[2]); cy = 0.5f * (bx[1] + bx[3]); }
+        const unsigned qx = (unsigned)fminf(fmaxf(cx, 0.f), 65535.f), qy = (unsigned)fminf(fmaxf(cy, 0.f), 65535.f);
         const unsigned morton = part1by1(qx) | (part1by1(qy) << 1);
-        key = ((unsigned long long)morton << 20) | (unsigned long long)r;
+        // class first (boxes of different classes never interact), then the Z-order of the centre
+        const unsigned long long cls = keys[(long long)b * P.n + i] >> 52;
+        key = (cls << 52) | ((unsigned long long)morton << 20) | (unsigned long long)r;
     }
     skeys[(long long)b * P.n + r] = key;
 }
 
 // after sorting skeys: rank_of_spos[spos] = score rank (the sort's payload).  Build the quads in spatial
 // order, the inverse map, and the hull of every 64-box tile (one warp pair per tile).
-__global__ void __launch_bounds__(kTile) spatial_gather_kernel(GatherParams P, const int* order, const int* m, LargeWs w) {
+template <bool ROT>
+__global__ void __launch_bounds__(kTile) spatial_gather_kernel(GatherParams P, const unsigned long long* keys, const int* order,
+                                                               const int* m, LargeWs w) {
     const int tile = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
     const int mb = m[b];
     const int spos = tile * kTile + t;
     __shared__ float4 part[2];
+    __shared__ int2 cpart[2];
     float x0 = 3.0e18f, y0 = 3.0e18f, x1 = -3.0e18f, y1 = -3.0e18f;
+    int c_lo = 0x7fffffff, c_hi = -1;
     if (spos < mb) {
         const long long row = (long long)b * P.n + spos;
         const int r = w.rank_of_spos[row];
         const int i = order[(long long)b * P.n + r];
         const float* bx = P.boxes + ((long long)b * P.pitch + i) * P.n_param;
-        float v[5] = {bx[0], bx[1], bx[2], bx[3], bx[4]};
-        RotBox q;
-        make_rot_box(v, q.x, q.y, q.r);
-        q.cx = v[0]; q.cy = v[1];
-        q.area2 = (float)signed_area2_f64(q.x, q.y);
-        rot_box_hull(q);
-        w.rbox[row] = q;
+        if (ROT) {
+            float v[5] = {bx[0], bx[1], bx[2], bx[3], bx[4]};
+            RotBox q;
+            make_rot_box(v, q.x, q.y, q.r);
+            q.cx = v[0]; q.cy = v[1];
+            q.area2 = (float)signed_area2_f64(q.x, q.y);
+            rot_box_hull(q);
+            w.rbox[row] = q;
+            x0 = q.x0; y0 = q.y0; x1 = q.x1; y1 = q.y1;
+        } else {
+            const float v0 = bx[0], v1 = bx[1], v2 = bx[2], v3 = bx[3];
+            float4 c4;
+            if (P.box_format == MYDET_BOX_CXCYWH) {
+                const float hw = __fmul_rn(v2, 0.5f), hh = __fmul_rn(v3, 0.5f);
+                c4 = make_float4(__fsub_rn(v0, hw), __fsub_rn(v1, hh), __fadd_rn(v0, hw), __fadd_rn(v1, hh));
+            } else {
+                c4 = make_float4(v0, v1, v2, v3);
+            }
+            w.box[row] = c4;
+            w.area[row] = __fmul_rn(__fsub_rn(c4.z, c4.x), __fsub_rn(c4.w, c4.y));
+            const int c = (int)(keys[(long long)b * P.n + i] >> 52);
+            w.cls[row] = c;
+            c_lo = c_hi = c;
+            x0 = fminf(c4.x, c4.z); y0 = fminf(c4.y, c4.w); x1 = fmaxf(c4.x, c4.z); y1 = fmaxf(c4.y, c4.w);
+        }
         w.spos_of_rank[(long long)b * P.n + r] = spos;
-        x0 = q.x0; y0 = q.y0; x1 = q.x1; y1 = q.y1;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o));
         x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+        c_lo = min(c_lo, __shfl_xor_sync(0xffffffffu, c_lo, o)); c_hi = max(c_hi, __shfl_xor_sync(0xffffffffu, c_hi, o));
     }
-    if ((t & 31) == 0) part[t >> 5] = make_float4(x0, y0, x1, y1);
+    if ((t & 31) == 0) { part[t >> 5] = make_float4(x0, y0, x1, y1); cpart[t >> 5] = make_int2(c_lo, c_hi); }
     __syncthreads();
-    if (t == 0 && tile * kTile < mb)
+    if (t == 0 && tile * kTile < mb) {
         w.tile_hull[(long long)b * w.words + tile] = make_float4(fminf(part[0].x, part[1].x) - 1e-2f, fminf(part[0].y, part[1].y) - 1e-2f,
                                                                  fmaxf(part[0].z, part[1].z) + 1e-2f, fmaxf(part[0].w, part[1].w) + 1e-2f);
+        w.tile_cls[(long long)b * w.words + tile] = make_int2(min(cpart[0].x, cpart[1].x), max(cpart[0].y, cpart[1].y));
+    }
+}
+
+// Axis-aligned mask in spatial order.  grid (row tile ti, chunk of column tiles, image); unordered tile pairs
+// ti <= tj once; pairs of tiles with disjoint hulls or class ranges are skipped.  The IoU is torchvision's
+// arithmetic (iou_corners); a hit sets the bit in the row of the higher-ranked box with a global atomicOr.
+__global__ void __launch_bounds__(kTile) mask_aabb_spatial_kernel(LargeWs w, const int* m, int n, float thr_f) {
+    const int ti = blockIdx.x, cc = blockIdx.y, b = blockIdx.z;
+    const int T = (n + kTile - 1) / kTile;
+    const int tj_lo = max(ti, cc * kColChunk), tj_hi = min(T, (cc + 1) * kColChunk);
+    if (tj_lo >= tj_hi) return;
+    const int mb = m[b];
+    if (ti * kTile >= mb || tj_lo * kTile >= mb) return;
+    const long long base = (long long)b * n;
+    const int t = threadIdx.x;
+    const int r = ti * kTile + t;
+    __shared__ float4 cbox[2][kTile];
+    __shared__ float carea[2][kTile];
+    __shared__ int ccls[2][kTile];
+    const float4 my_hull = w.tile_hull[(long long)b * w.words + ti];
+    const int2 my_cls = w.tile_cls[(long long)b * w.words + ti];
+    float4 a = make_float4(3.0e18f, 3.0e18f, 3.0e18f, 3.0e18f);
+    float aarea = 0.f;
+    int ac = -2, arank = 0;
+    if (r < mb) { a = w.box[base + r]; aarea = w.area[base + r]; ac = w.cls[base + r]; arank = w.rank_of_spos[base + r]; }
+    unsigned* mask32 = reinterpret_cast<unsigned*>(w.mask);
+    int buf = 0;
+#pragma unroll 1
+    for (int tj = tj_lo; tj < tj_hi; ++tj) {
+        const int c0 = tj * kTile;
+        if (c0 >= mb) break;
+        const float4 oh = w.tile_hull[(long long)b * w.words + tj];
+        const int2 oc = w.tile_cls[(long long)b * w.words + tj];
+        if (oh.x > my_hull.z || my_hull.x > oh.z || oh.y > my_hull.w || my_hull.y > oh.w) continue;   // patches apart
+        if (oc.x > my_cls.y || my_cls.x > oc.y) continue;                                             // no common class
+        if (c0 + t < mb) { cbox[buf][t] = w.box[base + c0 + t]; carea[buf][t] = w.area[base + c0 + t]; ccls[buf][t] = w.cls[base + c0 + t]; }
+        else { cbox[buf][t] = make_float4(-3.0e18f, -3.0e18f, -3.0e18f, -3.0e18f); carea[buf][t] = 0.f; ccls[buf][t] = -1; }
+        __syncthreads();
+        if (r < mb) {
+            const int j0 = (tj == ti) ? t + 1 : 0;                           // each unordered pair once
+#pragma unroll 4
+            for (int j = j0; j < kTile; ++j) {
+                const float4 c4 = cbox[buf][j];
+                // cheap reject: different class or no overlap at all (the common case)
+                if (ccls[buf][j] != ac || !(fminf(a.z, c4.z) > fmaxf(a.x, c4.x)) || !(fminf(a.w, c4.w) > fmaxf(a.y, c4.y))) continue;
+                const int pb = c0 + j;
+                const bool a_first = arank < w.rank_of_spos[base + pb];
+                // torchvision evaluates the pair from the higher-ranked box
+                const float ovr = a_first ? iou_corners(a.x, a.y, a.z, a.w, aarea, c4.x, c4.y, c4.z, c4.w, carea[buf][j])
+                                          : iou_corners(c4.x, c4.y, c4.z, c4.w, carea[buf][j], a.x, a.y, a.z, a.w, aarea);
+                if (ovr > thr_f) {
+                    const int row = a_first ? r : pb, col = a_first ? pb : r;
+                    atomicOr(&mask32[((base + row) * w.words + (col >> 6)) * 2 + ((col >> 5) & 1)], 1u << (col & 31));
+                    const int trow = row >> 6, tcol = col >> 6;
+                    atomicOr(&w.tile_adj[((long long)b * w.words + trow) * w.aw + (tcol >> 6)], 1ull << (tcol & 63));
+                }
+            }
+        }
+        buf ^= 1;
+    }
 }
 
 // grid (row tile ti, chunk of column tiles, image).  Unordered tile pairs ti <= tj are visited once; a hit
@@ -537,7 +633,7 @@ __global__ void __launch_bounds__(kTile) mask_rot_spatial_kernel(LargeWs w, cons
                 const int row = a_first ? pa : pb, col = a_first ? pb : pa;           // the higher-scored box suppresses
                 atomicOr(&mask32[((base + row) * w.words + (col >> 6)) * 2 + ((col >> 5) & 1)], 1u << (col & 31));
                 const int trow = row >> 6, tcol = col >> 6;
-                atomicOr(&w.tile_adj[((long long)b * w.words + trow) * 4 + (tcol >> 6)], 1ull << (tcol & 63));
+                atomicOr(&w.tile_adj[((long long)b * w.words + trow) * w.aw + (tcol >> 6)], 1ull << (tcol & 63));
             }
         }
     };
@@ -613,15 +709,16 @@ __global__ void __launch_bounds__(512) spatial_diag_kernel(LargeWs w, const int*
     const long long base_n = (long long)b * n;
     const unsigned long long* mask = w.mask + base_n * w.words;
     __shared__ int s_sp[kTile];
-    __shared__ unsigned long long s_adj[kTile][4];
+    __shared__ unsigned long long s_adj[kTile][kAdjMax];
     __shared__ unsigned long long s_d[kTile];
+    const int aw = w.aw;
     if (tid < kTile) { s_sp[tid] = (tid < rows) ? w.spos_of_rank[base_n + r0 + tid] : 0; s_d[tid] = 0ull; }
     __syncthreads();
-    if (tid < kTile * 4) {
-        const int a = tid >> 2, q = tid & 3;
-        const unsigned long long v = (a < rows) ? w.tile_adj[((long long)b * w.words + (s_sp[a] >> 6)) * 4 + q] : 0ull;
+    for (int e = tid; e < kTile * aw; e += 512) {
+        const int a = e / aw, q = e - a * aw;
+        const unsigned long long v = (a < rows) ? w.tile_adj[((long long)b * w.words + (s_sp[a] >> 6)) * aw + q] : 0ull;
         s_adj[a][q] = v;
-        w.adj_blk[((long long)b * w.words + t) * (kTile * 4) + tid] = v;      // staged per block for the sweep
+        w.adj_blk[((long long)b * w.words + t) * (kTile * aw) + e] = v;      // staged per block for the sweep
     }
     __syncthreads();
     const int a = tid & (kTile - 1), cg = tid >> 6;              // 64 rows x 8 column groups
@@ -676,23 +773,35 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(LargeWs w, const i
         // Software-pipelined: the data of block t+1 (positions, adjacency rows, gathered diagonal words) does
         // not depend on the removed vector, so it is loaded while thread 0 resolves block t.
         __shared__ int sp2[2][kTile];
-        __shared__ unsigned long long adj2[2][kTile][4];
+        __shared__ unsigned long long adj2[2][kTile][kAdjMax];
+        const int aw = w.aw;
+        constexpr int kAdjPerThread = (kTile * kAdjMax + kSweepThreads - 1) / kSweepThreads;   // 2
         __shared__ unsigned long long dg2[2][kTile];
-        auto fetch = [&](int t, int& v_sp, unsigned long long& v_dg, unsigned long long& v_adj) {
-            v_sp = 0; v_dg = 0ull; v_adj = 0ull;
+        auto fetch = [&](int t, int& v_sp, unsigned long long& v_dg, unsigned long long (&v_adj)[kAdjPerThread]) {
+            v_sp = 0; v_dg = 0ull;
+#pragma unroll
+            for (int q = 0; q < kAdjPerThread; ++q) v_adj[q] = 0ull;
             if (t >= words) return;
             const int r0 = t * kTile, rows = min(kTile, mb - r0);
             if (tid < kTile && tid < rows) {
                 v_sp = w.spos_of_rank[base_n + r0 + tid];
                 v_dg = w.diag_all[((long long)b * w.words + t) * kTile + tid];
             }
-            if (tid < kTile * 4) v_adj = w.adj_blk[((long long)b * w.words + t) * (kTile * 4) + tid];
+#pragma unroll
+            for (int q = 0; q < kAdjPerThread; ++q) {
+                const int e = tid + q * kSweepThreads;
+                if (e < kTile * aw) v_adj[q] = w.adj_blk[((long long)b * w.words + t) * (kTile * aw) + e];
+            }
         };
-        auto stash = [&](int buf, int v_sp, unsigned long long v_dg, unsigned long long v_adj) {
+        auto stash = [&](int buf, int v_sp, unsigned long long v_dg, const unsigned long long (&v_adj)[kAdjPerThread]) {
             if (tid < kTile) { sp2[buf][tid] = v_sp; dg2[buf][tid] = v_dg; }
-            if (tid < kTile * 4) adj2[buf][tid >> 2][tid & 3] = v_adj;
+#pragma unroll
+            for (int q = 0; q < kAdjPerThread; ++q) {
+                const int e = tid + q * kSweepThreads;
+                if (e < kTile * aw) adj2[buf][e / aw][e % aw] = v_adj[q];
+            }
         };
-        int v_sp; unsigned long long v_dg, v_adj;
+        int v_sp; unsigned long long v_dg, v_adj[kAdjPerThread];
         fetch(0, v_sp, v_dg, v_adj);
         stash(0, v_sp, v_dg, v_adj);
         fetch(1, v_sp, v_dg, v_adj);              // two blocks of look-ahead: a full iteration to land
@@ -756,17 +865,20 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(LargeWs w, const i
                 for (int kr = warp; kr < nk; kr += kSweepThreads / 32) {
                     const unsigned long long* rowp = mask + (long long)klist[kr] * w.words;
                     const unsigned long long* adj = adj2[buf][kslot[kr]];
-                    unsigned long long v[8];
+#pragma unroll 1
+                    for (int w0 = 0; w0 < words; w0 += 256) {           // 256 words per round, 8 loads in flight
+                        unsigned long long v[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {                       // up to 256 words (n <= 16384)
-                        const int wd = lane + 32 * u;
-                        v[u] = (wd < words && ((adj[wd >> 6] >> (wd & 63)) & 1ull)) ? rowp[wd] : 0ull;
-                    }
+                        for (int u = 0; u < 8; ++u) {
+                            const int wd = w0 + lane + 32 * u;
+                            v[u] = (wd < words && ((adj[wd >> 6] >> (wd & 63)) & 1ull)) ? rowp[wd] : 0ull;
+                        }
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int wd = lane + 32 * u;
-                        if ((unsigned)v[u]) atomicOr(&removed32[2 * wd], (unsigned)v[u]);
-                        if ((unsigned)(v[u] >> 32)) atomicOr(&removed32[2 * wd + 1], (unsigned)(v[u] >> 32));
+                        for (int u = 0; u < 8; ++u) {
+                            const int wd = w0 + lane + 32 * u;
+                            if ((unsigned)v[u]) atomicOr(&removed32[2 * wd], (unsigned)v[u]);
+                            if ((unsigned)(v[u] >> 32)) atomicOr(&removed32[2 * wd + 1], (unsigned)(v[u] >> 32));
+                        }
                     }
                 }
             }
@@ -938,18 +1050,25 @@ int run_large(const LargeArgs& A, void* workspace, size_t workspace_bytes, cudaS
     const size_t smem = ((size_t)w.words * 2 + kTile) * sizeof(unsigned long long);
     MYDET_REQUIRE(smem <= 200 * 1024, "too many candidates per image for the sweep kernel");
     const int smem_attr = (int)smem > 48 * 1024 ? (int)smem : 48 * 1024;
-    // Morton-ordered mask for rotated boxes (the degenerate "IoU >= 0" threshold suppresses disjoint
-    // boxes too, which patch culling would miss: it keeps the score-ordered kernel)
-    const bool spatial = A.rot && n <= kSortMaxN && !(A.ge && A.thr <= 0.0);
+    // Morton-ordered mask (n <= 65 536).  The degenerate "IoU >= 0" threshold of the rotated API suppresses
+    // disjoint boxes too, which patch culling would miss: it keeps the score-ordered kernel.
+    const bool spatial = n <= kSpatialMaxN && !(A.rot && A.ge && A.thr <= 0.0);
     if (spatial) {
-        int npad = 64;
-        while (npad < n) npad <<= 1;
-        spatial_keys_kernel<<<dim3((n + 255) / 256, B), 256, 0, st>>>(G, w.order, w.m, w.skeys);
-        sort_smem_kernel<<<B, kSortThreads, (size_t)npad * 12, st>>>(w.skeys, w.rank_of_spos, n, npad);
+        spatial_keys_kernel<<<dim3((n + 255) / 256, B), 256, 0, st>>>(G, w.keys, w.order, w.m, w.skeys);
+        {
+            const int rc = sort_keys(w.skeys, w.rank_of_spos, n, B, w, st);
+            if (rc) return rc;
+        }
         MYDET_CUDA(cudaMemsetAsync(w.mask, 0, (size_t)B * n * w.words * sizeof(unsigned long long), st));
-        MYDET_CUDA(cudaMemsetAsync(w.tile_adj, 0, (size_t)B * w.words * 32, st));
-        spatial_gather_kernel<<<dim3(tiles, B), kTile, 0, st>>>(G, w.order, w.m, w);
-        mask_rot_spatial_kernel<<<dim3(tiles, (tiles + kColChunk - 1) / kColChunk, B), kTile, 0, st>>>(w, w.m, n, A.thr, A.ge);
+        MYDET_CUDA(cudaMemsetAsync(w.tile_adj, 0, (size_t)B * w.words * w.aw * 8, st));
+        const dim3 mgrid(tiles, (tiles + kColChunk - 1) / kColChunk, B);
+        if (A.rot) {
+            spatial_gather_kernel<true><<<dim3(tiles, B), kTile, 0, st>>>(G, w.keys, w.order, w.m, w);
+            mask_rot_spatial_kernel<<<mgrid, kTile, 0, st>>>(w, w.m, n, A.thr, A.ge);
+        } else {
+            spatial_gather_kernel<false><<<dim3(tiles, B), kTile, 0, st>>>(G, w.keys, w.order, w.m, w);
+            mask_aabb_spatial_kernel<<<mgrid, kTile, 0, st>>>(w, w.m, n, float_at_or_below(A.thr));
+        }
         spatial_diag_kernel<<<dim3(w.words, B), 512, 0, st>>>(w, w.m, n);
         MYDET_CUDA(cudaFuncSetAttribute(sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr));
         sweep_kernel<true><<<B, kSweepThreads, smem, st>>>(w, w.m, n, E);
