@@ -12,6 +12,11 @@
 // order is arbitrary, so the result does not depend on the compaction order.
 //
 // Stages (r1 profile notes in profiles/):
+//  (H)  when the decode kernel left a score histogram (mydet_decode_compact, score_hist): find the bin
+//       holding the K-th score from the histogram, then ONE pass over the scores puts everything above
+//       that bin straight into its slot and the bin's own candidates on a short list, of which the
+//       best are taken by counting (<= 128) or by the radix passes below.  Replaces (A0), (A), (B1):
+//       23 k of the kernel's 40 k cycles on the bench workload.  Without a histogram:
 //  (A0) stage 64-bit select keys (score key, ~index) in shared memory, count threshold survivors
 //  (A)  MSB-first 8-bit radix select of the K-th largest key; per-warp private histograms (scores
 //       cluster in a few digits: one shared histogram serialised 1024 threads on 2-3 addresses);
@@ -109,7 +114,8 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
     const float thr = P.conf_thres;
     const int K = P.topk;
 
-    if (tid == 0) { s_nsel = 0; s_total = 0; s_flags = 0; s_done = 0; s_prefix = 0ull; }
+    if (tid == 0) { s_nsel = 0; s_total = 0; s_flags = 0; s_done = 0; s_prefix = 0ull; s_ucount = 0; }
+    __syncthreads();
     PP_MARK(0);
 
     // select key of candidate i: (score key << 32) | ~tie index; 0 when it fails the threshold / is NaN
@@ -120,7 +126,264 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
         return ((unsigned long long)float_key(s) << 32) | (unsigned long long)(0xffffffffu - tie);
     };
     auto key_of = [&](int i) -> unsigned long long { return i < cache_n ? ckey[i] : key_global(i); };
+    auto key_list = [&](int i) -> unsigned long long { return ukey[i]; };
 
+    // ---- radix-select machinery, shared by the histogram front end (short list only) and the scan path
+    // start of a select: combine the per-warp AND / OR pairs left in hist[0..63] / hist[64..127] into the
+    // highest bit in which the keys differ at all (s_top) and their common prefix above it
+    auto select_init = [&](int need) {
+        __syncthreads();
+        if (warp == 0) {
+            unsigned a_lo = hist[2 * lane], a_hi = hist[2 * lane + 1], o_lo = hist[64 + 2 * lane], o_hi = hist[64 + 2 * lane + 1];
+            a_lo = __reduce_and_sync(0xffffffffu, a_lo); a_hi = __reduce_and_sync(0xffffffffu, a_hi);
+            o_lo = __reduce_or_sync(0xffffffffu, o_lo); o_hi = __reduce_or_sync(0xffffffffu, o_hi);
+            if (lane == 0) {
+                const unsigned long long all_and = ((unsigned long long)a_hi << 32) | a_lo, all_or = ((unsigned long long)o_hi << 32) | o_lo;
+                const unsigned long long diff = all_and ^ all_or;           // bits that are not common to every key
+                const int top = diff ? 63 - __clzll((long long)diff) : 0;   // highest differing bit
+                s_top = top;
+                s_need = need; s_prefix = (top >= 63) ? 0ull : (all_and & (~0ull << (top + 1)));
+            }
+        }
+        __syncthreads();
+    };
+    auto publish_and_or = [&](unsigned long long k_and, unsigned long long k_or) {
+        const unsigned a_lo = __reduce_and_sync(0xffffffffu, (unsigned)k_and), a_hi = __reduce_and_sync(0xffffffffu, (unsigned)(k_and >> 32));
+        const unsigned o_lo = __reduce_or_sync(0xffffffffu, (unsigned)k_or), o_hi = __reduce_or_sync(0xffffffffu, (unsigned)(k_or >> 32));
+        if (lane == 0) {
+            hist[2 * warp] = a_lo; hist[2 * warp + 1] = a_hi;
+            hist[64 + 2 * warp] = o_lo; hist[64 + 2 * warp + 1] = o_hi;
+        }
+    };
+    // one histogram pass over `cnt` keys delivered by key_at(i); digit = bits [hi_bit-7, hi_bit]
+    auto pass = [&](auto key_at, int cnt, int hi_bit, bool priv) -> int {
+        // priv: 32 padded per-warp histograms (all n keys: the digits cluster); else one shared one (short list)
+        const int shift = hi_bit >= 7 ? hi_bit - 7 : 0;
+        const unsigned dmask = (hi_bit >= 7) ? 255u : ((1u << (hi_bit + 1)) - 1u);
+        if (priv) { for (int i = tid; i < kPPWarps * 257; i += kPPThreads) whist[i] = 0u; }
+        else if (tid < 256) hist[tid] = 0u;
+        unsigned* myhist = priv ? whist + warp * 257 : hist;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        const unsigned long long himask = (hi_bit >= 63) ? 0ull : (~0ull << (hi_bit + 1));
+#pragma unroll 2
+        for (int base = 0; base < cnt; base += kPPThreads) {
+            const int i = base + tid;
+            unsigned digit = 256u;                              // not a candidate of this pass
+            if (i < cnt) {
+                const unsigned long long k = key_at(i);
+                if (k && (k & himask) == prefix) digit = (unsigned)(k >> shift) & dmask;
+            }
+            // scores cluster: when the whole warp agrees, one lane adds 32
+            const unsigned first = __shfl_sync(0xffffffffu, digit, 0);
+            if (__all_sync(0xffffffffu, digit == first)) {
+                if (lane == 0 && first < 256u) atomicAdd(&myhist[first], 32u);
+            } else if (digit < 256u) {
+                atomicAdd(&myhist[digit], 1u);
+            }
+        }
+        __syncthreads();
+        if (priv) {
+            if (tid < 256) {
+                unsigned sum = 0;
+#pragma unroll 8
+                for (int w = 0; w < kPPWarps; ++w) sum += whist[w * 257 + tid];
+                hist[tid] = sum;
+            }
+            __syncthreads();
+        }
+        if (tid < 32) {
+            // lane l owns digits [8l, 8l+8); find the digit that holds the need-th largest
+            unsigned h[8], mine = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { h[j] = hist[tid * 8 + j]; mine += h[j]; }
+            unsigned incl = mine;                               // suffix sum over lanes >= tid
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned v = __shfl_down_sync(0xffffffffu, incl, o);
+                if (tid + o < 32) incl += v;
+            }
+            const unsigned above = incl - mine;                 // keys in digits above this lane's range
+            const int need = s_need;
+            if ((int)above < need && need <= (int)(above + mine)) {
+                unsigned acc = above;
+#pragma unroll 1
+                for (int j = 7; j >= 0; --j) {
+                    if ((int)acc < need && need <= (int)(acc + h[j])) {
+                        s_prefix = prefix | ((unsigned long long)(tid * 8 + j) << shift);
+                        s_need = need - (int)acc;
+                        s_bucket = (int)h[j];
+                        if ((int)h[j] == need - (int)acc) s_done = 1;  // the whole bucket is taken
+                        break;
+                    }
+                    acc += h[j];
+                }
+            }
+        }
+        __syncthreads();
+        return shift;
+    };
+    // the undecided keys at or above the K-th key take the slots after the sure ones
+    auto append_list = [&](unsigned long long kth_key) {
+        const int ucount = min(s_ucount, kpad);
+        for (int base = 0; base < ucount; base += kPPThreads) {
+            const int u = base + tid;
+            const bool take = u < ucount && ukey[u] >= kth_key;
+            const unsigned bal = __ballot_sync(0xffffffffu, take);
+            if (bal) {
+                int slot0 = 0;
+                if (lane == 0) slot0 = atomicAdd(&s_nsel, __popc(bal));
+                slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                if (take) {
+                    const int slot = slot0 + __popc(bal & lt_mask);
+                    if (slot < kpad) { sel[slot] = uidx[u]; keys[slot] = ukey[u]; }
+                }
+            }
+        }
+        __syncthreads();
+    };
+
+    // ---- (H) histogram front end
+    bool hist_done = false;                      // block-uniform
+    if (P.hist != nullptr && !(flags & 4)) {
+        static_assert(kHistBins == 2 * kPPThreads, "thread t owns bins 2t and 2t+1");
+        int* hg = P.hist + (long long)b * kHistBins;
+        const int2 h = reinterpret_cast<const int2*>(hg)[tid];
+        if (P.consume) reinterpret_cast<int2*>(hg)[tid] = make_int2(0, 0);
+        for (int i = tid; i < kClassBins + 32; i += kPPThreads) { cstart[i] = 0; }
+        for (int i = tid; i < kClassBins; i += kPPThreads) { ccur[i] = 0; }
+        // suffix sums over the bins: `above` = candidates in bins above this thread's pair
+        const int mine = h.x + h.y;
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_down_sync(0xffffffffu, incl, o); if (lane + o < 32) incl += v; }
+        if (lane == 0) wtot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int v = wtot[lane];
+            int wi = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_down_sync(0xffffffffu, wi, o); if (lane + o < 32) wi += t; }
+            wtot[32 + lane] = wi - v;
+            if (lane == 0) s_total = wi;
+        }
+        __syncthreads();
+        const int htotal = s_total;
+        const bool consistent = (htotal == n);   // else: the histogram was not built from these candidates
+        if (consistent) {
+            const int above1 = wtot[32 + warp] + incl - mine;   // above bin 2*tid+1
+            const int above0 = above1 + h.y;                    // above bin 2*tid
+            if (htotal > K) {
+                // the one bin T with  above(T) < K <= above(T) + hist[T]  holds the K-th score
+                if (above1 < K && K <= above1 + h.y) { s_top = 2 * tid + 1; s_bucket = h.y; s_need = K - above1; }
+                else if (above0 < K && K <= above0 + h.x) { s_top = 2 * tid; s_bucket = h.x; s_need = K - above0; }
+            } else if (tid == 0) {
+                s_top = -1; s_bucket = 0; s_need = 0;           // everything is selected
+            }
+        }
+        __syncthreads();
+        PP_MARK(16);
+        if (consistent && s_bucket <= kpad) {
+            const int T = s_top, need = s_need;
+            const HistMap hm = P.hist_map;
+            // (H2) one pass: bins above T -> slots (one shared atomic per warp and round), bin T -> short list.
+            // Scores AND tie indices are loaded up front as one batch of independent loads (a dependent
+            // src_idx load per selected candidate inside the ballot loop serialised 8 round trips: 13 k cycles).
+            constexpr int U = 9;                 // 9 x 1024 >= 8 525: one round on the D1 @640 geometry
+#pragma unroll 1
+            for (int base = 0; base < n; base += U * kPPThreads) {
+                float sv[U];
+                unsigned tv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = base + u * kPPThreads + tid;
+                    sv[u] = (i < n) ? scores[i] : __int_as_float(0x7fc00000);
+                    tv[u] = (i < n && src) ? (unsigned)src[i] : (unsigned)i;
+                }
+                unsigned sure_bits = 0u, und_bits = 0u;
+                int off[U];                      // position among the warp's sure / undecided of this round
+                int ws = 0, wu = 0;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    off[u] = 0;
+                    if (base + u * kPPThreads < n) {            // block-uniform: skips the empty tail
+                        const float sc = sv[u];
+                        const int bin = hist_bin(float_key(sc), hm);
+                        const bool valid = (sc == sc);          // NaN pads the tail
+                        const bool sure = valid && bin > T, und = valid && bin == T;
+                        const unsigned bal_s = __ballot_sync(0xffffffffu, sure), bal_u = __ballot_sync(0xffffffffu, und);
+                        sure_bits |= (sure ? 1u : 0u) << u; und_bits |= (und ? 1u : 0u) << u;
+                        off[u] = sure ? ws + __popc(bal_s & lt_mask) : wu + __popc(bal_u & lt_mask);
+                        ws += __popc(bal_s); wu += __popc(bal_u);
+                    }
+                }
+                int bs = 0, bu = 0;
+                if (lane == 0) { if (ws) bs = atomicAdd(&s_nsel, ws); if (wu) bu = atomicAdd(&s_ucount, wu); }
+                bs = __shfl_sync(0xffffffffu, bs, 0); bu = __shfl_sync(0xffffffffu, bu, 0);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool sure = (sure_bits >> u) & 1u, und = (und_bits >> u) & 1u;
+                    if (sure || und) {
+                        const int i = base + u * kPPThreads + tid;
+                        const unsigned long long k = ((unsigned long long)float_key(sv[u]) << 32) | (unsigned long long)(0xffffffffu - tv[u]);
+                        if (sure) {
+                            const int slot = bs + off[u];
+                            if (slot < kpad) { sel[slot] = i; keys[slot] = k; }
+                        } else {
+                            const int q = bu + off[u];
+                            if (q < kpad) { ukey[q] = k; uidx[q] = i; }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            PP_MARK(17);
+            // (H3) the `need` best of the short list
+            const int ucount = min(s_ucount, kpad);
+            if (T >= 0 && ucount > 0) {
+                if (need >= ucount) {
+                    append_list(0ull);
+                } else if (ucount <= kPPThreads / 8) {
+                    // rank by counting, 8 threads per key (keys are unique: the tie index is)
+                    const int e = tid >> 3, part = tid & 7;
+                    const unsigned long long ke = (e < ucount) ? ukey[e] : 0ull;
+                    int rank = 0;
+                    if (e < ucount)
+                        for (int v = part; v < ucount; v += 8) rank += (ukey[v] > ke) ? 1 : 0;
+                    rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+                    rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+                    rank += __shfl_xor_sync(0xffffffffu, rank, 4);
+                    const bool take = e < ucount && part == 0 && rank < need;
+                    const unsigned bal = __ballot_sync(0xffffffffu, take);
+                    if (bal) {
+                        int slot0 = 0;
+                        if (lane == 0) slot0 = atomicAdd(&s_nsel, __popc(bal));
+                        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                        if (take) {
+                            const int slot = slot0 + __popc(bal & lt_mask);
+                            if (slot < kpad) { sel[slot] = uidx[e]; keys[slot] = ke; }
+                        }
+                    }
+                    __syncthreads();
+                } else {
+                    unsigned long long k_and = ~0ull, k_or = 0ull;
+                    for (int u = tid; u < ucount; u += kPPThreads) { const unsigned long long k = ukey[u]; k_and &= k; k_or |= k; }
+                    publish_and_or(k_and, k_or);
+                    select_init(need);
+                    int shift = pass(key_list, ucount, s_top, false);
+                    while (!(s_done || shift == 0)) shift = pass(key_list, ucount, shift - 1, false);
+                    append_list(s_prefix);
+                }
+            }
+            hist_done = true;
+        } else {
+            if (tid == 0) s_total = 0;           // the scan path below starts from scratch
+            __syncthreads();
+        }
+    }
+    PP_MARK(18);
+
+    if (!hist_done) {
     // ---- (A0) stage the keys, count the threshold survivors, AND / OR of all keys (common prefix)
     unsigned long long k_and = ~0ull, k_or = 0ull;
     {
@@ -148,13 +411,8 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
             }
         }
         local = __reduce_add_sync(0xffffffffu, local);
-        const unsigned a_lo = __reduce_and_sync(0xffffffffu, (unsigned)k_and), a_hi = __reduce_and_sync(0xffffffffu, (unsigned)(k_and >> 32));
-        const unsigned o_lo = __reduce_or_sync(0xffffffffu, (unsigned)k_or), o_hi = __reduce_or_sync(0xffffffffu, (unsigned)(k_or >> 32));
-        if (lane == 0) {
-            if (local) atomicAdd(&s_total, local);
-            hist[2 * warp] = a_lo; hist[2 * warp + 1] = a_hi;          // hist is free until the first pass
-            hist[64 + 2 * warp] = o_lo; hist[64 + 2 * warp + 1] = o_hi;
-        }
+        if (lane == 0 && local) atomicAdd(&s_total, local);
+        publish_and_or(k_and, k_or);                                    // hist is free until the first pass
     }
     __syncthreads();
     const int total = s_total;
@@ -167,134 +425,43 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
         // the keys differ at all.  Only the FIRST pass scans all n keys: the keys of the bucket that holds the
         // K-th key ("undecided", usually a few dozen) are then copied to a short list and the remaining passes
         // run on that list.  (Four full passes + two slot-assignment passes were 21 k of the kernel's 42 k cycles.)
-        {
-            if (warp == 0) {
-                // combine the per-warp AND / OR of the keys: lane w holds warp w's pair
-                unsigned a_lo = hist[2 * lane], a_hi = hist[2 * lane + 1], o_lo = hist[64 + 2 * lane], o_hi = hist[64 + 2 * lane + 1];
-                a_lo = __reduce_and_sync(0xffffffffu, a_lo); a_hi = __reduce_and_sync(0xffffffffu, a_hi);
-                o_lo = __reduce_or_sync(0xffffffffu, o_lo); o_hi = __reduce_or_sync(0xffffffffu, o_hi);
-                if (lane == 0) {
-                    const unsigned long long all_and = ((unsigned long long)a_hi << 32) | a_lo, all_or = ((unsigned long long)o_hi << 32) | o_lo;
-                    const unsigned long long diff = all_and ^ all_or;           // bits that are not common to every key
-                    const int top = diff ? 63 - __clzll((long long)diff) : 0;   // highest differing bit
-                    s_top = top;
-                    s_need = K; s_prefix = (top >= 63) ? 0ull : (all_and & (~0ull << (top + 1))); s_ucount = 0;
+        select_init(K);
+        if (tid == 0) s_ucount = 0;
+        int shift = pass(key_of, n, s_top, true);                           // the only pass over all n keys
+        bool done = s_done || shift == 0;
+        if (!done && s_bucket <= kpad) {
+            // copy the undecided bucket (key + candidate number) to the short list; count, per warp, the
+            // keys ABOVE the bucket: they are selected whatever happens next
+            const unsigned long long bucket = s_prefix, bmask = ~0ull << shift;
+            int sure = 0;
+#pragma unroll 1
+            for (int base = 0; base < n; base += kPPThreads) {
+                const int i = base + tid;
+                const unsigned long long k = (i < n) ? key_of(i) : 0ull;
+                const unsigned long long kb = k & bmask;
+                sure += __popc(__ballot_sync(0xffffffffu, k != 0ull && kb > bucket));
+                const bool inb = k != 0ull && kb == bucket;
+                const unsigned bal = __ballot_sync(0xffffffffu, inb);
+                if (bal) {
+                    int base_u = 0;
+                    if (lane == 0) base_u = atomicAdd(&s_ucount, __popc(bal));
+                    base_u = __shfl_sync(0xffffffffu, base_u, 0);
+                    if (inb) { const int u = base_u + __popc(bal & lt_mask); ukey[u] = k; uidx[u] = i; }
                 }
             }
+            if (lane == 0) wtot[warp] = sure;
             __syncthreads();
-            const int top = s_top;
-
-            // one histogram pass over `cnt` keys delivered by key_at(i); digit = bits [hi_bit-7, hi_bit]
-            auto pass = [&](auto key_at, int cnt, int hi_bit, bool priv) -> int {
-                // priv: 32 padded per-warp histograms (all n keys: the digits cluster); else one shared one (short list)
-                const int shift = hi_bit >= 7 ? hi_bit - 7 : 0;
-                const unsigned dmask = (hi_bit >= 7) ? 255u : ((1u << (hi_bit + 1)) - 1u);
-                if (priv) { for (int i = tid; i < kPPWarps * 257; i += kPPThreads) whist[i] = 0u; }
-                else if (tid < 256) hist[tid] = 0u;
-                unsigned* myhist = priv ? whist + warp * 257 : hist;
-                __syncthreads();
-                const unsigned long long prefix = s_prefix;
-                const unsigned long long himask = (hi_bit >= 63) ? 0ull : (~0ull << (hi_bit + 1));
-#pragma unroll 2
-                for (int base = 0; base < cnt; base += kPPThreads) {
-                    const int i = base + tid;
-                    unsigned digit = 256u;                              // not a candidate of this pass
-                    if (i < cnt) {
-                        const unsigned long long k = key_at(i);
-                        if (k && (k & himask) == prefix) digit = (unsigned)(k >> shift) & dmask;
-                    }
-                    // scores cluster: when the whole warp agrees, one lane adds 32
-                    const unsigned first = __shfl_sync(0xffffffffu, digit, 0);
-                    if (__all_sync(0xffffffffu, digit == first)) {
-                        if (lane == 0 && first < 256u) atomicAdd(&myhist[first], 32u);
-                    } else if (digit < 256u) {
-                        atomicAdd(&myhist[digit], 1u);
-                    }
-                }
-                __syncthreads();
-                if (priv) {
-                    if (tid < 256) {
-                        unsigned sum = 0;
-#pragma unroll 8
-                        for (int w = 0; w < kPPWarps; ++w) sum += whist[w * 257 + tid];
-                        hist[tid] = sum;
-                    }
-                    __syncthreads();
-                }
-                if (tid < 32) {
-                    // lane l owns digits [8l, 8l+8); find the digit that holds the need-th largest
-                    unsigned h[8], mine = 0;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { h[j] = hist[tid * 8 + j]; mine += h[j]; }
-                    unsigned incl = mine;                               // suffix sum over lanes >= tid
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const unsigned v = __shfl_down_sync(0xffffffffu, incl, o);
-                        if (tid + o < 32) incl += v;
-                    }
-                    const unsigned above = incl - mine;                 // keys in digits above this lane's range
-                    const int need = s_need;
-                    if ((int)above < need && need <= (int)(above + mine)) {
-                        unsigned acc = above;
-#pragma unroll 1
-                        for (int j = 7; j >= 0; --j) {
-                            if ((int)acc < need && need <= (int)(acc + h[j])) {
-                                s_prefix = prefix | ((unsigned long long)(tid * 8 + j) << shift);
-                                s_need = need - (int)acc;
-                                s_bucket = (int)h[j];
-                                if ((int)h[j] == need - (int)acc) s_done = 1;  // the whole bucket is taken
-                                break;
-                            }
-                            acc += h[j];
-                        }
-                    }
-                }
-                __syncthreads();
-                return shift;
-            };
-
-            PP_MARK(16);
-            int shift = pass(key_of, n, top, true);                           // the only pass over all n keys
-            PP_MARK(17);
-            bool done = s_done || shift == 0;
-            if (!done && s_bucket <= kpad) {
-                // copy the undecided bucket (key + candidate number) to the short list; count, per warp, the
-                // keys ABOVE the bucket: they are selected whatever happens next
-                const unsigned long long bucket = s_prefix, bmask = ~0ull << shift;
-                int sure = 0;
-#pragma unroll 1
-                for (int base = 0; base < n; base += kPPThreads) {
-                    const int i = base + tid;
-                    const unsigned long long k = (i < n) ? key_of(i) : 0ull;
-                    const unsigned long long kb = k & bmask;
-                    sure += __popc(__ballot_sync(0xffffffffu, k != 0ull && kb > bucket));
-                    const bool inb = k != 0ull && kb == bucket;
-                    const unsigned bal = __ballot_sync(0xffffffffu, inb);
-                    if (bal) {
-                        int base_u = 0;
-                        if (lane == 0) base_u = atomicAdd(&s_ucount, __popc(bal));
-                        base_u = __shfl_sync(0xffffffffu, base_u, 0);
-                        if (inb) { const int u = base_u + __popc(bal & lt_mask); ukey[u] = k; uidx[u] = i; }
-                    }
-                }
-                if (lane == 0) wtot[warp] = sure;
-                __syncthreads();
-                PP_MARK(18);
-                use_list = true;
-                list_bucket = bucket; list_mask = bmask;
-                const int ucount = s_ucount;
-                auto key_list = [&](int i) -> unsigned long long { return ukey[i]; };
-                int np_ = 0;
-                while (!done) {
-                    shift = pass(key_list, ucount, shift - 1, false);
-                    done = s_done || shift == 0;
-                    PP_MARK(19 + np_); ++np_;
-                }
-            } else {
-                while (!done) {                                         // heavy ties: keep scanning all keys
-                    shift = pass(key_of, n, shift - 1, true);
-                    done = s_done || shift == 0;
-                }
+            use_list = true;
+            list_bucket = bucket; list_mask = bmask;
+            const int ucount = s_ucount;
+            while (!done) {
+                shift = pass(key_list, ucount, shift - 1, false);
+                done = s_done || shift == 0;
+            }
+        } else {
+            while (!done) {                                         // heavy ties: keep scanning all keys
+                shift = pass(key_of, n, shift - 1, true);
+                done = s_done || shift == 0;
             }
         }
         kth = s_prefix;
@@ -341,25 +508,8 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
         }
     }
     __syncthreads();
-    if (use_list) {
-        // the undecided keys at or above the K-th key take the slots after the sure ones
-        const int ucount = s_ucount;
-        for (int base = 0; base < ucount; base += kPPThreads) {
-            const int u = base + tid;
-            const bool take = u < ucount && ukey[u] >= kth;
-            const unsigned bal = __ballot_sync(0xffffffffu, take);
-            if (bal) {
-                int slot0 = 0;
-                if (lane == 0) slot0 = atomicAdd(&s_nsel, __popc(bal));
-                slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-                if (take) {
-                    const int slot = slot0 + __popc(bal & lt_mask);
-                    if (slot < kpad) { sel[slot] = uidx[u]; keys[slot] = ukey[u]; }
-                }
-            }
-        }
-        __syncthreads();
-    }
+    if (use_list) append_list(kth);
+    }   // !hist_done
     const int m = min(s_nsel, kpad);
     PP_MARK(3);
 
@@ -593,6 +743,7 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
             if (nk > P.out_cap) { nk = P.out_cap; flags |= 2; }
             P.out_count[b] = nk;
             if (P.status) P.status[b] = flags | s_flags;
+            if (P.consume && P.counts) P.counts[b] = 0;   // every thread read it before the first barrier
             for (int q = 0; q < P.n_peers; ++q) {
                 int* counts_q = reinterpret_cast<int*>(P.peer[q] + P.peer_rows_total * P.out_cap * (P.n_param + 2));
                 counts_q[P.peer_row0 + b] = nk;

@@ -18,9 +18,9 @@ class BoundCall:
 
     Every buffer and every ctypes argument is prepared once; launch() / launch_decode() /
     launch_postprocess() are then single C calls with no Python-side allocation, so the host stays
-    far ahead of the GPU (a step is two kernel launches and one 256-byte memset)."""
+    far ahead of the GPU (a step is two kernel launches)."""
 
-    def __init__(self, pipe, raws):
+    def __init__(self, pipe, raws, self_cleaning=True):
         self.pipe = pipe
         self.levels = ops.LevelSet(raws, pipe.strides, pipe.anchors, pipe.conf_key)
         ls, L, ptr = self.levels, _lib.lib(), ops._ptr
@@ -34,7 +34,13 @@ class BoundCall:
                      'score': torch.empty(B, N, dtype=torch.float32, device=dev),
                      'cls': torch.empty(B, N, dtype=torch.int32, device=dev),
                      'idx': torch.empty(B, N, dtype=torch.int32, device=dev),
-                     'count': torch.zeros(B, dtype=torch.int32, device=dev)}
+                     'count': torch.zeros(B, dtype=torch.int32, device=dev),
+                     # score histogram of the candidates (decode -> post-process).  Zeroed here once; every
+                     # launch_postprocess*() consumes count and hist and leaves them zero for the next decode
+                     'hist': torch.zeros(B, _lib.HIST_BINS, dtype=torch.int32, device=dev)}
+        single = (k if 0 < k < N else N) <= _lib.SMALL_K      # only the single-kernel post-process reads / cleans them
+        clean = 1 if (single and self_cleaning) else 0        # else: launch_decode() memsets count and hist itself
+        self.self_cleaning = bool(clean)
         self.pp_workspace = ops._workspace(L.mydet_postprocess_workspace_bytes(B, N, k), dev)
         o, c = self.out, self.cand
         img_h, img_w = float(pipe.img_hw[0]), float(pipe.img_hw[1])
@@ -44,11 +50,13 @@ class BoundCall:
                              ptr(o['count']), ptr(o['status']), o['box'].shape[1], ptr(self.workspace),
                              self.workspace.numel())
         self._decode_args = (pipe.kind, ls.array, ls.n_levels, B, ls.n_cls, P, img_h, img_w, pipe.conf_thres,
-                             ptr(c['box']), ptr(c['score']), ptr(c['cls']), ptr(c['idx']), ptr(c['count']), N)
+                             ptr(c['box']), ptr(c['score']), ptr(c['cls']), ptr(c['idx']), ptr(c['count']), N,
+                             ptr(c['hist']) if single else ptr(None), clean)
         self._pp_args = (ptr(c['box']), ptr(c['score']), ptr(c['cls']), 0, ptr(c['idx']), ptr(c['count']), B, N, N, P,
                          ops.BOX_CXCYWH, float('-inf'), k, pipe.nms_thres, ptr(o['box']), ptr(o['score']),
                          ptr(o['cls']), ptr(o['idx']), ptr(o['count']), ptr(o['status']), o['box'].shape[1],
                          ptr(self.pp_workspace), self.pp_workspace.numel())
+        self._hist_args = (ptr(c['hist']) if single else ptr(None), pipe.conf_thres, clean)
         self.graph = None
 
     @staticmethod
@@ -63,7 +71,14 @@ class BoundCall:
         return self.out
 
     # stage-wise entry points: the same two kernels as launch(), exposed so that bench.py can put
-    # CUDA events around the decode kernel
+    # CUDA events around the decode kernel.  They must alternate: the decode relies on the candidate
+    # state (count, hist) being zero, which the post-process that consumed it guarantees
+    # (state_clean / consume of include/mydet.h) -- no memset in the step.  reset_state() re-arms it
+    # after a decode whose candidates were not post-processed.
+    def reset_state(self):
+        self.cand['count'].zero_()
+        self.cand['hist'].zero_()
+
     def launch_decode(self):
         rc = self._L.mydet_decode_compact(*self._decode_args, self._stream())
         if rc:
@@ -71,7 +86,7 @@ class BoundCall:
         return self.cand
 
     def launch_postprocess(self):
-        rc = self._L.mydet_postprocess(*self._pp_args, self._stream())
+        rc = self._L.mydet_postprocess(*self._pp_args, *self._hist_args, self._stream())
         if rc:
             _lib.check(rc, 'mydet_postprocess')
         return self.out
@@ -89,7 +104,7 @@ class BoundCall:
         return self
 
     def launch_postprocess_scatter(self):
-        rc = self._L.mydet_postprocess_scatter(*self._scatter_args, self._stream())
+        rc = self._L.mydet_postprocess_scatter(*self._scatter_args, *self._hist_args, self._stream())
         if rc:
             _lib.check(rc, 'mydet_postprocess_scatter')
         return self.out
@@ -122,8 +137,10 @@ class DetectionPipeline:
         self.conf_thres, self.nms_thres, self.topk = float(conf_thres), float(nms_thres), topk
         self.conf_key = conf_key
 
-    def bind(self, raws):
-        return BoundCall(self, raws)
+    def bind(self, raws, self_cleaning=True):
+        """self_cleaning=False: launch_decode() zeroes the candidate state itself (two memsets), so it may be
+        called without a matching launch_postprocess()."""
+        return BoundCall(self, raws, self_cleaning)
 
     def __call__(self, raws):
         """raws: list (one per level) of raw dicts of CUDA head views -> detections dict."""

@@ -32,7 +32,11 @@ else:
     _lib.lib().mydet_debug_pp_clocks.argtypes = [ctypes.POINTER(ctypes.c_longlong)]
     _lib.lib().mydet_debug_pp_clocks(buf)
     t = list(buf)
+    # histogram front end (marks 0,16,17,18,3) instead of A0 / A / B1 (marks 0,1,2,3)
+    print(f'{"H1 histogram scan":18s} {t[16] - t[0]:8d} cycles')
+    print(f'{"H2 one pass":18s} {t[17] - t[16]:8d} cycles')
+    print(f'{"H3 short list":18s} {t[18] - t[17]:8d} cycles')
     for i, nm in enumerate(NAMES):
-        print(f'{nm:18s} {t[i + 1] - t[i]:8d} cycles')
+        if i >= 3:
+            print(f'{nm:18s} {t[i + 1] - t[i]:8d} cycles')
     print(f'{"total":18s} {t[9] - t[0]:8d} cycles')
-    print('select detail: prefix', t[16]-t[1], 'pass1', t[17]-t[16], 'build', t[18]-t[17], 'list passes', [t[19+i]-t[18+i] for i in range(6) if t[19+i] > t[18+i]])

@@ -302,6 +302,101 @@ def test_detect_score_ties_are_broken_by_flat_index(golden):
             assert torch.equal(out['box'][b, :k].cpu(), box[b][want])
 
 
+def same_dets(a, b, what=''):
+    assert torch.equal(a['count'], b['count']), what
+    for i in range(a['count'].numel()):
+        n = int(a['count'][i])
+        for k in ('box', 'score', 'cls', 'idx'):
+            assert torch.equal(a[k][i, :n], b[k][i, :n]), (what, i, k)
+
+
+def _hist_map(lo):
+    """Python restatement of make_hist_map / hist_bin (csrc/common.cuh)."""
+    lo = np.float32(max(lo, 0.0)) if lo == lo else np.float32(0.0)
+    key = lambda f: int(np.float32(f).view(np.uint32)) | 0x80000000     # non-negative floats only
+    key_lo, rng, shift = key(lo), max(key(1.0) - key(lo), 0), 0
+    while (rng >> shift) >= 2048:
+        shift += 1
+    return key_lo, shift
+
+
+@pytest.mark.parametrize('quantise', [False, True])
+def test_histogram_select_equals_scan(golden, quantise):
+    """The decode kernel's score histogram (mydet_decode_compact score_hist) must hold exactly the candidates,
+    and the post-process that starts from it must give the same bits as the one that scans the scores:
+    random scores (short undecided list: counting), quantised logits (heavy ties: long list -> radix passes, or
+    a boundary bin above 1024 candidates -> fallback to the scan), every K regime, and `consume`."""
+    from mydetection_b200 import ops
+    g = golden('decode')
+    d = dev()
+    strides = (8, 16, 32, 64, 128)
+    raws = []
+    for li in range(5):
+        bb, cc = T(g[f'fcos{li}_bbox_in']), T(g[f'fcos{li}_cls_in'])
+        if quantise:
+            bb, cc = (bb * 2).round() / 2, cc.round()
+        raws.append({k: v.to(d) for k, v in efdet_views(bb, cc).items()})
+    ls = ops.LevelSet(raws, strides)
+    for thr in (-float('inf'), 0.005, 0.05, 0.3):
+        c = ops.decode_compact(ops.KIND_FCOS, ls, (256, 384), thr, want_hist=True)
+        torch.cuda.synchronize()
+        key_lo, shift = _hist_map(thr)
+        for b in range(c['count'].numel()):
+            n = int(c['count'][b])
+            keys = c['score'][b, :n].cpu().numpy().view(np.uint32).astype(np.int64) | 0x80000000
+            bins = np.clip((np.maximum(keys - key_lo, 0) >> shift), 0, 2047)
+            want = np.bincount(bins, minlength=2048)
+            assert np.array_equal(c['hist'][b].cpu().numpy(), want), (thr, b)
+        for topk in (1, 8, 100, 512, 1000, None):
+            plain = ops.postprocess(c['box'], c['score'], c['cls'], -float('inf'), 0.5, topk=topk, counts=c['count'],
+                                    src_idx=c['idx'])
+            fast = ops.postprocess(c['box'], c['score'], c['cls'], -float('inf'), 0.5, topk=topk, counts=c['count'],
+                                   src_idx=c['idx'], hist=c['hist'], hist_lo=thr)
+            torch.cuda.synchronize()
+            assert int(fast['status'].abs().sum()) == 0
+            same_dets(plain, fast, (thr, topk))
+        # consume: same result, and the candidate state is left zeroed
+        want = ops.postprocess(c['box'], c['score'], c['cls'], -float('inf'), 0.5, topk=512, counts=c['count'], src_idx=c['idx'])
+        got = ops.postprocess(c['box'], c['score'], c['cls'], -float('inf'), 0.5, topk=512, counts=c['count'],
+                              src_idx=c['idx'], hist=c['hist'], hist_lo=thr, consume=True)
+        torch.cuda.synchronize()
+        same_dets(want, got, 'consume')
+        assert int(c['count'].abs().sum()) == 0 and int(c['hist'].abs().sum()) == 0
+    # a histogram that does not belong to the candidates is detected (sum != count) and ignored
+    c = ops.decode_compact(ops.KIND_FCOS, ls, (256, 384), 0.05, want_hist=True)
+    want = ops.postprocess(c['box'], c['score'], c['cls'], -float('inf'), 0.5, topk=100, counts=c['count'], src_idx=c['idx'])
+    c['hist'][:, 2000] += 3
+    got = ops.postprocess(c['box'], c['score'], c['cls'], -float('inf'), 0.5, topk=100, counts=c['count'],
+                          src_idx=c['idx'], hist=c['hist'], hist_lo=0.05)
+    torch.cuda.synchronize()
+    same_dets(want, got, 'foreign histogram')
+
+
+def test_pipeline_stagewise_self_cleaning(golden):
+    """BoundCall.launch_decode() + launch_postprocess() without any memset in between steps (the post-process
+    leaves count and histogram zeroed): repeated steps must reproduce mydet_detect exactly."""
+    from mydetection_b200 import pipeline as pl
+    g = golden('decode')
+    d = dev()
+    strides = (8, 16, 32, 64, 128)
+    raws = [{k: v.to(d) for k, v in efdet_views(T(g[f'fcos{li}_bbox_in']), T(g[f'fcos{li}_cls_in'])).items()} for li in range(5)]
+    pipe = pl.DetectionPipeline('FCOS2', strides, 6, (256, 384), 0.05, 0.5, 512)
+    bc = pipe.bind(raws)
+    assert bc.self_cleaning
+    want = {k: v.clone() for k, v in bc.launch().items()}
+    for rep in range(3):
+        bc.launch_decode()
+        out = bc.launch_postprocess()
+        torch.cuda.synchronize()
+        assert int(bc.cand['count'].abs().sum()) == 0 and int(bc.cand['hist'].abs().sum()) == 0
+        same_dets(out, want, rep)
+    loose = pipe.bind(raws, self_cleaning=False)           # decode memsets its own state: may be repeated
+    loose.launch_decode(); loose.launch_decode()
+    out = loose.launch_postprocess()
+    torch.cuda.synchronize()
+    same_dets(out, want, 'self_cleaning=False')
+
+
 def test_fused_exchange_layout_single_gpu(golden):
     """mydet_postprocess_scatter with ONE peer (a local buffer): the rows the kernel's output stage stores
     into the gathered buffer must equal the separately packed detections, counts in the int32 tail."""
