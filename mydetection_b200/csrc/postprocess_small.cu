@@ -286,9 +286,16 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
         if (consistent && s_bucket <= kpad) {
             const int T = s_top, need = s_need;
             const HistMap hm = P.hist_map;
-            // (H2) one pass: bins above T -> slots (one shared atomic per warp and round), bin T -> short list.
-            // Scores AND tie indices are loaded up front as one batch of independent loads (a dependent
-            // src_idx load per selected candidate inside the ballot loop serialised 8 round trips: 13 k cycles).
+            // (H2) one pass: bins above T -> slots, bin T -> short list.  Scores AND tie indices are loaded up
+            // front as one batch of independent loads (a dependent src_idx load per selected candidate inside
+            // the loop serialised 8 round trips: 13 k cycles).  hist_bin is monotone in the key and the key in
+            // the float, so membership is two float compares against the edges of bin T (the clamped end bins
+            // are open):  bin >= T  <=>  score >= edge_lo,  bin > T  <=>  score >= edge_hi.
+            float edge_lo = -INFINITY, edge_hi = -INFINITY;     // T == -1: everything is selected
+            if (T >= 0) {
+                if (T > 0) edge_lo = key_float(hm.key_lo + ((uint32_t)T << hm.shift));
+                edge_hi = (T >= kHistBins - 1) ? INFINITY : key_float(hm.key_lo + ((uint32_t)(T + 1) << hm.shift));
+            }
             constexpr int U = 9;                 // 9 x 1024 >= 8 525: one round on the D1 @640 geometry
 #pragma unroll 1
             for (int base = 0; base < n; base += U * kPPThreads) {
@@ -297,41 +304,43 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int i = base + u * kPPThreads + tid;
-                    sv[u] = (i < n) ? scores[i] : __int_as_float(0x7fc00000);
+                    sv[u] = (i < n) ? scores[i] : __int_as_float(0x7fc00000);   // NaN pads the tail: fails both compares
                     tv[u] = (i < n && src) ? (unsigned)src[i] : (unsigned)i;
                 }
                 unsigned sure_bits = 0u, und_bits = 0u;
-                int off[U];                      // position among the warp's sure / undecided of this round
-                int ws = 0, wu = 0;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    off[u] = 0;
-                    if (base + u * kPPThreads < n) {            // block-uniform: skips the empty tail
-                        const float sc = sv[u];
-                        const int bin = hist_bin(float_key(sc), hm);
-                        const bool valid = (sc == sc);          // NaN pads the tail
-                        const bool sure = valid && bin > T, und = valid && bin == T;
-                        const unsigned bal_s = __ballot_sync(0xffffffffu, sure), bal_u = __ballot_sync(0xffffffffu, und);
-                        sure_bits |= (sure ? 1u : 0u) << u; und_bits |= (und ? 1u : 0u) << u;
-                        off[u] = sure ? ws + __popc(bal_s & lt_mask) : wu + __popc(bal_u & lt_mask);
-                        ws += __popc(bal_s); wu += __popc(bal_u);
-                    }
+                    const bool sure = sv[u] >= edge_hi, ge = sv[u] >= edge_lo;
+                    sure_bits |= (sure ? 1u : 0u) << u;
+                    und_bits |= ((ge && !sure) ? 1u : 0u) << u;
                 }
-                int bs = 0, bu = 0;
-                if (lane == 0) { if (ws) bs = atomicAdd(&s_nsel, ws); if (wu) bu = atomicAdd(&s_ucount, wu); }
-                bs = __shfl_sync(0xffffffffu, bs, 0); bu = __shfl_sync(0xffffffffu, bu, 0);
+                // slots: exclusive warp scan of (sure count | undecided count << 16), one shared atomic per warp
+                const int packed = __popc(sure_bits) | (__popc(und_bits) << 16);
+                int incl = packed;
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const bool sure = (sure_bits >> u) & 1u, und = (und_bits >> u) & 1u;
-                    if (sure || und) {
-                        const int i = base + u * kPPThreads + tid;
-                        const unsigned long long k = ((unsigned long long)float_key(sv[u]) << 32) | (unsigned long long)(0xffffffffu - tv[u]);
-                        if (sure) {
-                            const int slot = bs + off[u];
-                            if (slot < kpad) { sel[slot] = i; keys[slot] = k; }
-                        } else {
-                            const int q = bu + off[u];
-                            if (q < kpad) { ukey[q] = k; uidx[q] = i; }
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                const int wtotal = __shfl_sync(0xffffffffu, incl, 31);
+                int bs = 0, bu = 0;
+                if (lane == 0) {
+                    if (wtotal & 0xffff) bs = atomicAdd(&s_nsel, wtotal & 0xffff);
+                    if (wtotal >> 16) bu = atomicAdd(&s_ucount, wtotal >> 16);
+                }
+                bs = __shfl_sync(0xffffffffu, bs, 0) + ((incl - packed) & 0xffff);
+                bu = __shfl_sync(0xffffffffu, bu, 0) + ((incl - packed) >> 16);
+                if (sure_bits | und_bits) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const bool sure = (sure_bits >> u) & 1u, und = (und_bits >> u) & 1u;
+                        if (sure || und) {
+                            const int i = base + u * kPPThreads + tid;
+                            const unsigned long long k = ((unsigned long long)float_key(sv[u]) << 32) | (unsigned long long)(0xffffffffu - tv[u]);
+                            if (sure) {
+                                if (bs < kpad) { sel[bs] = i; keys[bs] = k; }
+                                ++bs;
+                            } else {
+                                if (bu < kpad) { ukey[bu] = k; uidx[bu] = i; }
+                                ++bu;
+                            }
                         }
                     }
                 }
@@ -618,43 +627,45 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
 
     // ---- (C) IoU bit matrix, LOWER triangle: mask[r][w] bit j  <=>  box (32w+j) ranks before r,
     // has r's class and iou > thr, i.e. it suppresses r if it is itself kept.  Row r only needs the
-    // words [seg0>>5, r>>5].  Rows with at most 8 predecessors in their class are done by their own
-    // thread (multi-class case: ~3 IoUs), longer ones by a whole warp, one 32-column word at a time.
-    constexpr int kShortRow = 8;
+    // words [seg0>>5, r>>5].  A group of 8 lanes owns a row and takes 8 predecessors per step, one IoU
+    // per lane: the multi-class case (a handful of predecessors per row) is ONE IoU latency per row instead
+    // of a serial per-thread loop (r1 profile: 6.7 k cycles), the single-class case stays balanced because
+    // rows are dealt round-robin (row r and row m-1-r cost the same as two average rows).
     {
         const float thr_f = P.nms_thr_f;
-        const int r = tid;
-        if (r < m && r - seg0 <= kShortRow) {
-            const float4 a = sbox[r];
-            const float aarea = sarea[r];
-            const int w_lo = seg0 >> 5, w_hi = r >> 5;      // at most two words
-            unsigned bits_lo = 0u, bits_hi = 0u;
+        const int grp = tid >> 3, part = tid & 7, gshift = lane & 24;   // group's byte inside the warp ballot
+        constexpr int kGroups = kPPThreads / 8;
+        const int rounds = (m + kGroups - 1) / kGroups;                 // block-uniform trip count: ballots stay full
 #pragma unroll 1
-            for (int j = seg0; j < r; ++j) {
-                const float4 c4 = sbox[j];
-                if (iou_corners(c4.x, c4.y, c4.z, c4.w, sarea[j], a.x, a.y, a.z, a.w, aarea) > thr_f) {
-                    if ((j >> 5) == w_lo) bits_lo |= 1u << (j & 31); else bits_hi |= 1u << (j & 31);
-                }
-            }
-            mask[r * Wp + w_lo] = bits_lo;
-            if (w_hi != w_lo) mask[r * Wp + w_hi] = bits_hi;
-        }
+        for (int t = 0; t < rounds; ++t) {
+            const int r = t * kGroups + grp;
+            const bool live = r < m;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            float aarea = 0.f;
+            int s0 = 0;
+            if (live) { a = sbox[r]; aarea = sarea[r]; s0 = sseg[r]; }
+            // chunks of 8 predecessors, aligned to 8 so that a chunk never straddles a mask word; the warp walks
+            // the longest row of its 4 groups.  The chunk holding r itself is included, so that every word
+            // of [seg0>>5, r>>5] the sweep reads is written.
+            const int j_first = s0 & ~7;
+            const int steps = live ? (((r - j_first) >> 3) + 1) : 0;
+            int wsteps = steps;
+            wsteps = max(wsteps, __shfl_xor_sync(0xffffffffu, wsteps, 8));
+            wsteps = max(wsteps, __shfl_xor_sync(0xffffffffu, wsteps, 16));
+            unsigned acc = 0u;                                          // the mask word being assembled (leader)
 #pragma unroll 1
-        for (int rr = warp; rr < m; rr += kPPWarps) {
-            const int s0 = sseg[rr];
-            if (rr - s0 <= kShortRow) continue;             // warp-uniform
-            const float4 a = sbox[rr];
-            const float aarea = sarea[rr];
-#pragma unroll 2
-            for (int w = rr >> 5; w >= (s0 >> 5); --w) {
-                const int j = (w << 5) + lane;
+            for (int c = 0; c < wsteps; ++c) {
+                const int j0 = j_first + (c << 3), j = j0 + part;
                 bool hit = false;
-                if (j >= s0 && j < rr) {
+                if (c < steps && j >= s0 && j < r) {
                     const float4 c4 = sbox[j];
                     hit = iou_corners(c4.x, c4.y, c4.z, c4.w, sarea[j], a.x, a.y, a.z, a.w, aarea) > thr_f;
                 }
-                const unsigned bits = __ballot_sync(0xffffffffu, hit);
-                if (lane == 0) mask[rr * Wp + w] = bits;
+                const unsigned byte = (__ballot_sync(0xffffffffu, hit) >> gshift) & 0xffu;
+                if (part == 0 && c < steps) {
+                    acc |= byte << (j0 & 24);
+                    if ((j0 & 24) == 24 || c == steps - 1) { mask[r * Wp + (j0 >> 5)] = acc; acc = 0u; }
+                }
             }
         }
     }
@@ -696,16 +707,23 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
 
     // ---- (E) ordered output, everything from shared memory
     {
-        int nk = 0;
-#pragma unroll 1
-        for (int w = 0; w < W; ++w) nk += __popc(keptw[w]);
+        // exclusive prefix of the kept-word popcounts, once (every thread looping over the words was 10 % of the
+        // kernel's instructions): wtot[w] = kept rows before word w, wtot[32] = all kept rows
+        if (warp == 0) {
+            const int v = (lane < W) ? __popc(keptw[lane]) : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            wtot[lane] = incl - v;
+            if (lane == 31) wtot[32] = incl;
+        }
+        __syncthreads();
+        int nk = wtot[32];
         const int r = tid;
         if (r < m) {
             const unsigned wbits = keptw[r >> 5];
             if ((wbits >> (r & 31)) & 1u) {
-                int pos = __popc(wbits & ((1u << (r & 31)) - 1u));
-#pragma unroll 1
-                for (int w = 0; w < (r >> 5); ++w) pos += __popc(keptw[w]);
+                const int pos = wtot[r >> 5] + __popc(wbits & ((1u << (r & 31)) - 1u));
                 if (pos < P.out_cap) {
                     const unsigned long long k = keys[r];
                     const int slot = pay[r];
