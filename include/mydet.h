@@ -34,7 +34,9 @@ extern "C" {
 #define MYDET_MAX_CLASS_ID 4095      /* class ids must lie in [0, 4095]                    */
 #define MYDET_MAX_CANDIDATES 1048575 /* candidates per image must be < 2^20                */
 #define MYDET_SMALL_K 1024           /* <= this many survivors: single fused kernel per image */
-#define MYDET_HIST_BINS 2048         /* bins of the per-image score histogram (see mydet_decode_compact) */
+
+#define MYDET_PP_CONSUME 1           /* mydet_postprocess flags                            */
+#define MYDET_PP_FORCE_SCAN 2
 
 enum {
     MYDET_OK = 0,
@@ -96,19 +98,13 @@ int mydet_decode_dense(int kind, const mydet_level_t* levels, int n_levels, int 
  *   cand_box (B,capacity,P) f32, cand_score (B,capacity) f32, cand_cls (B,capacity) i32,
  *   cand_idx (B,capacity) i32, cand_count (B) i32; the count may exceed capacity (the overflow is
  *   dropped, consumers clamp).
- *   score_hist  optional (B, MYDET_HIST_BINS) i32: per-image histogram of the candidates' scores over
- *               [max(conf_thres,0), 1] (bin = ((order-preserving key of the score) - key(lo)) >> shift,
- *               clamped; the map is fixed by lo alone).  mydet_postprocess uses it to find the bin that
- *               holds the top-k boundary without scanning the scores (the radix select's full passes were
- *               half of that kernel).  NULL = not wanted.
- *   state_clean 0: cand_count and score_hist are zeroed by this call (two memsets in front of the kernel);
- *               non-zero: the caller guarantees they are zero already -- true after a one-time memset and
- *               then after every mydet_postprocess(..., consume = 1) that consumed them. */
+ *   state_clean 0: cand_count is zeroed by this call (a memset in front of the kernel); non-zero: the
+ *               caller guarantees it is zero already -- true after a one-time memset and then after every
+ *               mydet_postprocess(..., consume = 1) that consumed the candidates. */
 int mydet_decode_compact(int kind, const mydet_level_t* levels, int n_levels, int batch, int n_cls,
                          int n_param, float img_h, float img_w, float conf_thres, float* cand_box,
                          float* cand_score, int32_t* cand_cls, int32_t* cand_idx,
-                         int32_t* cand_count, int32_t capacity, int32_t* score_hist, int state_clean,
-                         void* stream);
+                         int32_t* cand_count, int32_t capacity, int state_clean, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Threshold -> top-k -> class-aware axis-aligned NMS, batched.  Replaces
@@ -126,13 +122,12 @@ int mydet_decode_compact(int kind, const mydet_level_t* levels, int n_levels, in
  *   status   optional (B) i32 written with a bit mask: 1 = class id out of range, 2 = output
  *            truncated to out_cap, 4 = input count exceeded n_per_image, 8 = a src_idx
  *            value does not fit 20 bits (tie-break between equal scores then uses its low bits).
- *   score_hist optional (B, MYDET_HIST_BINS) i32 as written by mydet_decode_compact for exactly these
- *            candidates with hist_lo = max(its conf_thres, 0); requires counts, and conf_thres <= hist_lo
- *            (the candidates are already thresholded).  A histogram that does not add up to the count, or a
- *            boundary bin with more than MYDET_SMALL_K candidates (heavy ties), falls back to the scan.
- *            Used by the single-kernel path only (effective top-k <= MYDET_SMALL_K), ignored otherwise.
- *   consume  non-zero: counts[b] and the histogram are zeroed once read, which leaves the candidate
- *            state ready for the next mydet_decode_compact(..., state_clean = 1).  Single-kernel path only.
+ *   flags    MYDET_PP_CONSUME: counts[b] is zeroed once read, which leaves the candidate state ready for
+ *            the next mydet_decode_compact(..., state_clean = 1): a decode + post-process step is then two
+ *            kernel launches and nothing else.  Single-kernel path only (effective top-k <= MYDET_SMALL_K).
+ *            MYDET_PP_FORCE_SCAN: skip the sampled front end of the select (the kernel then scans every
+ *            score with radix passes, as it does on its own when the sample misleads); results are
+ *            identical either way -- the flag exists so that tests can prove that.
  * Workspace: mydet_postprocess_workspace_bytes(...) bytes, 256-byte aligned. */
 size_t mydet_postprocess_workspace_bytes(int batch, int n_per_image, int topk);
 int mydet_postprocess(const float* boxes, const float* scores, const void* cls, int cls_is_i64,
@@ -140,8 +135,7 @@ int mydet_postprocess(const float* boxes, const float* scores, const void* cls, 
                       int n_per_image, int n_param, int box_format, float conf_thres, int topk,
                       double nms_thres, float* out_box, float* out_score, int64_t* out_cls,
                       int32_t* out_idx, int32_t* out_count, int32_t* status, int out_cap,
-                      void* workspace, size_t workspace_bytes, int32_t* score_hist, float hist_lo,
-                      int consume, void* stream);
+                      void* workspace, size_t workspace_bytes, int flags, void* stream);
 
 /* mydet_postprocess fused with the path's only multi-GPU exchange: besides the local
  * outputs, every surviving detection is stored -- packed as P box floats, score, (float)class -- into the
@@ -158,8 +152,7 @@ int mydet_postprocess_scatter(const float* boxes, const float* scores, const voi
                               double nms_thres, float* out_box, float* out_score, int64_t* out_cls,
                               int32_t* out_idx, int32_t* out_count, int32_t* status, int out_cap,
                               void* workspace, size_t workspace_bytes, void* const* peer_bufs, int n_peers,
-                              int64_t image_offset, int64_t images_total, int32_t* score_hist, float hist_lo,
-                              int consume, void* stream);
+                              int64_t image_offset, int64_t images_total, int flags, void* stream);
 
 /* Whole path in one call: decode_compact + postprocess (what api/detection.py:168-172 does per
  * image, here for the batch).  Workspace: mydet_detect_workspace_bytes(...). */

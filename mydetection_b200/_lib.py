@@ -13,7 +13,6 @@ LIB_PATH = os.path.join(HERE, 'libmydet.so')
 MAX_LEVELS = 8
 MAX_ANCHORS = 16
 SMALL_K = 1024
-HIST_BINS = 2048
 MAX_CLASS_ID = 4095
 MAX_CANDIDATES = 1048575
 
@@ -39,14 +38,14 @@ SIGNATURES = {
     'mydet_decode_dense': (c_int, [c_int, ctypes.POINTER(Level), c_int, c_int, c_int, c_int, c_f32, c_f32,
                                    c_vp, c_vp, c_vp, c_i64, c_vp]),
     'mydet_decode_compact': (c_int, [c_int, ctypes.POINTER(Level), c_int, c_int, c_int, c_int, c_f32, c_f32, c_f32,
-                                     c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int32, c_vp, c_int, c_vp]),
+                                     c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int32, c_int, c_vp]),
     'mydet_postprocess_workspace_bytes': (c_sz, [c_int, c_int, c_int]),
     'mydet_postprocess': (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_f32,
                                   c_int, c_f64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_sz,
-                                  c_vp, c_f32, c_int, c_vp]),
+                                  c_int, c_vp]),
     'mydet_postprocess_scatter': (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_f32,
                                           c_int, c_f64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_sz,
-                                          ctypes.POINTER(c_vp), c_int, c_i64, c_i64, c_vp, c_f32, c_int, c_vp]),
+                                          ctypes.POINTER(c_vp), c_int, c_i64, c_i64, c_int, c_vp]),
     'mydet_detect_workspace_bytes': (c_sz, [c_int, c_i64, c_int, c_int]),
     'mydet_detect': (c_int, [c_int, ctypes.POINTER(Level), c_int, c_int, c_int, c_int, c_f32, c_f32, c_f32, c_int,
                              c_f64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),

@@ -37,8 +37,7 @@ static int postprocess_impl(const float* boxes, const float* scores, const void*
                             double nms_thres, float* out_box, float* out_score, int64_t* out_cls,
                             int32_t* out_idx, int32_t* out_count, int32_t* status, int out_cap,
                             void* workspace, size_t workspace_bytes, void* const* peers, int n_peers,
-                            int64_t peer_row0, int64_t peer_rows_total, int32_t* score_hist, float hist_lo,
-                            int consume, void* stream) {
+                            int64_t peer_row0, int64_t peer_rows_total, int pp_flags, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     MYDET_REQUIRE(n_peers >= 0 && n_peers <= 8, "n_peers must be in [0,8]");
     MYDET_REQUIRE(n_peers == 0 || (peers && peer_row0 >= 0 && peer_row0 + batch <= peer_rows_total),
@@ -48,9 +47,8 @@ static int postprocess_impl(const float* boxes, const float* scores, const void*
     MYDET_REQUIRE(box_format == MYDET_BOX_CXCYWH || box_format == MYDET_BOX_X1Y1X2Y2, "unknown box format");
     MYDET_REQUIRE(n_per_image <= MYDET_MAX_CANDIDATES, "more than %d candidates per image", MYDET_MAX_CANDIDATES);
     MYDET_REQUIRE(out_count && (batch == 0 || out_cap > 0), "NULL out_count or out_cap <= 0");
-    MYDET_REQUIRE(!score_hist || counts, "score_hist needs counts");
-    MYDET_REQUIRE(!score_hist || !(conf_thres > (hist_lo > 0.f ? hist_lo : 0.f)),
-                  "conf_thres %g is above the histogram's lower bound %g", (double)conf_thres, (double)hist_lo);
+    const int consume = pp_flags & MYDET_PP_CONSUME;
+    MYDET_REQUIRE(!consume || counts, "consume needs counts");
     if (batch == 0) return 0;
     const bool single = effective_k(n_per_image, topk) <= MYDET_SMALL_K;
     MYDET_REQUIRE(!consume || (single && n_per_image > 0), "consume is implemented for the single-kernel path only");
@@ -71,7 +69,7 @@ static int postprocess_impl(const float* boxes, const float* scores, const void*
         P.out_idx = out_idx; P.out_count = out_count; P.status = status; P.out_cap = out_cap;
         P.n_peers = n_peers; P.peer_row0 = peer_row0; P.peer_rows_total = peer_rows_total;
         for (int q = 0; q < 8; ++q) P.peer[q] = q < n_peers ? static_cast<float*>(peers[q]) : nullptr;
-        P.hist = score_hist; P.hist_map = make_hist_map(hist_lo); P.consume = consume;
+        P.consume = consume; P.force_scan = (pp_flags & MYDET_PP_FORCE_SCAN) ? 1 : 0;
         return launch_postprocess_small(P, batch, st);
     }
     MYDET_REQUIRE(n_peers == 0, "the fused exchange is implemented for the single-kernel path only (<= %d survivors)", MYDET_SMALL_K);
@@ -86,12 +84,10 @@ MYDET_API int mydet_postprocess(const float* boxes, const float* scores, const v
                                 int n_per_image, int n_param, int box_format, float conf_thres, int topk,
                                 double nms_thres, float* out_box, float* out_score, int64_t* out_cls,
                                 int32_t* out_idx, int32_t* out_count, int32_t* status, int out_cap,
-                                void* workspace, size_t workspace_bytes, int32_t* score_hist, float hist_lo,
-                                int consume, void* stream) {
+                                void* workspace, size_t workspace_bytes, int flags, void* stream) {
     return postprocess_impl(boxes, scores, cls, cls_is_i64, src_idx, counts, batch, pitch, n_per_image, n_param,
                             box_format, conf_thres, topk, nms_thres, out_box, out_score, out_cls, out_idx, out_count,
-                            status, out_cap, workspace, workspace_bytes, nullptr, 0, 0, 0, score_hist, hist_lo, consume,
-                            stream);
+                            status, out_cap, workspace, workspace_bytes, nullptr, 0, 0, 0, flags, stream);
 }
 
 MYDET_API int mydet_postprocess_scatter(const float* boxes, const float* scores, const void* cls, int cls_is_i64,
@@ -100,38 +96,28 @@ MYDET_API int mydet_postprocess_scatter(const float* boxes, const float* scores,
                                         double nms_thres, float* out_box, float* out_score, int64_t* out_cls,
                                         int32_t* out_idx, int32_t* out_count, int32_t* status, int out_cap,
                                         void* workspace, size_t workspace_bytes, void* const* peer_bufs, int n_peers,
-                                        int64_t image_offset, int64_t images_total, int32_t* score_hist,
-                                        float hist_lo, int consume, void* stream) {
+                                        int64_t image_offset, int64_t images_total, int flags, void* stream) {
     return postprocess_impl(boxes, scores, cls, cls_is_i64, src_idx, counts, batch, pitch, n_per_image, n_param,
                             box_format, conf_thres, topk, nms_thres, out_box, out_score, out_cls, out_idx, out_count,
                             status, out_cap, workspace, workspace_bytes, peer_bufs, n_peers, image_offset, images_total,
-                            score_hist, hist_lo, consume, stream);
+                            flags, stream);
 }
 
 // ---- whole path: candidate buffers live in the workspace
 namespace {
-struct DetectWs {
-    float* box; float* score; int32_t* cls; int32_t* idx;
-    int32_t* count; int32_t* hist; size_t state_bytes;   // count and histogram are contiguous: one memset
-    void* rest; size_t rest_bytes;
-};
+struct DetectWs { float* box; float* score; int32_t* cls; int32_t* idx; int32_t* count; void* rest; size_t rest_bytes; };
 size_t carve_detect(DetectWs& w, void* base, size_t bytes, int batch, int64_t cap, int n_param, int topk) {
     size_t off = 0;
     auto take = [&](size_t b) { size_t o = off; off = align_up(off + b, 256); return o; };
     const size_t bn = (size_t)batch * (size_t)cap;
     const size_t o_box = take(bn * n_param * 4), o_score = take(bn * 4), o_cls = take(bn * 4), o_idx = take(bn * 4);
-    const size_t cnt_bytes = align_up((size_t)batch * 4, 256);
-    const bool single = effective_k((int)cap, topk) <= MYDET_SMALL_K;       // only that path reads the histogram
-    const size_t state_bytes = cnt_bytes + (single ? (size_t)batch * kHistBins * 4 : 0);
-    const size_t o_cnt = take(state_bytes);
+    const size_t o_cnt = take((size_t)batch * 4);
     const size_t pp = mydet_postprocess_workspace_bytes(batch, (int)cap, topk);
     const size_t o_rest = take(pp);
     if (base) {
         char* p = static_cast<char*>(base);
         w.box = (float*)(p + o_box); w.score = (float*)(p + o_score); w.cls = (int32_t*)(p + o_cls);
-        w.idx = (int32_t*)(p + o_idx); w.count = (int32_t*)(p + o_cnt);
-        w.hist = single ? (int32_t*)(p + o_cnt + cnt_bytes) : nullptr; w.state_bytes = state_bytes;
-        w.rest = p + o_rest; w.rest_bytes = pp;
+        w.idx = (int32_t*)(p + o_idx); w.count = (int32_t*)(p + o_cnt); w.rest = p + o_rest; w.rest_bytes = pp;
     }
     return off;
 }
@@ -157,14 +143,13 @@ MYDET_API int mydet_detect(int kind, const mydet_level_t* levels, int n_levels, 
         return MYDET_ERR_WORKSPACE;
     }
     if (batch == 0) return 0;
-    MYDET_CUDA(cudaMemsetAsync(w.count, 0, w.state_bytes, st));
     int rc = decode_compact_impl(kind, levels, n_levels, batch, n_cls, n_param, img_h, img_w, conf_thres, w.box, w.score,
-                                 w.cls, w.idx, w.count, (int32_t)n_total, w.hist, /*state_clean=*/1, nullptr, st);
+                                 w.cls, w.idx, w.count, (int32_t)n_total, /*state_clean=*/0, nullptr, st);
     if (rc) return rc;
     // the decode already applied conf_thres; the post-process sees only survivors
     return mydet_postprocess(w.box, w.score, w.cls, 0, w.idx, w.count, batch, n_total, (int)n_total, n_param,
                              MYDET_BOX_CXCYWH, -INFINITY, topk, nms_thres, out_box, out_score, out_cls, out_idx,
-                             out_count, status, out_cap, w.rest, w.rest_bytes, w.hist, conf_thres, /*consume=*/0, st);
+                             out_count, status, out_cap, w.rest, w.rest_bytes, /*flags=*/0, st);
 }
 
 namespace mydet {

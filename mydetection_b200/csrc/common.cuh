@@ -43,29 +43,6 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 constexpr int kNumSMs = 148;  // B200
 
-// ---- per-image score histogram shared by the decode kernel (producer) and the post-process kernel
-// (consumer): MYDET_HIST_BINS bins over the order-preserving keys of [lo, 1]; fixed by `lo` alone.
-constexpr int kHistBins = MYDET_HIST_BINS;
-struct HistMap {
-    uint32_t key_lo;   // key of max(lo, 0)
-    int shift;         // smallest shift with (key(1.0f) - key_lo) >> shift < kHistBins
-};
-static inline uint32_t float_key_host(float s) {
-    union { float f; uint32_t u; } v;
-    v.f = s + 0.0f;
-    return (v.u & 0x80000000u) ? ~v.u : (v.u | 0x80000000u);
-}
-static inline HistMap make_hist_map(float lo) {
-    if (!(lo > 0.0f)) lo = 0.0f;          // scores are products / roots of sigmoids: never negative
-    HistMap m;
-    m.key_lo = float_key_host(lo);
-    const uint32_t hi = float_key_host(1.0f);
-    const uint32_t range = hi > m.key_lo ? hi - m.key_lo : 0u;
-    m.shift = 0;
-    while ((range >> m.shift) >= (uint32_t)kHistBins) ++m.shift;
-    return m;
-}
-
 // ------------------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__
 
@@ -97,12 +74,6 @@ __device__ __forceinline__ uint32_t float_key(float s) {
 __device__ __forceinline__ float key_float(uint32_t k) {
     uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
     return __uint_as_float(u);
-}
-
-// bin of a score key; monotone (non-strictly) in the key, clamped at both ends
-__device__ __forceinline__ int hist_bin(uint32_t key, const HistMap& m) {
-    const uint32_t d = (key > m.key_lo ? key - m.key_lo : 0u) >> m.shift;
-    return (int)min(d, (uint32_t)(kHistBins - 1));
 }
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }

@@ -63,8 +63,6 @@ struct DecodeParams {
     int* cand_idx;
     int* cand_count;
     int capacity;
-    int* hist;          // optional (B, kHistBins) score histogram of the candidates
-    HistMap hist_map;
 };
 
 // Running arg-max over class logits, plus the runner-up value.
@@ -331,14 +329,6 @@ __device__ __forceinline__ void decode_unit(const DecodeParams& P, const LevelDe
             total += __popc(ballots[j]);
         }
         if (total == 0) return;
-        if (P.hist) {
-            // fire-and-forget RED.ADDs (no return value): the post-process kernel finds the top-k boundary
-            // bin from this histogram instead of scanning all scores
-            int* hb = P.hist + (long long)b * kHistBins;
-#pragma unroll
-            for (int j = 0; j < VEC; ++j)
-                if ((ballots[j] >> lane) & 1u) atomicAdd(hb + hist_bin(float_key(score[j]), P.hist_map), 1);
-        }
         int base = 0;
         if (lane == 0) base = atomicAdd(P.cand_count + b, total);
         base = __shfl_sync(0xffffffffu, base, 0);
@@ -458,7 +448,7 @@ static int launch_decode(int kind, const DecodeParams& P, int blocks, cudaStream
 int decode_compact_impl(int kind, const mydet_level_t* levels, int n_levels, int batch, int n_cls, int n_param,
                         float img_h, float img_w, float conf_thres, float* cand_box, float* cand_score,
                         int32_t* cand_cls, int32_t* cand_idx, int32_t* cand_count, int32_t capacity,
-                        int32_t* score_hist, int state_clean, int64_t* n_total_out, cudaStream_t st) {
+                        int state_clean, int64_t* n_total_out, cudaStream_t st) {
     DecodeParams P;
     int blocks = 0;
     int64_t n_total = 0;
@@ -469,13 +459,9 @@ int decode_compact_impl(int kind, const mydet_level_t* levels, int n_levels, int
     P.thr = conf_thres;
     P.cand_box = cand_box; P.cand_score = cand_score; P.cand_cls = cand_cls; P.cand_idx = cand_idx;
     P.cand_count = cand_count; P.capacity = capacity;
-    P.hist = score_hist; P.hist_map = make_hist_map(conf_thres);
     if (n_total_out) *n_total_out = n_total;
     if (batch == 0) return 0;
-    if (!state_clean) {
-        MYDET_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(int32_t) * (size_t)batch, st));
-        if (score_hist) MYDET_CUDA(cudaMemsetAsync(score_hist, 0, sizeof(int32_t) * (size_t)batch * kHistBins, st));
-    }
+    if (!state_clean) MYDET_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(int32_t) * (size_t)batch, st));
     return launch_decode<true>(kind, P, blocks, st);
 }
 
@@ -502,8 +488,8 @@ MYDET_API int mydet_decode_dense(int kind, const mydet_level_t* levels, int n_le
 MYDET_API int mydet_decode_compact(int kind, const mydet_level_t* levels, int n_levels, int batch, int n_cls,
                                    int n_param, float img_h, float img_w, float conf_thres, float* cand_box,
                                    float* cand_score, int32_t* cand_cls, int32_t* cand_idx, int32_t* cand_count,
-                                   int32_t capacity, int32_t* score_hist, int state_clean, void* stream) {
+                                   int32_t capacity, int state_clean, void* stream) {
     return decode_compact_impl(kind, levels, n_levels, batch, n_cls, n_param, img_h, img_w, conf_thres, cand_box,
-                               cand_score, cand_cls, cand_idx, cand_count, capacity, score_hist, state_clean, nullptr,
+                               cand_score, cand_cls, cand_idx, cand_count, capacity, state_clean, nullptr,
                                (cudaStream_t)stream);
 }

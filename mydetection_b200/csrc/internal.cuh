@@ -30,10 +30,8 @@ struct PPParams {
     int n_peers;
     long long peer_row0;        // first image row of this rank inside the gathered buffer
     long long peer_rows_total;  // images in the gathered buffer (all ranks)
-    // score histogram written by the decode kernel for these candidates (optional) and its bin map
-    int* hist;
-    HistMap hist_map;
-    int consume;                // zero counts[b] and the histogram once they have been read
+    int consume;                // zero counts[b] once it has been read
+    int force_scan;             // skip the sampled front end of the select (tests)
 };
 int launch_postprocess_small(const PPParams& P, int batch, cudaStream_t st);
 
@@ -52,6 +50,6 @@ size_t large_workspace_bytes(int batch, int n, bool rot);
 int decode_compact_impl(int kind, const mydet_level_t* levels, int n_levels, int batch, int n_cls, int n_param,
                         float img_h, float img_w, float conf_thres, float* cand_box, float* cand_score,
                         int32_t* cand_cls, int32_t* cand_idx, int32_t* cand_count, int32_t capacity,
-                        int32_t* score_hist, int state_clean, int64_t* n_total_out, cudaStream_t st);
+                        int state_clean, int64_t* n_total_out, cudaStream_t st);
 
 }  // namespace mydet

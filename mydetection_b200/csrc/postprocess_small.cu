@@ -12,11 +12,10 @@
 // order is arbitrary, so the result does not depend on the compaction order.
 //
 // Stages (r1 profile notes in profiles/):
-//  (H)  when the decode kernel left a score histogram (mydet_decode_compact, score_hist): find the bin
-//       holding the K-th score from the histogram, then ONE pass over the scores puts everything above
-//       that bin straight into its slot and the bin's own candidates on a short list, of which the
-//       best are taken by counting (<= 128) or by the radix passes below.  Replaces (A0), (A), (B1):
-//       23 k of the kernel's 40 k cycles on the bench workload.  Without a histogram:
+//  (S)  sampled front end: bracket the K-th score from a 2048-bin histogram of a SAMPLE of the scores, copy
+//       the candidates above that edge to a short list in ONE pass, verify the list holds >= K of them,
+//       radix-select on the list alone.  Exact whatever the sample says; when the check fails (or the list
+//       would not fit) the scan path (A0)-(B1) runs instead:
 //  (A0) stage 64-bit select keys (score key, ~index) in shared memory, count threshold survivors
 //  (A)  MSB-first 8-bit radix select of the K-th largest key; per-warp private histograms (scores
 //       cluster in a few digits: one shared histogram serialised 1024 threads on 2-3 addresses);
@@ -61,6 +60,7 @@ __host__ __device__ inline size_t pp_mask_bytes(int kpad) {
 }
 
 constexpr int kClassBins = MYDET_MAX_CLASS_ID + 1;   // 4096
+constexpr int kHistBins = 2 * kPPThreads;            // sample histogram of the front end
 
 __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const PPParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
     unsigned long long* ukey = reinterpret_cast<unsigned long long*>(gbox);                 // undecided bucket of the select: keys ...
     int* uidx = reinterpret_cast<int*>(sarea);                                              // ... and candidate numbers (both die before (B2))
     __shared__ unsigned long long s_prefix;
-    __shared__ int s_need, s_done, s_nsel, s_total, s_flags, s_bucket, s_ucount, s_top;
+    __shared__ int s_need, s_done, s_nsel, s_total, s_flags, s_bucket, s_ucount, s_top, s_nvalid;
 
     int n = P.n_per_image;
     int flags = 0;
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
     const float thr = P.conf_thres;
     const int K = P.topk;
 
-    if (tid == 0) { s_nsel = 0; s_total = 0; s_flags = 0; s_done = 0; s_prefix = 0ull; s_ucount = 0; }
+    if (tid == 0) { s_nsel = 0; s_total = 0; s_flags = 0; s_done = 0; s_prefix = 0ull; s_ucount = 0; s_nvalid = 0; }
     __syncthreads();
     PP_MARK(0);
 
@@ -243,17 +243,48 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
         __syncthreads();
     };
 
-    // ---- (H) histogram front end
-    bool hist_done = false;                      // block-uniform
-    if (P.hist != nullptr && !(flags & 4)) {
+    // ---- (S) sampled front end.  The K-th score is bracketed from a SAMPLE of the scores (every s-th
+    // candidate, <= 2048 of them, one or two loads per thread) binned into a 2048-bin shared-memory histogram:
+    // the bin below which  K/s + 4 sqrt(K/s) + 4  samples lie gives a float edge that, with high probability,
+    // has between K and ~1.5 K candidates at or above it.  ONE pass over all scores then copies exactly those
+    // candidates to a short list and counts them; if the list holds >= K entries (or every valid candidate)
+    // the top K of the list are the top K of the image -- exact, whatever the sample looked like -- and are
+    // picked by radix passes over the list alone.  Otherwise (estimate too tight, list overflow, huge n) the
+    // scan path below runs.  Replaces staging + full radix pass + slot assignment: 23 k -> ~9 k cycles.
+    bool fast_done = false;                      // block-uniform
+    const int list_cap = 2 * kpad;
+    if (!P.force_scan) {
+        unsigned* sh = mask;                     // 2048 sample bins (the mask region is free until (B2))
+        int* lidx = reinterpret_cast<int*>(sbox);            // list: candidate numbers (2 kpad ints; tkey's space)
+        const int stride = max(1, (n + 2 * kPPThreads - 1) / (2 * kPPThreads));
         static_assert(kHistBins == 2 * kPPThreads, "thread t owns bins 2t and 2t+1");
-        int* hg = P.hist + (long long)b * kHistBins;
-        const int2 h = reinterpret_cast<const int2*>(hg)[tid];
-        if (P.consume) reinterpret_cast<int2*>(hg)[tid] = make_int2(0, 0);
-        for (int i = tid; i < kClassBins + 32; i += kPPThreads) { cstart[i] = 0; }
-        for (int i = tid; i < kClassBins; i += kPPThreads) { ccur[i] = 0; }
-        // suffix sums over the bins: `above` = candidates in bins above this thread's pair
-        const int mine = h.x + h.y;
+        reinterpret_cast<uint2*>(sh)[tid] = make_uint2(0u, 0u);
+        const int i0 = tid * stride + (stride >> 1), i1 = (tid + kPPThreads) * stride + (stride >> 1);
+        const float q0 = (i0 < n) ? scores[i0] : __int_as_float(0x7fc00000);
+        const float q1 = (i1 < n) ? scores[i1] : __int_as_float(0x7fc00000);
+        const bool ok0 = q0 >= thr, ok1 = q1 >= thr;            // NaN fails
+        // range of the valid samples: the bins are linear over [smin, smax], whatever the score scale is
+        {
+            unsigned kmin = 0xffffffffu, kmax = 0u;
+            if (ok0) { const unsigned k = float_key(q0); kmin = min(kmin, k); kmax = max(kmax, k); }
+            if (ok1) { const unsigned k = float_key(q1); kmin = min(kmin, k); kmax = max(kmax, k); }
+            kmin = __reduce_min_sync(0xffffffffu, kmin); kmax = __reduce_max_sync(0xffffffffu, kmax);
+            if (lane == 0) { wtot[warp] = (int)kmin; wtot[32 + warp] = (int)kmax; }
+        }
+        __syncthreads();
+        const float smin = key_float(__reduce_min_sync(0xffffffffu, (unsigned)wtot[lane]));
+        const float smax = key_float(__reduce_max_sync(0xffffffffu, (unsigned)wtot[32 + lane]));
+        const float scale = (smax > smin) ? __fdiv_rn((float)(kHistBins - 1), __fsub_rn(smax, smin)) : 0.0f;
+        auto sample_bin = [&](float q) -> int {
+            const float f = __fmul_rn(__fsub_rn(q, smin), scale);
+            return min(kHistBins - 1, max(0, (int)f));          // the verification below makes rounding harmless
+        };
+        if (ok0) atomicAdd(&sh[sample_bin(q0)], 1u);
+        if (ok1) atomicAdd(&sh[sample_bin(q1)], 1u);
+        __syncthreads();
+        // suffix sums over the bins: `above` = samples in bins above this thread's pair
+        const uint2 h = reinterpret_cast<const uint2*>(sh)[tid];
+        const int mine = (int)(h.x + h.y);
         int incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_down_sync(0xffffffffu, incl, o); if (lane + o < 32) incl += v; }
@@ -268,35 +299,34 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
             if (lane == 0) s_total = wi;
         }
         __syncthreads();
-        const int htotal = s_total;
-        const bool consistent = (htotal == n);   // else: the histogram was not built from these candidates
-        if (consistent) {
+        const int stotal = s_total;              // valid samples
+        const float ks = (float)K / (float)stride;
+        const int target = (stride == 1) ? K : (int)(ks + 4.0f * sqrtf(ks) + 4.0f);
+        {
             const int above1 = wtot[32 + warp] + incl - mine;   // above bin 2*tid+1
-            const int above0 = above1 + h.y;                    // above bin 2*tid
-            if (htotal > K) {
-                // the one bin T with  above(T) < K <= above(T) + hist[T]  holds the K-th score
-                if (above1 < K && K <= above1 + h.y) { s_top = 2 * tid + 1; s_bucket = h.y; s_need = K - above1; }
-                else if (above0 < K && K <= above0 + h.x) { s_top = 2 * tid; s_bucket = h.x; s_need = K - above0; }
+            const int above0 = above1 + (int)h.y;               // above bin 2*tid
+            if (stotal >= target) {
+                // the one bin T with  above(T) < target <= above(T) + hist[T]
+                if (above1 < target && target <= above1 + (int)h.y) { s_top = 2 * tid + 1; s_bucket = above1 + (int)h.y; }
+                else if (above0 < target && target <= above0 + (int)h.x) { s_top = 2 * tid; s_bucket = above0 + (int)h.x; }
             } else if (tid == 0) {
-                s_top = -1; s_bucket = 0; s_need = 0;           // everything is selected
+                s_top = 0; s_bucket = stotal;                   // few valid candidates: all of them go to the list
             }
         }
         __syncthreads();
         PP_MARK(16);
-        if (consistent && s_bucket <= kpad) {
-            const int T = s_top, need = s_need;
-            const HistMap hm = P.hist_map;
-            // (H2) one pass: bins above T -> slots, bin T -> short list.  Scores AND tie indices are loaded up
-            // front as one batch of independent loads (a dependent src_idx load per selected candidate inside
-            // the loop serialised 8 round trips: 13 k cycles).  hist_bin is monotone in the key and the key in
-            // the float, so membership is two float compares against the edges of bin T (the clamped end bins
-            // are open):  bin >= T  <=>  score >= edge_lo,  bin > T  <=>  score >= edge_hi.
-            float edge_lo = -INFINITY, edge_hi = -INFINITY;     // T == -1: everything is selected
-            if (T >= 0) {
-                if (T > 0) edge_lo = key_float(hm.key_lo + ((uint32_t)T << hm.shift));
-                edge_hi = (T >= kHistBins - 1) ? INFINITY : key_float(hm.key_lo + ((uint32_t)(T + 1) << hm.shift));
-            }
+        for (int i = tid; i < kClassBins + 32; i += kPPThreads) { cstart[i] = 0; }   // class histogram (the sample bins are dead)
+        for (int i = tid; i < kClassBins; i += kPPThreads) { ccur[i] = 0; }
+        // expected list length; leave the fast path to the scan when it would not fit
+        if ((long long)s_bucket * stride <= (long long)list_cap - list_cap / 8) {
+            const int T = s_top;
+            // lower edge of bin T (approximately: exactness comes from the count check below, not from here)
+            float edge = thr;
+            if (T > 0 && scale > 0.0f) edge = fmaxf(thr, __fadd_rn(smin, __fdiv_rn((float)T, scale)));
+            if (!(edge == edge)) edge = thr;                    // NaN threshold: nothing is valid either way
+            // (S2) one pass: scores AND tie indices are loaded up front as one batch of independent loads
             constexpr int U = 9;                 // 9 x 1024 >= 8 525: one round on the D1 @640 geometry
+            int nvalid = 0;
 #pragma unroll 1
             for (int base = 0; base < n; base += U * kPPThreads) {
                 float sv[U];
@@ -304,65 +334,59 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int i = base + u * kPPThreads + tid;
-                    sv[u] = (i < n) ? scores[i] : __int_as_float(0x7fc00000);   // NaN pads the tail: fails both compares
+                    sv[u] = (i < n) ? scores[i] : __int_as_float(0x7fc00000);   // NaN pads the tail: fails the compares
                     tv[u] = (i < n && src) ? (unsigned)src[i] : (unsigned)i;
                 }
-                unsigned sure_bits = 0u, und_bits = 0u;
+                unsigned bits = 0u;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const bool sure = sv[u] >= edge_hi, ge = sv[u] >= edge_lo;
-                    sure_bits |= (sure ? 1u : 0u) << u;
-                    und_bits |= ((ge && !sure) ? 1u : 0u) << u;
+                    bits |= ((sv[u] >= edge) ? 1u : 0u) << u;
+                    nvalid += (sv[u] >= thr) ? 1 : 0;
                 }
-                // slots: exclusive warp scan of (sure count | undecided count << 16), one shared atomic per warp
-                const int packed = __popc(sure_bits) | (__popc(und_bits) << 16);
-                int incl = packed;
+                // list positions: exclusive warp scan of the per-thread counts, one shared atomic per warp
+                const int cnt = __popc(bits);
+                int incl2 = cnt;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-                const int wtotal = __shfl_sync(0xffffffffu, incl, 31);
-                int bs = 0, bu = 0;
-                if (lane == 0) {
-                    if (wtotal & 0xffff) bs = atomicAdd(&s_nsel, wtotal & 0xffff);
-                    if (wtotal >> 16) bu = atomicAdd(&s_ucount, wtotal >> 16);
-                }
-                bs = __shfl_sync(0xffffffffu, bs, 0) + ((incl - packed) & 0xffff);
-                bu = __shfl_sync(0xffffffffu, bu, 0) + ((incl - packed) >> 16);
-                if (sure_bits | und_bits) {
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl2, o); if (lane >= o) incl2 += t; }
+                const int wtotal = __shfl_sync(0xffffffffu, incl2, 31);
+                int pos = 0;
+                if (lane == 0 && wtotal) pos = atomicAdd(&s_ucount, wtotal);
+                pos = __shfl_sync(0xffffffffu, pos, 0) + incl2 - cnt;
+                if (bits) {
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        const bool sure = (sure_bits >> u) & 1u, und = (und_bits >> u) & 1u;
-                        if (sure || und) {
-                            const int i = base + u * kPPThreads + tid;
-                            const unsigned long long k = ((unsigned long long)float_key(sv[u]) << 32) | (unsigned long long)(0xffffffffu - tv[u]);
-                            if (sure) {
-                                if (bs < kpad) { sel[bs] = i; keys[bs] = k; }
-                                ++bs;
-                            } else {
-                                if (bu < kpad) { ukey[bu] = k; uidx[bu] = i; }
-                                ++bu;
+                        if ((bits >> u) & 1u) {
+                            if (pos < list_cap) {
+                                ukey[pos] = ((unsigned long long)float_key(sv[u]) << 32) | (unsigned long long)(0xffffffffu - tv[u]);
+                                lidx[pos] = base + u * kPPThreads + tid;
                             }
+                            ++pos;
                         }
                     }
                 }
             }
+            nvalid = __reduce_add_sync(0xffffffffu, nvalid);
+            if (lane == 0 && nvalid) atomicAdd(&s_nvalid, nvalid);
             __syncthreads();
             PP_MARK(17);
-            // (H3) the `need` best of the short list
-            const int ucount = min(s_ucount, kpad);
-            if (T >= 0 && ucount > 0) {
-                if (need >= ucount) {
-                    append_list(0ull);
-                } else if (ucount <= kPPThreads / 8) {
-                    // rank by counting, 8 threads per key (keys are unique: the tie index is)
-                    const int e = tid >> 3, part = tid & 7;
-                    const unsigned long long ke = (e < ucount) ? ukey[e] : 0ull;
-                    int rank = 0;
-                    if (e < ucount)
-                        for (int v = part; v < ucount; v += 8) rank += (ukey[v] > ke) ? 1 : 0;
-                    rank += __shfl_xor_sync(0xffffffffu, rank, 1);
-                    rank += __shfl_xor_sync(0xffffffffu, rank, 2);
-                    rank += __shfl_xor_sync(0xffffffffu, rank, 4);
-                    const bool take = e < ucount && part == 0 && rank < need;
+            const int c = s_ucount, v = s_nvalid;
+            if (c <= list_cap && (c >= K || c == v)) {
+                // (S3) the K best of the list (all of it when it has no more than K entries)
+                unsigned long long kth_key = 0ull;
+                if (c > K) {
+                    unsigned long long k_and = ~0ull, k_or = 0ull;
+                    for (int u = tid; u < c; u += kPPThreads) { const unsigned long long k = ukey[u]; k_and &= k; k_or |= k; }
+                    publish_and_or(k_and, k_or);
+                    select_init(K);
+                    int shift = pass(key_list, c, s_top, false);
+                    while (!(s_done || shift == 0)) shift = pass(key_list, c, shift - 1, false);
+                    kth_key = s_prefix;
+                }
+                // entries at or above the K-th key -> slots (sel / keys live apart from the list)
+                for (int base = 0; base < c; base += kPPThreads) {
+                    const int u = base + tid;
+                    const unsigned long long k = (u < c) ? ukey[u] : 0ull;
+                    const bool take = u < c && k >= kth_key;
                     const unsigned bal = __ballot_sync(0xffffffffu, take);
                     if (bal) {
                         int slot0 = 0;
@@ -370,29 +394,22 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
                         slot0 = __shfl_sync(0xffffffffu, slot0, 0);
                         if (take) {
                             const int slot = slot0 + __popc(bal & lt_mask);
-                            if (slot < kpad) { sel[slot] = uidx[e]; keys[slot] = ke; }
+                            if (slot < kpad) { sel[slot] = lidx[u]; keys[slot] = k; }
                         }
                     }
-                    __syncthreads();
-                } else {
-                    unsigned long long k_and = ~0ull, k_or = 0ull;
-                    for (int u = tid; u < ucount; u += kPPThreads) { const unsigned long long k = ukey[u]; k_and &= k; k_or |= k; }
-                    publish_and_or(k_and, k_or);
-                    select_init(need);
-                    int shift = pass(key_list, ucount, s_top, false);
-                    while (!(s_done || shift == 0)) shift = pass(key_list, ucount, shift - 1, false);
-                    append_list(s_prefix);
                 }
+                __syncthreads();
+                fast_done = true;
             }
-            hist_done = true;
-        } else {
-            if (tid == 0) s_total = 0;           // the scan path below starts from scratch
+        }
+        if (!fast_done) {                        // the scan path below starts from scratch
+            if (tid == 0) { s_total = 0; s_ucount = 0; s_nsel = 0; s_done = 0; s_prefix = 0ull; }
             __syncthreads();
         }
     }
     PP_MARK(18);
 
-    if (!hist_done) {
+    if (!fast_done) {
     // ---- (A0) stage the keys, count the threshold survivors, AND / OR of all keys (common prefix)
     unsigned long long k_and = ~0ull, k_or = 0ull;
     {
@@ -518,7 +535,7 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
     }
     __syncthreads();
     if (use_list) append_list(kth);
-    }   // !hist_done
+    }   // !fast_done
     const int m = min(s_nsel, kpad);
     PP_MARK(3);
 

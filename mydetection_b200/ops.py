@@ -124,11 +124,10 @@ def decode_dense(kind, levels: LevelSet, img_hw):
     return box, cls, score
 
 
-def decode_compact(kind, levels: LevelSet, img_hw, conf_thres, capacity=None, want_hist=False):
+def decode_compact(kind, levels: LevelSet, img_hw, conf_thres, capacity=None):
     """Decode fused with `score >= conf_thres` and per-image compaction.
 
-    Returns dict(box (B,cap,P), score (B,cap), cls (B,cap) i32, idx (B,cap) i32, count (B) i32
-    [, hist (B, HIST_BINS) i32: the candidates' score histogram, see include/mydet.h])."""
+    Returns dict(box (B,cap,P), score (B,cap), cls (B,cap) i32, idx (B,cap) i32, count (B) i32)."""
     B, N, P = levels.batch, levels.n_total, levels.n_param
     cap = int(capacity or N)
     dev = levels.device
@@ -137,14 +136,11 @@ def decode_compact(kind, levels: LevelSet, img_hw, conf_thres, capacity=None, wa
            'cls': torch.empty(B, cap, dtype=torch.int32, device=dev),
            'idx': torch.empty(B, cap, dtype=torch.int32, device=dev),
            'count': torch.empty(B, dtype=torch.int32, device=dev)}
-    if want_hist:
-        out['hist'] = torch.empty(B, _lib.HIST_BINS, dtype=torch.int32, device=dev)
-        out['hist_lo'] = float(conf_thres)
     with torch.cuda.device(dev):
         rc = _lib.lib().mydet_decode_compact(kind, levels.array, levels.n_levels, B, levels.n_cls, P,
                                              float(img_hw[0]), float(img_hw[1]), float(conf_thres),
                                              _ptr(out['box']), _ptr(out['score']), _ptr(out['cls']), _ptr(out['idx']),
-                                             _ptr(out['count']), cap, _ptr(out.get('hist')), 0, _stream())
+                                             _ptr(out['count']), cap, 0, _stream())
     _lib.check(rc, 'mydet_decode_compact')
     return out
 
@@ -160,13 +156,13 @@ def _alloc_dets(B, cap, P, dev):
 
 
 def postprocess(boxes, scores, cls, conf_thres, nms_thres, topk=512, box_format='cxcywh', counts=None,
-                src_idx=None, out_cap=None, out=None, hist=None, hist_lo=0.0, consume=False):
+                src_idx=None, out_cap=None, out=None, consume=False, force_scan=False):
     """Batched threshold -> top-k -> class-aware NMS.  boxes (B,n,P), scores (B,n), cls (B,n) i32|i64.
 
     topk=None removes the cap.  Returns dict(box, score, cls (i64), idx (i32), count, status);
     rows [0, count[b]) of image b are valid and ordered class asc / score desc.
-    hist / hist_lo: the score histogram decode_compact(want_hist=True) wrote for these candidates and the
-    conf_thres it was given; consume=True zeroes counts and hist once read (include/mydet.h)."""
+    consume=True zeroes `counts` once read (include/mydet.h: the state a decode_compact with state_clean needs);
+    force_scan=True skips the sampled front end of the select (tests: the result must not change)."""
     boxes = _dev(boxes, torch.float32, 'boxes')
     scores = _dev(scores, torch.float32, 'scores')
     if cls.dtype not in (torch.int32, torch.int64):
@@ -191,7 +187,7 @@ def postprocess(boxes, scores, cls, conf_thres, nms_thres, topk=512, box_format=
                                  _ptr(src_idx), _ptr(counts), B, n, n, P, BOX_FORMATS[box_format],
                                  float(conf_thres), k, float(nms_thres), _ptr(out['box']), _ptr(out['score']),
                                  _ptr(out['cls']), _ptr(out['idx']), _ptr(out['count']), _ptr(out['status']), cap,
-                                 _ptr(ws), ws.numel(), _ptr(hist), float(hist_lo), 1 if consume else 0, _stream())
+                                 _ptr(ws), ws.numel(), (1 if consume else 0) | (2 if force_scan else 0), _stream())
     _lib.check(rc, 'mydet_postprocess')
     return out
 

@@ -34,12 +34,11 @@ class BoundCall:
                      'score': torch.empty(B, N, dtype=torch.float32, device=dev),
                      'cls': torch.empty(B, N, dtype=torch.int32, device=dev),
                      'idx': torch.empty(B, N, dtype=torch.int32, device=dev),
-                     'count': torch.zeros(B, dtype=torch.int32, device=dev),
-                     # score histogram of the candidates (decode -> post-process).  Zeroed here once; every
-                     # launch_postprocess*() consumes count and hist and leaves them zero for the next decode
-                     'hist': torch.zeros(B, _lib.HIST_BINS, dtype=torch.int32, device=dev)}
-        single = (k if 0 < k < N else N) <= _lib.SMALL_K      # only the single-kernel post-process reads / cleans them
-        clean = 1 if (single and self_cleaning) else 0        # else: launch_decode() memsets count and hist itself
+                     # zeroed here once; every launch_postprocess*() consumes the count and leaves it zero for
+                     # the next decode (state_clean / consume of include/mydet.h): no memset in the step
+                     'count': torch.zeros(B, dtype=torch.int32, device=dev)}
+        single = (k if 0 < k < N else N) <= _lib.SMALL_K      # only the single-kernel post-process cleans it
+        clean = 1 if (single and self_cleaning) else 0        # else: launch_decode() memsets the count itself
         self.self_cleaning = bool(clean)
         self.pp_workspace = ops._workspace(L.mydet_postprocess_workspace_bytes(B, N, k), dev)
         o, c = self.out, self.cand
@@ -50,13 +49,12 @@ class BoundCall:
                              ptr(o['count']), ptr(o['status']), o['box'].shape[1], ptr(self.workspace),
                              self.workspace.numel())
         self._decode_args = (pipe.kind, ls.array, ls.n_levels, B, ls.n_cls, P, img_h, img_w, pipe.conf_thres,
-                             ptr(c['box']), ptr(c['score']), ptr(c['cls']), ptr(c['idx']), ptr(c['count']), N,
-                             ptr(c['hist']) if single else ptr(None), clean)
+                             ptr(c['box']), ptr(c['score']), ptr(c['cls']), ptr(c['idx']), ptr(c['count']), N, clean)
         self._pp_args = (ptr(c['box']), ptr(c['score']), ptr(c['cls']), 0, ptr(c['idx']), ptr(c['count']), B, N, N, P,
                          ops.BOX_CXCYWH, float('-inf'), k, pipe.nms_thres, ptr(o['box']), ptr(o['score']),
                          ptr(o['cls']), ptr(o['idx']), ptr(o['count']), ptr(o['status']), o['box'].shape[1],
                          ptr(self.pp_workspace), self.pp_workspace.numel())
-        self._hist_args = (ptr(c['hist']) if single else ptr(None), pipe.conf_thres, clean)
+        self._consume_args = (clean,)
         self.graph = None
 
     @staticmethod
@@ -72,12 +70,11 @@ class BoundCall:
 
     # stage-wise entry points: the same two kernels as launch(), exposed so that bench.py can put
     # CUDA events around the decode kernel.  They must alternate: the decode relies on the candidate
-    # state (count, hist) being zero, which the post-process that consumed it guarantees
-    # (state_clean / consume of include/mydet.h) -- no memset in the step.  reset_state() re-arms it
-    # after a decode whose candidates were not post-processed.
+    # count being zero, which the post-process that consumed it guarantees (state_clean / consume of
+    # include/mydet.h) -- no memset in the step.  reset_state() re-arms it after a decode whose
+    # candidates were not post-processed.
     def reset_state(self):
         self.cand['count'].zero_()
-        self.cand['hist'].zero_()
 
     def launch_decode(self):
         rc = self._L.mydet_decode_compact(*self._decode_args, self._stream())
@@ -86,7 +83,7 @@ class BoundCall:
         return self.cand
 
     def launch_postprocess(self):
-        rc = self._L.mydet_postprocess(*self._pp_args, *self._hist_args, self._stream())
+        rc = self._L.mydet_postprocess(*self._pp_args, *self._consume_args, self._stream())
         if rc:
             _lib.check(rc, 'mydet_postprocess')
         return self.out
@@ -104,7 +101,7 @@ class BoundCall:
         return self
 
     def launch_postprocess_scatter(self):
-        rc = self._L.mydet_postprocess_scatter(*self._scatter_args, *self._hist_args, self._stream())
+        rc = self._L.mydet_postprocess_scatter(*self._scatter_args, *self._consume_args, self._stream())
         if rc:
             _lib.check(rc, 'mydet_postprocess_scatter')
         return self.out
@@ -138,7 +135,7 @@ class DetectionPipeline:
         self.conf_key = conf_key
 
     def bind(self, raws, self_cleaning=True):
-        """self_cleaning=False: launch_decode() zeroes the candidate state itself (two memsets), so it may be
+        """self_cleaning=False: launch_decode() zeroes the candidate count itself (a memset), so it may be
         called without a matching launch_postprocess()."""
         return BoundCall(self, raws, self_cleaning)
 

@@ -21,7 +21,7 @@ else:
     _lib.LIB_PATH = LIBP
     dev = torch.device('cuda', 0)
     gen = torch.Generator(device=dev).manual_seed(2000)
-    _, raws = bench.make_batch(gen, dev)
+    _, raws, _ = bench.make_batch(gen, dev)
     pipe = pl.DetectionPipeline('FCOS2', bench.STRIDES, bench.N_CLS, (bench.IMG, bench.IMG), bench.CONF_THRES,
                                 bench.NMS_THRES, bench.TOPK)
     bc = pipe.bind(raws)
@@ -32,10 +32,10 @@ else:
     _lib.lib().mydet_debug_pp_clocks.argtypes = [ctypes.POINTER(ctypes.c_longlong)]
     _lib.lib().mydet_debug_pp_clocks(buf)
     t = list(buf)
-    # histogram front end (marks 0,16,17,18,3) instead of A0 / A / B1 (marks 0,1,2,3)
-    print(f'{"H1 histogram scan":18s} {t[16] - t[0]:8d} cycles')
-    print(f'{"H2 one pass":18s} {t[17] - t[16]:8d} cycles')
-    print(f'{"H3 short list":18s} {t[18] - t[17]:8d} cycles')
+    # sampled front end (marks 0,16,17,18,3) instead of A0 / A / B1 (marks 0,1,2,3)
+    print(f'{"S1 sample + edge":18s} {t[16] - t[0]:8d} cycles')
+    print(f'{"S2 one pass":18s} {t[17] - t[16]:8d} cycles')
+    print(f'{"S3 list select":18s} {t[18] - t[17]:8d} cycles')
     for i, nm in enumerate(NAMES):
         if i >= 3:
             print(f'{nm:18s} {t[i + 1] - t[i]:8d} cycles')

@@ -40,7 +40,7 @@ def run():
         _lib.LIB_PATH = path
         pipe = pl.DetectionPipeline('FCOS2', bench.STRIDES, bench.N_CLS, (bench.IMG, bench.IMG), bench.CONF_THRES,
                                     bench.NMS_THRES, bench.TOPK)
-        bound = [pipe.bind(r, self_cleaning=False) for _, r in batches]
+        bound = [pipe.bind(r, self_cleaning=False) for _, r, _ in batches]
         for i in range(6):
             bound[i % 3].launch_decode()
         torch.cuda.synchronize()

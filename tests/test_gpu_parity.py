@@ -310,22 +310,11 @@ def same_dets(a, b, what=''):
             assert torch.equal(a[k][i, :n], b[k][i, :n]), (what, i, k)
 
 
-def _hist_map(lo):
-    """Python restatement of make_hist_map / hist_bin (csrc/common.cuh)."""
-    lo = np.float32(max(lo, 0.0)) if lo == lo else np.float32(0.0)
-    key = lambda f: int(np.float32(f).view(np.uint32)) | 0x80000000     # non-negative floats only
-    key_lo, rng, shift = key(lo), max(key(1.0) - key(lo), 0), 0
-    while (rng >> shift) >= 2048:
-        shift += 1
-    return key_lo, shift
-
-
 @pytest.mark.parametrize('quantise', [False, True])
-def test_histogram_select_equals_scan(golden, quantise):
-    """The decode kernel's score histogram (mydet_decode_compact score_hist) must hold exactly the candidates,
-    and the post-process that starts from it must give the same bits as the one that scans the scores:
-    random scores (short undecided list: counting), quantised logits (heavy ties: long list -> radix passes, or
-    a boundary bin above 1024 candidates -> fallback to the scan), every K regime, and `consume`."""
+def test_sampled_select_equals_scan(golden, quantise):
+    """The post-process brackets the K-th score from a sample and verifies the bracket by counting; when
+    the check fails it scans.  Both routes must give the same bits: random scores, quantised logits (heavy
+    ties: the verified list overflows -> scan), every K regime, several thresholds, and `consume`."""
     from mydetection_b200 import ops
     g = golden('decode')
     d = dev()
@@ -337,39 +326,47 @@ def test_histogram_select_equals_scan(golden, quantise):
             bb, cc = (bb * 2).round() / 2, cc.round()
         raws.append({k: v.to(d) for k, v in efdet_views(bb, cc).items()})
     ls = ops.LevelSet(raws, strides)
+    box, cls, score = ops.decode_dense(ops.KIND_FCOS, ls, (256, 384))
     for thr in (-float('inf'), 0.005, 0.05, 0.3):
-        c = ops.decode_compact(ops.KIND_FCOS, ls, (256, 384), thr, want_hist=True)
-        torch.cuda.synchronize()
-        key_lo, shift = _hist_map(thr)
-        for b in range(c['count'].numel()):
-            n = int(c['count'][b])
-            keys = c['score'][b, :n].cpu().numpy().view(np.uint32).astype(np.int64) | 0x80000000
-            bins = np.clip((np.maximum(keys - key_lo, 0) >> shift), 0, 2047)
-            want = np.bincount(bins, minlength=2048)
-            assert np.array_equal(c['hist'][b].cpu().numpy(), want), (thr, b)
+        c = ops.decode_compact(ops.KIND_FCOS, ls, (256, 384), thr)
         for topk in (1, 8, 100, 512, 1000, None):
-            plain = ops.postprocess(c['box'], c['score'], c['cls'], -float('inf'), 0.5, topk=topk, counts=c['count'],
-                                    src_idx=c['idx'])
-            fast = ops.postprocess(c['box'], c['score'], c['cls'], -float('inf'), 0.5, topk=topk, counts=c['count'],
-                                   src_idx=c['idx'], hist=c['hist'], hist_lo=thr)
-            torch.cuda.synchronize()
-            assert int(fast['status'].abs().sum()) == 0
-            same_dets(plain, fast, (thr, topk))
-        # consume: same result, and the candidate state is left zeroed
+            # compacted candidates (already thresholded) and the dense arrays (threshold applied by the kernel)
+            for args, kw in (((c['box'], c['score'], c['cls'], -float('inf'), 0.5), dict(counts=c['count'], src_idx=c['idx'])),
+                             ((box, score, cls, thr, 0.5), {})):
+                scan = ops.postprocess(*args, topk=topk, force_scan=True, **kw)
+                fast = ops.postprocess(*args, topk=topk, **kw)
+                torch.cuda.synchronize()
+                assert int(fast['status'].abs().sum()) == 0
+                same_dets(scan, fast, (thr, topk))
         want = ops.postprocess(c['box'], c['score'], c['cls'], -float('inf'), 0.5, topk=512, counts=c['count'], src_idx=c['idx'])
         got = ops.postprocess(c['box'], c['score'], c['cls'], -float('inf'), 0.5, topk=512, counts=c['count'],
-                              src_idx=c['idx'], hist=c['hist'], hist_lo=thr, consume=True)
+                              src_idx=c['idx'], consume=True)
         torch.cuda.synchronize()
         same_dets(want, got, 'consume')
-        assert int(c['count'].abs().sum()) == 0 and int(c['hist'].abs().sum()) == 0
-    # a histogram that does not belong to the candidates is detected (sum != count) and ignored
-    c = ops.decode_compact(ops.KIND_FCOS, ls, (256, 384), 0.05, want_hist=True)
-    want = ops.postprocess(c['box'], c['score'], c['cls'], -float('inf'), 0.5, topk=100, counts=c['count'], src_idx=c['idx'])
-    c['hist'][:, 2000] += 3
-    got = ops.postprocess(c['box'], c['score'], c['cls'], -float('inf'), 0.5, topk=100, counts=c['count'],
-                          src_idx=c['idx'], hist=c['hist'], hist_lo=0.05)
-    torch.cuda.synchronize()
-    same_dets(want, got, 'foreign histogram')
+        assert int(c['count'].abs().sum()) == 0
+
+
+@pytest.mark.parametrize('n,scale', [(700, 1.0), (5000, 1.0), (20000, 1.0), (20000, 1e4), (3000, 0.0)])
+def test_sampled_select_score_scales(n, scale):
+    """Scores outside [0, 1] (logits, huge magnitudes, all equal): the sample bins adapt to the range, and
+    the count check keeps the result exact; fast and scan routes agree and match the oracle."""
+    from mydetection_b200 import ops
+    from oracle import postprocess as opp
+    gen = torch.Generator().manual_seed(77 + n)
+    xy = torch.rand(n, 2, generator=gen) * 600
+    wh = torch.rand(n, 2, generator=gen) * 60 + 4
+    boxes = torch.cat([xy, wh], 1)
+    scores = (torch.randn(n, generator=gen) * scale) if scale > 0 else torch.full((n,), 0.25)
+    cats = torch.randint(0, 20, (n,), generator=gen)
+    d = dev()
+    for topk in (64, 512):
+        fast = ops.postprocess(boxes[None].to(d), scores[None].to(d), cats[None].to(d), -float('inf'), 0.5, topk=topk)
+        scan = ops.postprocess(boxes[None].to(d), scores[None].to(d), cats[None].to(d), -float('inf'), 0.5, topk=topk, force_scan=True)
+        torch.cuda.synchronize()
+        same_dets(scan, fast, (n, scale, topk))
+        want = opp.post_process(boxes, cats, scores, -float('inf'), 0.5, 'cxcywh', topk)
+        k = int(fast['count'][0])
+        assert k == want.numel() and torch.equal(fast['idx'][0, :k].cpu().long(), want)
 
 
 def test_pipeline_stagewise_self_cleaning(golden):
@@ -388,7 +385,7 @@ def test_pipeline_stagewise_self_cleaning(golden):
         bc.launch_decode()
         out = bc.launch_postprocess()
         torch.cuda.synchronize()
-        assert int(bc.cand['count'].abs().sum()) == 0 and int(bc.cand['hist'].abs().sum()) == 0
+        assert int(bc.cand['count'].abs().sum()) == 0
         same_dets(out, want, rep)
     loose = pipe.bind(raws, self_cleaning=False)           # decode memsets its own state: may be repeated
     loose.launch_decode(); loose.launch_decode()

@@ -51,11 +51,11 @@ def test_argument_validation_without_launch():
     rc = L.mydet_decode_dense(_lib.KIND_RAPID, lv, 1, 1, 0, 4, 640.0, 640.0, None, None, None, 0, None)
     assert rc == -1 and b'n_param == 5' in L.mydet_last_error()
     rc = L.mydet_postprocess(None, None, None, 0, None, None, 1, 10, 10, 3, 0, 0.0, 512, 0.5, None, None, None, None,
-                             None, None, 1, None, 0, None, 0.0, 0, None)
+                             None, None, 1, None, 0, 0, None)
     assert rc == -1 and b'n_param' in L.mydet_last_error()
     rc = L.mydet_postprocess(None, None, None, 0, None, None, 1, 10, 10, 4, 0, 0.0, 512, 0.5, None, None, None, None,
-                             1, None, 1, None, 0, 1, 0.0, 0, None)           # a histogram without counts
-    assert rc == -1 and b'score_hist needs counts' in L.mydet_last_error()
+                             1, None, 1, None, 0, 1, None)                   # consume without counts
+    assert rc == -1 and b'consume needs counts' in L.mydet_last_error()
     rc = L.mydet_iou_aabb_pairwise(None, -1, None, 3, 0, None, None)
     assert rc == -1
     with pytest.raises(_lib.MydetError):
