@@ -201,7 +201,7 @@ def run_reference(args, budget_s=150.0):
 
 
 # ------------------------------------------------------------------------------------- rotated NMS
-def rotated_nms_metric(dev, batch=32, n=10000, iters=10):
+def rotated_nms_metric(dev, batch=32, n=10000, iters=10, chunks=None):
     """Second half of BASELINE.json's metric: rotated-NMS us/image at 10 000 boxes (configs[2]: RAPiD
     @1024, batch 32).  Boxes are the 10 000 best of 64 512 decoded candidates per image; timed with CUDA
     events; the oracle (exact polygon clipping, nms_rotbb control flow) is timed on one image beside it."""
@@ -224,12 +224,12 @@ def rotated_nms_metric(dev, batch=32, n=10000, iters=10):
     rb = torch.gather(box, 1, top[..., None].expand(-1, -1, 5)).contiguous()
     rs = torch.gather(score, 1, top).contiguous()
     for _ in range(3):
-        keep, cnt = ops.nms_rot(rb, rs, 0.45)
+        keep, cnt = ops.nms_rot(rb, rs, 0.45, chunks=chunks)
     torch.cuda.synchronize(dev)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(iters):
-        keep, cnt = ops.nms_rot(rb, rs, 0.45)
+        keep, cnt = ops.nms_rot(rb, rs, 0.45, chunks=chunks)
     b.record()
     torch.cuda.synchronize(dev)
     us = a.elapsed_time(b) * 1e3 / iters / batch

@@ -34,7 +34,9 @@ struct LargeWs {          // carved out of the caller's workspace
     // spatially ordered variant (rotated path, n <= 16384): boxes live in Morton order of their centres
     unsigned long long* bk;     // B*npad   big sort (n > 16384): keys ...
     int* bp;                    // B*npad   ... and payload
-    unsigned long long* skeys;  // B*n      (morton << 20 | score rank), indexed by score rank
+    unsigned long long* skeys;  // B*n      (class << 52 | morton << 20 | tie), indexed by candidate slot
+    int* slot_of_spos;          // B*n      spatial position -> candidate slot (payload of the Morton sort)
+    int* rank_of_slot;          // B*n      candidate slot -> score rank (inverse of `order`)
     int* rank_of_spos;          // B*n      spatial position -> score rank
     int* spos_of_rank;          // B*n      score rank -> spatial position
     float4* tile_hull;          // B*tiles  hull of the 64 boxes of a spatial tile
@@ -62,6 +64,7 @@ static size_t carve(LargeWs& w, void* base, int batch, int n, bool rot) {
     const bool sp = n <= kSpatialMaxN;            // buffers of the spatially ordered path
     w.aw = (w.words + 63) / 64;
     const size_t o_skeys = take(sp ? bn * 8 : 0), o_ros = take(sp ? bn * 4 : 0), o_sor = take(sp ? bn * 4 : 0);
+    const size_t o_sos = take(sp ? bn * 4 : 0), o_rosl = take(sp ? bn * 4 : 0);
     const size_t o_hull = take(sp ? (size_t)batch * w.words * 16 : 0);
     const size_t o_tcls = take(sp ? (size_t)batch * w.words * 8 : 0);
     const size_t o_adj = take(sp ? (size_t)batch * w.words * w.aw * 8 : 0);
@@ -76,6 +79,7 @@ static size_t carve(LargeWs& w, void* base, int batch, int n, bool rot) {
         w.rowpos = (int*)(p + o_rowpos);
         w.bk = (unsigned long long*)(p + o_bk); w.bp = (int*)(p + o_bp);
         w.skeys = (unsigned long long*)(p + o_skeys); w.rank_of_spos = (int*)(p + o_ros); w.spos_of_rank = (int*)(p + o_sor);
+        w.slot_of_spos = (int*)(p + o_sos); w.rank_of_slot = (int*)(p + o_rosl);
         w.tile_hull = (float4*)(p + o_hull);
         w.tile_cls = (int2*)(p + o_tcls);
         w.tile_adj = (unsigned long long*)(p + o_adj);
@@ -95,7 +99,20 @@ struct KeyParams {
     const float* scores; const void* cls; const int* counts; const int* src_idx;
     long long pitch; int n, cls_is_i64, use_cls; float thr;
     int* status;
+    // spatially ordered path: Morton keys of the box centres, written next to the score keys so that both
+    // sorts are independent of each other and run in ONE launch
+    const float* boxes; int n_param, box_format;
+    unsigned long long* skeys;
 };
+
+__device__ __forceinline__ unsigned part1by1(unsigned v) {      // spread the low 16 bits to the even positions
+    v &= 0x0000ffffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
 
 __global__ void keys_kernel(KeyParams P, unsigned long long* keys, int* m) {
     const int b = blockIdx.y;
@@ -103,7 +120,7 @@ __global__ void keys_kernel(KeyParams P, unsigned long long* keys, int* m) {
     int n = P.n;
     if (P.counts) { const int c = P.counts[b]; n = c < n ? (c < 0 ? 0 : c) : n; }
     bool valid = false;
-    unsigned long long key = ~0ull;
+    unsigned long long key = ~0ull, skey = ~0ull;
     if (i < n) {
         const float s = P.scores[(long long)b * P.pitch + i];
         if (s >= P.thr) {
@@ -119,9 +136,22 @@ __global__ void keys_kernel(KeyParams P, unsigned long long* keys, int* m) {
             if (tie > 0xfffffu && P.status) atomicOr(P.status + b, 8);
             key = ((unsigned long long)c << 52) | ((unsigned long long)(~float_key(s)) << 20) | (unsigned long long)(tie & 0xfffffu);
             valid = true;
+            if (P.skeys) {
+                const float* bx = P.boxes + ((long long)b * P.pitch + i) * P.n_param;
+                float cx = bx[0], cy = bx[1];
+                if (P.box_format == MYDET_BOX_X1Y1X2Y2) { cx = 0.5f * (bx[0] + bx[2]); cy = 0.5f * (bx[1] + bx[3]); }
+                const unsigned qx = (unsigned)fminf(fmaxf(cx, 0.f), 65535.f), qy = (unsigned)fminf(fmaxf(cy, 0.f), 65535.f);
+                const unsigned morton = part1by1(qx) | (part1by1(qy) << 1);
+                // class first (boxes of different classes never interact), then the Z-order of the centre;
+                // equal codes in slot order (any order is valid: mask bits are directed by score rank)
+                skey = ((unsigned long long)c << 52) | ((unsigned long long)morton << 20) | (unsigned long long)((unsigned)i & 0xfffffu);
+            }
         }
     }
-    if (i < P.n) keys[(long long)b * P.n + i] = key;
+    if (i < P.n) {
+        keys[(long long)b * P.n + i] = key;
+        if (P.skeys) P.skeys[(long long)b * P.n + i] = skey;
+    }
     const unsigned bal = __ballot_sync(0xffffffffu, valid);
     if ((threadIdx.x & 31) == 0 && bal) atomicAdd(m + b, __popc(bal));
 }
@@ -132,11 +162,17 @@ __global__ void keys_kernel(KeyParams P, unsigned long long* keys, int* m) {
 // all-pairs rank kernel (rank = number of smaller keys) needed 545 us for the same batch.
 constexpr int kSortThreads = 1024;
 constexpr int kSortMaxN = 16384;
-__global__ void __launch_bounds__(kSortThreads, 1) sort_smem_kernel(const unsigned long long* keys, int* order, int n, int npad) {
+// grid = B CTAs, or 2 B when a second, independent key array is sorted by the same launch (score keys + Morton
+// keys: 64 CTAs of a 32-image batch instead of twice 32).  inv (first array only, optional): inverse permutation.
+__global__ void __launch_bounds__(kSortThreads, 1) sort_smem_kernel(const unsigned long long* keys, int* order, int* inv,
+                                                                    const unsigned long long* keys2, int* order2,
+                                                                    int n, int npad, int B) {
     extern __shared__ unsigned long long skeys[];
     int* spay = reinterpret_cast<int*>(skeys + npad);
-    const int b = blockIdx.x, tid = threadIdx.x;
-    const unsigned long long* kb = keys + (long long)b * n;
+    const bool second = (int)blockIdx.x >= B;
+    const int b = second ? blockIdx.x - B : blockIdx.x, tid = threadIdx.x;
+    const unsigned long long* kb = (second ? keys2 : keys) + (long long)b * n;
+    int* ob = (second ? order2 : order) + (long long)b * n;
     for (int i = tid; i < npad; i += kSortThreads) { skeys[i] = (i < n) ? kb[i] : ~0ull; spay[i] = i; }
     __syncthreads();
 #pragma unroll 1
@@ -158,7 +194,10 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_smem_kernel(const unsign
         }
     }
     for (int i = tid; i < n; i += kSortThreads)
-        if (skeys[i] != ~0ull) order[(long long)b * n + i] = spay[i];
+        if (skeys[i] != ~0ull) {
+            ob[i] = spay[i];
+            if (inv && !second) inv[(long long)b * n + spay[i]] = i;
+        }
 }
 
 // Sort for larger images (16 384 < n <= 2^20): the same bitonic network split over CTAs.  16 384-key chunks
@@ -219,15 +258,12 @@ __global__ void sort_big_store_kernel(const unsigned long long* bk, const int* b
     if (i < n && bk[(long long)b * npad + i] != ~0ull) order[(long long)b * n + i] = bp[(long long)b * npad + i];
 }
 
-// order[b][rank] = index of the rank-th smallest key of image b (invalid keys ~0 are left out)
-static int sort_keys(const unsigned long long* keys, int* order, int n, int B, LargeWs& w, cudaStream_t st) {
-    if (n <= kSortMaxN) {
-        int npad = 64;
-        while (npad < n) npad <<= 1;
-        MYDET_CUDA(cudaFuncSetAttribute(sort_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortMaxN * 12)));
-        sort_smem_kernel<<<B, kSortThreads, (size_t)npad * 12, st>>>(keys, order, n, npad);
-        return launch_status("sort_smem_kernel");
-    }
+__global__ void invert_kernel(const int* order, const int* m, int* inv, int n) {
+    const int b = blockIdx.y, r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < m[b]) inv[(long long)b * n + order[(long long)b * n + r]] = r;
+}
+
+static int sort_big(const unsigned long long* keys, int* order, int n, int B, LargeWs& w, cudaStream_t st) {
     int npad = 2 * kChunk;
     while (npad < n) npad <<= 1;
     const int chunks = npad / kChunk;
@@ -241,6 +277,24 @@ static int sort_keys(const unsigned long long* keys, int* order, int n, int B, L
     }
     sort_big_store_kernel<<<dim3((n + 255) / 256, B), 256, 0, st>>>(w.bk, w.bp, order, n, npad);
     return launch_status("sort_big kernels");
+}
+
+// order[b][rank] = index of the rank-th smallest key of image b (invalid keys ~0 are left out); inv (optional)
+// = its inverse.  keys2 / order2 (optional): a second key array of the same shape, sorted alongside.
+static int sort_keys(const unsigned long long* keys, int* order, int* inv, const unsigned long long* keys2, int* order2,
+                     int n, int B, LargeWs& w, cudaStream_t st) {
+    if (n <= kSortMaxN) {
+        int npad = 64;
+        while (npad < n) npad <<= 1;
+        MYDET_CUDA(cudaFuncSetAttribute(sort_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortMaxN * 12)));
+        sort_smem_kernel<<<keys2 ? 2 * B : B, kSortThreads, (size_t)npad * 12, st>>>(keys, order, inv, keys2, order2, n, npad, B);
+        return launch_status("sort_smem_kernel");
+    }
+    int rc = sort_big(keys, order, n, B, w, st);
+    if (rc) return rc;
+    if (inv) invert_kernel<<<dim3((n + 255) / 256, B), 256, 0, st>>>(order, w.m, inv, n);
+    if (keys2) rc = sort_big(keys2, order2, n, B, w, st);
+    return rc;
 }
 
 // ---------------------------------------------------------------------------- gather
@@ -447,37 +501,9 @@ __global__ void __launch_bounds__(kTile) mask_rot_kernel(LargeWs w, const int* m
 // whose hulls are disjoint are skipped outright (~90 % of them), and the bit for an overlapping pair is set
 // in the row of the higher-scored box (rank comparison) instead of being implied by the tile position.
 // The sweep still visits boxes in score order and gathers the bits it needs through the rank<->position maps.
-__device__ __forceinline__ unsigned part1by1(unsigned v) {      // spread the low 16 bits to the even positions
-    v &= 0x0000ffffu;
-    v = (v | (v << 8)) & 0x00ff00ffu;
-    v = (v | (v << 4)) & 0x0f0f0f0fu;
-    v = (v | (v << 2)) & 0x33333333u;
-    v = (v | (v << 1)) & 0x55555555u;
-    return v;
-}
-
-__global__ void spatial_keys_kernel(GatherParams P, const unsigned long long* keys, const int* order, const int* m,
-                                    unsigned long long* skeys) {
-    const int b = blockIdx.y;
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= P.n) return;
-    unsigned long long key = ~0ull;
-    if (r < m[b]) {
-        const int i = order[(long long)b * P.n + r];
-        const float* bx = P.boxes + ((long long)b * P.pitch + i) * P.n_param;
-        float cx = bx[0], cy = bx[1];
-        if (P.box_format == MYDET_BOX_X1Y1X2Y2) { cx = 0.5f * (bx[0] + bx[2]); cy = 0.5f * (bx[1] + bx[3]); }
-        const unsigned qx = (unsigned)fminf(fmaxf(cx, 0.f), 65535.f), qy = (unsigned)fminf(fmaxf(cy, 0.f), 65535.f);
-        const unsigned morton = part1by1(qx) | (part1by1(qy) << 1);
-        // class first (boxes of different classes never interact), then the Z-order of the centre
-        const unsigned long long cls = keys[(long long)b * P.n + i] >> 52;
-        key = (cls << 52) | ((unsigned long long)morton << 20) | (unsigned long long)r;
-    }
-    skeys[(long long)b * P.n + r] = key;
-}
-
-// after sorting skeys: rank_of_spos[spos] = score rank (the sort's payload).  Build the quads in spatial
-// order, the inverse map, and the hull of every 64-box tile (one warp pair per tile).
+// after both sorts: slot_of_spos[spos] = candidate slot (payload of the Morton sort), rank_of_slot = inverse of the
+// score order.  Build the quads in spatial order, both rank <-> position maps, and the hull of every 64-box tile
+// (one warp pair per tile).
 template <bool ROT>
 __global__ void __launch_bounds__(kTile) spatial_gather_kernel(GatherParams P, const unsigned long long* keys, const int* order,
                                                                const int* m, LargeWs w) {
@@ -490,8 +516,9 @@ __global__ void __launch_bounds__(kTile) spatial_gather_kernel(GatherParams P, c
     int c_lo = 0x7fffffff, c_hi = -1;
     if (spos < mb) {
         const long long row = (long long)b * P.n + spos;
-        const int r = w.rank_of_spos[row];
-        const int i = order[(long long)b * P.n + r];
+        const int i = w.slot_of_spos[row];
+        const int r = w.rank_of_slot[(long long)b * P.n + i];
+        w.rank_of_spos[row] = r;
         const float* bx = P.boxes + ((long long)b * P.pitch + i) * P.n_param;
         if (ROT) {
             float v[5] = {bx[0], bx[1], bx[2], bx[3], bx[4]};
@@ -1037,10 +1064,16 @@ int run_large(const LargeArgs& A, void* workspace, size_t workspace_bytes, cudaS
     const int B = A.batch, n = A.n;
     MYDET_CUDA(cudaMemsetAsync(w.m, 0, sizeof(int) * (size_t)B, st));
     if (A.status) MYDET_CUDA(cudaMemsetAsync(A.status, 0, sizeof(int) * (size_t)B, st));
-    KeyParams K{A.scores, A.cls, A.counts, A.src_idx, A.pitch, n, A.cls_is_i64, (A.cls && !A.rot) ? 1 : 0, A.conf_thres, A.status};
+    // Morton-ordered mask (n <= 65 536).  The degenerate "IoU >= 0" threshold of the rotated API suppresses
+    // disjoint boxes too, which patch culling would miss: it keeps the score-ordered kernel.
+    const bool spatial = n <= kSpatialMaxN && !(A.rot && A.ge && A.thr <= 0.0);
+    KeyParams K{A.scores, A.cls, A.counts, A.src_idx, A.pitch, n, A.cls_is_i64, (A.cls && !A.rot) ? 1 : 0, A.conf_thres, A.status,
+                A.boxes, A.n_param, A.box_format, spatial ? w.skeys : nullptr};
     keys_kernel<<<dim3((n + 255) / 256, B), 256, 0, st>>>(K, w.keys, w.m);
     {
-        const int rc = sort_keys(w.keys, w.order, n, B, w, st);
+        // score order and Morton order do not depend on each other: one launch sorts both
+        const int rc = spatial ? sort_keys(w.keys, w.order, w.rank_of_slot, w.skeys, w.slot_of_spos, n, B, w, st)
+                               : sort_keys(w.keys, w.order, nullptr, nullptr, nullptr, n, B, w, st);
         if (rc) return rc;
     }
     GatherParams G{A.boxes, A.pitch, n, A.n_param, A.box_format};
@@ -1050,15 +1083,7 @@ int run_large(const LargeArgs& A, void* workspace, size_t workspace_bytes, cudaS
     const size_t smem = ((size_t)w.words * 2 + kTile) * sizeof(unsigned long long);
     MYDET_REQUIRE(smem <= 200 * 1024, "too many candidates per image for the sweep kernel");
     const int smem_attr = (int)smem > 48 * 1024 ? (int)smem : 48 * 1024;
-    // Morton-ordered mask (n <= 65 536).  The degenerate "IoU >= 0" threshold of the rotated API suppresses
-    // disjoint boxes too, which patch culling would miss: it keeps the score-ordered kernel.
-    const bool spatial = n <= kSpatialMaxN && !(A.rot && A.ge && A.thr <= 0.0);
     if (spatial) {
-        spatial_keys_kernel<<<dim3((n + 255) / 256, B), 256, 0, st>>>(G, w.keys, w.order, w.m, w.skeys);
-        {
-            const int rc = sort_keys(w.skeys, w.rank_of_spos, n, B, w, st);
-            if (rc) return rc;
-        }
         MYDET_CUDA(cudaMemsetAsync(w.mask, 0, (size_t)B * n * w.words * sizeof(unsigned long long), st));
         MYDET_CUDA(cudaMemsetAsync(w.tile_adj, 0, (size_t)B * w.words * w.aw * 8, st));
         const dim3 mgrid(tiles, (tiles + kColChunk - 1) / kColChunk, B);

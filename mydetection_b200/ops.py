@@ -219,10 +219,25 @@ def detect_workspace(levels: LevelSet, topk=512):
 
 
 # --------------------------------------------------------------------------------------- rotated NMS / IoU
-def nms_rot(boxes, scores, thr, ge=True, counts=None, want_votes=False):
+_SIDE_STREAMS = {}
+
+
+def _side_streams(dev, k):
+    """k cached side streams of a device (fork / join helpers of the chunked large-NMS calls)."""
+    pool = _SIDE_STREAMS.setdefault(dev.index if dev.index is not None else torch.cuda.current_device(), [])
+    while len(pool) < k:
+        pool.append(torch.cuda.Stream(dev))
+    return pool[:k]
+
+
+def nms_rot(boxes, scores, thr, ge=True, counts=None, want_votes=False, chunks=None):
     """Batched single-class rotated NMS.  boxes (B,n,5) degrees, scores (B,n).
     Returns (keep (B,n) i64, keep_count (B) i32[, votes (B,n) i32]): kept indices per image in
-    descending score; votes[b, p] = 1 + number of dropped boxes whose best overlap was keep[b, p]."""
+    descending score; votes[b, p] = 1 + number of dropped boxes whose best overlap was keep[b, p].
+
+    Large batches are issued as `chunks` (default 2) independent C calls on forked streams that join the
+    current stream again: the per-image stages of the pipeline (shared-memory sort, greedy sweep: one CTA
+    per image) of one chunk then run beside the grid-filling mask kernel of the other."""
     boxes = _dev(boxes, torch.float32, 'boxes').contiguous()
     scores = _dev(scores, torch.float32, 'scores').contiguous()
     if boxes.dim() != 3 or boxes.shape[-1] != 5:
@@ -233,11 +248,29 @@ def nms_rot(boxes, scores, thr, ge=True, counts=None, want_votes=False):
     cnt = torch.zeros(B, dtype=torch.int32, device=dev)
     votes = torch.empty(B, max(n, 1), dtype=torch.int32, device=dev) if want_votes else None
     L = _lib.lib()
-    ws = _workspace(L.mydet_nms_rot_workspace_bytes(B, n), dev)
+    if chunks is None:
+        chunks = 2 if (B >= 4 and n >= 2048) else 1
+    chunks = max(1, min(int(chunks), B))
+    bounds = [(B * c // chunks, B * (c + 1) // chunks) for c in range(chunks)]
+    wss = [_workspace(L.mydet_nms_rot_workspace_bytes(hi - lo, n), dev) for lo, hi in bounds]
+
+    def call(lo, hi, ws, stream):
+        sub = lambda t: _ptr(t[lo:hi]) if t is not None else _ptr(None)
+        rc = L.mydet_nms_rot(sub(boxes), sub(scores), sub(counts), hi - lo, n, n, float(thr), 1 if ge else 0,
+                             sub(keep), sub(cnt), sub(votes), _ptr(ws), ws.numel(), ctypes.c_void_p(stream.cuda_stream))
+        _lib.check(rc, 'mydet_nms_rot')
+
     with torch.cuda.device(dev):
-        rc = L.mydet_nms_rot(_ptr(boxes), _ptr(scores), _ptr(counts), B, n, n, float(thr), 1 if ge else 0,
-                             _ptr(keep), _ptr(cnt), _ptr(votes), _ptr(ws), ws.numel(), _stream())
-    _lib.check(rc, 'mydet_nms_rot')
+        main = torch.cuda.current_stream()
+        if chunks == 1:
+            call(0, B, wss[0], main)
+        else:
+            fork = torch.cuda.Event()
+            fork.record(main)
+            for (lo, hi), ws, side in zip(bounds, wss, _side_streams(dev, chunks)):
+                side.wait_event(fork)
+                call(lo, hi, ws, side)
+                main.wait_stream(side)
     return (keep, cnt, votes) if want_votes else (keep, cnt)
 
 

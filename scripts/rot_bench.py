@@ -8,4 +8,7 @@ sys.path.insert(0, ROOT)
 import torch
 import bench
 
-print(json.dumps(bench.rotated_nms_metric(torch.device('cuda', 0))))
+for ch in ([int(a) for a in sys.argv[1:]] or [None]):
+    r = bench.rotated_nms_metric(torch.device('cuda', 0), chunks=ch)
+    r['chunks'] = ch
+    print(json.dumps(r))
