@@ -190,6 +190,16 @@ int mydet_nms_rot(const float* boxes, const float* scores, const int32_t* counts
 /* bboxes_iou (utils/bbox_ops.py:6-49): a (N,4), b (K,4) -> out (N,K) f32, bit-exact arithmetic. */
 int mydet_iou_aabb_pairwise(const float* a, int64_t n, const float* b, int64_t k, int xyxy,
                             float* out, void* stream);
+/* Row-wise max / arg-max of that matrix, batched, without materialising it: `bboxes_iou(a, gt).max(dim=1)` of the
+ * training branches (models/detlayers/yolov3.py:94-95 and :106-107, fcos2.py:104-106, retinanet.py:106-107).
+ *   a        row boxes: image b, row i at a + b*a_batch_stride + i*a_pitch (elements; a_pitch >= 4 lets (n,5) rows
+ *            pass, a_batch_stride = 0 shares one set of boxes -- e.g. anchors -- between all images)
+ *   gt       (B, max_gt, 4), gt_count (B) i32 or NULL (= max_gt everywhere)
+ *   out_max  (B, n) f32, out_arg (B, n) i64 or NULL: first index of the maximum (torch.max); NaN propagates;
+ *            images without GT get -1 / -1. */
+int mydet_iou_aabb_rowmax(const float* a, int64_t a_batch_stride, int64_t a_pitch, int64_t n, const float* gt,
+                          const int32_t* gt_count, int max_gt, int batch, int xyxy, float* out_max,
+                          int64_t* out_arg, void* stream);
 /* iou_rle (utils/bbox_ops.py:52-100): a (N,5), b (K,5) degrees -> out (N,K) f64, exact clipping. */
 int mydet_iou_rot_pairwise(const float* a, int64_t n, const float* b, int64_t k, double* out,
                            void* stream);
@@ -222,6 +232,18 @@ int mydet_atss_assign(const float* t_ltrb, const int64_t t_stride[4], int batch,
                       uint8_t* positive, uint8_t* ignored, float* target_ltrb, float* target_conf,
                       float* target_cls, float* thr_out, int thr_is_input, void* workspace,
                       size_t workspace_bytes, void* stream);
+
+/* Target assignment of FCOSLayer.forward (models/detlayers/fcos2.py:84-143), one pyramid level: the same
+ * outputs and GT conventions as mydet_atss_assign, with FCOSLayer's rule for a positive cell -- the cell centre
+ * lies strictly inside the GT shrunk by center_region (0.5 in the reference) and
+ * anch_min < max(l,t,r,b) < anch_max (cfg 'model.fcos.anchors'[level], [level+1]).
+ * Workspace: mydet_atss_workspace_bytes(batch, max_gt). */
+int mydet_fcos_assign(const float* t_ltrb, const int64_t t_stride[4], int batch, int stride, int img_h,
+                      int img_w, const float* gt_box, const int64_t* gt_cls, const int32_t* gt_count,
+                      int max_gt, float center_region, float anch_min, float anch_max, float ignore_thres,
+                      int n_cls, uint8_t* positive, uint8_t* ignored, float* target_ltrb,
+                      float* target_conf, float* target_cls, void* workspace, size_t workspace_bytes,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -53,6 +53,7 @@ SIGNATURES = {
     'mydet_nms_rot_workspace_bytes': (c_sz, [c_int, c_int]),
     'mydet_nms_rot': (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_f64, c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     'mydet_iou_aabb_pairwise': (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp]),
+    'mydet_iou_aabb_rowmax': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     'mydet_iou_rot_pairwise': (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
     'mydet_cxcywh_to_x1y1x2y2': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     'mydet_xywha2vertex': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
@@ -60,6 +61,8 @@ SIGNATURES = {
     'mydet_atss_assign': (c_int, [c_vp, ctypes.POINTER(c_i64), c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int32),
                                   ctypes.POINTER(c_f32), c_int, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_f32, c_int,
                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),
+    'mydet_fcos_assign': (c_int, [c_vp, ctypes.POINTER(c_i64), c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int,
+                                  c_f32, c_f32, c_f32, c_f32, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
 }
 
 _LIB = None

@@ -144,6 +144,7 @@ struct AssignParams {
     const float* t; long long ts_b, ts_h, ts_w, ts_p;
     int n_h, n_w, n_cls, max_gt;
     float stride, side, ignore_thres;
+    float center_region, anch_min, anch_max;     // FCOS mode (FCOSLayer, fcos2.py:113-133)
     const int* gt_count;
     unsigned char* positive; unsigned char* ignored;
     float* target_ltrb; float* target_conf; float* target_cls;
@@ -151,7 +152,11 @@ struct AssignParams {
 
 constexpr int kAssignThreads = 128;
 
-__global__ void __launch_bounds__(kAssignThreads) atss_assign_kernel(AssignParams P, AtssWs w) {
+// ATSS: positive iff IoU(anchor, GT) > adaptive threshold and the cell lies inside the GT (fcos2.py:321-331).
+// !ATSS: FCOSLayer's rule (fcos2.py:113-133): the cell centre lies strictly inside the GT's central region
+// (the GT shrunk by center_region) and anch_min < max(l,t,r,b) < anch_max.  Everything else is shared.
+template <bool ATSS>
+__global__ void __launch_bounds__(kAssignThreads) assign_kernel(AssignParams P, AtssWs w) {
     extern __shared__ float4 s_gt[];                       // max_gt boxes, then thr, then cls
     float* s_thr = reinterpret_cast<float*>(s_gt + P.max_gt);
     int* s_cls = reinterpret_cast<int*>(s_thr + P.max_gt);
@@ -161,7 +166,7 @@ __global__ void __launch_bounds__(kAssignThreads) atss_assign_kernel(AssignParam
     const int n_gt = min(max(P.gt_count[b], 0), P.max_gt);
     for (int i = threadIdx.x; i < n_gt; i += kAssignThreads) {
         s_gt[i] = w.gt_sorted[(long long)b * P.max_gt + i];
-        s_thr[i] = w.thr[(long long)b * P.max_gt + i];
+        s_thr[i] = ATSS ? w.thr[(long long)b * P.max_gt + i] : 0.f;
         s_cls[i] = w.cls_sorted[(long long)b * P.max_gt + i];
     }
     // zero this CTA's slab of the class target (coalesced), ones are scattered after the barrier
@@ -196,9 +201,20 @@ __global__ void __launch_bounds__(kAssignThreads) atss_assign_kernel(AssignParam
         const float hw = __fmul_rn(gt.z, 0.5f), hh = __fmul_rn(gt.w, 0.5f);                  // :408-414, cr = 1
         const float tl = __fsub_rn(gx, __fsub_rn(gt.x, hw)), tt = __fsub_rn(gy, __fsub_rn(gt.y, hh));
         const float tr = __fsub_rn(__fadd_rn(gt.x, hw), gx), tb = __fsub_rn(__fadd_rn(gt.y, hh), gy);
-        const bool inside = tl > 0.f && tt > 0.f && tr > 0.f && tb > 0.f;                    // :321
-        const float iou = iou_cxcywh(gx, gy, P.side, P.side, gt.x, gt.y, gt.z, gt.w);        // :329
-        if (inside && iou > s_thr[g]) {                                                      // :330-331
+        bool pos;
+        if (ATSS) {
+            const bool inside = tl > 0.f && tt > 0.f && tr > 0.f && tb > 0.f;                // :321
+            const float iou = iou_cxcywh(gx, gy, P.side, P.side, gt.x, gt.y, gt.z, gt.w);    // :329
+            pos = inside && iou > s_thr[g];                                                  // :330-331
+        } else {
+            // _xywh_to_xyxy(bb, cr): c -/+ (w * cr) / 2                                        :408-414
+            const float chw = __fmul_rn(__fmul_rn(gt.z, P.center_region), 0.5f), chh = __fmul_rn(__fmul_rn(gt.w, P.center_region), 0.5f);
+            const bool centre = gx > __fsub_rn(gt.x, chw) && gx < __fadd_rn(gt.x, chw) &&
+                                gy > __fsub_rn(gt.y, chh) && gy < __fadd_rn(gt.y, chh);      // :123-124
+            const float mx = fmaxf(fmaxf(tl, tt), fmaxf(tr, tb));                            // :126
+            pos = centre && P.anch_min < mx && mx < P.anch_max;                              // :127-129
+        }
+        if (pos) {
             positive = true;
             ltrb = make_float4(tl, tt, tr, tb);                                              // :335, last writer wins
             const int c = s_cls[g];
@@ -269,6 +285,40 @@ MYDET_API int mydet_atss_assign(const float* t_ltrb, const int64_t t_stride[4], 
     P.target_ltrb = target_ltrb; P.target_conf = target_conf; P.target_cls = target_cls;
     const int n_hw = P.n_h * P.n_w;
     const size_t smem = (size_t)max_gt * (16 + 4 + 4);
-    atss_assign_kernel<<<dim3((n_hw + kAssignThreads - 1) / kAssignThreads, batch), kAssignThreads, smem, st>>>(P, w);
+    P.center_region = 0.f; P.anch_min = 0.f; P.anch_max = 0.f;
+    assign_kernel<true><<<dim3((n_hw + kAssignThreads - 1) / kAssignThreads, batch), kAssignThreads, smem, st>>>(P, w);
     return launch_status("atss kernels");
+}
+
+MYDET_API int mydet_fcos_assign(const float* t_ltrb, const int64_t t_stride[4], int batch, int stride, int img_h, int img_w,
+                                const float* gt_box, const int64_t* gt_cls, const int32_t* gt_count, int max_gt,
+                                float center_region, float anch_min, float anch_max, float ignore_thres, int n_cls,
+                                uint8_t* positive, uint8_t* ignored, float* target_ltrb, float* target_conf,
+                                float* target_cls, void* workspace, size_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    MYDET_REQUIRE(t_stride && stride > 0, "NULL stride array / bad stride");
+    MYDET_REQUIRE(batch >= 0 && max_gt >= 0 && n_cls > 0, "bad batch / max_gt / n_cls");
+    MYDET_REQUIRE(max_gt <= 2048, "more than 2048 GT boxes per image");
+    if (batch == 0) return 0;
+    MYDET_REQUIRE(t_ltrb && gt_count && positive && ignored && target_ltrb && target_conf && target_cls, "NULL tensor pointer");
+    MYDET_REQUIRE(max_gt == 0 || (gt_box && gt_cls), "NULL GT pointer");
+    AtssWs w;
+    const size_t need = carve_atss(w, workspace, batch, max_gt);
+    if (!workspace || need > workspace_bytes) {
+        set_error("workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+        return MYDET_ERR_WORKSPACE;
+    }
+    if (max_gt > 0)
+        atss_prepare_kernel<<<batch, 128, sizeof(float) * max_gt, st>>>(gt_box, reinterpret_cast<const long long*>(gt_cls), gt_count, max_gt, w);
+    AssignParams P;
+    P.t = t_ltrb; P.ts_b = t_stride[0]; P.ts_h = t_stride[1]; P.ts_w = t_stride[2]; P.ts_p = t_stride[3];
+    P.n_h = img_h / stride; P.n_w = img_w / stride; P.n_cls = n_cls; P.max_gt = max_gt;   // int(img / stride), fcos2.py:27
+    P.stride = (float)stride; P.side = 0.f; P.ignore_thres = ignore_thres;
+    P.center_region = center_region; P.anch_min = anch_min; P.anch_max = anch_max;
+    P.gt_count = gt_count; P.positive = positive; P.ignored = ignored;
+    P.target_ltrb = target_ltrb; P.target_conf = target_conf; P.target_cls = target_cls;
+    const int n_hw = P.n_h * P.n_w;
+    const size_t smem = (size_t)max_gt * (16 + 4 + 4);
+    assign_kernel<false><<<dim3((n_hw + kAssignThreads - 1) / kAssignThreads, batch), kAssignThreads, smem, st>>>(P, w);
+    return launch_status("fcos assign kernels");
 }

@@ -87,6 +87,75 @@ __global__ void __launch_bounds__(kIouCols) iou_rot_kernel(const float* __restri
     }
 }
 
+// Row-wise max / arg-max of the bboxes_iou matrix, batched, WITHOUT materialising it: what every training
+// branch does next with that matrix (`bboxes_iou(...).max(dim=1)`: yolov3.py:106-107 and :94-95, fcos2.py:104-106,
+// retinanet.py:106-107).  One thread per row box; the image's GT boxes are staged in shared memory (corners
+// and areas computed once).  Same float32 arithmetic as iou_aabb_kernel, torch.max semantics: first index of
+// the maximum, NaN propagates (the first NaN wins).
+constexpr int kRowmaxThreads = 128;
+constexpr int kRowmaxStage = 512;          // GT boxes per shared-memory stage
+__global__ void __launch_bounds__(kRowmaxThreads) iou_rowmax_kernel(const float* __restrict__ a, long long a_bs, long long a_pitch,
+                                                                    long long n, const float* __restrict__ gt,
+                                                                    const int* __restrict__ gt_count, int max_gt, int xyxy,
+                                                                    float* __restrict__ out_max, long long* __restrict__ out_arg) {
+    __shared__ float4 s_box[kRowmaxStage];
+    __shared__ float s_area[kRowmaxStage];
+    const int b = blockIdx.y;
+    const long long row = (long long)blockIdx.x * kRowmaxThreads + threadIdx.x;
+    int n_gt = max_gt;
+    if (gt_count) n_gt = min(max(gt_count[b], 0), max_gt);
+    float4 ca = make_float4(0.f, 0.f, 0.f, 0.f);
+    float area_a = 0.f;
+    if (row < n) {
+        const float* p = a + b * a_bs + row * a_pitch;
+        const float v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3];
+        if (xyxy) {
+            ca = make_float4(v0, v1, v2, v3);
+            area_a = __fmul_rn(__fsub_rn(v2, v0), __fsub_rn(v3, v1));
+        } else {
+            const float hw = __fmul_rn(v2, 0.5f), hh = __fmul_rn(v3, 0.5f);
+            ca = make_float4(__fsub_rn(v0, hw), __fsub_rn(v1, hh), __fadd_rn(v0, hw), __fadd_rn(v1, hh));
+            area_a = __fmul_rn(v2, v3);
+        }
+    }
+    float best = -1.0f;
+    long long arg = -1;
+    bool have = false, is_nan = false;
+    for (int g0 = 0; g0 < n_gt; g0 += kRowmaxStage) {
+        const int cnt = min(kRowmaxStage, n_gt - g0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt; i += kRowmaxThreads) {
+            const float4 v = reinterpret_cast<const float4*>(gt)[(long long)b * max_gt + g0 + i];
+            if (xyxy) {
+                s_box[i] = v;
+                s_area[i] = __fmul_rn(__fsub_rn(v.z, v.x), __fsub_rn(v.w, v.y));
+            } else {
+                const float hw = __fmul_rn(v.z, 0.5f), hh = __fmul_rn(v.w, 0.5f);
+                s_box[i] = make_float4(__fsub_rn(v.x, hw), __fsub_rn(v.y, hh), __fadd_rn(v.x, hw), __fadd_rn(v.y, hh));
+                s_area[i] = __fmul_rn(v.z, v.w);
+            }
+        }
+        __syncthreads();
+        if (row < n && !is_nan) {
+#pragma unroll 4
+            for (int i = 0; i < cnt; ++i) {
+                const float4 cb = s_box[i];
+                const float tlx = fmaxf(ca.x, cb.x), tly = fmaxf(ca.y, cb.y);
+                const float brx = fminf(ca.z, cb.z), bry = fminf(ca.w, cb.w);
+                const float en = (tlx < brx && tly < bry) ? 1.0f : 0.0f;
+                const float inter = __fmul_rn(__fmul_rn(__fsub_rn(brx, tlx), __fsub_rn(bry, tly)), en);
+                const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, s_area[i]), inter));
+                if (iou != iou) { if (!is_nan) { best = iou; arg = g0 + i; is_nan = true; } }
+                else if (!is_nan && (!have || iou > best)) { best = iou; arg = g0 + i; have = true; }
+            }
+        }
+    }
+    if (row < n) {
+        out_max[(long long)b * n + row] = best;
+        if (out_arg) out_arg[(long long)b * n + row] = arg;
+    }
+}
+
 __global__ void corners_kernel(const float* __restrict__ in, long long n, int n_param, float* __restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -152,4 +221,18 @@ MYDET_API int mydet_iou_rot_pairwise(const float* a, int64_t n, const float* b, 
     MYDET_REQUIRE(grid.y <= 65535, "too many rows for one launch");
     iou_rot_kernel<<<grid, kIouCols, 0, (cudaStream_t)stream>>>(a, n, b, k, out);
     return launch_status("iou_rot_kernel");
+}
+
+MYDET_API int mydet_iou_aabb_rowmax(const float* a, int64_t a_batch_stride, int64_t a_pitch, int64_t n, const float* gt,
+                                    const int32_t* gt_count, int max_gt, int batch, int xyxy, float* out_max,
+                                    int64_t* out_arg, void* stream) {
+    MYDET_REQUIRE(n >= 0 && batch >= 0 && max_gt >= 0 && a_pitch >= 4 && a_batch_stride >= 0, "bad sizes / strides");
+    if (n == 0 || batch == 0) return 0;
+    MYDET_REQUIRE(a && out_max && (max_gt == 0 || gt), "NULL tensor pointer");
+    MYDET_REQUIRE(((uintptr_t)gt & 15) == 0, "GT boxes must be 16-byte aligned");
+    MYDET_REQUIRE(batch <= 65535, "batch too large for one launch");
+    const dim3 grid((unsigned)((n + kRowmaxThreads - 1) / kRowmaxThreads), (unsigned)batch);
+    iou_rowmax_kernel<<<grid, kRowmaxThreads, 0, (cudaStream_t)stream>>>(a, a_batch_stride, a_pitch, n, gt, gt_count, max_gt, xyxy,
+                                                                      out_max, reinterpret_cast<long long*>(out_arg));
+    return launch_status("iou_rowmax_kernel");
 }

@@ -5,14 +5,15 @@ import torch
 from .. import _lib, ops
 
 
-def stage_raw(raw, keys):
+def stage_raw(raw, keys, detach=True):
     """The raw dict with every tensor on a CUDA device.  `.to()` keeps the strides of the permuted
-    NCHW views, so the kernel still reads channel planes."""
+    NCHW views, so the kernel still reads channel planes.  detach=False keeps the autograd graph (the
+    training branches compute their loss on these tensors)."""
     if not torch.cuda.is_available():
         raise _lib.MydetError('mydetection_b200 needs a CUDA device (B200); there is no CPU fallback')
     out = {}
     for k in keys:
-        t = raw[k].detach()
+        t = raw[k].detach() if detach else raw[k]
         out[k] = t if t.is_cuda else t.to(torch.device('cuda', torch.cuda.current_device()))
     return out
 
@@ -26,7 +27,24 @@ def decode_level(kind, raw, stride, img_size, anchors=None, conf_key='conf', key
     return {'bbox': box, 'class_idx': cls, 'score': score}
 
 
+def pack_labels(labels, n_param, device):
+    """List of per-image GT (objects with .bboxes (n,P) / .cats (n,)) -> padded device tensors
+    (gt_box (B,G,P) f32, gt_cls (B,G) i64, gt_count (B) i32) with ONE host-to-device copy each."""
+    n_b = len(labels)
+    max_gt = max([len(l) for l in labels] + [1])
+    gt_box = torch.zeros(n_b, max_gt, n_param, dtype=torch.float32)
+    gt_cls = torch.zeros(n_b, max_gt, dtype=torch.int64)
+    counts = torch.zeros(n_b, dtype=torch.int32)
+    for b, l in enumerate(labels):
+        n = len(l)
+        if n:
+            gt_box[b, :n] = l.bboxes.detach().cpu()[:, :n_param]
+            gt_cls[b, :n] = l.cats.detach().cpu()
+        counts[b] = n
+    return gt_box.to(device), gt_cls.to(device), counts.to(device)
+
+
 def no_training(name):
     raise NotImplementedError(
         f'{name}: training-time target assignment is outside the post-processing hot path '
-        '(SURVEY.md section 8f, rank 2); only the ATSS layer implements forward(..., labels)')
+        '(SURVEY.md section 8f, rank 2); the YOLO, FCOS2 and FCOS2-ATSS layers implement forward(..., labels)')

@@ -2,7 +2,7 @@ import torch
 import torch.nn.functional as tnf
 
 from .. import ops
-from ._base import decode_level, no_training, stage_raw
+from ._base import decode_level, pack_labels, stage_raw
 
 
 _THR_CACHE = {}   # (id(labels), img_size, batch, max_gt) -> thresholds of the forward pass in progress
@@ -18,24 +18,58 @@ def _check_shapes(raw, img_size, stride, n_cls):
     return n_b, n_h, n_w
 
 
+def _fcos2_loss(layer, staged, tg, n_b, n_h, n_w):
+    """Loss of both FCOS2 layers on top of kernel-built targets: smooth-L1 on log-ltrb, BCE on conf where
+    positive or not ignored, BCE on classes at positives (reference fcos2.py:157-189 == :351-382); plain torch
+    functional ops, outside the kernel path."""
+    t_ltrb, conf_logits, cls_logits = staged['bbox'], staged['conf'], staged['class']
+    pos, ign = tg['PositiveMask'], tg['IgnoredMask']
+    p_ltrb, t_ltrb_tgt = t_ltrb[pos], torch.log(tg['TargetLTRB'][pos] / layer.stride)
+    err = torch.abs(p_ltrb - t_ltrb_tgt)
+    beta = 0.2
+    loss_bbox = torch.where(err <= beta, 0.5 * err.pow(2) / beta, err - 0.5 * beta).sum()
+    penalty = pos | (~ign)
+    loss_conf = tnf.binary_cross_entropy_with_logits(conf_logits[penalty], tg['TargetConf'][penalty], reduction='sum')
+    loss_cls = tnf.binary_cross_entropy_with_logits(cls_logits[pos], tg['TargetCls'][pos], reduction='sum')
+    pos_num, ignored_num = int(pos.sum()), int((ign & (~pos)).sum())
+    total = n_b * n_h * n_w
+    layer.loss_str = (f'level_{n_h}x{n_w}, pos {pos_num}/{total}, ignored {ignored_num}/{total}: '
+                      f'bbox/gt {loss_bbox:.3f}, conf {loss_conf:.3f}, class/gt {loss_cls:.3f}')
+    return loss_bbox + loss_conf + loss_cls
+
+
 class FCOSLayer(torch.nn.Module):
-    '''FCOS2 layer (conf + class heads), test-mode decode (reference: models/detlayers/fcos2.py:11-69).'''
+    '''FCOS2 layer (conf + class heads) (reference: models/detlayers/fcos2.py:11-190).
+    Test mode: decode.  Training mode: the target maps come from libmydet (mydet_fcos_assign: ignore mask =
+    row-max IoU of the un-clamped predictions with the GT, positives by central region and ltrb range); the
+    loss on top of them is the reference's (:157-180), divided by the batch size (:181).'''
     def __init__(self, level_i: int, cfg: dict):
         super().__init__()
         self.anch_min = cfg['model.fcos.anchors'][level_i]
         self.anch_max = cfg['model.fcos.anchors'][level_i + 1]
         self.stride = cfg['model.fpn.out_strides'][level_i]
         self.n_cls = cfg['general.num_class']
+        self.center_region = 0.5
         self.ignore_thre = cfg['model.fcos2.ignored_threshold']
         self.bb_format = cfg['general.pred_bbox_format']
         self.loss_str = ''
 
+    def assign(self, t_ltrb, img_size, labels):
+        gt_box, gt_cls, counts = pack_labels(labels, 4, t_ltrb.device)
+        return ops.fcos_assign(t_ltrb, self.stride, img_size, gt_box, gt_cls, counts, self.center_region,
+                               self.anch_min, self.anch_max, self.ignore_thre, self.n_cls)
+
     def forward(self, raw, img_size, labels=None):
         assert isinstance(raw, dict)
-        _check_shapes(raw, img_size, self.stride, self.n_cls)
-        if labels is not None:
-            no_training('FCOSLayer (FCOS2)')
-        return decode_level(ops.KIND_FCOS, raw, self.stride, img_size), None
+        n_b, n_h, n_w = _check_shapes(raw, img_size, self.stride, self.n_cls)
+        preds = decode_level(ops.KIND_FCOS, raw, self.stride, img_size)
+        if labels is None:
+            return preds, None
+        assert isinstance(labels, list) and len(labels) == n_b and self.n_cls > 0
+        staged = stage_raw(raw, ('bbox', 'conf', 'class'), detach=False)
+        tg = self.assign(staged['bbox'].detach(), img_size, labels)
+        loss = _fcos2_loss(self, staged, tg, n_b, n_h, n_w) / n_b                  # :181
+        return preds, loss
 
 
 class FCOS_ATSS_Layer(torch.nn.Module):
@@ -56,24 +90,15 @@ class FCOS_ATSS_Layer(torch.nn.Module):
 
     def assign(self, t_ltrb, img_size, labels):
         '''ATSS targets of this level for a list of per-image GT (objects with .bboxes / .cats).'''
-        dev = t_ltrb.device
         n_b = len(labels)
-        max_gt = max([len(l) for l in labels] + [1])
-        gt_box = torch.zeros(n_b, max_gt, 4, dtype=torch.float32)
-        gt_cls = torch.zeros(n_b, max_gt, dtype=torch.int64)
-        counts = torch.zeros(n_b, dtype=torch.int32)
-        for b, l in enumerate(labels):
-            n = len(l)
-            if n:
-                gt_box[b, :n] = l.bboxes.detach().cpu()
-                gt_cls[b, :n] = l.cats.detach().cpu()
-            counts[b] = n
+        gt_box, gt_cls, counts = pack_labels(labels, 4, t_ltrb.device)
+        max_gt = gt_box.shape[1]
         # the adaptive threshold of a GT is level independent: the first level's call computes it, the
         # other levels of the same forward pass (same labels list) reuse it
         key = (id(labels), tuple(img_size), n_b, max_gt)
         thr = _THR_CACHE.get(key)
         out = ops.atss_assign(t_ltrb, self.level_i, self.strides_all, self.anchors_all, img_size,
-                              gt_box.to(dev), gt_cls.to(dev), counts.to(dev), self.topk, self.ignore_thre,
+                              gt_box, gt_cls, counts, self.topk, self.ignore_thre,
                               self.n_cls, thr=thr)
         _THR_CACHE.clear()
         if self.level_i + 1 < len(self.strides_all):
@@ -87,22 +112,7 @@ class FCOS_ATSS_Layer(torch.nn.Module):
         if labels is None:
             return preds, None
         assert isinstance(labels, list) and self.n_cls > 0
-        staged = stage_raw(raw, ('bbox', 'conf', 'class'))
-        t_ltrb, conf_logits, cls_logits = staged['bbox'], staged['conf'], staged['class']
-        tg = self.assign(t_ltrb.detach(), img_size, labels)
-        pos, ign = tg['PositiveMask'], tg['IgnoredMask']
-        # loss: reference fcos2.py:351-371 (smooth-L1 on log-ltrb, BCE on conf where positive or not
-        # ignored, BCE on classes at positives); plain torch functional ops, outside the kernel path
-        p_ltrb, t_ltrb_tgt = t_ltrb[pos], torch.log(tg['TargetLTRB'][pos] / self.stride)
-        err = torch.abs(p_ltrb - t_ltrb_tgt)
-        beta = 0.2
-        loss_bbox = torch.where(err <= beta, 0.5 * err.pow(2) / beta, err - 0.5 * beta).sum()
-        penalty = pos | (~ign)
-        loss_conf = tnf.binary_cross_entropy_with_logits(conf_logits[penalty], tg['TargetConf'][penalty], reduction='sum')
-        loss_cls = tnf.binary_cross_entropy_with_logits(cls_logits[pos], tg['TargetCls'][pos], reduction='sum')
-        loss = loss_bbox + loss_conf + loss_cls
-        pos_num, ignored_num = int(pos.sum()), int((ign & (~pos)).sum())
-        total = n_b * n_h * n_w
-        self.loss_str = (f'level_{n_h}x{n_w}, pos {pos_num}/{total}, ignored {ignored_num}/{total}: '
-                         f'bbox/gt {loss_bbox:.3f}, conf {loss_conf:.3f}, class/gt {loss_cls:.3f}')
+        staged = stage_raw(raw, ('bbox', 'conf', 'class'), detach=False)
+        tg = self.assign(staged['bbox'].detach(), img_size, labels)
+        loss = _fcos2_loss(self, staged, tg, n_b, n_h, n_w)
         return preds, loss

@@ -285,6 +285,37 @@ def iou_aabb(a, b, xyxy=False):
     return out
 
 
+def iou_rowmax(a, gt, gt_count=None, xyxy=False, want_arg=True):
+    """`bboxes_iou(a[b], gt[b]).max(dim=1)` for every image, without the matrix (mydet_iou_aabb_rowmax).
+    a: (B,n,P>=4) or (n,P) shared by all images; gt: (B,G,4); gt_count: (B,) i32 or None.
+    Returns (max (B,n) f32, arg (B,n) i64 | None); images without GT give -1 / -1."""
+    a = _dev(a, torch.float32, 'a')
+    gt = _dev(gt, torch.float32, 'gt').contiguous()
+    if gt.dim() != 3 or gt.shape[-1] != 4:
+        raise ValueError('gt must be (B,G,4)')
+    B, G, _ = gt.shape
+    shared = a.dim() == 2
+    if a.shape[-1] < 4 or a.dim() not in (2, 3) or (not shared and a.shape[0] != B):
+        raise IndexError('a must be (B,n,P>=4) or (n,P>=4)')
+    a = a.contiguous()
+    n, pitch = a.shape[-2], a.shape[-1]
+    dev = a.device
+    out_max = torch.empty(B, n, dtype=torch.float32, device=dev)
+    out_arg = torch.empty(B, n, dtype=torch.int64, device=dev) if want_arg else None
+    if gt_count is not None:
+        gt_count = _dev(gt_count, torch.int32, 'gt_count').contiguous()
+    if G == 0:                                  # keep the 16-byte alignment check away from an empty tensor
+        out_max.fill_(-1.0)
+        if want_arg:
+            out_arg.fill_(-1)
+        return out_max, out_arg
+    with torch.cuda.device(dev):
+        rc = _lib.lib().mydet_iou_aabb_rowmax(_ptr(a), 0 if shared else n * pitch, pitch, n, _ptr(gt), _ptr(gt_count), G, B,
+                                              1 if xyxy else 0, _ptr(out_max), _ptr(out_arg), _stream())
+    _lib.check(rc, 'mydet_iou_aabb_rowmax')
+    return out_max, out_arg
+
+
 def iou_rot(a, b):
     a = _dev(a, torch.float32, 'boxes1').contiguous()
     b = _dev(b, torch.float32, 'boxes2').contiguous()
@@ -296,6 +327,33 @@ def iou_rot(a, b):
 
 
 # --------------------------------------------------------------------------------------- ATSS
+def fcos_assign(t_ltrb, stride, img_hw, gt_box, gt_cls, gt_count, center_region, anch_min, anch_max, ignore_thres, n_cls):
+    """FCOSLayer's targets of one level (mydet_fcos_assign).  Same tensors as atss_assign (no 'thr')."""
+    t = _dev(t_ltrb, torch.float32, 't_ltrb')
+    gt_box = _dev(gt_box, torch.float32, 'gt_box').contiguous()
+    gt_cls = _dev(gt_cls, torch.int64, 'gt_cls').contiguous()
+    gt_count = _dev(gt_count, torch.int32, 'gt_count').contiguous()
+    B, n_h, n_w, _ = t.shape
+    G = gt_box.shape[1]
+    dev = t.device
+    pos = torch.empty(B, n_h, n_w, dtype=torch.uint8, device=dev)
+    ign = torch.empty(B, n_h, n_w, dtype=torch.uint8, device=dev)
+    t_box = torch.empty(B, n_h, n_w, 4, dtype=torch.float32, device=dev)
+    t_conf = torch.empty(B, n_h, n_w, 1, dtype=torch.float32, device=dev)
+    t_cls = torch.empty(B, n_h, n_w, n_cls, dtype=torch.float32, device=dev)
+    L = _lib.lib()
+    ws = _workspace(L.mydet_atss_workspace_bytes(B, G), dev)
+    st = (ctypes.c_int64 * 4)(*t.stride())
+    with torch.cuda.device(dev):
+        rc = L.mydet_fcos_assign(_ptr(t), st, B, int(stride), int(img_hw[0]), int(img_hw[1]), _ptr(gt_box), _ptr(gt_cls),
+                                 _ptr(gt_count), G, float(center_region), float(anch_min), float(anch_max),
+                                 float(ignore_thres), int(n_cls), _ptr(pos), _ptr(ign), _ptr(t_box), _ptr(t_conf),
+                                 _ptr(t_cls), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, 'mydet_fcos_assign')
+    return {'PositiveMask': pos.view(torch.bool), 'IgnoredMask': ign.view(torch.bool), 'TargetLTRB': t_box, 'TargetConf': t_conf,
+            'TargetCls': t_cls}
+
+
 def atss_assign(t_ltrb, level, strides, anchor_sides, img_hw, gt_box, gt_cls, gt_count, topk, ignore_thres, n_cls,
                 thr=None):
     """Targets of one level.  t_ltrb (B,nH,nW,4) view; gt_box (B,G,4) f32, gt_cls (B,G) i64,

@@ -335,6 +335,81 @@ def gen_atss():
     save('atss', **out)
 
 
+def _grab_forward(layer, names, *args):
+    """Run layer(*args) and return (result, {name: clone of the forward()'s local tensor})."""
+    grabbed = {}
+
+    def prof(frame, event, arg):
+        if event == 'return' and frame.f_code.co_name == 'forward' and names[0] in frame.f_locals:
+            for k in names:
+                v = frame.f_locals.get(k)
+                if torch.is_tensor(v):
+                    grabbed[k] = v.detach().clone().cpu()
+    sys.setprofile(prof)
+    try:
+        res = layer(*args)
+    finally:
+        sys.setprofile(None)
+    return res, grabbed
+
+
+def _random_gt(gen, n, img_hw, n_cls, lo=10.0, hi=200.0):
+    bx = torch.empty(n, 4)
+    bx[:, 0] = torch.rand(n, generator=gen) * (img_hw[1] - 40) + 20
+    bx[:, 1] = torch.rand(n, generator=gen) * (img_hw[0] - 40) + 20
+    bx[:, 2:4] = torch.exp(torch.rand(n, 2, generator=gen) * (np.log(hi) - np.log(lo)) + np.log(lo))
+    ct = torch.randint(0, n_cls, (n,), generator=gen)
+    assert (bx[:, 2] * bx[:, 3]).unique().numel() == n          # area ties would leave the GT order open
+    return bx, ct
+
+
+def gen_train():
+    """Training branches: YOLOLayer and FCOSLayer (FCOS2) forward(raw, img_size, labels) of the
+    unmodified reference -- target tensors captured from forward()'s locals, and the loss."""
+    from models.detlayers.yolov3 import YOLOLayer
+    from models.detlayers.fcos2 import FCOSLayer
+    from utils.structures import ImageObjects
+    gen = torch.Generator().manual_seed(1006)
+    img_hw = (256, 320)
+    n_cls = 5
+    counts = [9, 0, 4]
+    out, labels = {}, []
+    for b, n in enumerate(counts):
+        bx, ct = _random_gt(gen, n, img_hw, n_cls, 10.0, 330.0) if n else (torch.zeros(0, 4), torch.zeros(0, dtype=torch.int64))
+        if b == 0:
+            bx[-1, 2:4] = torch.tensor([300.0, 270.0])            # a GT for the coarsest YOLO level
+            bx[-2, 2:4] = torch.tensor([150.0, 180.0])
+        labels.append(ImageObjects(bx, ct, bb_format='cxcywh', img_hw=img_hw))
+        out[f'gt{b}_boxes'], out[f'gt{b}_cats'] = bx, ct
+    # ---- YOLO, three levels
+    cfg = {'model.yolo.anchors': YOLO_ANCHORS, 'model.yolo.anchor_indices': IDX3, 'model.yolo.anchor.negative_threshold': 0.3,
+           'model.fpn.out_strides': [8, 16, 32], 'general.num_class': n_cls}
+    for li, s in enumerate(cfg['model.fpn.out_strides']):
+        store, raw = head_views(gen, len(counts), 3, img_hw[0] // s, img_hw[1] // s, 4, n_cls, conf_mu=-1.0)
+        layer = YOLOLayer(li, cfg)
+        (_, loss), g = _grab_forward(layer, ['gt_mask', 'conf_loss_mask', 'tgt_xywh', 'tgt_cls', 'weighted'], raw, img_hw, labels)
+        out[f'yolo{li}_in'] = store['nchw']
+        out[f'yolo{li}_loss'] = loss
+        out[f'yolo{li}_assigned'] = torch.tensor(int(layer._assigned_num))
+        out.update({f'yolo{li}_{k}': v for k, v in g.items()})
+    # ---- FCOS2 (FCOSLayer), three of the five levels
+    strides = [8, 16, 32, 64, 128]
+    cfg = {'model.fcos.anchors': [0, 64, 128, 256, 512, 100000000], 'model.fpn.out_strides': strides, 'general.num_class': n_cls,
+           'model.fcos2.ignored_threshold': 0.2, 'general.pred_bbox_format': 'cxcywh'}
+    n_pos = n_ign = 0
+    for li in (0, 1, 2):
+        s = strides[li]
+        store, raw = head_views(gen, len(counts), 1, img_hw[0] // s, img_hw[1] // s, 4, n_cls, separate=True)
+        layer = FCOSLayer(li, cfg)
+        (_, loss), g = _grab_forward(layer, ['PositiveMask', 'IgnoredMask', 'TargetConf', 'TargetLTRB', 'TargetCls'], raw, img_hw, labels)
+        out[f'fcos{li}_bbox_in'], out[f'fcos{li}_cls_in'] = store['bbox_nchw'], store['cls_nchw']
+        out[f'fcos{li}_loss'] = loss
+        out.update({f'fcos{li}_{k}': v for k, v in g.items()})
+        n_pos += int(g['PositiveMask'].sum()); n_ign += int(g['IgnoredMask'].sum())
+    assert n_pos > 0 and n_ign > 0
+    save('train', **out)
+
+
 if __name__ == '__main__':
     import_reference()
     torch.set_grad_enabled(False)
@@ -342,3 +417,4 @@ if __name__ == '__main__':
     gen_postprocess()
     gen_iou()
     gen_atss()
+    gen_train()

@@ -128,3 +128,28 @@ def test_atss(golden):
         for k, v in out.items():
             assert torch.equal(v, T(g[f'atss{li}_{k}'])), (li, k)
     assert sum(int(g[f'atss{li}_PositiveMask'].sum()) for li in range(5)) > 0
+
+
+def test_training_targets(golden):
+    """oracle/train.py against tensors captured from the unmodified reference's YOLOLayer / FCOSLayer
+    forward(raw, img_size, labels) (tests/golden/train.npz): bit-exact."""
+    from oracle import decode as od, train as ot
+    from helpers import yolo_views, YOLO_ANCHORS
+    g = golden('train')
+    gts = [(T(g[f'gt{b}_boxes']), T(g[f'gt{b}_cats'])) for b in range(3)]
+    idx3 = [[0, 1, 2], [3, 4, 5], [6, 7, 8]]
+    for li, s in enumerate((8, 16, 32)):
+        raw = yolo_views(T(g[f'yolo{li}_in']), 3, 4, 5)
+        anchors = torch.tensor(YOLO_ANCHORS, dtype=torch.float32)[idx3[li]]
+        box, _, _ = od.decode_yolo(raw, anchors, s, 5)
+        n_h, n_w = raw['bbox'].shape[2:4]
+        tg = ot.yolo_targets(box, gts, (256, 320), s, YOLO_ANCHORS, idx3[li], 0.3, 5, (n_h, n_w))
+        for k in ('gt_mask', 'conf_loss_mask', 'tgt_xywh', 'tgt_cls', 'weighted'):
+            assert torch.equal(tg[k], T(g[f'yolo{li}_{k}'])), (li, k)
+        assert tg['valid_gt_num'] == int(g[f'yolo{li}_assigned'])
+    fa = [0, 64, 128, 256, 512, 100000000]
+    for li, s in zip((0, 1, 2), (8, 16, 32)):
+        t = T(g[f'fcos{li}_bbox_in']).permute(0, 2, 3, 1)
+        tg = ot.fcos2_targets(t, gts, (256, 320), s, fa[li], fa[li + 1], 0.2, 5)
+        for k in ('PositiveMask', 'IgnoredMask', 'TargetConf', 'TargetLTRB', 'TargetCls'):
+            assert torch.equal(tg[k], T(g[f'fcos{li}_{k}'])), (li, k)
