@@ -267,7 +267,9 @@ def run_gpu(args):
     comm = torch.cuda.Stream(dev) if world > 1 else None
     P = 4
     exchange_mode = 'none'
-    if world > 1:
+    if world > 1 and args.no_exchange:
+        exchange_mode = 'none (--no-exchange: diagnostic run, detections stay on their rank)'
+    if world > 1 and not args.no_exchange:
         exchange_mode = 'nccl_all_gather'
         if not args.nccl_exchange:
             try:   # fused exchange: the post-process kernel stores its rows into every rank's buffer (NVLink)
@@ -312,7 +314,7 @@ def run_gpu(args):
             bc.launch_postprocess_scatter()
         else:
             bc.launch_postprocess()
-            if world > 1:
+            if world > 1 and not args.no_exchange:
                 exchange(i)
         return bc
 
@@ -332,7 +334,7 @@ def run_gpu(args):
             graphs.append(g)
 
     pipe_graph, PIPE_STEPS = None, max(N_ROTATE, args.pipe_steps // N_ROTATE * N_ROTATE)
-    if args.launch == 'pipelined' and (world == 1 or fused):
+    if args.launch == 'pipelined' and (world == 1 or fused or args.no_exchange):
         # one CUDA graph spanning PIPE_STEPS steps with a fork: decode(k+1) runs on the capture stream while
         # post-process(k) runs on a second, higher-priority stream (only the candidate-buffer reuse and the
         # final join order them)
@@ -429,7 +431,7 @@ def run_gpu(args):
                 bc.launch_postprocess_scatter()
             else:
                 bc.launch_postprocess()
-                if world > 1:
+                if world > 1 and not args.no_exchange:
                     exchange(i)
         if world > 1:
             torch.cuda.current_stream().wait_stream(comm)
@@ -483,7 +485,7 @@ def run_gpu(args):
     e2e_value = world * BATCH * e2e_steps / (e2e_ms * 1e-3)
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     exchange_ok = None
-    if world > 1:
+    if world > 1 and not args.no_exchange:
         # outside the timed region: what the exchange delivered must equal an NCCL all-gather of the
         # separately packed detections of every rank
         bc = bound[0]
@@ -563,6 +565,7 @@ def main():
     ap.add_argument('--pipe-steps', type=int, default=24, help='steps per pipelined CUDA graph')
     ap.add_argument('--decode-streams', type=int, default=2, help='pipelined mode: streams the decode launches alternate on')
     ap.add_argument('--nccl-exchange', action='store_true', help='N>1: use the NCCL all-gather instead of peer stores')
+    ap.add_argument('--no-exchange', action='store_true', help='N>1 diagnostic: skip the detections exchange')
     ap.add_argument('--no-rot', action='store_true', help='skip the rotated-NMS side metric')
     args = ap.parse_args()
     if args.impl == 'reference':

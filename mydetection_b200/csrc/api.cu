@@ -69,6 +69,9 @@ static int postprocess_impl(const float* boxes, const float* scores, const void*
         P.out_idx = out_idx; P.out_count = out_count; P.status = status; P.out_cap = out_cap;
         P.n_peers = n_peers; P.peer_row0 = peer_row0; P.peer_rows_total = peer_rows_total;
         for (int q = 0; q < 8; ++q) P.peer[q] = q < n_peers ? static_cast<float*>(peers[q]) : nullptr;
+        P.peer_vec = (n_peers > 0 && ((long long)out_cap * (n_param + 2)) % 4 == 0) ? 1 : 0;
+        for (int q = 0; q < n_peers; ++q)
+            if (reinterpret_cast<uintptr_t>(peers[q]) & 15) P.peer_vec = 0;
         P.consume = consume; P.force_scan = (pp_flags & MYDET_PP_FORCE_SCAN) ? 1 : 0;
         return launch_postprocess_small(P, batch, st);
     }

@@ -30,6 +30,7 @@ struct PPParams {
     int n_peers;
     long long peer_row0;        // first image row of this rank inside the gathered buffer
     long long peer_rows_total;  // images in the gathered buffer (all ranks)
+    int peer_vec;               // image blocks of the gathered buffers are 16-byte aligned: coalesced vector stores
     int consume;                // zero counts[b] once it has been read
     int force_scan;             // skip the sampled front end of the select (tests)
 };

@@ -736,6 +736,7 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
         }
         __syncthreads();
         int nk = wtot[32];
+        float* stage = reinterpret_cast<float*>(mask);      // packed rows for the vector peer stores (mask is dead)
         const int r = tid;
         if (r < m) {
             const unsigned wbits = keptw[r >> 5];
@@ -758,20 +759,44 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
                     P.out_cls[orow] = cl;
                     P.out_idx[orow] = gsrc[slot];
                     if (P.n_peers > 0) {
-                        // the path's only exchange, fused: this row goes straight into every rank's
-                        // gathered buffer (peer stores over NVLink / NVSwitch; own copy included)
+                        // the path's only exchange, fused: this row goes into every rank's gathered buffer (peer
+                        // stores over NVLink / NVSwitch; own copy included).  Vector mode: the packed rows of the image
+                        // are first assembled in shared memory (the dead mask region) and sent as coalesced 16-byte
+                        // stores below -- per-row scalar stores cost ~6 us PER PEER (partial-sector NVLink writes).
                         const int np2 = P.n_param + 2;
-                        const long long grow = ((P.peer_row0 + b) * P.out_cap + pos) * np2;
                         const float ang = (P.n_param == 5) ? gang[slot] : 0.f;
-#pragma unroll 1
-                        for (int q = 0; q < P.n_peers; ++q) {
-                            float* o = P.peer[q] + grow;
+                        if (P.peer_vec) {
+                            float* o = stage + pos * np2;
                             o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
                             if (P.n_param == 5) { o[4] = ang; o[5] = sc; o[6] = (float)cl; }
                             else { o[4] = sc; o[5] = (float)cl; }
+                        } else {
+                            const long long grow = ((P.peer_row0 + b) * P.out_cap + pos) * np2;
+#pragma unroll 1
+                            for (int q = 0; q < P.n_peers; ++q) {
+                                float* o = P.peer[q] + grow;
+                                o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+                                if (P.n_param == 5) { o[4] = ang; o[5] = sc; o[6] = (float)cl; }
+                                else { o[4] = sc; o[5] = (float)cl; }
+                            }
                         }
                     }
                 }
+            }
+        }
+        if (P.n_peers > 0 && P.peer_vec) {
+            const int np2 = P.n_param + 2;
+            const int nrow = min(nk, P.out_cap);
+            const int nfl = nrow * np2, nvec = (nfl + 3) >> 2;
+            if (tid < 4 && nfl + tid < 4 * nvec) stage[nfl + tid] = 0.f;       // pad the last vector
+            __syncthreads();
+            const long long img0 = (P.peer_row0 + b) * (long long)P.out_cap * np2;   // 16-byte aligned (host check)
+            const float4* sv4 = reinterpret_cast<const float4*>(stage);
+#pragma unroll 1
+            for (int i = tid; i < nvec; i += kPPThreads) {
+                const float4 val = sv4[i];
+#pragma unroll 1
+                for (int q = 0; q < P.n_peers; ++q) reinterpret_cast<float4*>(P.peer[q] + img0)[i] = val;
             }
         }
         if (tid == 0) {

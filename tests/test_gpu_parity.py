@@ -394,23 +394,25 @@ def test_pipeline_stagewise_self_cleaning(golden):
     same_dets(out, want, 'self_cleaning=False')
 
 
-def test_fused_exchange_layout_single_gpu(golden):
+@pytest.mark.parametrize('topk', [512, 511, 100])
+def test_fused_exchange_layout_single_gpu(golden, topk):
     """mydet_postprocess_scatter with ONE peer (a local buffer): the rows the kernel's output stage stores
-    into the gathered buffer must equal the separately packed detections, counts in the int32 tail."""
+    into the gathered buffer must equal the separately packed detections, counts in the int32 tail.
+    top-k 512 / 100: image blocks are 16-byte aligned -> staged, coalesced vector stores; 511: scalar stores."""
     from mydetection_b200 import ops, pipeline as pl
     g = golden('decode')
     d = dev()
     strides = (8, 16, 32, 64, 128)
     raws = [{k: v.to(d) for k, v in efdet_views(T(g[f'fcos{li}_bbox_in']), T(g[f'fcos{li}_cls_in'])).items()} for li in range(5)]
-    pipe = pl.DetectionPipeline('FCOS2', strides, 6, (256, 384), 0.05, 0.5, 512)
+    pipe = pl.DetectionPipeline('FCOS2', strides, 6, (256, 384), 0.05, 0.5, topk)
     bc = pipe.bind(raws)
-    ex = pl.PeerExchange(2, 512, 4, d, local_only=True)
+    ex = pl.PeerExchange(2, topk, 4, d, local_only=True)
     bc.bind_exchange(ex)
     bc.launch_decode()
     out = bc.launch_postprocess_scatter()
     torch.cuda.synchronize()
     rows, counts = ex.views()
-    want_rows, want_counts = pl.unpack_gathered(pl.pack_detections(out), 1, 2, 512, 4)
+    want_rows, want_counts = pl.unpack_gathered(pl.pack_detections(out), 1, 2, topk, 4)
     assert torch.equal(counts, out['count']) and torch.equal(counts, want_counts)
     for b in range(2):
         n = int(counts[b])
