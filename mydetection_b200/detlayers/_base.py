@@ -44,7 +44,18 @@ def pack_labels(labels, n_param, device):
     return gt_box.to(device), gt_cls.to(device), counts.to(device)
 
 
+def last_writer(lin, n_cells):
+    """Mask over the entries of `lin` (flat target-cell indices, in GT order) that are the LAST one aimed at their
+    cell: the reference assigns targets GT by GT, so when two GTs share a cell the later one owns it.  A plain
+    vectorised index assignment with duplicates has no defined order on the GPU."""
+    order = torch.arange(lin.numel(), device=lin.device)
+    winner = torch.full((n_cells,), -1, dtype=torch.int64, device=lin.device)
+    winner.scatter_reduce_(0, lin, order, reduce='amax', include_self=True)
+    return winner[lin] == order
+
+
 def no_training(name):
     raise NotImplementedError(
         f'{name}: training-time target assignment is outside the post-processing hot path '
-        '(SURVEY.md section 8f, rank 2); the YOLO, FCOS2 and FCOS2-ATSS layers implement forward(..., labels)')
+        '(SURVEY.md section 8f, rank 2); the YOLO, FCOS2, FCOS2-ATSS, RetinaNet and RAPiD layers implement '
+        'forward(..., labels)')

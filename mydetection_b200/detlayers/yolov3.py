@@ -2,7 +2,7 @@ import torch
 import torch.nn.functional as tnf
 
 from .. import ops
-from ._base import decode_level, pack_labels, stage_raw
+from ._base import decode_level, last_writer, pack_labels, stage_raw
 
 
 class YOLOLayer(torch.nn.Module):
@@ -71,13 +71,16 @@ class YOLOLayer(torch.nn.Module):
             anchors = self.anchors.to(dev)
             conf_loss_mask[bi, tn, tj, ti] = True
             gt_mask[bi, tn, tj, ti] = True
+            if self.n_cls > 0:
+                tgt_cls[bi, tn, tj, ti, gt_cls[bi, gi]] = 1                                  # classes accumulate
+            # several GTs aimed at one cell: the last one (GT order) owns the other targets, as on the CPU
+            keep = last_writer(((bi * n_a + tn) * n_h + tj) * n_w + ti, n_b * n_a * n_h * n_w)
+            bi, tn, tj, ti, g, grid_tx, grid_ty = bi[keep], tn[keep], tj[keep], ti[keep], g[keep], grid_tx[keep], grid_ty[keep]
             tgt_xywh[bi, tn, tj, ti, 0] = grid_tx - grid_tx.floor()
             tgt_xywh[bi, tn, tj, ti, 1] = grid_ty - grid_ty.floor()
             tgt_xywh[bi, tn, tj, ti, 2] = torch.log(g[:, 2] / anchors[tn, 0] + 1e-8)
             tgt_xywh[bi, tn, tj, ti, 3] = torch.log(g[:, 3] / anchors[tn, 1] + 1e-8)
             tgt_conf[bi, tn, tj, ti] = 1
-            if self.n_cls > 0:
-                tgt_cls[bi, tn, tj, ti, gt_cls[bi, gi]] = 1
             img_area = img_size[0] * img_size[1]
             weighted[bi, tn, tj, ti] = 2 - g[:, 2] * g[:, 3] / img_area
         weighted = weighted.unsqueeze(-1)

@@ -100,3 +100,52 @@ def fcos2_targets(t_ltrb, gts, img_hw, stride, anch_min, anch_max, ignore_thre, 
             t_cls[b, hi, wi, cidx] = 1
             pos_all[b] = pos_all[b] | pos_mask
     return {'PositiveMask': pos_all, 'IgnoredMask': ign_all, 'TargetConf': t_conf, 'TargetLTRB': t_box, 'TargetCls': t_cls}
+
+
+def retina_anchors(img_hw, stride, anchor_wh):
+    """(nA, nH, nW, 4) cxcywh anchor boxes -- retinanet.py:54-60, :85-90."""
+    img_h, img_w = img_hw
+    n_a = anchor_wh.shape[0]
+    n_h, n_w = int(img_h / stride), int(img_w / stride)
+    a_cx = torch.arange(stride / 2, img_w, stride).view(1, 1, n_w, 1)
+    a_cy = torch.arange(stride / 2, img_h, stride).view(1, n_h, 1, 1)
+    a_wh = anchor_wh.view(n_a, 1, 1, 2)
+    return torch.cat([a_cx.expand(n_a, n_h, n_w, 1), a_cy.expand(n_a, n_h, n_w, 1), a_wh.expand(n_a, n_h, n_w, 2)], dim=-1)
+
+
+def retina_targets_and_loss(t_xywh, cls_logits, gts, img_hw, stride, anchor_wh, pos_thres, neg_thres):
+    """RetinaLayer's training branch for 'cxcywh' boxes and ONE class (the reference's squeeze(-1), :125, supports
+    nothing else) -- retinanet.py:84-160.  t_xywh (B,nA,nH,nW,4), cls_logits (B,nA,nH,nW,1).
+    Returns (per-image list of dict(M_pos, M_neg, gt_idx, tgt_xywh, tgt_cls, cls_penalty_mask) or None, loss, pos)."""
+    import math
+    import torch.nn.functional as tnf
+    n_b, n_a, n_h, n_w = t_xywh.shape[:4]
+    anch = retina_anchors(img_hw, stride, anchor_wh)
+    loss_xywh, loss_cls, total_pos, per_image = 0, 0, 0, []
+    for b, (gt_bbs, cats) in enumerate(gts):
+        if gt_bbs.shape[0] == 0:                                               # :97-101
+            loss_cls = loss_cls + tnf.binary_cross_entropy_with_logits(cls_logits[b], torch.zeros(n_a, n_h, n_w, 1), reduction='sum')
+            per_image.append(None)
+            continue
+        ious = bboxes_iou(anch.view(-1, 4), gt_bbs[:, :4])                     # :106
+        iou_with_gt, gt_idx = ious.max(dim=1)
+        iou_with_gt, gt_idx = iou_with_gt.view(n_a, n_h, n_w), gt_idx.view(n_a, n_h, n_w)
+        m_pos, m_neg = iou_with_gt > pos_thres, iou_with_gt < neg_thres        # :110-111
+        total_pos += int(m_pos.sum())
+        g = gt_bbs[gt_idx, :]
+        tgt_xywh = torch.zeros(n_a, n_h, n_w, 4)
+        tgt_xywh[..., 0:2] = (g[..., 0:2] - anch[..., 0:2]) / anch[..., 2:4]
+        tgt_xywh[..., 2:4] = torch.log(g[..., 2:4] / anch[..., 2:4] + 1e-8)
+        tgt_cls = torch.zeros(n_a, n_h, n_w, 1)
+        tgt_cls[m_pos, cats[gt_idx[m_pos]]] = 1
+        logit = cls_logits[b].detach().squeeze(-1)
+        need_higher = m_pos & (logit < math.log(0.95 / (1 - 0.95)))
+        need_lower = m_neg & (logit > math.log(0.01 / (1 - 0.01)))
+        penalty = need_higher | need_lower
+        if int(m_pos.sum()) > 0:                                               # fvcore.nn.smooth_l1_loss, beta 0.1
+            n = torch.abs(t_xywh[b][m_pos][:, 0:4] - tgt_xywh[m_pos, :])
+            loss_xywh = loss_xywh + torch.where(n < 0.1, 0.5 * n ** 2 / 0.1, n - 0.05).sum()
+        loss_cls = loss_cls + tnf.binary_cross_entropy_with_logits(cls_logits[b, penalty], tgt_cls[penalty], reduction='sum')
+        per_image.append({'M_pos': m_pos, 'M_neg': m_neg, 'gt_idx': gt_idx, 'tgt_xywh': tgt_xywh, 'tgt_cls': tgt_cls,
+                          'cls_penalty_mask': penalty})
+    return per_image, (loss_xywh + loss_cls) / n_b, total_pos

@@ -74,7 +74,12 @@ def install_stubs():
     mod('pycocotools.cocoeval', COCOeval=object)
     plt = mod('matplotlib.pyplot')
     mod('matplotlib', pyplot=plt)
-    nn = mod('fvcore.nn', smooth_l1_loss=None, sigmoid_focal_loss=None)
+    def smooth_l1_loss(input, target, beta, reduction='none'):
+        # fvcore.nn.smooth_l1_loss restated (fvcore is not in this image); only RetinaLayer's training loss uses it
+        n = torch.abs(input - target)
+        loss = torch.where(n < beta, 0.5 * n ** 2 / beta, n - 0.5 * beta) if beta >= 1e-5 else n
+        return loss.sum() if reduction == 'sum' else (loss.mean() if reduction == 'mean' else loss)
+    nn = mod('fvcore.nn', smooth_l1_loss=smooth_l1_loss, sigmoid_focal_loss=None)
     mod('fvcore', nn=nn)
 
 
@@ -407,6 +412,49 @@ def gen_train():
         out.update({f'fcos{li}_{k}': v for k, v in g.items()})
         n_pos += int(g['PositiveMask'].sum()); n_ign += int(g['IgnoredMask'].sum())
     assert n_pos > 0 and n_ign > 0
+    # ---- RetinaNet, single class (the reference's training branch squeezes the class dim, retinanet.py:125)
+    from models.detlayers.retinanet import RetinaLayer
+    rcfg = {'model.fpn.out_strides': strides, 'model.retina.anchor.base': 4, 'model.retina.anchor.scales': [1, 1.26, 1.5874],
+            'model.retina.anchor.ratios': [[1, 1], [1.4, 0.7], [0.7, 1.4]], 'model.retina.anchor.positive_threshold': 0.5,
+            'model.retina.anchor.negative_threshold': 0.4, 'general.num_class': 1, 'general.pred_bbox_format': 'cxcywh',
+            'general.bbox_param': 4}
+    labels1 = [ImageObjects(l.bboxes, torch.zeros_like(l.cats), bb_format='cxcywh', img_hw=img_hw) for l in labels]
+    for li in (1, 2, 3):
+        s = strides[li]
+        n_h, n_w = img_hw[0] // s, img_hw[1] // s
+        bb = torch.randn(len(counts), 9 * 4, n_h, n_w, generator=gen) * 0.3
+        cc = torch.randn(len(counts), 9 * 1, n_h, n_w, generator=gen) * 3.0
+        raw = {'bbox': bb.view(len(counts), 9, 4, n_h, n_w).permute(0, 1, 3, 4, 2),
+               'class': cc.view(len(counts), 9, 1, n_h, n_w).permute(0, 1, 3, 4, 2)}
+        layer = RetinaLayer(li, rcfg)
+        (_, loss), _ = _grab_forward(layer, ['M_pos'], raw, img_hw, labels1)
+        out[f'retina{li}_bbox_in'], out[f'retina{li}_cls_in'] = bb, cc
+        out[f'retina{li}_loss'] = loss
+        out[f'retina{li}_loss_str'] = np.array(layer.loss_str)
+    # ---- RAPiD (rotated boxes, no classes): the stub pycocotools (exact polygon clipper) drives iou_rle, so this pins
+    # the CONTROL FLOW of the training branch; rotated IoU values stay "parity unpinned"
+    from models.detlayers.rapid import RAPiDLayer
+    pcfg = {'model.rapid.anchors': RAPID_ANCHORS, 'model.rapid.anchor_indices': IDX3, 'model.fpn.out_strides': [8, 16, 32],
+            'general.num_class': 0, 'model.rapid.wh_smooth_l1_beta': 1, 'model.angle.loss_angle': 'Periodic_L1',
+            'model.angle.pred_range': 360}
+    rlabels = []
+    for b, n in enumerate(counts):
+        bx = torch.zeros(n, 5)
+        if n:
+            bx[:, :4] = labels[b].bboxes
+            bx[:, 2:4] = torch.exp(torch.rand(n, 2, generator=gen) * (np.log(260.0) - np.log(15.0)) + np.log(15.0))
+            bx[:, 4] = torch.rand(n, generator=gen) * 180 - 90
+        rlabels.append(ImageObjects(bx, torch.zeros(n, dtype=torch.int64), bb_format='cxcywhd', img_hw=img_hw))
+        out[f'rgt{b}_boxes'] = bx
+    for li, s in enumerate(pcfg['model.fpn.out_strides']):
+        store, raw = head_views(gen, len(counts), 3, img_hw[0] // s, img_hw[1] // s, 5, 0, conf_mu=-7.5)
+        layer = RAPiDLayer(li, pcfg)
+        layer.ignore_thre = 0.1        # instance attribute (0.6 in __init__): random predictions rarely reach 0.6
+        (_, loss), g = _grab_forward(layer, ['PositiveMask', 'IgnoredMask', 'TargetXYWH', 'TargetAngle', 'TargetConf'], raw, img_hw, rlabels)
+        out[f'rapid{li}_in'] = store['nchw']
+        out[f'rapid{li}_loss'] = loss
+        out.update({f'rapid{li}_{k}': v for k, v in g.items()})
+        print('rapid', li, layer.loss_str)
     save('train', **out)
 
 

@@ -153,3 +153,16 @@ def test_training_targets(golden):
         tg = ot.fcos2_targets(t, gts, (256, 320), s, fa[li], fa[li + 1], 0.2, 5)
         for k in ('PositiveMask', 'IgnoredMask', 'TargetConf', 'TargetLTRB', 'TargetCls'):
             assert torch.equal(tg[k], T(g[f'fcos{li}_{k}'])), (li, k)
+
+    # RetinaNet (single class): loss and positive count of the reference run (its per-image targets are loop locals)
+    scales, ratios = [1, 1.26, 1.5874], [[1, 1], [1.4, 0.7], [0.7, 1.4]]
+    gts1 = [(b, torch.zeros_like(c)) for b, c in gts]
+    for li, s in zip((1, 2, 3), (16, 32, 64)):
+        wh = torch.Tensor([(4 * s * sc * rt[0], 4 * s * sc * rt[1]) for sc in scales for rt in ratios])
+        bb, cc = T(g[f'retina{li}_bbox_in']), T(g[f'retina{li}_cls_in'])
+        n_b, _, n_h, n_w = bb.shape
+        t = bb.view(n_b, 9, 4, n_h, n_w).permute(0, 1, 3, 4, 2)
+        c = cc.view(n_b, 9, 1, n_h, n_w).permute(0, 1, 3, 4, 2)
+        _, loss, pos = ot.retina_targets_and_loss(t, c, gts1, (256, 320), s, wh, 0.5, 0.4)
+        assert float(loss) == float(g[f'retina{li}_loss']), li
+        assert f' pos {pos}/' in str(g[f'retina{li}_loss_str'])
