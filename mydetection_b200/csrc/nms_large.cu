@@ -888,24 +888,32 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(LargeWs w, const i
                 const int nk = __popcll(kept);
                 unsigned* removed32 = reinterpret_cast<unsigned*>(removed);
                 const int warp = tid >> 5, lane = tid & 31;
+                constexpr int kWarps = kSweepThreads / 32;          // 16: a block has at most 64 kept rows = 4 per warp
+                constexpr int kRowsPerWarp = kTile / kWarps;        // all of a warp's rows are loaded in ONE round trip
+                                                                    // (row after row was 3-4 dependent L2 latencies per block)
 #pragma unroll 1
-                for (int kr = warp; kr < nk; kr += kSweepThreads / 32) {
-                    const unsigned long long* rowp = mask + (long long)klist[kr] * w.words;
-                    const unsigned long long* adj = adj2[buf][kslot[kr]];
-#pragma unroll 1
-                    for (int w0 = 0; w0 < words; w0 += 256) {           // 256 words per round, 8 loads in flight
-                        unsigned long long v[8];
+                for (int w0 = 0; w0 < words; w0 += 256) {               // 256 words per round, 8 loads per row in flight
+                    unsigned long long v[kRowsPerWarp][8];
+#pragma unroll
+                    for (int j = 0; j < kRowsPerWarp; ++j) {
+                        const int kr = warp + j * kWarps;
+                        const bool live = kr < nk;
+                        const unsigned long long* rowp = mask + (long long)(live ? klist[kr] : 0) * w.words;
+                        const unsigned long long* adj = adj2[buf][live ? kslot[kr] : 0];
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
                             const int wd = w0 + lane + 32 * u;
-                            v[u] = (wd < words && ((adj[wd >> 6] >> (wd & 63)) & 1ull)) ? rowp[wd] : 0ull;
+                            v[j][u] = (live && wd < words && ((adj[wd >> 6] >> (wd & 63)) & 1ull)) ? rowp[wd] : 0ull;
                         }
+                    }
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int wd = w0 + lane + 32 * u;
-                            if ((unsigned)v[u]) atomicOr(&removed32[2 * wd], (unsigned)v[u]);
-                            if ((unsigned)(v[u] >> 32)) atomicOr(&removed32[2 * wd + 1], (unsigned)(v[u] >> 32));
-                        }
+                    for (int u = 0; u < 8; ++u) {
+                        const int wd = w0 + lane + 32 * u;
+                        unsigned long long acc = 0ull;
+#pragma unroll
+                        for (int j = 0; j < kRowsPerWarp; ++j) acc |= v[j][u];
+                        if ((unsigned)acc) atomicOr(&removed32[2 * wd], (unsigned)acc);
+                        if ((unsigned)(acc >> 32)) atomicOr(&removed32[2 * wd + 1], (unsigned)(acc >> 32));
                     }
                 }
             }
