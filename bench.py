@@ -333,7 +333,10 @@ def run_gpu(args):
                 step_body()
             graphs.append(g)
 
-    pipe_graph, PIPE_STEPS = None, max(N_ROTATE, args.pipe_steps // N_ROTATE * N_ROTATE)
+    # steps per pipelined graph: a multiple of the buffer rotation, no longer than the run itself, so that a short
+    # `--steps K` is still measured in the pipelined mode; the remainder (< PIPE_STEPS) gets its own graph
+    pipe_graph, tail_graph = None, None
+    PIPE_STEPS = max(N_ROTATE, min(args.pipe_steps, steps) // N_ROTATE * N_ROTATE)
     if args.launch == 'pipelined' and (world == 1 or fused or args.no_exchange):
         # one CUDA graph spanning PIPE_STEPS steps with a fork: decode(k+1) runs on the capture stream while
         # post-process(k) runs on a second, higher-priority stream (only the candidate-buffer reuse and the
@@ -348,29 +351,36 @@ def run_gpu(args):
         # decodes alternate between two streams, so the launch ramp / drain tail of one overlaps the next
         n_dec = max(1, min(args.decode_streams, N_ROTATE))
         s_dec = [s_cap] + [torch.cuda.Stream(dev) for _ in range(n_dec - 1)]
-        pipe_graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(pipe_graph, stream=s_cap):
-            pp_ev = []
-            for s in s_dec[1:]:
-                s.wait_stream(s_cap)
-            for k in range(PIPE_STEPS):
-                j = k % N_ROTATE
-                sd = s_dec[k % n_dec]
-                with torch.cuda.stream(sd):
-                    if k >= N_ROTATE:
-                        sd.wait_event(pp_ev[k - N_ROTATE])
-                    bound[j].launch_decode()
-                    ev = torch.cuda.Event()
-                    ev.record(sd)
-                with torch.cuda.stream(s_pp):
-                    s_pp.wait_event(ev)
-                    pp_launch(bound[j])
-                    e2 = torch.cuda.Event()
-                    e2.record(s_pp)
-                    pp_ev.append(e2)
-            for s in s_dec[1:]:
-                s_cap.wait_stream(s)
-            s_cap.wait_stream(s_pp)
+
+        def capture_pipeline(n_steps):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s_cap):
+                pp_ev = []
+                for s in s_dec[1:]:
+                    s.wait_stream(s_cap)
+                for k in range(n_steps):
+                    j = k % N_ROTATE
+                    sd = s_dec[k % n_dec]
+                    with torch.cuda.stream(sd):
+                        if k >= N_ROTATE:
+                            sd.wait_event(pp_ev[k - N_ROTATE])
+                        bound[j].launch_decode()
+                        ev = torch.cuda.Event()
+                        ev.record(sd)
+                    with torch.cuda.stream(s_pp):
+                        s_pp.wait_event(ev)
+                        pp_launch(bound[j])
+                        e2 = torch.cuda.Event()
+                        e2.record(s_pp)
+                        pp_ev.append(e2)
+                for s in s_dec[1:]:
+                    s_cap.wait_stream(s)
+                s_cap.wait_stream(s_pp)
+            return g
+
+        pipe_graph = capture_pipeline(PIPE_STEPS)
+        if steps % PIPE_STEPS:
+            tail_graph = capture_pipeline(steps % PIPE_STEPS)   # PIPE_STEPS is a multiple of N_ROTATE: it starts at buffer 0 too
 
     def barrier():
         if world > 1:
@@ -380,6 +390,9 @@ def run_gpu(args):
     sampler = ClockSampler(local) if rank == 0 else None
     for i in range(warmup):
         step(i)
+    for g in (pipe_graph, tail_graph):     # first replay of a graph uploads it: keep that out of the timed region
+        if g is not None:
+            g.replay()
     barrier()
 
     # ---- timed region: whole step + the decode kernel alone (events on the launching stream)
@@ -391,8 +404,8 @@ def run_gpu(args):
     if pipe_graph is not None:
         for i in range(steps // PIPE_STEPS):
             pipe_graph.replay()
-        for i in range(steps - steps % PIPE_STEPS, steps):
-            step(i)
+        if tail_graph is not None:
+            tail_graph.replay()
     elif graphs is not None:
         for i in range(steps):
             graphs[i % N_ROTATE].replay()
