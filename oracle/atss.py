@@ -46,6 +46,22 @@ def atss_threshold(gt_box, anchors_per_level, k):
     return ious.mean() + ious.std()                                          # :403-404
 
 
+def atss_threshold_index_ties(gt_box, anchors_per_level, k):
+    """atss_threshold with the DECLARED tie policy of the kernels: anchors at equal distance are taken in ascending
+    index order (stable sort).  torch.topk(sorted=False) leaves the choice among equidistant anchors open (it happens
+    when a GT centre sits exactly on a cell boundary), and anchors mirrored across the diagonal have different IoUs
+    with a non-square GT, so the reference's own result is implementation-defined there."""
+    cx, cy = gt_box[0], gt_box[1]
+    cand = []
+    for anchors in anchors_per_level:
+        d2 = (cx - anchors[:, 0]).pow(2) + (cy - anchors[:, 1]).pow(2)
+        near = torch.sort(d2, stable=True).indices[:k]
+        cand.append(anchors[near, :])
+    cand = torch.cat(cand, dim=0)
+    ious = bboxes_iou(gt_box.view(1, 4), cand, xyxy=False).squeeze()
+    return ious.mean() + ious.std()
+
+
 def unclamped_cxcywh(t_ltrb, stride):
     """exp-ltrb -> cxcywh WITHOUT clamping, the boxes the ignore mask uses -- fcos2.py:42, :253, :444-450."""
     n_h, n_w = t_ltrb.shape[-3], t_ltrb.shape[-2]

@@ -207,6 +207,38 @@ def test_cfg4_atss_100gt():
     assert flips <= 2, flips
 
 
+def test_atss_threshold_window_edges():
+    """The k nearest anchors are searched in an 11x11 window around the GT centre (exhaustively when the centre is
+    outside the image): GT centres on corners, edges, cell boundaries, half cells and outside the image must give
+    the oracle's adaptive threshold (torch.topk over ALL anchors of every level)."""
+    from mydetection_b200 import ops
+    from oracle import atss as oa
+    strides, sides, img = [8, 16, 32, 64, 128], [24, 48, 96, 192, 384], (384, 640)
+    pts = [(0, 0), (640, 384), (0, 384), (640, 0), (320, 0), (0, 192), (4, 4), (8, 8), (12, 12), (636, 380), (64, 64), (128, 256),
+           (63.999, 64.001), (320, 192), (-30, 100), (700, 200), (100, -5), (300, 500), (-1e-3, 50), (639.5, 383.5), (3.9, 380.1),
+           (37.3, 211.7), (501.2, 17.9), (1.1, 2.3), (638.7, 1.4), (333.3, 383.9), (-7.7, 391.3)]
+    gt = torch.tensor([[x, y, 90.0 + 7 * i, 60.0 + 5 * i] for i, (x, y) in enumerate(pts)], dtype=torch.float32)[None]
+    cls = torch.zeros(1, len(pts), dtype=torch.int64)
+    counts = torch.tensor([len(pts)], dtype=torch.int32)
+    t = torch.zeros(1, 48, 80, 4)
+    out = ops.atss_assign(t.to(DEV), 0, strides, sides, img, gt.to(DEV), cls.to(DEV), counts.to(DEV), 9, 0.7, 3)
+    torch.cuda.synchronize()
+    anchors = oa.all_level_anchors(img, strides, sides)
+    n_ref = 0
+    for i in range(len(pts)):
+        got = float(out['thr'][0, i])
+        # declared tie policy (ascending index among equidistant anchors): always
+        want = float(oa.atss_threshold_index_ties(gt[0, i], anchors, 9))
+        assert abs(got - want) <= 2e-6 * max(1.0, abs(want)), (pts[i], got, want)
+        # the reference's torch.topk: wherever the k-th distance is not tied (centres off the cell boundaries)
+        ref = float(oa.atss_threshold(gt[0, i], anchors, 9))
+        on_boundary = any(pts[i][0] % (s / 2) == 0 or pts[i][1] % (s / 2) == 0 for s in strides)
+        if not on_boundary:
+            n_ref += 1
+            assert abs(got - ref) <= 2e-6 * max(1.0, abs(ref)), (pts[i], got, ref)
+    assert n_ref >= 8
+
+
 # ---------------------------------------------------------------------------------------------- config 5
 @pytest.mark.parametrize('img,batch', [(704, 6), (1024, 3), (1536, 2)])
 def test_cfg5_dense_scene_uncapped(img, batch):
