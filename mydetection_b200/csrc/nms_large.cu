@@ -200,6 +200,107 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_smem_kernel(const unsign
         }
 }
 
+// The same network for npad == 16 384 with the data in REGISTERS: thread t owns the 16 consecutive elements
+// 16t .. 16t+15.  Strides 1..8 are compare-exchanges inside a thread, strides 16..256 are warp shuffles with lane
+// t ^ (stride/16), and only strides >= 512 (15 of the 105 steps) go through shared memory.  The all-shared-memory
+// kernel above is bound by shared-memory bandwidth (2 x 12 B per element and step): 244 us -> ~90 us per launch.
+constexpr int kRegSortN = 16384, kRegSortE = 16;
+__device__ __forceinline__ int sort_pad(int g) { return g + (g >> 5); }       // 1 pad word per 32: blocked access is 2-way at worst
+// PIK ("payload in key"): the low 20 bits of the key ARE the element's slot (Morton keys always; score keys when no
+// src_idx remaps the tie index), so only the 16 keys are carried (32 registers instead of 48: no spills at 1024 threads).
+template <int S, bool PIK>
+__device__ __forceinline__ void sort_reg_step(unsigned long long (&k)[kRegSortE], int (&p)[kRegSortE], int g0, int size) {
+#pragma unroll
+    for (int e = 0; e < kRegSortE; ++e) {
+        if ((e & S) == 0) {
+            const bool up = ((g0 + e) & size) == 0;
+            const unsigned long long a = k[e], c = k[e + S];
+            if ((a > c) == up) {
+                k[e] = c; k[e + S] = a;
+                if (!PIK) { const int t = p[e]; p[e] = p[e + S]; p[e + S] = t; }
+            }
+        }
+    }
+}
+template <bool PIK>
+__device__ __forceinline__ void sort_reg16k_body(const unsigned long long* kb, int* ob, int* invb, int n,
+                                                 unsigned long long* skeys, int* spay) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int g0 = tid * kRegSortE;
+    unsigned long long k[kRegSortE];
+    int p[kRegSortE];
+#pragma unroll
+    for (int e = 0; e < kRegSortE; ++e) { const int g = g0 + e; k[e] = (g < n) ? kb[g] : ~0ull; p[e] = g; }
+#pragma unroll 1
+    for (int size = 2; size <= kRegSortN; size <<= 1) {
+        if (size >= 1024) {
+            // strides size/2 .. 512 in shared memory (8 pairs per thread), then back to the registers
+            __syncthreads();                                           // everybody has read the previous contents
+#pragma unroll
+            for (int e = 0; e < kRegSortE; ++e) { skeys[sort_pad(g0 + e)] = k[e]; if (!PIK) spay[sort_pad(g0 + e)] = p[e]; }
+            __syncthreads();
+#pragma unroll 1
+            for (int stride = size >> 1; stride >= 512; stride >>= 1) {
+#pragma unroll 4
+                for (int t = tid; t < (kRegSortN >> 1); t += kSortThreads) {
+                    const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                    const bool up = (lo & size) == 0;
+                    const int il = sort_pad(lo), ih = sort_pad(hi);
+                    const unsigned long long a = skeys[il], c = skeys[ih];
+                    if ((a > c) == up) {
+                        skeys[il] = c; skeys[ih] = a;
+                        if (!PIK) { const int pa = spay[il]; spay[il] = spay[ih]; spay[ih] = pa; }
+                    }
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int e = 0; e < kRegSortE; ++e) { k[e] = skeys[sort_pad(g0 + e)]; if (!PIK) p[e] = spay[sort_pad(g0 + e)]; }
+        }
+        // strides 256 .. 16: the partner element lives in lane ^ d, same slot
+#pragma unroll 1
+        for (int d = min(size >> 5, 16); d >= 1; d >>= 1) {
+            const bool lower = (lane & d) == 0;
+#pragma unroll
+            for (int e = 0; e < kRegSortE; ++e) {
+                const bool up = ((g0 + e) & size) == 0;
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, k[e], d);
+                int op = 0;
+                if (!PIK) op = __shfl_xor_sync(0xffffffffu, p[e], d);
+                const bool take = (lower == up) ? (other < k[e]) : (other > k[e]);     // keep the min / the max
+                if (take) { k[e] = other; if (!PIK) p[e] = op; }
+            }
+        }
+        if (size >= 16) sort_reg_step<8, PIK>(k, p, g0, size);
+        if (size >= 8) sort_reg_step<4, PIK>(k, p, g0, size);
+        if (size >= 4) sort_reg_step<2, PIK>(k, p, g0, size);
+        sort_reg_step<1, PIK>(k, p, g0, size);
+    }
+#pragma unroll
+    for (int e = 0; e < kRegSortE; ++e) {
+        const int g = g0 + e;
+        if (g < n && k[e] != ~0ull) {
+            const int slot = PIK ? (int)(k[e] & 0xfffffull) : p[e];
+            ob[g] = slot;
+            if (invb) invb[slot] = g;
+        }
+    }
+}
+// grid = B CTAs, or 2 B (score keys, then Morton keys: always payload-in-key); pik1: the first array is too
+__global__ void __launch_bounds__(kSortThreads, 1) sort_reg16k_kernel(const unsigned long long* keys, int* order, int* inv,
+                                                                      const unsigned long long* keys2, int* order2, int n, int B,
+                                                                      int pik1) {
+    extern __shared__ unsigned long long skeys[];                      // sort_pad(16384) keys, then as many payloads
+    int* spay = reinterpret_cast<int*>(skeys + sort_pad(kRegSortN));
+    const bool second = (int)blockIdx.x >= B;
+    const int b = second ? blockIdx.x - B : blockIdx.x;
+    const unsigned long long* kb = (second ? keys2 : keys) + (long long)b * n;
+    int* ob = (second ? order2 : order) + (long long)b * n;
+    int* invb = (inv && !second) ? inv + (long long)b * n : nullptr;
+    if (second || pik1) sort_reg16k_body<true>(kb, ob, invb, n, skeys, spay);
+    else sort_reg16k_body<false>(kb, ob, invb, n, skeys, spay);
+}
+
 // Sort for larger images (16 384 < n <= 2^20): the same bitonic network split over CTAs.  16 384-key chunks
 // are sorted / merged in shared memory (strides < 16 384), the few stages with longer strides are
 // compare-exchanges in global memory.  Replaces the O(n^2) all-pairs rank kernel (2.3e9 compares at 48 k).
@@ -282,10 +383,16 @@ static int sort_big(const unsigned long long* keys, int* order, int n, int B, La
 // order[b][rank] = index of the rank-th smallest key of image b (invalid keys ~0 are left out); inv (optional)
 // = its inverse.  keys2 / order2 (optional): a second key array of the same shape, sorted alongside.
 static int sort_keys(const unsigned long long* keys, int* order, int* inv, const unsigned long long* keys2, int* order2,
-                     int n, int B, LargeWs& w, cudaStream_t st) {
+                     int n, int B, LargeWs& w, cudaStream_t st, bool pik1 = false) {
     if (n <= kSortMaxN) {
         int npad = 64;
         while (npad < n) npad <<= 1;
+        if (npad == kRegSortN) {
+            const size_t smem = (size_t)(kRegSortN + kRegSortN / 32) * 12;
+            MYDET_CUDA(cudaFuncSetAttribute(sort_reg16k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            sort_reg16k_kernel<<<keys2 ? 2 * B : B, kSortThreads, smem, st>>>(keys, order, inv, keys2, order2, n, B, pik1 ? 1 : 0);
+            return launch_status("sort_reg16k_kernel");
+        }
         MYDET_CUDA(cudaFuncSetAttribute(sort_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortMaxN * 12)));
         sort_smem_kernel<<<keys2 ? 2 * B : B, kSortThreads, (size_t)npad * 12, st>>>(keys, order, inv, keys2, order2, n, npad, B);
         return launch_status("sort_smem_kernel");
@@ -1080,8 +1187,9 @@ int run_large(const LargeArgs& A, void* workspace, size_t workspace_bytes, cudaS
     keys_kernel<<<dim3((n + 255) / 256, B), 256, 0, st>>>(K, w.keys, w.m);
     {
         // score order and Morton order do not depend on each other: one launch sorts both
-        const int rc = spatial ? sort_keys(w.keys, w.order, w.rank_of_slot, w.skeys, w.slot_of_spos, n, B, w, st)
-                               : sort_keys(w.keys, w.order, nullptr, nullptr, nullptr, n, B, w, st);
+        const bool pik1 = A.src_idx == nullptr;      // the tie index of the score keys is the slot itself
+        const int rc = spatial ? sort_keys(w.keys, w.order, w.rank_of_slot, w.skeys, w.slot_of_spos, n, B, w, st, pik1)
+                               : sort_keys(w.keys, w.order, nullptr, nullptr, nullptr, n, B, w, st, pik1);
         if (rc) return rc;
     }
     GatherParams G{A.boxes, A.pitch, n, A.n_param, A.box_format};
