@@ -801,13 +801,22 @@ __global__ void __launch_bounds__(kTile) mask_rot_spatial_kernel(LargeWs w, cons
             for (int j = 0; j < 32; ++j) {
                 const float4 c = ccull[buf][j];
                 const float dx = mcx - c.x, dy = mcy - c.y, rr = fmaf(c.z, 1.00001f, mr);
+#ifdef MYDET_AREA_IN_CULL
+                // circle test AND area-ratio bound (IoU <= min/max of the areas), both branch-free
+                if (fmaf(dx, dx, dy * dy) <= rr * rr && fminf(ma, c.w) * 1.0001f >= thr_f * fmaxf(ma, c.w)) cand_lo |= 1u << j;
+#else
                 if (fmaf(dx, dx, dy * dy) <= rr * rr) cand_lo |= 1u << j;
+#endif
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const float4 c = ccull[buf][32 + j];
                 const float dx = mcx - c.x, dy = mcy - c.y, rr = fmaf(c.z, 1.00001f, mr);
+#ifdef MYDET_AREA_IN_CULL
+                if (fmaf(dx, dx, dy * dy) <= rr * rr && fminf(ma, c.w) * 1.0001f >= thr_f * fmaxf(ma, c.w)) cand_hi |= 1u << j;
+#else
                 if (fmaf(dx, dx, dy * dy) <= rr * rr) cand_hi |= 1u << j;
+#endif
             }
             unsigned long long cand = ((unsigned long long)cand_hi << 32) | cand_lo;
             if (tj == ti) cand = (t >= kTile - 1) ? 0ull : (cand & (~0ull << (t + 1)));   // each unordered pair once

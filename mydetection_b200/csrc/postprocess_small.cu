@@ -208,14 +208,15 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
             const int need = s_need;
             if ((int)above < need && need <= (int)(above + mine)) {
                 unsigned acc = above;
-#pragma unroll 1
-                for (int j = 7; j >= 0; --j) {
-                    if ((int)acc < need && need <= (int)(acc + h[j])) {
+                bool found = false;
+#pragma unroll
+                for (int j = 7; j >= 0; --j) {                         // unrolled: h[] stays in registers
+                    if (!found && (int)acc < need && need <= (int)(acc + h[j])) {
                         s_prefix = prefix | ((unsigned long long)(tid * 8 + j) << shift);
                         s_need = need - (int)acc;
                         s_bucket = (int)h[j];
                         if ((int)h[j] == need - (int)acc) s_done = 1;  // the whole bucket is taken
-                        break;
+                        found = true;
                     }
                     acc += h[j];
                 }

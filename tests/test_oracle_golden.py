@@ -166,3 +166,18 @@ def test_training_targets(golden):
         _, loss, pos = ot.retina_targets_and_loss(t, c, gts1, (256, 320), s, wh, 0.5, 0.4)
         assert float(loss) == float(g[f'retina{li}_loss']), li
         assert f' pos {pos}/' in str(g[f'retina{li}_loss_str'])
+
+
+def test_atss_threshold_tie_policy_variant():
+    """atss_threshold_index_ties (the kernels' declared tie policy) equals the reference-faithful atss_threshold
+    wherever the k-th nearest anchor is not tied, i.e. for GT centres off the cell boundaries."""
+    from oracle import atss as oa
+    strides, sides, img = [8, 16, 32, 64, 128], [24, 48, 96, 192, 384], (384, 640)
+    anchors = oa.all_level_anchors(img, strides, sides)
+    gen = torch.Generator().manual_seed(3)
+    for _ in range(40):
+        c = torch.rand(2, generator=gen) * torch.tensor([640.0, 384.0])
+        wh = torch.rand(2, generator=gen) * 200 + 10
+        gt = torch.cat([c, wh])
+        a, b = float(oa.atss_threshold(gt, anchors, 9)), float(oa.atss_threshold_index_ties(gt, anchors, 9))
+        assert abs(a - b) <= 1e-6 * max(1.0, abs(a))     # same anchors, the summation order of mean / std may differ
