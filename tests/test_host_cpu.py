@@ -200,3 +200,23 @@ def test_gather_detections_gloo_world2(tmp_path):
         # live rows carry the boxes, rows beyond the count are zeroed
         assert torch.equal(res[r]['mine'][0, :r + 1, :4], res[r]['box'][0, :r + 1])
         assert float(res[r]['mine'][1].abs().sum()) == 0.0
+
+
+def test_training_host_helpers():
+    """Host-side pieces of the training branches that need no GPU: last-writer selection for duplicate target cells
+    (the reference assigns targets GT by GT, so the later GT owns a shared cell) and label packing."""
+    import torch
+    from mydetection_b200.detlayers._base import last_writer, pack_labels
+    lin = torch.tensor([5, 2, 5, 7, 2, 2, 9])
+    keep = last_writer(lin, 12)
+    assert keep.tolist() == [False, False, True, True, False, True, True]
+    assert last_writer(torch.zeros(0, dtype=torch.int64), 4).numel() == 0
+
+    class L:                                            # duck-typed ImageObjects
+        def __init__(self, n):
+            self.bboxes, self.cats = torch.arange(n * 5, dtype=torch.float32).view(n, 5), torch.arange(n)
+        def __len__(self):
+            return self.bboxes.shape[0]
+    box, cls, cnt = pack_labels([L(3), L(0), L(1)], 4, torch.device('cpu'))
+    assert box.shape == (3, 3, 4) and cnt.tolist() == [3, 0, 1] and cnt.dtype == torch.int32 and cls.dtype == torch.int64
+    assert torch.equal(box[0], L(3).bboxes[:, :4]) and float(box[1].abs().sum()) == 0 and torch.equal(cls[2, :1], torch.tensor([0]))
