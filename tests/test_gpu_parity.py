@@ -227,6 +227,38 @@ def test_nms_random_vs_oracle(n, n_cls, topk):
     assert torch.equal(out['idx'][0, :cnt].cpu().long(), want)
 
 
+def test_postprocess_randomised_sweep():
+    """Seeded sweep over candidate counts, class counts, top-k, thresholds and score distributions (uniform, heavily
+    quantised, concentrated near 1, nearly all below the threshold): one batched launch per case against the
+    oracle image by image.  Exercises the sampled front end and its fallback, the pair-balanced and the
+    row-group IoU matrices (few / many same-class pairs) and the k-pad variants."""
+    from mydetection_b200 import ops
+    from oracle import postprocess as opp
+    gen = torch.Generator().manual_seed(2024)
+    d = dev()
+    cases = 0
+    for n in (7, 64, 700, 2049, 8525, 20000):
+        for n_cls in (1, 5, 80):
+            for topk in (16, 512, 1000):
+                kind = cases % 4
+                B = 3
+                boxes = torch.cat([torch.rand(B, n, 2, generator=gen) * 500, torch.rand(B, n, 2, generator=gen) * 80 + 2], 2)
+                u = torch.rand(B, n, generator=gen)
+                scores = [u, (u * 50).round() / 50, 1 - u.pow(4) * 0.05, u * 0.12][kind]
+                cats = torch.randint(0, n_cls, (B, n), generator=gen)
+                thr = 0.1
+                out = ops.postprocess(boxes.to(d), scores.to(d), cats.to(d), thr, 0.5, topk=topk)
+                torch.cuda.synchronize()
+                assert int(out['status'].abs().sum()) == 0
+                for b in range(B):
+                    want = opp.post_process(boxes[b], cats[b], scores[b], thr, 0.5, 'cxcywh', topk)
+                    k = int(out['count'][b])
+                    assert k == want.numel(), (n, n_cls, topk, kind, b)
+                    assert torch.equal(out['idx'][b, :k].cpu().long(), want), (n, n_cls, topk, kind, b)
+                cases += 1
+    assert cases == 54
+
+
 def test_postprocess_batched_ragged_counts():
     """Several images of different candidate counts in one launch, including an empty one."""
     from mydetection_b200 import ops
