@@ -12,10 +12,14 @@
 // order is arbitrary, so the result does not depend on the compaction order.
 //
 // Stages (r1 profile notes in profiles/):
-//  (S)  sampled front end: bracket the K-th score from a 2048-bin histogram of a SAMPLE of the scores, copy
-//       the candidates above that edge to a short list in ONE pass, verify the list holds >= K of them,
-//       radix-select on the list alone.  Exact whatever the sample says; when the check fails (or the list
-//       would not fit) the scan path (A0)-(B1) runs instead:
+//  (R)  n <= 9 216: scores and tie indices are loaded ONCE into registers; an exact 2048-bin shared-memory
+//       histogram of the valid scores gives the bin that holds the K-th score and the exact count above it; the
+//       register-resident scores are classified without a second pass: bins above go straight to their slots, the
+//       boundary bin (a handful of candidates) to a short list whose best are taken by counting.
+//  (S)  larger n: the K-th score is bracketed from a histogram of a SAMPLE of the scores, ONE pass copies the
+//       candidates above that edge to a short list and counts them, the count is verified (>= K), radix passes run
+//       on the list alone.  Exact whatever the sample says; when the check fails (or a list would not fit, e.g.
+//       heavy ties) the scan path (A0)-(B1) runs instead:
 //  (A0) stage 64-bit select keys (score key, ~index) in shared memory, count threshold survivors
 //  (A)  MSB-first 8-bit radix select of the K-th largest key; per-warp private histograms (scores
 //       cluster in a few digits: one shared histogram serialised 1024 threads on 2-3 addresses);
@@ -245,6 +249,188 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
         __syncthreads();
     };
 
+    // list entries (ukey / lidx) at or above kth_key -> selection slots
+    int* lidx = reinterpret_cast<int*>(sbox);                // list: candidate numbers (2 kpad ints; tkey's space)
+    auto take_from_list = [&](int c, unsigned long long kth_key) {
+        for (int base = 0; base < c; base += kPPThreads) {
+            const int u = base + tid;
+            const unsigned long long k = (u < c) ? ukey[u] : 0ull;
+            const bool take = u < c && k >= kth_key;
+            const unsigned bal = __ballot_sync(0xffffffffu, take);
+            if (bal) {
+                int slot0 = 0;
+                if (lane == 0) slot0 = atomicAdd(&s_nsel, __popc(bal));
+                slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                if (take) {
+                    const int slot = slot0 + __popc(bal & lt_mask);
+                    if (slot < kpad) { sel[slot] = lidx[u]; keys[slot] = k; }
+                }
+            }
+        }
+        __syncthreads();
+    };
+    // K-th largest key of the list by 8-bit radix passes (the list has more than `need` entries)
+    auto list_kth = [&](int c, int need) -> unsigned long long {
+        unsigned long long k_and = ~0ull, k_or = 0ull;
+        for (int u = tid; u < c; u += kPPThreads) { const unsigned long long k = ukey[u]; k_and &= k; k_or |= k; }
+        publish_and_or(k_and, k_or);
+        select_init(need);
+        int shift = pass(key_list, c, s_top, false);
+        while (!(s_done || shift == 0)) shift = pass(key_list, c, shift - 1, false);
+        return s_prefix;
+    };
+    const int list_cap = 2 * kpad;
+    bool fast_done = false;                      // block-uniform
+
+    // ---- (R) register-resident front end (n <= 9 216, e.g. the 8 525 candidates of D1 @640).  Scores and tie
+    // indices are loaded ONCE into registers; an EXACT 2048-bin histogram of all valid scores (shared-memory atomics,
+    // bins linear over the score range) gives the bin T that holds the K-th score and the exact count above it; the
+    // register-resident scores are then classified without a second pass over memory: bins above T go straight to
+    // their slots, bin T (a handful of candidates) to the short list, of which the best are taken by counting.
+    constexpr int UR = 9;
+    const bool reg_path = !P.force_scan && n <= UR * kPPThreads;
+    if (reg_path) {
+        unsigned* sh = mask;                     // 2048 bins (the mask region is free until (B2))
+        static_assert(kHistBins == 2 * kPPThreads, "thread t owns bins 2t and 2t+1");
+        reinterpret_cast<uint2*>(sh)[tid] = make_uint2(0u, 0u);
+        float sv[UR];
+        unsigned tv[UR];
+#pragma unroll
+        for (int u = 0; u < UR; ++u) {
+            const int i = u * kPPThreads + tid;
+            sv[u] = (i < n) ? scores[i] : __int_as_float(0x7fc00000);   // NaN pads the tail: fails every compare
+            tv[u] = (i < n && src) ? (unsigned)src[i] : (unsigned)i;
+        }
+        unsigned kmin = 0xffffffffu, kmax = 0u;
+#pragma unroll
+        for (int u = 0; u < UR; ++u)
+            if (sv[u] >= thr) { const unsigned k = float_key(sv[u]); kmin = min(kmin, k); kmax = max(kmax, k); }
+        kmin = __reduce_min_sync(0xffffffffu, kmin); kmax = __reduce_max_sync(0xffffffffu, kmax);
+        if (lane == 0) { wtot[warp] = (int)kmin; wtot[32 + warp] = (int)kmax; }
+        __syncthreads();
+        const float smin = key_float(__reduce_min_sync(0xffffffffu, (unsigned)wtot[lane]));
+        const float smax = key_float(__reduce_max_sync(0xffffffffu, (unsigned)wtot[32 + lane]));
+        const float scale = (smax > smin) ? __fdiv_rn((float)(kHistBins - 1), __fsub_rn(smax, smin)) : 0.0f;
+        auto bin_of = [&](float q) -> int {                  // the SAME function builds and reads the histogram
+            return min(kHistBins - 1, max(0, (int)__fmul_rn(__fsub_rn(q, smin), scale)));
+        };
+#pragma unroll
+        for (int u = 0; u < UR; ++u)
+            if (sv[u] >= thr) atomicAdd(&sh[bin_of(sv[u])], 1u);
+        __syncthreads();
+        // suffix sums over the bins: `above` = candidates in bins above this thread's pair
+        const uint2 h = reinterpret_cast<const uint2*>(sh)[tid];
+        const int mine = (int)(h.x + h.y);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_down_sync(0xffffffffu, incl, o); if (lane + o < 32) incl += v; }
+        if (lane == 0) wtot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int v = wtot[lane];
+            int wi = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_down_sync(0xffffffffu, wi, o); if (lane + o < 32) wi += t; }
+            wtot[32 + lane] = wi - v;
+            if (lane == 0) s_total = wi;
+        }
+        __syncthreads();
+        {
+            const int total_valid = s_total;
+            const int above1 = wtot[32 + warp] + incl - mine;   // above bin 2*tid+1
+            const int above0 = above1 + (int)h.y;               // above bin 2*tid
+            if (total_valid > K) {
+                // the one bin T with  above(T) < K <= above(T) + hist[T]  holds the K-th score
+                if (above1 < K && K <= above1 + (int)h.y) { s_top = 2 * tid + 1; s_bucket = (int)h.y; s_need = K - above1; }
+                else if (above0 < K && K <= above0 + (int)h.x) { s_top = 2 * tid; s_bucket = (int)h.x; s_need = K - above0; }
+            } else if (tid == 0) {
+                s_top = -1; s_bucket = 0; s_need = 0;           // everything valid is selected
+            }
+        }
+        __syncthreads();
+        PP_MARK(16);
+        for (int i = tid; i < kClassBins + 32; i += kPPThreads) { cstart[i] = 0; }   // class histogram (the bins are dead)
+        for (int i = tid; i < kClassBins; i += kPPThreads) { ccur[i] = 0; }
+        if (s_bucket <= list_cap) {
+            const int T = s_top, need = s_need;
+            unsigned sure_bits = 0u, und_bits = 0u;
+#pragma unroll
+            for (int u = 0; u < UR; ++u) {
+                const bool valid = sv[u] >= thr;
+                const int bq = bin_of(sv[u]);
+                sure_bits |= ((valid && bq > T) ? 1u : 0u) << u;
+                und_bits |= ((valid && bq == T) ? 1u : 0u) << u;
+            }
+            // slots: exclusive warp scan of (sure count | undecided count << 16), one shared atomic per warp
+            const int packed = __popc(sure_bits) | (__popc(und_bits) << 16);
+            int pin = packed;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, pin, o); if (lane >= o) pin += t; }
+            const int wtotal = __shfl_sync(0xffffffffu, pin, 31);
+            int bs = 0, bu = 0;
+            if (lane == 0) {
+                if (wtotal & 0xffff) bs = atomicAdd(&s_nsel, wtotal & 0xffff);
+                if (wtotal >> 16) bu = atomicAdd(&s_ucount, wtotal >> 16);
+            }
+            bs = __shfl_sync(0xffffffffu, bs, 0) + ((pin - packed) & 0xffff);
+            bu = __shfl_sync(0xffffffffu, bu, 0) + ((pin - packed) >> 16);
+            if (sure_bits | und_bits) {
+#pragma unroll
+                for (int u = 0; u < UR; ++u) {
+                    const bool sure = (sure_bits >> u) & 1u, und = (und_bits >> u) & 1u;
+                    if (sure || und) {
+                        const int i = u * kPPThreads + tid;
+                        const unsigned long long k = ((unsigned long long)float_key(sv[u]) << 32) | (unsigned long long)(0xffffffffu - tv[u]);
+                        if (sure) {
+                            if (bs < kpad) { sel[bs] = i; keys[bs] = k; }
+                            ++bs;
+                        } else {
+                            if (bu < list_cap) { ukey[bu] = k; lidx[bu] = i; }
+                            ++bu;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            PP_MARK(17);
+            const int ucount = min(s_ucount, list_cap);
+            if (T >= 0 && ucount > 0) {
+                if (need >= ucount) {
+                    take_from_list(ucount, 0ull);
+                } else if (ucount <= kPPThreads / 8) {
+                    // rank by counting, 8 threads per key (keys are unique: the tie index is)
+                    const int e = tid >> 3, part = tid & 7;
+                    const unsigned long long ke = (e < ucount) ? ukey[e] : 0ull;
+                    int rank = 0;
+                    if (e < ucount)
+                        for (int v = part; v < ucount; v += 8) rank += (ukey[v] > ke) ? 1 : 0;
+                    rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+                    rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+                    rank += __shfl_xor_sync(0xffffffffu, rank, 4);
+                    const bool take = e < ucount && part == 0 && rank < need;
+                    const unsigned bal = __ballot_sync(0xffffffffu, take);
+                    if (bal) {
+                        int slot0 = 0;
+                        if (lane == 0) slot0 = atomicAdd(&s_nsel, __popc(bal));
+                        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                        if (take) {
+                            const int slot = slot0 + __popc(bal & lt_mask);
+                            if (slot < kpad) { sel[slot] = lidx[e]; keys[slot] = ke; }
+                        }
+                    }
+                    __syncthreads();
+                } else {
+                    take_from_list(ucount, list_kth(ucount, need));
+                }
+            }
+            fast_done = true;
+        } else {                                 // a boundary bin too full for the list (heavy ties): scan path
+            if (tid == 0) { s_total = 0; s_ucount = 0; s_nsel = 0; s_done = 0; s_prefix = 0ull; }
+            __syncthreads();
+        }
+    }
+    PP_MARK(18);
+
     // ---- (S) sampled front end.  The K-th score is bracketed from a SAMPLE of the scores (every s-th
     // candidate, <= 2048 of them, one or two loads per thread) binned into a 2048-bin shared-memory histogram:
     // the bin below which  K/s + 4 sqrt(K/s) + 4  samples lie gives a float edge that, with high probability,
@@ -253,11 +439,8 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
     // the top K of the list are the top K of the image -- exact, whatever the sample looked like -- and are
     // picked by radix passes over the list alone.  Otherwise (estimate too tight, list overflow, huge n) the
     // scan path below runs.  Replaces staging + full radix pass + slot assignment: 23 k -> ~9 k cycles.
-    bool fast_done = false;                      // block-uniform
-    const int list_cap = 2 * kpad;
-    if (!P.force_scan) {
+    if (!P.force_scan && !reg_path) {
         unsigned* sh = mask;                     // 2048 sample bins (the mask region is free until (B2))
-        int* lidx = reinterpret_cast<int*>(sbox);            // list: candidate numbers (2 kpad ints; tkey's space)
         const int stride = max(1, (n + 2 * kPPThreads - 1) / (2 * kPPThreads));
         static_assert(kHistBins == 2 * kPPThreads, "thread t owns bins 2t and 2t+1");
         reinterpret_cast<uint2*>(sh)[tid] = make_uint2(0u, 0u);
@@ -374,33 +557,7 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
             const int c = s_ucount, v = s_nvalid;
             if (c <= list_cap && (c >= K || c == v)) {
                 // (S3) the K best of the list (all of it when it has no more than K entries)
-                unsigned long long kth_key = 0ull;
-                if (c > K) {
-                    unsigned long long k_and = ~0ull, k_or = 0ull;
-                    for (int u = tid; u < c; u += kPPThreads) { const unsigned long long k = ukey[u]; k_and &= k; k_or |= k; }
-                    publish_and_or(k_and, k_or);
-                    select_init(K);
-                    int shift = pass(key_list, c, s_top, false);
-                    while (!(s_done || shift == 0)) shift = pass(key_list, c, shift - 1, false);
-                    kth_key = s_prefix;
-                }
-                // entries at or above the K-th key -> slots (sel / keys live apart from the list)
-                for (int base = 0; base < c; base += kPPThreads) {
-                    const int u = base + tid;
-                    const unsigned long long k = (u < c) ? ukey[u] : 0ull;
-                    const bool take = u < c && k >= kth_key;
-                    const unsigned bal = __ballot_sync(0xffffffffu, take);
-                    if (bal) {
-                        int slot0 = 0;
-                        if (lane == 0) slot0 = atomicAdd(&s_nsel, __popc(bal));
-                        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-                        if (take) {
-                            const int slot = slot0 + __popc(bal & lt_mask);
-                            if (slot < kpad) { sel[slot] = lidx[u]; keys[slot] = k; }
-                        }
-                    }
-                }
-                __syncthreads();
+                take_from_list(c, (c > K) ? list_kth(c, K) : 0ull);
                 fast_done = true;
             }
         }
