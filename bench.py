@@ -38,9 +38,10 @@ UNIT = 'images/s'
 
 
 def workload_config(n_gpus):
+    point = 'all-pass operating point' if CONF_MU >= 2.0 else 'operating point'
     return {'workload': 'd1_fcs2 decode+NMS: batch 64 per GPU @640x640, 5 levels (8525 loc/img), 80 classes, '
-                        'all-pass operating point (conf logit ~N(2,1.5^2)), conf 0.005, top-512, nms 0.5',
-            'images_per_step_per_gpu': BATCH, 'candidates_per_image': 8525,
+                        f'{point} (conf logit ~N({CONF_MU:g},1.5^2)), conf 0.005, top-512, nms 0.5',
+            'images_per_step_per_gpu': BATCH, 'candidates_per_image': 8525 if CONF_MU >= 2.0 else 'measured: see roofline',
             'l2_policy': f'inputs larger than L2: {N_ROTATE} rotating 185.5 MB batches',
             'sharding': f'images, {n_gpus} x {BATCH}'}
 
@@ -547,7 +548,7 @@ def run_gpu(args):
                 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(world),
                 'roofline': {'bound': 'hbm', 'kernel': 'decode_kernel<FCOS,compact>', 'achieved': achieved,
                              'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
-                             'algorithmic_bytes_per_launch': alg, 'kernel_ms': kernel_ms,
+                             'algorithmic_bytes_per_launch': alg, 'candidates_written_per_launch': cand, 'kernel_ms': kernel_ms,
                              'kernel_ms_how': ('timed region / launches (overlapped decode launches, see DESIGN.md section 6)'
                                                if pipe_graph is not None else 'CUDA events around each launch in the timed region'),
                              'single_eager_launch_ms': dec_ms, 'single_eager_launch_gbs': alg / (dec_ms * 1e-3) / 1e9,
@@ -580,7 +581,12 @@ def main():
     ap.add_argument('--nccl-exchange', action='store_true', help='N>1: use the NCCL all-gather instead of peer stores')
     ap.add_argument('--no-exchange', action='store_true', help='N>1 diagnostic: skip the detections exchange')
     ap.add_argument('--no-rot', action='store_true', help='skip the rotated-NMS side metric')
+    ap.add_argument('--conf-mu', type=float, default=None,
+                    help='mean of the objectness logits (default 2.0: every cell is a candidate; -4: "trained-like", SURVEY 8d)')
     args = ap.parse_args()
+    if args.conf_mu is not None:
+        global CONF_MU
+        CONF_MU = args.conf_mu
     if args.impl == 'reference':
         run_reference(args)
     else:
