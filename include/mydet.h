@@ -100,7 +100,7 @@ int mydet_decode_dense(int kind, const mydet_level_t* levels, int n_levels, int 
  *   dropped, consumers clamp).
  *   state_clean 0: cand_count is zeroed by this call (a memset in front of the kernel); non-zero: the
  *               caller guarantees it is zero already -- true after a one-time memset and then after every
- *               mydet_postprocess(..., consume = 1) that consumed the candidates. */
+ *               mydet_postprocess(..., flags = MYDET_PP_CONSUME) that consumed the candidates. */
 int mydet_decode_compact(int kind, const mydet_level_t* levels, int n_levels, int batch, int n_cls,
                          int n_param, float img_h, float img_w, float conf_thres, float* cand_box,
                          float* cand_score, int32_t* cand_cls, int32_t* cand_idx,
@@ -125,9 +125,10 @@ int mydet_decode_compact(int kind, const mydet_level_t* levels, int n_levels, in
  *   flags    MYDET_PP_CONSUME: counts[b] is zeroed once read, which leaves the candidate state ready for
  *            the next mydet_decode_compact(..., state_clean = 1): a decode + post-process step is then two
  *            kernel launches and nothing else.  Single-kernel path only (effective top-k <= MYDET_SMALL_K).
- *            MYDET_PP_FORCE_SCAN: skip the sampled front end of the select (the kernel then scans every
- *            score with radix passes, as it does on its own when the sample misleads); results are
- *            identical either way -- the flag exists so that tests can prove that.
+ *            MYDET_PP_FORCE_SCAN: skip the histogram front ends of the top-k select (the kernel then scans
+ *            every score with radix passes, as it does on its own when a front end cannot decide: heavy
+ *            ties, a misleading sample); results are identical either way -- the flag exists so that tests
+ *            can prove that.
  * Workspace: mydet_postprocess_workspace_bytes(...) bytes, 256-byte aligned. */
 size_t mydet_postprocess_workspace_bytes(int batch, int n_per_image, int topk);
 int mydet_postprocess(const float* boxes, const float* scores, const void* cls, int cls_is_i64,
@@ -143,7 +144,7 @@ int mydet_postprocess(const float* boxes, const float* scores, const void* cls, 
  * IPC / symmetric memory; the own buffer is one of them), and the per-image count into the int32 tail:
  *     peer_bufs[q]: float rows[images_total][out_cap][P+2];  int32 counts[images_total];
  * This rank's images occupy rows [image_offset, image_offset + batch).  Rows beyond an image's count
- * are not written.  Peer stores are complete when the kernel has completed on `stream`; consumers
+ * are unspecified (at most the three floats that complete the last 16-byte store are zeroed).  Peer stores are complete when the kernel has completed on `stream`; consumers
  * on other ranks order themselves with a stream/host barrier.  peer_bufs is a HOST array.
  * Only the single-kernel path (effective top-k <= MYDET_SMALL_K) supports it. */
 int mydet_postprocess_scatter(const float* boxes, const float* scores, const void* cls, int cls_is_i64,
