@@ -149,3 +149,56 @@ def retina_targets_and_loss(t_xywh, cls_logits, gts, img_hw, stride, anchor_wh, 
         per_image.append({'M_pos': m_pos, 'M_neg': m_neg, 'gt_idx': gt_idx, 'tgt_xywh': tgt_xywh, 'tgt_cls': tgt_cls,
                           'cls_penalty_mask': penalty})
     return per_image, (loss_xywh + loss_cls) / n_b, total_pos
+
+
+def rapid_targets(p_xywha, conf_logits, gts, img_hw, stride, anchors_all, indices, n_cls, grid_hw, ignore_thre=0.6):
+    """RAPiDLayer's target assignment -- rapid.py:84-167, with the oracle's exact rotated IoU (oracle/iou.py: iou_rot)
+    in place of the pycocotools raster (rotated IoU VALUES are "parity unpinned"; the control flow is what this pins).
+    p_xywha (B, nA*nH*nW, 5) decoded boxes (degrees), conf_logits (B,nA,nH,nW,1), gts: list of (boxes (n,5), cats (n,)).
+    Returns dict(PositiveMask, IgnoredMask, TargetXYWH, TargetAngle, TargetConf, TargetCls, weighted)."""
+    import math
+    from .iou import iou_rot
+    n_b = p_xywha.shape[0]
+    n_a, (n_h, n_w) = len(indices), grid_hw
+    anchors_all = torch.tensor(anchors_all, dtype=torch.float32)
+    anchors = anchors_all[indices, :]
+    anch_00wha_all = torch.zeros(len(anchors_all), 5)
+    anch_00wha_all[:, 2:4] = anchors_all
+    idx_t = torch.tensor(indices)
+    pos = torch.zeros(n_b, n_a, n_h, n_w, dtype=torch.bool)
+    ign = torch.zeros(n_b, n_a, n_h, n_w, dtype=torch.bool)
+    weighted = torch.zeros(n_b, n_a, n_h, n_w)
+    t_xywh = torch.zeros(n_b, n_a, n_h, n_w, 4)
+    t_angle = torch.zeros(n_b, n_a, n_h, n_w)
+    t_conf = torch.zeros(n_b, n_a, n_h, n_w, 1)
+    t_cls = torch.zeros(n_b, n_a, n_h, n_w, max(n_cls, 1))
+    p5 = p_xywha.view(n_b, n_a, n_h, n_w, 5)
+    for b, (gt_bboxes, gt_cats) in enumerate(gts):
+        if gt_bboxes.shape[0] == 0:                                            # rapid.py:106-107
+            continue
+        selected = (conf_logits[b] > -math.log(1 / 0.005 - 1)).squeeze(-1)     # :115-116
+        p_sel = p5[b][selected]
+        if 0 < len(p_sel) < 1000:                                              # :120
+            ious = iou_rot(p_sel.reshape(-1, 5), gt_bboxes)
+            ign[b, selected] = ious.max(dim=1).values > ignore_thre            # :123-126
+        for gt_bb, gt_c in zip(gt_bboxes, gt_cats):                            # :129
+            g0 = gt_bb.clone()
+            g0[0:2] = 0
+            g0[4] = 0
+            anch_idx_all = int(torch.argmax(iou_rot(g0.unsqueeze(0), anch_00wha_all), dim=1))   # :134-136
+            if not bool((idx_t == anch_idx_all).any()):
+                continue
+            ta = anch_idx_all % n_a
+            ti, tj = int(gt_bb[0] / stride), int(gt_bb[1] / stride)            # :148-149
+            pos[b, ta, tj, ti] = True
+            t_xywh[b, ta, tj, ti, 0] = (gt_bb[0] / stride) % 1
+            t_xywh[b, ta, tj, ti, 1] = (gt_bb[1] / stride) % 1
+            t_xywh[b, ta, tj, ti, 2] = torch.log(gt_bb[2] / anchors[ta, 0] + 1e-8)
+            t_xywh[b, ta, tj, ti, 3] = torch.log(gt_bb[3] / anchors[ta, 1] + 1e-8)
+            t_angle[b, ta, tj, ti] = gt_bb[4] / 180 * math.pi
+            t_conf[b, ta, tj, ti] = 1
+            if n_cls > 0:
+                t_cls[b, ta, tj, ti, gt_c] = 1
+            weighted[b, ta, tj, ti] = 2 - gt_bb[2] * gt_bb[3] / (img_hw[0] * img_hw[1])
+    return {'PositiveMask': pos, 'IgnoredMask': ign, 'TargetXYWH': t_xywh, 'TargetAngle': t_angle, 'TargetConf': t_conf,
+            'TargetCls': t_cls, 'weighted': weighted}

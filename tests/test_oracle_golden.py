@@ -168,6 +168,24 @@ def test_training_targets(golden):
         assert f' pos {pos}/' in str(g[f'retina{li}_loss_str'])
 
 
+def test_rapid_training_targets(golden):
+    """oracle/train.py: rapid_targets against the RAPiDLayer tensors captured from the reference driven by the exact
+    polygon-clipping pycocotools stub (control flow; rotated IoU values stay "parity unpinned")."""
+    from oracle import decode as od, train as ot
+    from helpers import yolo_views, RAPID_ANCHORS
+    g = golden('train')
+    gts = [(T(g[f'rgt{b}_boxes']), torch.zeros(len(g[f'rgt{b}_boxes']), dtype=torch.int64)) for b in range(3)]
+    idx3 = [[0, 1, 2], [3, 4, 5], [6, 7, 8]]
+    for li, s in enumerate((8, 16, 32)):
+        raw = yolo_views(T(g[f'rapid{li}_in']), 3, 5, 0)
+        anchors = torch.tensor(RAPID_ANCHORS, dtype=torch.float32)[idx3[li]]
+        box, _, _ = od.decode_rapid(raw, anchors, s, 0)
+        n_h, n_w = raw['bbox'].shape[2:4]
+        tg = ot.rapid_targets(box, raw['conf'], gts, (256, 320), s, RAPID_ANCHORS, idx3[li], 0, (n_h, n_w), ignore_thre=0.1)
+        for k in ('PositiveMask', 'IgnoredMask', 'TargetXYWH', 'TargetAngle', 'TargetConf'):
+            assert torch.equal(tg[k], T(g[f'rapid{li}_{k}'])), (li, k)
+
+
 def test_atss_threshold_tie_policy_variant():
     """atss_threshold_index_ties (the kernels' declared tie policy) equals the reference-faithful atss_threshold
     wherever the k-th nearest anchor is not tied, i.e. for GT centres off the cell boundaries."""
