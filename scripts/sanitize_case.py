@@ -25,5 +25,26 @@ big = ops.postprocess(boxes, scores, cls, 0.1, 0.5, topk=None)                  
 rb = torch.cat([boxes, (torch.rand(2, n, 1, generator=g) * 360 - 180).to(d)], 2).contiguous()
 keep, cnt, votes = ops.nms_rot(rb, scores, 0.3, want_votes=True)                      # rotated path + votes
 iou = ops.iou_rot(rb[0, :200], rb[1, :100])
+# top-k front ends of the small path: register-resident (n <= 9216), sampled (n > 9216), forced scan; consume flag
+n2 = 12000
+b2 = torch.cat([torch.rand(2, n2, 2, generator=g) * 500, torch.rand(2, n2, 2, generator=g) * 60 + 4], 2).to(d)
+s2 = torch.rand(2, n2, generator=g).to(d)
+c2 = torch.randint(0, 80, (2, n2), generator=g).to(d)
+cnt2 = torch.tensor([n2, 9000], dtype=torch.int32, device=d)
+front = [ops.postprocess(b2, s2, c2, 0.1, 0.5, topk=512, counts=cnt2.clone()),
+         ops.postprocess(b2[:, :8000], s2[:, :8000], c2[:, :8000], 0.1, 0.5, topk=512),
+         ops.postprocess(b2, s2, c2, 0.1, 0.5, topk=512, counts=cnt2.clone(), force_scan=True),
+         ops.postprocess(b2[:, :8000], s2[:, :8000], c2[:, :8000] * 0, 0.1, 0.5, topk=1000, counts=cnt2.clone(), consume=True)]
+# fused exchange (vector peer stores into a local buffer), IoU row-max, FCOS assign, register sort (8192 < n <= 16384)
+bc = pl.DetectionPipeline('FCOS2', strides, 5, img, 0.05, 0.5, 128).bind(raws)
+bc.bind_exchange(pl.PeerExchange(2, 128, 4, d, local_only=True))
+bc.launch_decode(); bc.launch_postprocess_scatter()
+mx, arg = ops.iou_rowmax(b2[:, :3000].contiguous(), b2[:, 3000:3700].contiguous(), None)
+tg = ops.fcos_assign(raws[0]['bbox'], 8, img, b2[:, :7].contiguous() * 0.4, c2[:, :7].contiguous() % 5,
+                     torch.tensor([7, 3], dtype=torch.int32, device=d), 0.5, 0, 64, 0.5, 5)
+n3 = 8300
+b3 = torch.cat([b2[:1, :n3, :2], b2[:1, :n3, 2:] * 0.3 + 2, (torch.rand(1, n3, 1, generator=g) * 180 - 90).to(d)], 2).contiguous()
+keep3, cnt3 = ops.nms_rot(b3, s2[:1, :n3].contiguous(), 0.45)
 torch.cuda.synchronize()
-print('ok', out['count'].tolist(), big['count'].tolist(), cnt.tolist(), float(iou.max()))
+print('ok', out['count'].tolist(), big['count'].tolist(), cnt.tolist(), float(iou.max()), [f['count'].tolist() for f in front],
+      bc.out['count'].tolist(), float(mx.max()), int(tg['PositiveMask'].sum()), cnt3.tolist())
