@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT_DIR = os.path.join(HERE, '_build')
 LIB = os.path.join(OUT_DIR, 'liboracle.so')
-SOURCES = ['nms.c', 'rotiou.c']
+SOURCES = ['nms.c', 'rotiou.c', 'raster.c']
 
 
 def build(force=False):

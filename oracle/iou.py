@@ -26,6 +26,8 @@ def lib():
         L.oracle_argsort_desc_stable.argtypes = [f32p, i64, i64p]
         L.oracle_rot_iou_pairwise.restype = None
         L.oracle_rot_iou_pairwise.argtypes = [f32p, i64, f32p, i64, f64p]
+        L.oracle_raster_iou_pairwise.restype = None
+        L.oracle_raster_iou_pairwise.argtypes = [f64p, i64, f64p, i64, i64, i64, f64p]
         L.oracle_nms_rot.restype = i64
         L.oracle_nms_rot.argtypes = [f32p, f32p, i64, ctypes.c_double, i64, i64p]
         _LIB = L
@@ -97,6 +99,27 @@ def iou_rot(b1, b2):
     out = np.empty((a1.shape[0], a2.shape[0]), dtype=np.float64)
     lib().oracle_rot_iou_pairwise(p1, a1.shape[0], p2, a2.shape[0],
                                   out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+    return torch.from_numpy(out)
+
+
+def iou_rle_raster(b1, b2, canvas=2048):
+    """Rasterised rotated IoU (N,M) float64 in the manner of the reference's iou_rle (utils/bbox_ops.py:84-96):
+    corners from xywha2vertex in float32, then pycocotools-style polygon rasterisation on a canvas x canvas grid
+    (the reference always uses 2048: its callers pass `img_size=` but iou_rle reads kwargs['img_hw']).
+    PARITY UNPINNED: oracle/raster.c restates the published maskApi algorithm and could not be checked against the
+    real library.  Only used to REPORT the raster-vs-exact gap."""
+    def corners(b):
+        if b.dim() == 1:
+            b = b.unsqueeze(0)
+        rad = b.clone().float()
+        rad[:, 4] = deg2rad_f32(rad[:, 4])                                # :88-89
+        v = xywha2vertex(rad)                                             # (N,4,2) tl,tr,br,bl
+        return np.ascontiguousarray(v.reshape(-1, 8).double().numpy())
+    c1, c2 = corners(b1), corners(b2)
+    out = np.empty((c1.shape[0], c2.shape[0]), dtype=np.float64)
+    f64p = ctypes.POINTER(ctypes.c_double)
+    lib().oracle_raster_iou_pairwise(c1.ctypes.data_as(f64p), c1.shape[0], c2.ctypes.data_as(f64p), c2.shape[0],
+                                     int(canvas), int(canvas), out.ctypes.data_as(f64p))
     return torch.from_numpy(out)
 
 
