@@ -458,6 +458,41 @@ def gen_train():
     save('train', **out)
 
 
+def gen_preprocess():
+    """Detector._preprocess_pil + tvf.to_tensor + format_tensor_img (api/detection.py:158-162, :177-205) of the unmodified
+    reference on small seeded uint8 images: every pre-processing name x every input format, up- and down-scaling."""
+    import PIL.Image
+    import torchvision.transforms.functional as tvf
+    from api.detection import Detector
+    import utils.image_ops as imgUtils
+    rng = np.random.default_rng(77)
+    det = Detector.__new__(Detector)          # no model needed for the pre-processing methods
+    out, cases = {}, []
+    specs = [((67, 101), 'pad_divisible', None, 32, 'RGB_1'),
+             ((96, 64), 'pad_divisible', None, 32, 'BGR_255_norm'),          # already divisible: no padding at all
+             ((150, 201), 'resize_pad_divisible', 96, 32, 'RGB_1_norm'),
+             ((201, 150), 'resize_pad_divisible', 128, 128, 'BGR_255_norm'),
+             ((45, 80), 'resize_pad_divisible', 160, 32, 'RGB_1'),           # up-scaling
+             ((240, 135), 'resize_pad_square', 96, 32, 'RGB_1_norm'),
+             ((77, 77), 'resize_pad_square', 64, 32, 'RGB_1'),
+             ((50, 121), 'resize_pad_square', 192, 32, 'BGR_255_norm'),      # up-scaling + centred padding
+             ((64, 64), 'resize_pad_square', 64, 32, 'RGB_1_norm')]          # identity resize
+    for i, (hw, name, size, div, code) in enumerate(specs):
+        img = rng.integers(0, 256, hw + (3,), dtype=np.uint8)
+        if i % 2:                                                            # smooth content on every other case
+            yy, xx = np.mgrid[0:hw[0], 0:hw[1]]
+            img = np.stack([(yy * 3 + xx) % 256, (xx * 5) % 256, (yy * 2 + xx * 7) % 256], -1).astype(np.uint8)
+        det.divisibe = div
+        pil, pad_info = det._preprocess_pil(PIL.Image.fromarray(img), name, size)
+        t = imgUtils.format_tensor_img(tvf.to_tensor(pil), code=code)
+        out[f'pre{i}_img'] = img
+        out[f'pre{i}_out'] = t
+        out[f'pre{i}_pad'] = np.array(pad_info if pad_info is not None else [-1] * 6, dtype=np.int64)
+        cases.append(f'{name}|{size}|{div}|{code}')
+    out['cases'] = np.array(cases)
+    save('preprocess', **out)
+
+
 if __name__ == '__main__':
     import_reference()
     torch.set_grad_enabled(False)
@@ -466,3 +501,4 @@ if __name__ == '__main__':
     gen_iou()
     gen_atss()
     gen_train()
+    gen_preprocess()

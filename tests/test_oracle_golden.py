@@ -220,3 +220,32 @@ def test_raster_vs_exact_gap():
         gap = (r - e).abs()
         assert float(gap.max()) < bound, (lo, hi, float(gap.max()))
         assert bool(((r > 0) == (e > 1e-3))[e > 0.02].all())          # same overlap structure
+
+
+def test_preprocess_against_reference(golden):
+    """oracle/preprocess.py against the unmodified reference's Detector._preprocess_pil + to_tensor + format_tensor_img
+    (api/detection.py:158-162, :177-205): every output float bit-exact, pad_info equal."""
+    from oracle import preprocess as op
+    g = golden('preprocess')
+    for i, case in enumerate(g['cases']):
+        name, size, div, code = str(case).split('|')
+        got, pad = op.preprocess(g[f'pre{i}_img'], name, None if size == 'None' else int(size), int(div), code)
+        assert got.dtype == np.float32 and got.shape == g[f'pre{i}_out'].shape, case
+        assert np.array_equal(got.view(np.int32), g[f'pre{i}_out'].view(np.int32)), case
+        assert (list(pad) if pad is not None else [-1] * 6) == g[f'pre{i}_pad'].tolist(), case
+
+
+def test_resize_restatement_matches_pillow():
+    """The restated two-pass 8-bit resampler against the installed Pillow (through torchvision's resize, as the reference
+    calls it): random sizes, up- and down-scaling, one or both axes unchanged."""
+    import PIL.Image
+    import torchvision.transforms.functional as tvf
+    from oracle import preprocess as op
+    rng = np.random.default_rng(5)
+    for it in range(40):
+        h, w, oh, ow = (int(v) for v in rng.integers(3, 200, 4))
+        ow = w if it % 7 == 0 else ow
+        oh = h if it % 11 == 0 else oh
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        want = np.array(tvf.resize(PIL.Image.fromarray(img), (oh, ow)))
+        assert np.array_equal(op.resize_bilinear_u8(img, oh, ow), want), (h, w, oh, ow)
