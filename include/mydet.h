@@ -246,6 +246,31 @@ int mydet_fcos_assign(const float* t_ltrb, const int64_t t_stride[4], int batch,
                       float* target_conf, float* target_cls, void* workspace, size_t workspace_bytes,
                       void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Image pre-processing in front of the model.  Replaces, for a batch of equally
+ * sized uint8 RGB frames, Detector._preprocess_pil + tvf.to_tensor + format_tensor_img
+ * (api/detection.py:158-162, :177-205; utils/image_ops.py:22-52 resize_pil / pad_to_divisible, :55-106
+ * rect_to_square(aug=False), :165-188 format_tensor_img): Pillow's anti-aliased BILINEAR Image.resize (two-pass
+ * 8 bits-per-channel resampler, bit-exact), zero padding of the uint8 image, /255, normalisation / channel order.
+ *   src         (batch, in_h, in_w, 3) uint8, row pitch and image stride in BYTES
+ *   resized_*   size after the resize (the caller computes it with the reference's own Python expressions, see
+ *               mydetection_b200/image_ops.py: plan); == in_* when the image is only padded
+ *   left, top   position of the resized image inside the (out_h, out_w) output; everything else is the
+ *               normalised value of a zero pixel
+ *   format      MYDET_FORMAT_*: cfg 'model.input_format'
+ *   dst         (batch, 3, out_h, out_w) float32, fully written
+ * Workspace: mydet_preprocess_workspace_bytes(...), 256-byte aligned (filter banks + the uint8 intermediate of
+ * the horizontal pass); not needed when resized_* == in_*. */
+typedef enum {
+    MYDET_FORMAT_RGB_1 = 0,        /* 'RGB_1'                                                  */
+    MYDET_FORMAT_RGB_1_NORM = 1,   /* 'RGB_1_norm'   (x - mean) / std, ImageNet constants      */
+    MYDET_FORMAT_BGR_255_NORM = 2  /* 'BGR_255_norm' channels reversed, x * 255 - mean         */
+} mydet_input_format_t;
+size_t mydet_preprocess_workspace_bytes(int batch, int in_h, int in_w, int resized_h, int resized_w);
+int mydet_preprocess(const uint8_t* src, int batch, int64_t src_image_stride, int64_t src_row_pitch, int in_h,
+                     int in_w, int resized_h, int resized_w, int left, int top, int out_h, int out_w, int format,
+                     float* dst, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,7 @@ MAX_CANDIDATES = 1048575
 
 KIND_YOLO, KIND_FCOS, KIND_RAPID, KIND_RETINA, KIND_UV5 = range(5)
 BOX_CXCYWH, BOX_X1Y1X2Y2 = 0, 1
+INPUT_FORMATS = {'RGB_1': 0, 'RGB_1_norm': 1, 'BGR_255_norm': 2}   # utils/image_ops.py:174-186
 
 c_int, c_i64, c_f32, c_f64, c_vp, c_sz = (ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double,
                                           ctypes.c_void_p, ctypes.c_size_t)
@@ -63,6 +64,9 @@ SIGNATURES = {
                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),
     'mydet_fcos_assign': (c_int, [c_vp, ctypes.POINTER(c_i64), c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int,
                                   c_f32, c_f32, c_f32, c_f32, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'mydet_preprocess_workspace_bytes': (c_sz, [c_int, c_int, c_int, c_int, c_int]),
+    'mydet_preprocess': (c_int, [c_vp, c_int, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_vp, c_vp, c_sz, c_vp]),
 }
 
 _LIB = None
