@@ -45,7 +45,7 @@ def _as_u8_frames(images):
     """PIL image | (H,W,3) / (B,H,W,3) uint8 ndarray or tensor  ->  (B,H,W,3) uint8 tensor (CPU or CUDA)."""
     if hasattr(images, 'mode') and hasattr(images, 'size') and not torch.is_tensor(images):   # PIL.Image.Image
         assert images.mode == 'RGB', 'input must be an RGB image'
-        images = np.asarray(images)
+        images = np.array(images)                                # a writable copy: torch.from_numpy warns on read-only arrays
     if isinstance(images, np.ndarray):
         images = torch.from_numpy(np.ascontiguousarray(images))
     if not torch.is_tensor(images) or images.dtype != torch.uint8:
@@ -86,8 +86,6 @@ def preprocess(images, pre_proc_name, input_size=None, divisible=1, input_format
                                       frames.stride(1), in_h, in_w, rs_h, rs_w, left, top, out_h, out_w,
                                       _lib.INPUT_FORMATS[input_format], ops._ptr(out), ops._ptr(ws), ws.numel(),
                                       ops._stream()), 'mydet_preprocess')
-    ws.record_stream(torch.cuda.current_stream(dev))
-    frames.record_stream(torch.cuda.current_stream(dev))
     return out, pad_info
 
 
