@@ -46,3 +46,16 @@ def install():
     models_pkg = _parent('models')
     models_pkg.detlayers = detlayers
     return {'utils.bbox_ops': bbox_ops, 'utils.structures': structures, 'models.detlayers': detlayers}
+
+
+def install_preprocess(detector_cls=None):
+    """Route Detector._predict_pil (api/detection.py:142-175) through the device pre-processing of
+    mydetection_b200.image_ops (resize / pad / normalise in libmydet instead of Pillow on the CPU).
+    `detector_cls` defaults to the reference's api.detection.Detector (the reference root must be on sys.path).
+    Returns the patched class; detect_one / evaluation_predict / detect_imgs call _predict_pil unchanged."""
+    from . import image_ops
+    if detector_cls is None:
+        import importlib
+        detector_cls = importlib.import_module('api.detection').Detector
+    detector_cls._predict_pil = image_ops.predict_pil
+    return detector_cls

@@ -150,3 +150,41 @@ def test_preprocess_needs_cuda_and_validates():
     assert rc == -1 and b'format' in L.mydet_last_error()
     assert L.mydet_preprocess_workspace_bytes(1, 1080, 1920, 342, 608) >= 1080 * 608 * 3
     assert L.mydet_preprocess_workspace_bytes(1, 608, 608, 608, 608) == 256        # padding only: no workspace
+
+
+def test_predict_pil_control_flow(monkeypatch):
+    """predict_pil mirrors Detector._predict_pil (api/detection.py:142-175): kwargs override the detector's defaults,
+    the model sees the pre-processed batch, post_process and bboxes_to_original_ are applied in that order.
+    (The device call itself is replaced here: no GPU.)"""
+    import torch
+    from mydetection_b200 import dropin, image_ops
+    calls = []
+
+    class Dts:
+        def post_process(self, conf, nms):
+            calls.append(('post_process', conf, nms))
+            return self
+
+        def bboxes_to_original_(self, pad_info):
+            calls.append(('to_original', pad_info))
+
+    class Model:
+        input_format = 'RGB_1_norm'
+
+        def __call__(self, x):
+            calls.append(('model', tuple(x.shape)))
+            return [Dts()]
+
+    class Detector:                                   # the attributes Detector.__init__ sets (api/detection.py:44-53)
+        divisibe, input_size, preprocess, conf_thres, nms_thres = 32, 96, 'resize_pad_square', 0.3, 0.45
+        model = Model()
+
+    def fake_preprocess(images, name, size, div, code):
+        calls.append(('preprocess', name, size, div, code))
+        return torch.zeros(1, 3, size, size), image_ops.plan(60, 80, name, size, div)[-1]
+    monkeypatch.setattr(image_ops, 'preprocess', fake_preprocess)
+    assert dropin.install_preprocess(Detector) is Detector
+    out = Detector()._predict_pil(object(), input_size=64, conf_thres=0.1)
+    assert isinstance(out, Dts)
+    assert calls == [('preprocess', 'resize_pad_square', 64, 32, 'RGB_1_norm'), ('model', (1, 3, 64, 64)),
+                     ('post_process', 0.1, 0.45), ('to_original', (80, 60, 0, 8, 64, 48))]
