@@ -39,10 +39,12 @@ UNIT = 'images/s'
 
 def workload_config(n_gpus):
     point = 'all-pass operating point' if CONF_MU >= 2.0 else 'operating point'
-    return {'workload': 'd1_fcs2 decode+NMS: batch 64 per GPU @640x640, 5 levels (8525 loc/img), 80 classes, '
+    loc = sum((IMG // s) ** 2 for s in STRIDES)                   # 8 525 at 640 (the default), 12 276 at 768 (--img-size)
+    mb = BATCH * loc * 4 * (4 + 1 + N_CLS) / 1e6
+    return {'workload': f'd1_fcs2 decode+NMS: batch 64 per GPU @{IMG}x{IMG}, 5 levels ({loc} loc/img), 80 classes, '
                         f'{point} (conf logit ~N({CONF_MU:g},1.5^2)), conf 0.005, top-512, nms 0.5',
-            'images_per_step_per_gpu': BATCH, 'candidates_per_image': 8525 if CONF_MU >= 2.0 else 'measured: see roofline',
-            'l2_policy': f'inputs larger than L2: {N_ROTATE} rotating 185.5 MB batches',
+            'images_per_step_per_gpu': BATCH, 'candidates_per_image': loc if CONF_MU >= 2.0 else 'measured: see roofline',
+            'l2_policy': f'inputs larger than L2: {N_ROTATE} rotating {mb:.1f} MB batches',
             'sharding': f'images, {n_gpus} x {BATCH}'}
 
 
@@ -539,8 +541,8 @@ def run_gpu(args):
         kernel_ms = (ms / steps) if pipe_graph is not None else dec_ms
         achieved = alg / (kernel_ms * 1e-3) / 1e9
         traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'decode_traffic.json'))).get('dram_bytes_per_launch')
+        try:                                                      # the ncu capture was taken on the default geometry
+            traffic = None if IMG != 640 else json.load(open(os.path.join(ROOT, 'profiles', 'decode_traffic.json'))).get('dram_bytes_per_launch')
         except (OSError, ValueError):
             pass
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': warmup,
@@ -584,10 +586,17 @@ def main():
     ap.add_argument('--no-rot', action='store_true', help='skip the rotated-NMS side metric')
     ap.add_argument('--conf-mu', type=float, default=None,
                     help='mean of the objectness logits (default 2.0: every cell is a candidate; -4: "trained-like", SURVEY 8d)')
+    ap.add_argument('--img-size', type=int, default=640,
+                    help='square input size (default 640 = BASELINE configs[1], 8 525 cells; 768 gives 12 276 cells: '
+                         'the ">= 10k pre-NMS candidates" statement of the north star, SURVEY 8d)')
     args = ap.parse_args()
+    global CONF_MU, IMG, METRIC
     if args.conf_mu is not None:
-        global CONF_MU
         CONF_MU = args.conf_mu
+    if args.img_size != IMG:
+        assert args.img_size % 128 == 0, '--img-size must be a multiple of the coarsest stride (128)'
+        IMG = args.img_size
+        METRIC = METRIC.replace('640x640', f'{IMG}x{IMG}')
     if args.impl == 'reference':
         run_reference(args)
     else:
