@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
 # 1. the verified path must still be green, then the pre-processing tests on their own with the xfail marker ignored
 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest gpu rc=$?"
-python -m pytest tests/test_zz_preprocess_gpu.py -q -m gpu --runxfail > gpurun_out/pytest_preprocess.log 2>&1; echo "preprocess rc=$?"
+python -m pytest tests/test_zz_preprocess_gpu.py tests/test_zz_fullmodel_gpu.py -q -m gpu --runxfail > gpurun_out/pytest_preprocess.log 2>&1; echo "preprocess rc=$?"
 tail -3 gpurun_out/pytest_gpu.log gpurun_out/pytest_preprocess.log
 # 2. numbers: pre-processing (1080p -> 608 and CEPDOF-like 2048 -> 1024), the >= 10k-candidate bench point
 python scripts/preprocess_bench.py 64 1080 1920 608 > gpurun_out/preprocess_bench.log 2>&1

@@ -493,6 +493,71 @@ def gen_preprocess():
     save('preprocess', **out)
 
 
+def gen_fullmodel():
+    """BASELINE configs[0] end to end through the UNMODIFIED reference: OneStageBBox(configs/yolov3_80.json) with
+    random-initialised weights (Darknet-53 + YOLOv3 FPN + YOLO head), one synthetic image, forward -> det layers ->
+    level concatenation (models/general.py:67-84) -> ImageObjects.post_process (api/detection.py:172).
+    The ImageNet checkpoint the registry wants (models/registry.py:15) does not exist here: torch.load is answered with a
+    freshly initialised Darknet53 state dict while the model is built.  A random-init network in eval mode emits logits of
+    ~1e-3 (exact score ties); the three 1x1 head convolutions are therefore re-drawn and scaled so that the logits
+    have a standard deviation of 1.5 -- still random weights, but a tie-free ranking.  To keep the fixture small the image
+    is 256 x 256 (4 032 candidates) and the head outputs are rounded to float16-representable values BEFORE they enter the
+    reference's det layers, so 2 bytes per logit are stored and both sides see identical float32 inputs."""
+    import json
+    from models.general import OneStageBBox
+    from models.backbones import Darknet53
+    from utils.structures import ImageObjects
+    from utils.bbox_ops import bboxes_iou
+    cfg = json.load(open(os.path.join(REF, 'configs', 'yolov3_80.json')))
+    torch.manual_seed(2024)
+    real_load = torch.load
+    torch.load = lambda path, *a, **k: Darknet53(cfg).state_dict() if str(path).endswith('dark53_imgnet.pth') else real_load(path, *a, **k)
+    try:
+        model = OneStageBBox(cfg).eval()
+    finally:
+        torch.load = real_load
+    img_hw = (256, 256)
+    conf_thres, nms_thres = cfg['test.ap_conf_thres'], cfg['test.nms_thres']
+    for seed in range(11, 60):       # the first seed whose ranking has comfortable margins for a float32 GPU path
+        gen = torch.Generator().manual_seed(seed)
+        x = torch.rand(1, 3, *img_hw, generator=gen)
+        feats = model.fpn(model.backbone(x))
+        out, dts_all = {}, []
+        for i, conv in enumerate(model.rpn.heads):
+            conv.weight.copy_(torch.randn(conv.weight.shape, generator=gen))
+            conv.bias.zero_()
+            conv.weight.mul_(1.5 / float(conv(feats[i]).std()))
+            t = conv(feats[i]).half()                                   # (1, 255, nH, nW), what the fixture stores
+            out[f'head{i}_f16'] = t
+            p = t.float().view(1, 3, 85, t.shape[2], t.shape[3])        # YOLOHead.forward's views (models/rpns.py:29-34)
+            raw = {'bbox': p[:, :, 0:4].permute(0, 1, 3, 4, 2), 'conf': p[:, :, 4:5].permute(0, 1, 3, 4, 2),
+                   'class': p[:, :, 5:].permute(0, 1, 3, 4, 2)}
+            dts_all.append(model.det_layers[i](raw, img_hw, None)[0])
+        bbs = torch.cat([d['bbox'] for d in dts_all], dim=1)[0]         # models/general.py:74-76
+        cls = torch.cat([d['class_idx'] for d in dts_all], dim=1)[0]
+        sc = torch.cat([d['score'] for d in dts_all], dim=1)[0]
+        srt = sc.sort(descending=True).values
+        top = sc.argsort(descending=True)[:512]
+        iou = bboxes_iou(bbs[top], bbs[top])
+        same = cls[top][:, None] == cls[top][None, :]
+        margins = {'seed': seed, 'score_512_513': float(srt[511] - srt[512]), 'score_to_conf_thres': float((sc - conf_thres).abs().min()),
+                   'iou_to_nms_thres': float((iou[same] - nms_thres).abs().min()), 'distinct_scores': int(sc.unique().numel())}
+        if margins['score_512_513'] > 2e-4 and margins['score_to_conf_thres'] > 1e-4 and margins['iou_to_nms_thres'] > 2e-4:
+            break
+    else:
+        raise RuntimeError('no seed with safe margins')
+    res = ImageObjects(bboxes=bbs.clone(), cats=cls.clone(), scores=sc.clone(), bb_format=model.bb_format,
+                       img_hw=img_hw).post_process(conf_thres, nms_thres)
+    keys = torch.cat([bbs, sc[:, None], cls[:, None].float()], dim=1)
+    got = torch.cat([res.bboxes, res.scores[:, None], res.cats[:, None].float()], dim=1)
+    keep = torch.tensor([int(torch.nonzero((keys == g).all(dim=1))[0, 0]) for g in got], dtype=torch.int64)
+    assert keep.unique().numel() == keep.numel()
+    print('fullmodel', len(res), 'kept of', int((sc >= conf_thres).sum()), 'candidates;', margins)
+    out.update({'keep': keep, 'kept_boxes': res.bboxes, 'kept_scores': res.scores, 'kept_cats': res.cats,
+                'params': np.array([conf_thres, nms_thres, img_hw[0], img_hw[1]], dtype=np.float64)})
+    save('fullmodel', **out)
+
+
 if __name__ == '__main__':
     import_reference()
     torch.set_grad_enabled(False)
@@ -502,3 +567,4 @@ if __name__ == '__main__':
     gen_atss()
     gen_train()
     gen_preprocess()
+    gen_fullmodel()

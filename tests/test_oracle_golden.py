@@ -249,3 +249,22 @@ def test_resize_restatement_matches_pillow():
         img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
         want = np.array(tvf.resize(PIL.Image.fromarray(img), (oh, ow)))
         assert np.array_equal(op.resize_bilinear_u8(img, oh, ow), want), (h, w, oh, ow)
+
+
+def test_fullmodel_yolov3_end_to_end(golden):
+    """BASELINE configs[0]: the oracle's decode -> level concatenation -> post_process against the UNMODIFIED reference run
+    end to end (OneStageBBox(yolov3_80) with random-init Darknet-53 + FPN + head, det layers, general.py's concatenation,
+    ImageObjects.post_process) on head outputs of a real network forward (tests/golden/make_golden.py: gen_fullmodel).
+    Kept indices and their order, boxes, scores and classes: bit-exact."""
+    g = golden('fullmodel')
+    conf, nms, img_h, img_w = g['params']
+    levels = []
+    for li, s in enumerate((8, 16, 32)):
+        raw = yolo_views(T(g[f'head{li}_f16']).float(), 3, 4, 80)
+        levels.append(od.decode_yolo(raw, level_anchors(YOLO_ANCHORS, li), s, 80))
+    box, cls, score = (t[0] for t in od.merge_levels(levels))
+    assert box.shape[0] == 3 * (32 * 32 + 16 * 16 + 8 * 8)
+    keep = opp.post_process(box, cls, score, float(conf), float(nms), 'cxcywh', 512)
+    assert torch.equal(keep, T(g['keep']))
+    assert torch.equal(box[keep], T(g['kept_boxes'])) and torch.equal(score[keep], T(g['kept_scores']))
+    assert torch.equal(cls[keep], T(g['kept_cats']))
