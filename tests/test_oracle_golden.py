@@ -251,20 +251,37 @@ def test_resize_restatement_matches_pillow():
         assert np.array_equal(op.resize_bilinear_u8(img, oh, ow), want), (h, w, oh, ow)
 
 
-def test_fullmodel_yolov3_end_to_end(golden):
-    """BASELINE configs[0]: the oracle's decode -> level concatenation -> post_process against the UNMODIFIED reference run
-    end to end (OneStageBBox(yolov3_80) with random-init Darknet-53 + FPN + head, det layers, general.py's concatenation,
-    ImageObjects.post_process) on head outputs of a real network forward (tests/golden/make_golden.py: gen_fullmodel).
-    Kept indices and their order, boxes, scores and classes: bit-exact."""
-    g = golden('fullmodel')
-    conf, nms, img_h, img_w = g['params']
+def fullmodel_levels(g, name):
+    """Rebuild the raw dicts the reference heads emitted from the stored NCHW head outputs and decode them with the oracle.
+    Returns (box (N,P), cls (N,), score (N,), bb_format)."""
     levels = []
-    for li, s in enumerate((8, 16, 32)):
-        raw = yolo_views(T(g[f'head{li}_f16']).float(), 3, 4, 80)
-        levels.append(od.decode_yolo(raw, level_anchors(YOLO_ANCHORS, li), s, 80))
+    if name == 'd1_fcs2':
+        for li, s in enumerate((8, 16, 32, 64, 128)):
+            raw = efdet_views(T(g[f'head{li}_0']).float(), T(g[f'head{li}_1']).float())
+            levels.append(od.decode_fcos(raw, s, (int(g['params'][2]), int(g['params'][3]))))
+        fmt = 'cxcywh'
+    elif name == 'rapid':
+        for li, s in enumerate((8, 16, 32)):
+            levels.append(od.decode_rapid(yolo_views(T(g[f'head{li}_0']).float(), 3, 5, 0), level_anchors(RAPID_ANCHORS, li), s, 0))
+        fmt = 'cxcywhd'
+    else:
+        for li, s in enumerate((8, 16, 32)):
+            levels.append(od.decode_yolo(yolo_views(T(g[f'head{li}_0']).float(), 3, 4, 80), level_anchors(YOLO_ANCHORS, li), s, 80))
+        fmt = 'cxcywh'
     box, cls, score = (t[0] for t in od.merge_levels(levels))
-    assert box.shape[0] == 3 * (32 * 32 + 16 * 16 + 8 * 8)
-    keep = opp.post_process(box, cls, score, float(conf), float(nms), 'cxcywh', 512)
-    assert torch.equal(keep, T(g['keep']))
+    return box, cls, score, fmt
+
+
+@pytest.mark.parametrize('name', ['yolov3_80', 'rapid', 'd1_fcs2'])
+def test_fullmodel_end_to_end(golden, name):
+    """BASELINE configs[0] / [2] / [1] geometry end to end: the oracle's decode -> level concatenation -> post_process
+    against the UNMODIFIED reference (OneStageBBox(configs/<name>.json) with random weights: backbone + FPN + head, det
+    layers, general.py's concatenation, ImageObjects.post_process) on head outputs of a real network forward
+    (tests/golden/make_golden.py: gen_fullmodel).  Kept indices and their order, boxes, scores, classes: bit-exact."""
+    g = golden('fullmodel_' + name)
+    conf, nms = float(g['params'][0]), float(g['params'][1])
+    box, cls, score, fmt = fullmodel_levels(g, name)
+    keep = opp.post_process(box, cls, score, conf, nms, fmt, 512)
+    assert keep.numel() > 300 and torch.equal(keep, T(g['keep']))
     assert torch.equal(box[keep], T(g['kept_boxes'])) and torch.equal(score[keep], T(g['kept_scores']))
     assert torch.equal(cls[keep], T(g['kept_cats']))
