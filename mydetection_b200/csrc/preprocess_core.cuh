@@ -15,6 +15,7 @@
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #if defined(__CUDACC__)
 #define MYDET_HD __host__ __device__ __forceinline__
@@ -179,6 +180,17 @@ MYDET_HD void h_item(const Geometry& G, long long i, const uint8_t* src, long lo
     o[0] = px[0]; o[1] = px[1]; o[2] = px[2];
 }
 
+// Four consecutive floats as one 16-byte store.  The host build checks the alignment the device store needs and
+// writes the same four values, so the harness exercises this branch too.
+MYDET_HD void store4(float* p, float a, float b, float c, float d) {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+#else
+    if (reinterpret_cast<uintptr_t>(p) & 15) abort();
+    p[0] = a; p[1] = b; p[2] = c; p[3] = d;
+#endif
+}
+
 // i in [0, batch * out_h * quads_per_row): 4 consecutive output pixels (b, y, 4q .. 4q+3) in all three planes.
 // vec_ok: out_w % 4 == 0 and dst 16-byte aligned, so each plane takes one 16-byte store.
 MYDET_HD void final_item(const Geometry& G, long long i, const uint8_t* img, long long image_stride,
@@ -200,16 +212,10 @@ MYDET_HD void final_item(const Geometry& G, long long i, const uint8_t* img, lon
         v[k][0] = v[k][1] = v[k][2] = 0.f;
         if (x0 + k < G.out_w) final_pixel(G, im, row_pitch, bounds_v, kk_v, y, x0 + k, v[k]);
     }
-#if defined(__CUDA_ARCH__)
     if (vec_ok && x0 + 3 < G.out_w) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-            *reinterpret_cast<float4*>(o + c * plane + x0) = make_float4(v[0][c], v[1][c], v[2][c], v[3][c]);
+        for (int c = 0; c < 3; ++c) store4(o + c * plane + x0, v[0][c], v[1][c], v[2][c], v[3][c]);
         return;
     }
-#else
-    (void)vec_ok;
-#endif
     for (int k = 0; k < 4 && x0 + k < G.out_w; ++k)
         for (int c = 0; c < 3; ++c) o[c * plane + x0 + k] = v[k][c];
 }

@@ -29,16 +29,17 @@ int main(int argc, char** argv) {
     const long long row_pitch = 3ll * in_w + row_pad, image_stride = row_pitch * in_h;
     const size_t src_bytes = (size_t)batch * image_stride, dst_count = (size_t)batch * 3 * out_h * out_w;
     uint8_t* src = (uint8_t*)malloc(src_bytes ? src_bytes : 1);
-    float* dst = (float*)malloc(dst_count * sizeof(float) + 1);
+    float* dst = (float*)aligned_alloc(16, (dst_count * sizeof(float) + 15) / 16 * 16);   // torch allocations are 512-byte aligned
     char* ws = (char*)malloc(P.workspace_bytes);
     FILE* f = fopen(argv[1], "rb");
     if (!f || fread(src, 1, src_bytes, f) != src_bytes) { fprintf(stderr, "cannot read %s\n", argv[1]); return 4; }
     fclose(f);
     memset(dst, 0xff, dst_count * sizeof(float));            // NaN pattern: every element must be overwritten
     const Geometry& G = P.G;
+    const int vec_ok = (out_w % 4 == 0 && ((uintptr_t)dst & 15) == 0) ? 1 : 0;      // as mydet_preprocess decides
     if (G.direct) {
         for (long long i = 0; i < P.n_final_items; ++i)
-            final_item(G, i, src, image_stride, row_pitch, nullptr, nullptr, dst, P.quads_per_row, 0);
+            final_item(G, i, src, image_stride, row_pitch, nullptr, nullptr, dst, P.quads_per_row, vec_ok);
     } else {
         int* bounds_h = (int*)(ws + P.off_bounds_h);
         int* kk_h = (int*)(ws + P.off_kk_h);
@@ -49,7 +50,7 @@ int main(int argc, char** argv) {
         for (int i = 0; i < (P.n_coeff_items + 127) / 128 * 128; ++i) coeff_item(G, i, bounds_h, kk_h, bounds_v, kk_v);
         for (long long i = 0; i < P.n_h_items; ++i) h_item(G, i, src, image_stride, row_pitch, bounds_h, kk_h, tmp);
         for (long long i = 0; i < P.n_final_items; ++i)
-            final_item(G, i, tmp, P.tmp_image_stride, P.tmp_row_pitch, bounds_v, kk_v, dst, P.quads_per_row, 0);
+            final_item(G, i, tmp, P.tmp_image_stride, P.tmp_row_pitch, bounds_v, kk_v, dst, P.quads_per_row, vec_ok);
     }
     f = fopen(argv[2], "wb");
     if (!f || fwrite(dst, sizeof(float), dst_count, f) != dst_count) { fprintf(stderr, "cannot write %s\n", argv[2]); return 5; }
