@@ -220,3 +220,15 @@ def test_training_host_helpers():
     box, cls, cnt = pack_labels([L(3), L(0), L(1)], 4, torch.device('cpu'))
     assert box.shape == (3, 3, 4) and cnt.tolist() == [3, 0, 1] and cnt.dtype == torch.int32 and cls.dtype == torch.int64
     assert torch.equal(box[0], L(3).bboxes[:, :4]) and float(box[1].abs().sum()) == 0 and torch.equal(cls[2, :1], torch.tensor([0]))
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/mydet.h is the C-ABI contract: it must compile as C99 and as C++ with nothing but the standard headers."""
+    import subprocess
+    src = tmp_path / 'h.c'
+    src.write_text('#include "mydet.h"\nint main(void) { return mydet_version() == 0; }\n')
+    inc = os.path.join(ROOT, 'include')
+    for cmd in (['gcc', '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-fsyntax-only'],
+                ['g++', '-std=c++17', '-Wall', '-Werror', '-fsyntax-only', '-x', 'c++']):
+        res = subprocess.run(cmd + ['-I', inc, str(src)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert res.returncode == 0, res.stdout
