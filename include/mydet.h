@@ -251,7 +251,8 @@ int mydet_fcos_assign(const float* t_ltrb, const int64_t t_stride[4], int batch,
  * sized uint8 RGB frames, Detector._preprocess_pil + tvf.to_tensor + format_tensor_img
  * (api/detection.py:158-162, :177-205; utils/image_ops.py:22-52 resize_pil / pad_to_divisible, :55-106
  * rect_to_square(aug=False), :165-188 format_tensor_img): Pillow's anti-aliased BILINEAR Image.resize (two-pass
- * 8 bits-per-channel resampler, bit-exact), zero padding of the uint8 image, /255, normalisation / channel order.
+ * 8 bits-per-channel resampler, bit-exact, including Pillow's rule of resizing images more than 100 times taller
+ * than wide vertically first), zero padding of the uint8 image, /255, normalisation / channel order.
  *   src         (batch, in_h, in_w, 3) uint8, row pitch and image stride in BYTES
  *   resized_*   size after the resize (the caller computes it with the reference's own Python expressions, see
  *               mydetection_b200/image_ops.py: plan); == in_* when the image is only padded

@@ -4,8 +4,9 @@
 //
 // Three stream-ordered launches per batch of equally sized frames, no host synchronisation, caller-owned workspace:
 //   resample_coeff_kernel   the fixed-point filter banks of both axes (one thread per output coordinate)
-//   resample_h_kernel       horizontal pass: source rows -> uint8 intermediate (in_h x rs_w), as Pillow rounds it
-//   final_kernel            vertical pass + zero padding + /255 + normalisation / channel order -> float32 planes,
+//   first_pass_kernel       horizontal pass: source rows -> uint8 intermediate (in_h x rs_w), as Pillow rounds it
+//                           (vertical pass first for images more than 100x taller than wide: Pillow's own rule)
+//   final_kernel            the other pass + zero padding + /255 + normalisation / channel order -> float32 planes,
 //                           each thread produces 4 consecutive pixels of a row and writes three 16-byte vectors
 // Bandwidth-bound byte work: no tensor cores, no shared-memory staging (the taps of neighbouring threads overlap
 // and are served by L1; the intermediate of a 1080p frame is 2 MB and stays in L2).
@@ -22,18 +23,21 @@ __global__ void resample_coeff_kernel(Geometry G, int* __restrict__ bounds_h, in
     coeff_item(G, (int)(blockIdx.x * blockDim.x + threadIdx.x), bounds_h, kk_h, bounds_v, kk_v);
 }
 
-__global__ void resample_h_kernel(Geometry G, const uint8_t* __restrict__ src, long long src_image_stride,
-                                  long long src_row_pitch, const int* __restrict__ bounds_h,
-                                  const int* __restrict__ kk_h, uint8_t* __restrict__ tmp, long long total) {
+__global__ void first_pass_kernel(Geometry G, const uint8_t* __restrict__ src, long long src_image_stride,
+                                  long long src_row_pitch, const int* __restrict__ bounds_h, const int* __restrict__ kk_h,
+                                  const int* __restrict__ bounds_v, const int* __restrict__ kk_v,
+                                  uint8_t* __restrict__ tmp, long long total) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < total) h_item(G, i, src, src_image_stride, src_row_pitch, bounds_h, kk_h, tmp);
+    if (i < total) first_item(G, i, src, src_image_stride, src_row_pitch, bounds_h, kk_h, bounds_v, kk_v, tmp);
 }
 
 __global__ void final_kernel(Geometry G, const uint8_t* __restrict__ img, long long image_stride, long long row_pitch,
+                             const int* __restrict__ bounds_h, const int* __restrict__ kk_h,
                              const int* __restrict__ bounds_v, const int* __restrict__ kk_v, float* __restrict__ dst,
                              int quads_per_row, long long total_quads, int vec_ok) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < total_quads) final_item(G, i, img, image_stride, row_pitch, bounds_v, kk_v, dst, quads_per_row, vec_ok);
+    if (i < total_quads)
+        final_item(G, i, img, image_stride, row_pitch, bounds_h, kk_h, bounds_v, kk_v, dst, quads_per_row, vec_ok);
 }
 
 }  // namespace pre
@@ -62,8 +66,8 @@ MYDET_API int mydet_preprocess(const uint8_t* src, int batch, int64_t src_image_
     const int vec_ok = (out_w % 4 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) ? 1 : 0;
     const unsigned final_blocks = (unsigned)((P.n_final_items + 255) / 256);
     if (G.direct) {
-        pre::final_kernel<<<final_blocks, 256, 0, st>>>(G, src, src_image_stride, src_row_pitch, nullptr, nullptr, dst,
-                                                        P.quads_per_row, P.n_final_items, vec_ok);
+        pre::final_kernel<<<final_blocks, 256, 0, st>>>(G, src, src_image_stride, src_row_pitch, nullptr, nullptr, nullptr,
+                                                        nullptr, dst, P.quads_per_row, P.n_final_items, vec_ok);
         return launch_status("final_kernel");
     }
     MYDET_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
@@ -79,10 +83,10 @@ MYDET_API int mydet_preprocess(const uint8_t* src, int batch, int64_t src_image_
     uint8_t* tmp = reinterpret_cast<uint8_t*>(ws + P.off_tmp);
     pre::resample_coeff_kernel<<<(unsigned)((P.n_coeff_items + 127) / 128), 128, 0, st>>>(G, bounds_h, kk_h, bounds_v, kk_v);
     if (int rc = launch_status("resample_coeff_kernel")) return rc;
-    pre::resample_h_kernel<<<(unsigned)((P.n_h_items + 255) / 256), 256, 0, st>>>(
-        G, src, src_image_stride, src_row_pitch, bounds_h, kk_h, tmp, P.n_h_items);
-    if (int rc = launch_status("resample_h_kernel")) return rc;
-    pre::final_kernel<<<final_blocks, 256, 0, st>>>(G, tmp, P.tmp_image_stride, P.tmp_row_pitch, bounds_v, kk_v, dst,
-                                                    P.quads_per_row, P.n_final_items, vec_ok);
+    pre::first_pass_kernel<<<(unsigned)((P.n_first_items + 255) / 256), 256, 0, st>>>(
+        G, src, src_image_stride, src_row_pitch, bounds_h, kk_h, bounds_v, kk_v, tmp, P.n_first_items);
+    if (int rc = launch_status("first_pass_kernel")) return rc;
+    pre::final_kernel<<<final_blocks, 256, 0, st>>>(G, tmp, P.tmp_image_stride, P.tmp_row_pitch, bounds_h, kk_h, bounds_v,
+                                                    kk_v, dst, P.quads_per_row, P.n_final_items, vec_ok);
     return launch_status("final_kernel");
 }

@@ -134,18 +134,22 @@ struct Geometry {
     int ksize_h, ksize_v;
     int format;
     int direct;                // no resize at all: the output reads the source directly
+    int v_first;               // vertical pass first (Pillow's rule for very tall images, see make_plan)
 };
 
-// One output pixel (all three planes) of the final pass.  `img` is the uint8 intermediate of this image
-// (rows of 3 * rs_w bytes) or, when G.direct, the source image (rows of src_row_pitch bytes).
-MYDET_HD void final_pixel(const Geometry& G, const uint8_t* img, long long row_pitch, const int* bounds_v,
-                          const int* kk_v, int y, int x, float* out3) {
+// One output pixel (all three planes) of the final pass.  `img` is the uint8 intermediate of this image -- rows of
+// 3 * rs_w bytes after a horizontal first pass, rows of 3 * in_w bytes after a vertical one (G.v_first) -- or, when
+// G.direct, the source image (rows of src_row_pitch bytes).
+MYDET_HD void final_pixel(const Geometry& G, const uint8_t* img, long long row_pitch, const int* bounds_h, const int* kk_h,
+                          const int* bounds_v, const int* kk_v, int y, int x, float* out3) {
     uint8_t rgb[3] = {0, 0, 0};                                   // the zero padding of tvf.pad(fill=0)
     const int ry = y - G.top, rx = x - G.left;
     if (ry >= 0 && ry < G.rs_h && rx >= 0 && rx < G.rs_w) {
         if (G.direct) {
             const uint8_t* p = img + (long long)ry * row_pitch + 3ll * rx;
             rgb[0] = p[0]; rgb[1] = p[1]; rgb[2] = p[2];
+        } else if (G.v_first) {
+            resample_h_pixel(img + (long long)ry * row_pitch, bounds_h, kk_h, G.ksize_h, rx, rgb);
         } else {
             resample_v_pixel(img, row_pitch, bounds_v, kk_v, G.ksize_v, ry, rx, rgb);
         }
@@ -166,16 +170,22 @@ MYDET_HD void coeff_item(const Geometry& G, int i, int* bounds_h, int* kk_h, int
     }
 }
 
-// i in [0, batch * in_h * rs_w): one pixel of the uint8 intermediate (b, y, xx), xx fastest -- neighbouring threads
-// read overlapping spans of one source row and write neighbouring bytes.
-MYDET_HD void h_item(const Geometry& G, long long i, const uint8_t* src, long long src_image_stride,
-                     long long src_row_pitch, const int* bounds_h, const int* kk_h, uint8_t* tmp) {
-    const int xx = (int)(i % G.rs_w);
-    const long long row = i / G.rs_w;                         // b * in_h + y
-    const int y = (int)(row % G.in_h);
-    const long long b = row / G.in_h;
+// One pixel of the uint8 intermediate, x fastest -- neighbouring threads read overlapping spans of one source row (or
+// neighbouring bytes of the same source rows) and write neighbouring bytes.
+//   horizontal first pass: i in [0, batch * in_h * rs_w) = (b, y, xx),  intermediate in_h x rs_w
+//   vertical first pass:   i in [0, batch * rs_h * in_w) = (b, yy, x),  intermediate rs_h x in_w
+MYDET_HD void first_item(const Geometry& G, long long i, const uint8_t* src, long long src_image_stride,
+                         long long src_row_pitch, const int* bounds_h, const int* kk_h, const int* bounds_v,
+                         const int* kk_v, uint8_t* tmp) {
+    const int cols = G.v_first ? G.in_w : G.rs_w, rows = G.v_first ? G.rs_h : G.in_h;
+    const int x = (int)(i % cols);
+    const long long row = i / cols;                           // b * rows + y
+    const int y = (int)(row % rows);
+    const long long b = row / rows;
+    const uint8_t* image = src + b * src_image_stride;
     uint8_t px[3];
-    resample_h_pixel(src + b * src_image_stride + (long long)y * src_row_pitch, bounds_h, kk_h, G.ksize_h, xx, px);
+    if (G.v_first) resample_v_pixel(image, src_row_pitch, bounds_v, kk_v, G.ksize_v, y, x, px);
+    else resample_h_pixel(image + (long long)y * src_row_pitch, bounds_h, kk_h, G.ksize_h, x, px);
     uint8_t* o = tmp + i * 3;
     o[0] = px[0]; o[1] = px[1]; o[2] = px[2];
 }
@@ -194,8 +204,8 @@ MYDET_HD void store4(float* p, float a, float b, float c, float d) {
 // i in [0, batch * out_h * quads_per_row): 4 consecutive output pixels (b, y, 4q .. 4q+3) in all three planes.
 // vec_ok: out_w % 4 == 0 and dst 16-byte aligned, so each plane takes one 16-byte store.
 MYDET_HD void final_item(const Geometry& G, long long i, const uint8_t* img, long long image_stride,
-                         long long row_pitch, const int* bounds_v, const int* kk_v, float* dst, int quads_per_row,
-                         int vec_ok) {
+                         long long row_pitch, const int* bounds_h, const int* kk_h, const int* bounds_v, const int* kk_v,
+                         float* dst, int quads_per_row, int vec_ok) {
     const int q = (int)(i % quads_per_row);
     const long long row = i / quads_per_row;                  // b * out_h + y
     const int y = (int)(row % G.out_h);
@@ -210,7 +220,7 @@ MYDET_HD void final_item(const Geometry& G, long long i, const uint8_t* img, lon
 #endif
     for (int k = 0; k < 4; ++k) {
         v[k][0] = v[k][1] = v[k][2] = 0.f;
-        if (x0 + k < G.out_w) final_pixel(G, im, row_pitch, bounds_v, kk_v, y, x0 + k, v[k]);
+        if (x0 + k < G.out_w) final_pixel(G, im, row_pitch, bounds_h, kk_h, bounds_v, kk_v, y, x0 + k, v[k]);
     }
     if (vec_ok && x0 + 3 < G.out_w) {
         for (int c = 0; c < 3; ++c) store4(o + c * plane + x0, v[0][c], v[1][c], v[2][c], v[3][c]);
@@ -227,7 +237,7 @@ MYDET_HD void final_item(const Geometry& G, long long i, const uint8_t* img, lon
 struct Plan {
     Geometry G;
     int n_coeff_items;                 // rs_w + rs_h
-    long long n_h_items;               // batch * in_h * rs_w
+    long long n_first_items;           // pixels of the uint8 intermediate: batch * in_h * rs_w, or batch * rs_h * in_w (v_first)
     int quads_per_row;                 // ceil(out_w / 4)
     long long n_final_items;           // batch * out_h * quads_per_row
     size_t off_bounds_h, off_kk_h, off_bounds_v, off_kk_v, off_tmp, workspace_bytes;
@@ -248,21 +258,25 @@ inline const char* make_plan(int batch, int in_h, int in_w, int rs_h, int rs_w, 
     G.out_h = out_h; G.out_w = out_w; G.format = format;
     G.ksize_h = resample_ksize(in_w, rs_w); G.ksize_v = resample_ksize(in_h, rs_h);
     G.direct = (rs_h == in_h && rs_w == in_w) ? 1 : 0;       // Image.resize returns a copy when the size is unchanged
+    // Pillow's Image.resize (PIL/Image.py, as installed: 12.2.0) resizes a very tall image vertically first:
+    //   if self.size[1] > self.size[0] * 100 and size[1] < self.size[1]: vertical resize, then horizontal resize
+    // -- the rounding of the uint8 intermediate then happens on the other axis, so the rule is part of the bits.
+    G.v_first = (!G.direct && (long long)in_h > 100ll * in_w && rs_h < in_h) ? 1 : 0;
     P->n_coeff_items = rs_w + rs_h;
-    P->n_h_items = (long long)batch * in_h * rs_w;
+    P->n_first_items = G.v_first ? (long long)batch * rs_h * in_w : (long long)batch * in_h * rs_w;
     P->quads_per_row = (out_w + 3) / 4;
     P->n_final_items = (long long)batch * out_h * P->quads_per_row;
-    if (P->n_h_items / 256 >= 0x7fffffffll || P->n_final_items / 256 >= 0x7fffffffll) return "batch too large for one launch";
+    if (P->n_first_items / 256 >= 0x7fffffffll || P->n_final_items / 256 >= 0x7fffffffll) return "batch too large for one launch";
     size_t off = 0;
     auto take = [&off](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     P->off_bounds_h = take(sizeof(int) * 2 * (size_t)rs_w);
     P->off_kk_h = take(sizeof(int) * (size_t)rs_w * G.ksize_h);
     P->off_bounds_v = take(sizeof(int) * 2 * (size_t)rs_h);
     P->off_kk_v = take(sizeof(int) * (size_t)rs_h * G.ksize_v);
-    P->off_tmp = take(G.direct ? 0 : (size_t)P->n_h_items * 3);
+    P->off_tmp = take(G.direct ? 0 : (size_t)P->n_first_items * 3);
     P->workspace_bytes = G.direct ? 256 : off;
-    P->tmp_row_pitch = 3ll * rs_w;
-    P->tmp_image_stride = P->tmp_row_pitch * in_h;
+    P->tmp_row_pitch = 3ll * (G.v_first ? in_w : rs_w);
+    P->tmp_image_stride = P->tmp_row_pitch * (G.v_first ? rs_h : in_h);
     return nullptr;
 }
 

@@ -67,6 +67,10 @@ def resize_bilinear_u8(img, out_h, out_w):
     in_h, in_w = img.shape[:2]
     if (in_h, in_w) == (out_h, out_w):
         return img.copy()                                   # Image.resize returns a copy when nothing changes
+    if in_h > in_w * 100 and out_h < in_h and in_w != out_w:
+        # PIL/Image.py (Pillow 12.2.0), Image.resize: `if self.size[1] > self.size[0] * 100 and size[1] < self.size[1]`
+        # a very tall image is resized vertically first, then horizontally -- two separate resize calls
+        return resize_bilinear_u8(resize_bilinear_u8(img, out_h, in_w), out_h, out_w)
     src = img.astype(np.int64)
     need_h, need_v = out_w != in_w, out_h != in_h
     bv, kv = resample_coeffs(in_h, out_h)

@@ -39,7 +39,7 @@ int main(int argc, char** argv) {
     const int vec_ok = (out_w % 4 == 0 && ((uintptr_t)dst & 15) == 0) ? 1 : 0;      // as mydet_preprocess decides
     if (G.direct) {
         for (long long i = 0; i < P.n_final_items; ++i)
-            final_item(G, i, src, image_stride, row_pitch, nullptr, nullptr, dst, P.quads_per_row, vec_ok);
+            final_item(G, i, src, image_stride, row_pitch, nullptr, nullptr, nullptr, nullptr, dst, P.quads_per_row, vec_ok);
     } else {
         int* bounds_h = (int*)(ws + P.off_bounds_h);
         int* kk_h = (int*)(ws + P.off_kk_h);
@@ -48,9 +48,10 @@ int main(int argc, char** argv) {
         uint8_t* tmp = (uint8_t*)(ws + P.off_tmp);
         // the kernel is launched with ceil(n / 128) * 128 threads: run the surplus indices too, they must do nothing
         for (int i = 0; i < (P.n_coeff_items + 127) / 128 * 128; ++i) coeff_item(G, i, bounds_h, kk_h, bounds_v, kk_v);
-        for (long long i = 0; i < P.n_h_items; ++i) h_item(G, i, src, image_stride, row_pitch, bounds_h, kk_h, tmp);
+        for (long long i = 0; i < P.n_first_items; ++i)
+            first_item(G, i, src, image_stride, row_pitch, bounds_h, kk_h, bounds_v, kk_v, tmp);
         for (long long i = 0; i < P.n_final_items; ++i)
-            final_item(G, i, tmp, P.tmp_image_stride, P.tmp_row_pitch, bounds_v, kk_v, dst, P.quads_per_row, vec_ok);
+            final_item(G, i, tmp, P.tmp_image_stride, P.tmp_row_pitch, bounds_h, kk_h, bounds_v, kk_v, dst, P.quads_per_row, vec_ok);
     }
     f = fopen(argv[2], "wb");
     if (!f || fwrite(dst, sizeof(float), dst_count, f) != dst_count) { fprintf(stderr, "cannot write %s\n", argv[2]); return 5; }

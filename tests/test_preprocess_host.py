@@ -110,6 +110,24 @@ def test_kernel_code_realistic_frame(harness):
     assert same_bits(got[0], op.format_u8(canvas, 'RGB_1_norm'))
 
 
+def test_kernel_code_tall_images_follow_pillows_pass_order(harness):
+    """Pillow's Image.resize (PIL/Image.py, 12.2.0) resizes an image more than 100 times taller than wide vertically
+    FIRST when the height shrinks; the uint8 intermediate is then rounded on the other axis and the bits differ.  The
+    plan applies the same rule (Geometry.v_first); geometries on both sides of it, against Pillow."""
+    import PIL.Image
+    from oracle import preprocess as op
+    rng = np.random.default_rng(5)
+    for in_h, in_w, rs_h, rs_w in [(332, 2, 244, 72), (201, 2, 200, 30), (200, 2, 199, 30), (1601, 16, 800, 8), (801, 8, 802, 30),
+                                   (301, 3, 4, 200), (1001, 10, 1000, 10), (501, 5, 100, 2)]:
+        frames = rng.integers(0, 256, (2, in_h, in_w, 3), dtype=np.uint8)
+        got = harness(frames, rs_h, rs_w, 1, 2, rs_h + 3, rs_w + 3, 'RGB_1', row_pad=3)
+        for b in range(2):
+            canvas = np.zeros((rs_h + 3, rs_w + 3, 3), dtype=np.uint8)
+            canvas[2:2 + rs_h, 1:1 + rs_w] = np.array(PIL.Image.fromarray(frames[b]).resize((rs_w, rs_h), PIL.Image.BILINEAR))
+            assert same_bits(got[b], op.format_u8(canvas, 'RGB_1')), (in_h, in_w, rs_h, rs_w)
+            assert np.array_equal(op.resize_bilinear_u8(frames[b], rs_h, rs_w), canvas[2:2 + rs_h, 1:1 + rs_w])   # the oracle too
+
+
 def test_plan_rejects_bad_geometry(harness):
     frames = np.zeros((1, 8, 8, 3), dtype=np.uint8)
     res = harness(frames, 8, 8, 4, 0, 8, 8, 'RGB_1', expect_ok=False)       # left + rs_w > out_w

@@ -59,3 +59,23 @@ def test_preprocess_full_hd_frame():
     want, pad = op.preprocess(img, 'resize_pad_square', 608, 32, 'RGB_1')
     got, pad2 = image_ops.preprocess(img, 'resize_pad_square', 608, 32, 'RGB_1')
     assert pad == pad2 and same_bits(got[0].cpu().numpy(), want)
+
+
+def test_preprocess_tall_image_vertical_first():
+    """More than 100 times taller than wide and shrinking in height: Pillow's vertical-first rule (Geometry.v_first)."""
+    from mydetection_b200 import _lib, ops
+    from oracle import preprocess as op
+    rng = np.random.default_rng(23)
+    frames = rng.integers(0, 256, (2, 1601, 16, 3), dtype=np.uint8)
+    rs_h, rs_w = 800, 24
+    want = np.stack([op.format_u8(op.resize_bilinear_u8(f, rs_h, rs_w), 'RGB_1_norm') for f in frames])
+    dev = torch.device('cuda', 0)
+    src = torch.from_numpy(frames).to(dev)
+    out = torch.empty(2, 3, rs_h, rs_w, device=dev)
+    L = _lib.lib()
+    ws = ops._workspace(L.mydet_preprocess_workspace_bytes(2, 1601, 16, rs_h, rs_w), dev)
+    _lib.check(L.mydet_preprocess(ops._ptr(src), 2, src.stride(0), src.stride(1), 1601, 16, rs_h, rs_w, 0, 0, rs_h, rs_w,
+                                  _lib.INPUT_FORMATS['RGB_1_norm'], ops._ptr(out), ops._ptr(ws), ws.numel(), ops._stream()),
+               'mydet_preprocess')
+    torch.cuda.synchronize()
+    assert same_bits(out.cpu().numpy(), want)
