@@ -13,6 +13,7 @@
 //   emit   : ordered compaction of the survivors
 #include "internal.cuh"
 #include "rotgeom.cuh"
+#include "sweep_fixpoint.cuh"
 
 namespace mydet {
 
@@ -890,8 +891,11 @@ struct EmitParams {
     long long* keep64;   // rotated API: kept candidate indices as int64 (B, pitch)
 };
 
-template <bool SPATIAL>
+// MODE 0: score-ordered mask, block sweep.  MODE 1: spatially ordered mask, block sweep (the default).
+// MODE 2: spatially ordered mask, parallel fixed-point sweep of sweep_fixpoint.cuh (experimental, MYDET_SWEEP_FIXPOINT=1).
+template <int MODE>
 __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(LargeWs w, const int* m, int n, EmitParams E) {
+    constexpr bool SPATIAL = MODE == 1;
     extern __shared__ unsigned long long sm[];
     const int b = blockIdx.x, tid = threadIdx.x;
     const int mb = m[b];
@@ -909,7 +913,22 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(LargeWs w, const i
     for (int i = tid; i < w.words; i += kSweepThreads) { removed[i] = 0ull; keptw[i] = 0ull; }
     __syncthreads();
 
-    if (SPATIAL) {
+    if (MODE == 2) {
+        // Jacobi rounds until nothing changes; every round is parallel over the rows of the image
+        unsigned long long* keep = diag + kTile;             // w.words more (the launch sizes the buffer for it)
+        const fx::View V{mask, w.tile_adj + (long long)b * w.words * w.aw, w.spos_of_rank + base_n, mb, w.words, w.aw};
+        fx::phase_init(V, keep, removed, keptw, w.words, tid, kSweepThreads);
+        __syncthreads();
+        for (;;) {
+            fx::phase_scatter(V, keep, removed, tid, kSweepThreads);
+            __syncthreads();
+            if (!__syncthreads_or(fx::phase_update(V, keep, removed, w.words, tid, kSweepThreads))) break;
+        }
+        fx::phase_to_rank(V, keep, keptw, tid, kSweepThreads);
+        __syncthreads();
+        for (int i = tid; i < words; i += kSweepThreads) w.kept[(long long)b * w.words + i] = keptw[i];
+        __syncthreads();
+    } else if (SPATIAL) {
         // Software-pipelined: the data of block t+1 (positions, adjacency rows, gathered diagonal words) does
         // not depend on the removed vector, so it is loaded while thread 0 resolves block t.
         __shared__ int sp2[2][kTile];
@@ -1216,9 +1235,17 @@ int run_large(const LargeArgs& A, void* workspace, size_t workspace_bytes, cudaS
             spatial_gather_kernel<false><<<dim3(tiles, B), kTile, 0, st>>>(G, w.keys, w.order, w.m, w);
             mask_aabb_spatial_kernel<<<mgrid, kTile, 0, st>>>(w, w.m, n, float_at_or_below(A.thr));
         }
-        spatial_diag_kernel<<<dim3(w.words, B), 512, 0, st>>>(w, w.m, n);
-        MYDET_CUDA(cudaFuncSetAttribute(sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr));
-        sweep_kernel<true><<<B, kSweepThreads, smem, st>>>(w, w.m, n, E);
+        const char* fxenv = getenv("MYDET_SWEEP_FIXPOINT");       // experimental, not yet run on a GPU: off unless asked for
+        if (fxenv && fxenv[0] == '1') {
+            const size_t smem2 = smem + (size_t)w.words * sizeof(unsigned long long);
+            const int attr2 = (int)smem2 > 48 * 1024 ? (int)smem2 : 48 * 1024;
+            MYDET_CUDA(cudaFuncSetAttribute(sweep_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, attr2));
+            sweep_kernel<2><<<B, kSweepThreads, smem2, st>>>(w, w.m, n, E);
+        } else {
+            spatial_diag_kernel<<<dim3(w.words, B), 512, 0, st>>>(w, w.m, n);
+            MYDET_CUDA(cudaFuncSetAttribute(sweep_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr));
+            sweep_kernel<1><<<B, kSweepThreads, smem, st>>>(w, w.m, n, E);
+        }
     } else {
         if (A.rot) {
             gather_kernel<true><<<dim3((n + 255) / 256, B), 256, 0, st>>>(G, w.keys, w.order, w.m, w);
@@ -1227,8 +1254,8 @@ int run_large(const LargeArgs& A, void* workspace, size_t workspace_bytes, cudaS
             gather_kernel<false><<<dim3((n + 255) / 256, B), 256, 0, st>>>(G, w.keys, w.order, w.m, w);
             mask_kernel<<<dim3(tiles * (tiles + 1) / 2, B), kTile, 0, st>>>(w, w.m, n, float_at_or_below(A.thr));
         }
-        MYDET_CUDA(cudaFuncSetAttribute(sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr));
-        sweep_kernel<false><<<B, kSweepThreads, smem, st>>>(w, w.m, n, E);
+        MYDET_CUDA(cudaFuncSetAttribute(sweep_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr));
+        sweep_kernel<0><<<B, kSweepThreads, smem, st>>>(w, w.m, n, E);
     }
     if (A.rot && A.votes) {
         MYDET_CUDA(cudaMemsetAsync(A.votes, 0, sizeof(int) * (size_t)B * (size_t)A.pitch, st));

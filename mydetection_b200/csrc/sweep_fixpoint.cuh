@@ -1,0 +1,113 @@
+// Parallel fixed-point sweep for the large-N NMS (EXPERIMENTAL, opt-in: MYDET_SWEEP_FIXPOINT=1).
+//
+// The greedy NMS result is the unique fixed point of
+//     keep[i] = valid[i] and not any(keep[j] and M[j, i] for j ranked above i)
+// (M[j, i]: "j suppresses i"; the mask kernels only ever set the bit in the row of the higher-ranked box), and the
+// Jacobi iteration from keep = valid reaches it in (longest decisive suppression chain + 1) rounds: after round t the
+// decisions of every box whose chain is shorter than t are final.  scripts/fixpoint_depth.py measures 5-8 rounds on
+// every BASELINE workload, where the block sweep of nms_large.cu walks 157-757 blocks of 64 boxes one after the other.
+//
+// One CTA per image.  Each round:  scatter -- every still-kept row ORs its non-empty mask words (the per-tile adjacency
+// map says which words can be non-empty) into a shared `removed` vector;  update -- keep = valid & ~removed.
+// The phases are host/device functions of (thread id, thread count) with the barriers BETWEEN them, so that
+// tests/host_harness/sweep_fixpoint_host.cpp can run the same code on the CPU, one "thread" after the other, and
+// compare it with the serial greedy sweep.  Rows, words and the keep / removed vectors are indexed by SPATIAL position
+// (Morton order of the box centres), kept_by_rank by score rank, exactly as the spatial path of nms_large.cu stores them.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define FX_HD __host__ __device__ __forceinline__
+#else
+#define FX_HD inline
+#endif
+
+namespace mydet {
+namespace fx {
+
+struct View {                            // one image
+    const unsigned long long* mask;      // [position][words_total]: bit c of row p = "p suppresses c" (p ranked above c)
+    const unsigned long long* tile_adj;  // [tile][aw]: bit j = some row of the tile has a non-zero mask word j
+    const int* spos_of_rank;             // score rank -> spatial position
+    int mb;                              // valid boxes of the image
+    int words_total;                     // row pitch of the mask in 64-bit words
+    int aw;                              // adjacency words per tile
+};
+
+FX_HD int count_trailing_zeros(unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)v) - 1;
+#else
+    return __builtin_ctzll(v);
+#endif
+}
+
+// vec[word] |= bits.  Device: shared-memory atomics (two 32-bit halves, as the block sweep does); the host harness
+// runs the "threads" one after the other, so a plain OR is the same thing.
+FX_HD void or_bits(unsigned long long* vec, int word, unsigned long long bits) {
+#if defined(__CUDA_ARCH__)
+    unsigned* v32 = reinterpret_cast<unsigned*>(vec);
+    if ((unsigned)bits) atomicOr(&v32[2 * word], (unsigned)bits);
+    if ((unsigned)(bits >> 32)) atomicOr(&v32[2 * word + 1], (unsigned)(bits >> 32));
+#else
+    vec[word] |= bits;
+#endif
+}
+
+FX_HD unsigned long long valid_word(int mb, int wd) {             // positions [64 wd, 64 wd + 64) that are < mb
+    const int lo = wd * 64;
+    if (lo >= mb) return 0ull;
+    return (mb - lo >= 64) ? ~0ull : ((1ull << (mb - lo)) - 1ull);
+}
+
+// keep = valid, removed = 0, kept_by_rank = 0.   (barrier after)
+FX_HD void phase_init(const View& V, unsigned long long* keep, unsigned long long* removed, unsigned long long* kept_by_rank,
+                      int n_words, int tid, int nt) {
+    for (int wd = tid; wd < n_words; wd += nt) {
+        keep[wd] = valid_word(V.mb, wd);
+        removed[wd] = 0ull;
+        kept_by_rank[wd] = 0ull;
+    }
+}
+
+// Every still-kept row ORs its non-empty words into `removed`.   (barrier before and after)
+FX_HD void phase_scatter(const View& V, const unsigned long long* keep, unsigned long long* removed, int tid, int nt) {
+    for (int p = tid; p < V.mb; p += nt) {
+        if (!((keep[p >> 6] >> (p & 63)) & 1ull)) continue;
+        const unsigned long long* row = V.mask + (long long)p * V.words_total;
+        const unsigned long long* adj = V.tile_adj + (long long)(p >> 6) * V.aw;
+        for (int q = 0; q < V.aw; ++q) {
+            unsigned long long a = adj[q];
+            while (a) {
+                const int wc = q * 64 + count_trailing_zeros(a);
+                a &= a - 1ull;
+                const unsigned long long v = row[wc];
+                if (v) or_bits(removed, wc, v);
+            }
+        }
+    }
+}
+
+// keep = valid & ~removed; removed is cleared for the next round.  Returns whether this thread changed a word.
+// (barrier before; the caller ORs the return values over the CTA, which is also the barrier after)
+FX_HD int phase_update(const View& V, unsigned long long* keep, unsigned long long* removed, int n_words, int tid, int nt) {
+    int changed = 0;
+    for (int wd = tid; wd < n_words; wd += nt) {
+        const unsigned long long nk = valid_word(V.mb, wd) & ~removed[wd];
+        changed |= (nk != keep[wd]) ? 1 : 0;
+        keep[wd] = nk;
+        removed[wd] = 0ull;
+    }
+    return changed;
+}
+
+// Survivors by score rank (the order the emit stage walks).   (barrier before and after)
+FX_HD void phase_to_rank(const View& V, const unsigned long long* keep, unsigned long long* kept_by_rank, int tid, int nt) {
+    for (int r = tid; r < V.mb; r += nt) {
+        const int p = V.spos_of_rank[r];
+        if ((keep[p >> 6] >> (p & 63)) & 1ull) or_bits(kept_by_rank, r >> 6, 1ull << (r & 63));
+    }
+}
+
+}  // namespace fx
+}  // namespace mydet
