@@ -47,6 +47,9 @@ struct LargeWs {          // carved out of the caller's workspace
     int2* tile_cls;               // B*tiles     class range of a spatial tile (axis-aligned path)
     int aw;                       // adjacency words per tile = ceil(tiles / 64)
     int words;                  // ceil(n/64)
+    // appended last, so that every field above keeps its offset (and the kernels that take this struct their code)
+    int fx_cap;                 // entries per image of fx_list
+    fx::Entry* fx_list;         // B*fx_cap  non-empty mask words of an image (experimental fixed-point sweep)
 };
 
 static size_t carve(LargeWs& w, void* base, int batch, int n, bool rot) {
@@ -71,6 +74,8 @@ static size_t carve(LargeWs& w, void* base, int batch, int n, bool rot) {
     const size_t o_adj = take(sp ? (size_t)batch * w.words * w.aw * 8 : 0);
     const size_t o_diag = take(sp ? (size_t)batch * w.words * kTile * 8 : 0);
     const size_t o_adjb = take(sp ? (size_t)batch * w.words * kTile * w.aw * 8 : 0);
+    w.fx_cap = sp ? 4 * n : 0;                      // last in the layout: everything before keeps its offset
+    const size_t o_fx = take((size_t)batch * w.fx_cap * sizeof(fx::Entry));
     if (base) {
         char* p = static_cast<char*>(base);
         w.keys = (unsigned long long*)(p + o_keys); w.order = (int*)(p + o_order); w.m = (int*)(p + o_m);
@@ -86,6 +91,7 @@ static size_t carve(LargeWs& w, void* base, int batch, int n, bool rot) {
         w.tile_adj = (unsigned long long*)(p + o_adj);
         w.diag_all = (unsigned long long*)(p + o_diag);
         w.adj_blk = (unsigned long long*)(p + o_adjb);
+        w.fx_list = (fx::Entry*)(p + o_fx);
     }
     return off;
 }
@@ -917,10 +923,18 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(LargeWs w, const i
         // Jacobi rounds until nothing changes; every round is parallel over the rows of the image
         unsigned long long* keep = diag + kTile;             // w.words more (the launch sizes the buffer for it)
         const fx::View V{mask, w.tile_adj + (long long)b * w.words * w.aw, w.spos_of_rank + base_n, mb, w.words, w.aw};
+        fx::Entry* list = w.fx_list + (long long)b * w.fx_cap;
+        __shared__ int s_entries;
+        if (tid == 0) s_entries = 0;
         fx::phase_init(V, keep, removed, keptw, w.words, tid, kSweepThreads);
         __syncthreads();
+        fx::phase_build_list(V, list, w.fx_cap, &s_entries, tid, kSweepThreads);
+        __syncthreads();
+        const int n_entries = s_entries;
+        const bool use_list = n_entries <= w.fx_cap;            // else: walk the adjacency map every round
         for (;;) {
-            fx::phase_scatter(V, keep, removed, tid, kSweepThreads);
+            if (use_list) fx::phase_scatter_list(list, n_entries, keep, removed, tid, kSweepThreads);
+            else fx::phase_scatter(V, keep, removed, tid, kSweepThreads);
             __syncthreads();
             if (!__syncthreads_or(fx::phase_update(V, keep, removed, w.words, tid, kSweepThreads))) break;
         }

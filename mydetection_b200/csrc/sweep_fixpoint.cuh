@@ -70,7 +70,8 @@ FX_HD void phase_init(const View& V, unsigned long long* keep, unsigned long lon
     }
 }
 
-// Every still-kept row ORs its non-empty words into `removed`.   (barrier before and after)
+// Every still-kept row ORs its non-empty words into `removed`, reading the words through the adjacency map.
+// (barrier before and after)  Used when the entry list below overflowed.
 FX_HD void phase_scatter(const View& V, const unsigned long long* keep, unsigned long long* removed, int tid, int nt) {
     for (int p = tid; p < V.mb; p += nt) {
         if (!((keep[p >> 6] >> (p & 63)) & 1ull)) continue;
@@ -85,6 +86,59 @@ FX_HD void phase_scatter(const View& V, const unsigned long long* keep, unsigned
                 if (v) or_bits(removed, wc, v);
             }
         }
+    }
+}
+
+// The non-empty mask words of the image as a list: the rounds then touch a few thousand entries instead of walking
+// the adjacency map of every row again.
+struct Entry { int row; int word; unsigned long long bits; };     // 16 bytes
+
+FX_HD int counter_add(int* counter, int v) {                        // returns the old value
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(counter, v);
+#else
+    const int old = *counter;
+    *counter = old + v;
+    return old;
+#endif
+}
+
+// Appends every non-empty word the adjacency map points at.  *count may end above `cap`: the list has overflowed and the
+// caller falls back to phase_scatter.  Up to kBatch independent loads are in flight per thread.  (barrier before: *count = 0;
+// barrier after)
+constexpr int kBatch = 8;
+FX_HD void phase_build_list(const View& V, Entry* list, int cap, int* count, int tid, int nt) {
+    for (int p = tid; p < V.mb; p += nt) {
+        const unsigned long long* row = V.mask + (long long)p * V.words_total;
+        const unsigned long long* adj = V.tile_adj + (long long)(p >> 6) * V.aw;
+        for (int q = 0; q < V.aw; ++q) {
+            unsigned long long a = adj[q];
+            while (a) {
+                int wc[kBatch];
+                unsigned long long v[kBatch];
+                int k = 0;
+                for (; k < kBatch && a; ++k) {
+                    wc[k] = q * 64 + count_trailing_zeros(a);
+                    a &= a - 1ull;
+                }
+                for (int j = 0; j < kBatch; ++j) v[j] = (j < k) ? row[wc[j]] : 0ull;
+                for (int j = 0; j < kBatch; ++j) {
+                    if (v[j]) {
+                        const int at = counter_add(count, 1);
+                        if (at < cap) { list[at].row = p; list[at].word = wc[j]; list[at].bits = v[j]; }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// One round over the list.   (barrier before and after)
+FX_HD void phase_scatter_list(const Entry* list, int n_entries, const unsigned long long* keep, unsigned long long* removed,
+                              int tid, int nt) {
+    for (int e = tid; e < n_entries; e += nt) {
+        const Entry x = list[e];
+        if ((keep[x.row >> 6] >> (x.row & 63)) & 1ull) or_bits(removed, x.word, x.bits);
     }
 }
 

@@ -5,9 +5,9 @@
 // buffers sized exactly as the kernel sizes them (AddressSanitizer build).  tests/test_sweep_fixpoint_host.py feeds it
 // suppression matrices in the spatial layout of nms_large.cu and compares the survivors with the serial greedy sweep.
 //
-//   sweep_fixpoint_host <in.bin> <out.bin> nt
+//   sweep_fixpoint_host <in.bin> <out.bin> nt list_cap      (list_cap < 0: 4 * mb, as the library sizes it)
 // in.bin : int32 mb, words_total, aw; then mask[mb * words_total] u64, tile_adj[ceil(mb/64) * aw] u64, spos_of_rank[mb] i32
-// out.bin: int32 rounds; kept_by_rank[words_total] u64
+// out.bin: int32 rounds, entries, used_list; kept_by_rank[words_total] u64
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -17,7 +17,7 @@
 using namespace mydet::fx;
 
 int main(int argc, char** argv) {
-    if (argc != 4) return 2;
+    if (argc != 5) return 2;
     const int nt = atoi(argv[3]);
     FILE* f = fopen(argv[1], "rb");
     int hdr[3];
@@ -35,10 +35,18 @@ int main(int argc, char** argv) {
     unsigned long long* removed = (unsigned long long*)malloc(8 * (size_t)words_total);
     unsigned long long* keptw = (unsigned long long*)malloc(8 * (size_t)words_total);
     const View V{mask, adj, spos, mb, words_total, aw};
+    const int cap = atoi(argv[4]) < 0 ? 4 * mb : atoi(argv[4]);
+    Entry* list = (Entry*)malloc(sizeof(Entry) * (size_t)(cap > 0 ? cap : 1));
+    int entries = 0;                                     // the kernel's shared counter
     for (int t = 0; t < nt; ++t) phase_init(V, keep, removed, keptw, words_total, t, nt);
+    for (int t = 0; t < nt; ++t) phase_build_list(V, list, cap, &entries, t, nt);
+    const bool use_list = entries <= cap;
     int rounds = 0;
     for (;;) {
-        for (int t = 0; t < nt; ++t) phase_scatter(V, keep, removed, t, nt);
+        for (int t = 0; t < nt; ++t) {
+            if (use_list) phase_scatter_list(list, entries, keep, removed, t, nt);
+            else phase_scatter(V, keep, removed, t, nt);
+        }
         int changed = 0;
         for (int t = 0; t < nt; ++t) changed |= phase_update(V, keep, removed, words_total, t, nt);   // __syncthreads_or
         ++rounds;
@@ -46,8 +54,9 @@ int main(int argc, char** argv) {
     }
     for (int t = 0; t < nt; ++t) phase_to_rank(V, keep, keptw, t, nt);
     f = fopen(argv[2], "wb");
-    if (!f || fwrite(&rounds, sizeof(int), 1, f) != 1 || fwrite(keptw, 8, words_total, f) != (size_t)words_total) return 5;
+    const int head[3] = {rounds, entries, use_list ? 1 : 0};
+    if (!f || fwrite(head, sizeof(int), 3, f) != 3 || fwrite(keptw, 8, words_total, f) != (size_t)words_total) return 5;
     fclose(f);
-    free(mask); free(adj); free(spos); free(keep); free(removed); free(keptw);
+    free(mask); free(adj); free(spos); free(keep); free(removed); free(keptw); free(list);
     return 0;
 }

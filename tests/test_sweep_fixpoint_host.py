@@ -24,20 +24,20 @@ def harness(tmp_path_factory):
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert res.returncode == 0, res.stdout
 
-    def run(mask, adj, spos_of_rank, mb, words_total, aw, nt):
+    def run(mask, adj, spos_of_rank, mb, words_total, aw, nt, list_cap=-1):
         src, dst = str(d / 'in.bin'), str(d / 'out.bin')
         with open(src, 'wb') as f:
             np.array([mb, words_total, aw], dtype=np.int32).tofile(f)
             mask.astype(np.uint64).tofile(f)
             adj.astype(np.uint64).tofile(f)
             spos_of_rank.astype(np.int32).tofile(f)
-        res = subprocess.run([exe, src, dst, str(nt)], env=dict(os.environ, ASAN_OPTIONS='detect_leaks=0'),
+        res = subprocess.run([exe, src, dst, str(nt), str(list_cap)], env=dict(os.environ, ASAN_OPTIONS='detect_leaks=0'),
                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         assert res.returncode == 0, res.stderr[-2000:]
         raw = open(dst, 'rb').read()
-        rounds = int(np.frombuffer(raw[:4], dtype=np.int32)[0])
-        kept = np.frombuffer(raw[4:], dtype=np.uint64)
-        return rounds, kept
+        rounds, entries, used_list = (int(v) for v in np.frombuffer(raw[:12], dtype=np.int32))
+        kept = np.frombuffer(raw[12:], dtype=np.uint64)
+        return rounds, kept, entries, used_list
     return run
 
 
@@ -114,11 +114,15 @@ def test_fixpoint_sweep_equals_greedy(harness, nt):
             spos_of_rank = np.empty(mb, dtype=np.int64)
             spos_of_rank[pos_to_rank] = np.arange(mb)
             mask, adj, words_total, aw = layout(pairs, mb, cap, spos_of_rank, extra)
-            rounds, kept_words = harness(mask, adj, spos_of_rank, mb, words_total, aw, nt)
-            got, tail = unpack(kept_words, mb)
             want = greedy(pairs, mb)
-            assert np.array_equal(got, want), (name, perm, int((got != want).sum()))
-            assert not tail.any(), (name, 'bits beyond the valid boxes')
+            nonzero_words = int(np.count_nonzero(mask))
+            for list_cap in (-1, max(nonzero_words // 2, 0)):      # the library's capacity, and an overflowing list
+                rounds, kept_words, entries, used_list = harness(mask, adj, spos_of_rank, mb, words_total, aw, nt, list_cap)
+                got, tail = unpack(kept_words, mb)
+                assert np.array_equal(got, want), (name, perm, list_cap, int((got != want).sum()))
+                assert not tail.any(), (name, 'bits beyond the valid boxes')
+                fits = nonzero_words <= (4 * mb if list_cap < 0 else list_cap)
+                assert entries == nonzero_words and used_list == int(fits), (name, entries, nonzero_words, list_cap)
             if name == 'chain':
                 assert want.sum() == mb // 2 and rounds >= mb // 2       # alternate survivors; one chain link per round or two
             elif mb > 100:
@@ -126,5 +130,5 @@ def test_fixpoint_sweep_equals_greedy(harness, nt):
 
 
 def test_fixpoint_sweep_empty_image(harness):
-    rounds, kept = harness(np.zeros((0, 2), np.uint64), np.zeros((0, 1), np.uint64), np.zeros(0, np.int64), 0, 2, 1, 64)
-    assert rounds == 1 and not kept.any()
+    rounds, kept, entries, used_list = harness(np.zeros((0, 2), np.uint64), np.zeros((0, 1), np.uint64), np.zeros(0, np.int64), 0, 2, 1, 64)
+    assert rounds == 1 and entries == 0 and used_list == 1 and not kept.any()
