@@ -589,6 +589,47 @@ def gen_fullmodel(name='yolov3_80'):
     save('fullmodel_' + name, **out)
 
 
+def gen_fullmodel_atss():
+    """BASELINE configs[3] through the UNMODIFIED reference in TRAINING mode: OneStageBBox(configs/d1_fcs2_atss.json) with
+    random weights (see gen_fullmodel), one synthetic 384 x 384 image (the coarsest level must hold >= 9 anchors for
+    torch.topk, fcos2.py:397) with 100 GT boxes, model(x, labels): the ATSS target
+    tensors of all five FCOS_ATSS_Layer levels are captured from forward()'s locals.  Only the regression head output enters
+    the assignment (the ignore mask uses the predicted boxes); it is standardised per channel to sigma 0.5 and stored as
+    float16-representable values, as in gen_fullmodel."""
+    import json
+    from utils.structures import ImageObjects
+    cfg = json.load(open(os.path.join(REF, 'configs', 'd1_fcs2_atss.json')))
+    torch.manual_seed(2025)
+    model = _build_reference_model(cfg)
+    gen = torch.Generator().manual_seed(77)
+    img_hw = (384, 384)
+    n_gt, n_cls = 100, cfg['general.num_class']
+    bx = torch.empty(n_gt, 4)
+    bx[:, 0:2] = torch.rand(n_gt, 2, generator=gen) * 364 + 10
+    bx[:, 2:4] = torch.exp(torch.rand(n_gt, 2, generator=gen) * (np.log(140.0) - np.log(8.0)) + np.log(8.0))
+    ct = torch.randint(0, n_cls, (n_gt,), generator=gen)
+    assert (bx[:, 2] * bx[:, 3]).unique().numel() == n_gt
+    labels = [ImageObjects(bx, ct, bb_format='cxcywh', img_hw=img_hw)]
+    x = torch.rand(1, 3, *img_hw, generator=gen)
+    raws = model.rpn(model.fpn(model.backbone(x)))
+    out = {'gt_boxes': bx, 'gt_cats': ct, 'params': np.array([img_hw[0], img_hw[1], cfg['model.atss.topk_per_level'],
+                                                              cfg.get('model.fcos2.ignored_threshold', 0.7), n_cls], dtype=np.float64),
+           'strides': np.array(cfg['model.fpn.out_strides']), 'anchors': np.array(cfg['model.atss.anchors'], dtype=np.float64)}
+    names = ['PositiveMask', 'IgnoredMask', 'TargetConf', 'TargetLTRB', 'TargetCls']
+    n_pos = n_ign = 0
+    for i, raw in enumerate(raws):
+        bb = raw['bbox'].permute(0, 3, 1, 2).contiguous()
+        bb = ((bb - bb.mean(dim=(0, 2, 3), keepdim=True)) / bb.std(dim=(0, 2, 3), keepdim=True).clamp(min=1e-12) * 0.5).half()
+        out[f'atss{i}_bbox'] = bb
+        raw_in = {'bbox': bb.float().permute(0, 2, 3, 1), 'conf': raw['conf'], 'class': raw['class']}
+        _, g = _grab_forward(model.det_layers[i], names, raw_in, img_hw, labels)
+        out.update({f'atss{i}_{k}': g[k] for k in names})
+        n_pos += int(g['PositiveMask'].sum()); n_ign += int(g['IgnoredMask'].sum())
+    print('fullmodel atss: positives', n_pos, 'ignored', n_ign)
+    assert n_pos > 50
+    save('fullmodel_d1_fcs2_atss', **out)
+
+
 if __name__ == '__main__':
     import_reference()
     torch.set_grad_enabled(False)
@@ -600,3 +641,4 @@ if __name__ == '__main__':
     gen_preprocess()
     for cfg_name in ('yolov3_80', 'rapid', 'd1_fcs2'):
         gen_fullmodel(cfg_name)
+    gen_fullmodel_atss()

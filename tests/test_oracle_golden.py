@@ -285,3 +285,21 @@ def test_fullmodel_end_to_end(golden, name):
     assert keep.numel() > 300 and torch.equal(keep, T(g['keep']))
     assert torch.equal(box[keep], T(g['kept_boxes'])) and torch.equal(score[keep], T(g['kept_scores']))
     assert torch.equal(cls[keep], T(g['kept_cats']))
+
+
+def test_fullmodel_atss_training_targets(golden):
+    """BASELINE configs[3]: oracle/atss.py against the ATSS target tensors captured from the UNMODIFIED reference's
+    OneStageBBox(d1_fcs2_atss) in training mode (random weights, one 384 x 384 image, 100 GT boxes, all five levels;
+    tests/golden/make_golden.py: gen_fullmodel_atss).  Bit-exact."""
+    g = golden('fullmodel_d1_fcs2_atss')
+    img_h, img_w, topk, ign, n_cls = g['params']
+    gts = [(T(g['gt_boxes']), T(g['gt_cats']))]
+    strides, sides = [int(v) for v in g['strides']], [float(v) for v in g['anchors']]
+    n_pos = 0
+    for li in range(5):
+        t = T(g[f'atss{li}_bbox']).float().permute(0, 2, 3, 1)
+        out = oa.assign_level(li, t, gts, (int(img_h), int(img_w)), strides, sides, int(topk), float(ign), int(n_cls))
+        for k, v in out.items():
+            assert torch.equal(v, T(g[f'atss{li}_{k}'])), (li, k)
+        n_pos += int(out['PositiveMask'].sum())
+    assert n_pos > 500

@@ -44,3 +44,30 @@ def test_fullmodel_against_reference(golden, name):
     assert torch.equal(out['cls'][0, :n].cpu(), T(g['kept_cats']))
     assert torch.allclose(out['score'][0, :n].cpu(), T(g['kept_scores']), rtol=1e-5, atol=0)
     assert torch.allclose(out['box'][0, :n].cpu(), T(g['kept_boxes']), rtol=1e-5, atol=2 * float(np.spacing(np.float32(256))))
+
+
+def test_fullmodel_atss_targets_against_reference(golden):
+    """BASELINE configs[3]: mydet_atss_assign on the regression head of a real forward, 100 GT boxes, against the target
+    tensors of the unmodified reference in training mode (fullmodel_d1_fcs2_atss.npz).  A cell may flip only where an IoU
+    lies within 1e-6 of its adaptive threshold: at most 2 cells over the five levels."""
+    from mydetection_b200 import ops
+    g = golden('fullmodel_d1_fcs2_atss')
+    img_h, img_w, topk, ign, n_cls = g['params']
+    dev = torch.device('cuda', 0)
+    gt_box, gt_cls = T(g['gt_boxes'])[None].to(dev), T(g['gt_cats'])[None].to(dev)
+    cnt = torch.tensor([gt_box.shape[1]], dtype=torch.int32, device=dev)
+    strides, sides = [int(v) for v in g['strides']], [float(v) for v in g['anchors']]
+    flips, thr = 0, None
+    for li in range(5):
+        t = T(g[f'atss{li}_bbox']).float().to(dev).permute(0, 2, 3, 1)
+        out = ops.atss_assign(t, li, strides, sides, (int(img_h), int(img_w)), gt_box, gt_cls, cnt, int(topk), float(ign),
+                              int(n_cls), thr=thr)
+        thr = out['thr']                                   # level independent: computed once, reused (include/mydet.h)
+        torch.cuda.synchronize()
+        pos, want_pos = out['PositiveMask'].cpu(), T(g[f'atss{li}_PositiveMask'])
+        same = pos == want_pos
+        flips += int((~same).sum()) + int((out['IgnoredMask'].cpu() != T(g[f'atss{li}_IgnoredMask'])).sum())
+        assert torch.equal(out['TargetCls'].cpu()[same], T(g[f'atss{li}_TargetCls'])[same]), li
+        assert torch.equal(out['TargetConf'].cpu()[same], T(g[f'atss{li}_TargetConf'])[same]), li
+        assert torch.allclose(out['TargetLTRB'].cpu()[same], T(g[f'atss{li}_TargetLTRB'])[same], rtol=1e-5, atol=1e-4), li
+    assert flips <= 2, flips
