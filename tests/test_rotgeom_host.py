@@ -107,3 +107,17 @@ def test_pair_decision_against_oracle(harness, thr, ge):
             assert float(np.abs(o['iou32'][alive] - o['iou64'][alive]).max()) < f32_bound, name
         if name == 'at_threshold':
             assert (o['stage'] == 3).mean() > 0.99 and 0.3 < want.mean() < 0.7        # the family does sit at the threshold
+
+
+def test_float_vs_double_threshold_helpers(tmp_path):
+    """csrc/common.cuh: float_at_or_below / float_at_or_above turn torchvision's float-IoU-vs-double-threshold comparison
+    into a float-only one.  tests/host_harness/threshold_host.cpp checks the defining equivalence on the floats around
+    the cut for 10 M thresholds (random, exactly representable, one double ulp off a float)."""
+    exe = str(tmp_path / 'threshold_host')
+    cuda_inc = os.path.join(os.environ.get('CUDA_HOME', '/usr/local/cuda'), 'include')
+    res = subprocess.run(['g++', '-O2', '-std=c++17', '-I', cuda_inc, '-o', exe,
+                          os.path.join(ROOT, 'tests', 'host_harness', 'threshold_host.cpp')],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0, res.stdout
+    res = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
+    assert res.returncode == 0 and res.stdout.strip().endswith(' 0 violations'), res.stdout
