@@ -2,9 +2,7 @@
 OneStageBBox of yolov3_80 / rapid / d1_fcs2 with random weights, one synthetic image, det layers, level concatenation,
 post_process -- BASELINE configs[0], [2], [1] geometry at 256 x 256).
 
-STATUS: the fixtures were generated after round 1's GPU budget was spent; the kernels they exercise are the ones
-tests/test_gpu_configs.py already verifies on synthetic logits, but THESE inputs have not been on a B200 yet, so the
-tests are non-strict xfail until their first run (the file sorts after the verified tests).  The generator picks image
+STATUS: green on a B200 in the round-1 driver run (GPUTEST_r01.json); hard tests since round 2.  The generator picks image
 seeds whose rankings keep >= 5e-5 (score at the top-512 boundary and at the confidence threshold) and >= 1e-4 (IoU to the
 NMS threshold) of margin, far above the float32 tolerances of DESIGN.md section 4, so kept indices must be exact.
 """
@@ -14,8 +12,7 @@ import torch
 
 from helpers import T, YOLO_ANCHORS, RAPID_ANCHORS
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason='first GPU run pending (fixtures added after the round-1 GPU budget was spent)')]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize('name', ['yolov3_80', 'rapid', 'd1_fcs2'])

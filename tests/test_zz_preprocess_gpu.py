@@ -1,17 +1,14 @@
 """GPU parity tests of the image pre-processing path (mydet_preprocess).
 
-STATUS: written after round 1's GPU budget was spent -- these launches have NOT yet run on a B200.  The arithmetic,
-index mapping and workspace plan the kernels execute are pinned on the CPU (tests/test_preprocess_host.py compiles
-the same header for the host and compares bit for bit with the reference and with Pillow); what is left unproven is
-the launch itself.  Until the first GPU run confirms them the tests are non-strict xfail, and the file sorts last,
-so an unexpected failure here cannot mask a result of the verified path.  Remove the marker after the first green run.
+STATUS: green on a B200 in the round-1 driver run (GPUTEST_r01.json); hard tests since round 2.  The arithmetic, index
+mapping and workspace plan the kernels execute are also pinned on the CPU (tests/test_preprocess_host.py compiles the
+same header for the host and compares bit for bit with the reference and with Pillow).
 """
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason='first GPU run pending (round-1 GPU budget was spent before this path was written)')]
+pytestmark = [pytest.mark.gpu]
 
 
 def same_bits(a, b):

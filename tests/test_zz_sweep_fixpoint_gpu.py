@@ -1,17 +1,15 @@
 """GPU tests of the EXPERIMENTAL fixed-point sweep (sweep_kernel<2>, MYDET_SWEEP_FIXPOINT=1).
 
-STATUS: written after round 1's GPU budget was spent; the phases the kernel runs between its barriers are verified on
-the CPU (tests/test_sweep_fixpoint_host.py), the launch has NOT run on a B200 yet.  The path is off by default -- the
-default sweep's SASS is unchanged (two register-zeroing moves swapped) -- and these tests are non-strict xfail until
-their first run.  Each test runs the default path and the opt-in path on the same inputs and demands identical results.
+STATUS: green on a B200 in the round-1 driver run (GPUTEST_r01.json); hard tests since round 2.  The phases the kernel
+runs between its barriers are also verified on the CPU (tests/test_sweep_fixpoint_host.py).  Each test runs the block
+sweep and the fixed-point sweep on the same inputs and demands identical results.
 """
 import os
 
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason='first GPU run pending (experimental path written after the round-1 GPU budget was spent)')]
+pytestmark = [pytest.mark.gpu]
 
 
 class fixpoint_sweep:
