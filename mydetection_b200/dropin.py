@@ -24,6 +24,31 @@ def _parent(name):
         return pkg
 
 
+def _reference_structures(utils_pkg):
+    """The reference's real utils/structures.py, loaded from disk under a private name inside the `utils` package
+    (its relative imports `.bbox_ops`, `.tracking`, `.visualization`, `.constants`, `.kalman_filter` then resolve --
+    `.bbox_ops` to the mirror).  None when the reference is not on disk."""
+    import importlib.util
+    import os
+    for root in getattr(utils_pkg, '__path__', []):
+        path = os.path.join(root, 'structures.py')
+        if os.path.exists(path):
+            name = 'utils._structures_reference'
+            if name in sys.modules:
+                return sys.modules[name]
+            spec = importlib.util.spec_from_file_location(name, path)
+            mod = importlib.util.module_from_spec(spec)
+            mod.__package__ = 'utils'
+            sys.modules[name] = mod
+            try:
+                spec.loader.exec_module(mod)
+            except Exception:
+                del sys.modules[name]
+                return None
+            return mod
+    return None
+
+
 def install():
     """Alias the mirror modules as utils.bbox_ops, utils.structures and models.detlayers[.*].
 
@@ -42,6 +67,17 @@ def install():
         sys.modules['models.detlayers.' + name] = mod
     utils_pkg = _parent('utils')
     utils_pkg.bbox_ops, utils_pkg.structures = bbox_ops, structures
+    # everything of the reference's structures module that is NOT on the hot path keeps its own implementation:
+    # the tracklet classes (utils/structures.py:295-529) and any ImageObjects method the mirror does not define
+    ref = _reference_structures(utils_pkg)
+    if ref is not None:
+        for name, val in vars(ref).items():
+            if isinstance(val, type) and val.__module__ == ref.__name__ and not hasattr(structures, name):
+                setattr(structures, name, val)
+        for name, val in vars(ref.ImageObjects).items():
+            if not name.startswith('__') and name not in vars(structures.ImageObjects):
+                setattr(structures.ImageObjects, name, val)
+        ref.ImageObjects = structures.ImageObjects     # the tracklets' isinstance checks (:306, :344) see the class in use
     # importing `models` runs models/registry.py, whose det-layer imports are lazy (inside the function)
     models_pkg = _parent('models')
     models_pkg.detlayers = detlayers

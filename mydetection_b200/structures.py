@@ -2,8 +2,10 @@
 
 Same constructor, attributes and method names; `post_process` / `nms` / `non_max_suppression`
 (utils/structures.py:92-173) run in libmydet's CUDA kernels instead of boolean indexing +
-torch.topk + a Python loop over classes around torchvision.ops.nms on the CPU.  Tracklets,
-drawing and mask helpers of the reference file are outside the path and are not mirrored.
+torch.topk + a Python loop over classes around torchvision.ops.nms on the CPU.  The small helpers
+the API layer calls (`category_filter_`, `mask_to_bbox_`, `draw_on_np`, `to_json`, ...) are here too;
+the tracklet classes of the reference file (:295-529, host-side Kalman filters with no call site)
+are re-exported from the reference's own file by `dropin.install()`.
 """
 import torch
 
@@ -73,6 +75,29 @@ class ImageObjects():
             assert self.scores.shape[0] == self.bboxes.shape[0]
         assert self.img_hw is None or len(self.img_hw) == 2
 
+    def mask_to_bbox_(self):
+        '''utils/structures.py:59-66: the reference checks its preconditions, walks the masks and updates
+        nothing (the body was never finished); same observable behaviour here.'''
+        assert self.masks is not None
+        assert self._bb_format == 'cxcywh'
+
+    def category_filter_(self, categories) -> None:
+        '''Keep the objects of the given categories, in place (utils/structures.py:78-90).'''
+        assert self.masks is None, 'filtering with masks is not currently supported'
+        wanted = torch.as_tensor(list(categories), dtype=torch.int64, device=self.cats.device)
+        assert self.cats.dim() == 1 and wanted.dim() == 1
+        keep = torch.isin(self.cats, wanted)
+        self.bboxes, self.cats = self.bboxes[keep], self.cats[keep]
+        if self.scores is not None:
+            self.scores = self.scores[keep]
+
+    def draw_on_np(self, im, class_map='COCO', **kwargs):
+        '''Draw the boxes on a numpy image in place (utils/structures.py:215-219).  Drawing is outside the hot
+        path: this delegates to the reference's own utils.visualization (present wherever the drop-in is used).'''
+        assert self.bboxes.dim() == 2
+        from importlib import import_module
+        import_module('utils.visualization').draw_bboxes_on_np(im, self, class_map=class_map, **kwargs)
+
     # ------------------------------------------------------------------ the hot path
     def _run(self, conf_thres, nms_thres, topk):
         assert self.masks is None, 'nms with masks is not currently supported'
@@ -88,6 +113,11 @@ class ImageObjects():
         n, status = (int(v) for v in torch.stack([out['count'][0], out['status'][0]]).tolist())  # one D2H sync
         if status & 1:
             raise _lib.MydetError(f'category ids must lie in [0, {_lib.MAX_CLASS_ID}]')
+        if status & (2 | 4):   # cannot happen through this wrapper (out_cap and counts are derived from the input); never silent
+            raise _lib.MydetError(f'mydet_postprocess reported status {status} (2 = output truncated, 4 = count > capacity)')
+        if status & 8:
+            import warnings
+            warnings.warn('more than 2^20 candidates in one image: equal scores are ordered by the low 20 bits of the index')
         return ImageObjects(out['box'][0, :n], out['cls'][0, :n], None, out['score'][0, :n], self._bb_format,
                             img_hw=self.img_hw), out['idx'][0, :n]
 

@@ -28,6 +28,8 @@ def lib():
         L.oracle_rot_iou_pairwise.argtypes = [f32p, i64, f32p, i64, f64p]
         L.oracle_raster_iou_pairwise.restype = None
         L.oracle_raster_iou_pairwise.argtypes = [f64p, i64, f64p, i64, i64, i64, f64p]
+        L.oracle_quad_iou_pairwise.restype = None
+        L.oracle_quad_iou_pairwise.argtypes = [f64p, i64, f64p, i64, f64p]
         L.oracle_nms_rot.restype = i64
         L.oracle_nms_rot.argtypes = [f32p, f32p, i64, ctypes.c_double, i64, i64p]
         _LIB = L

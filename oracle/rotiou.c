@@ -105,6 +105,33 @@ void oracle_rot_iou_pairwise(const float* b1, int64_t n, const float* b2, int64_
     free(Q2);
 }
 
+/* out[i*m + j] = IoU of two quadrilaterals given by their corners (x0,y0,...,x3,y3) in double, the form the
+ * reference hands to pycocotools (utils/bbox_ops.py:91-96).  Used by oracle/refload.py's pycocotools stand-in. */
+static void quad_from_corners(const double* v, rquad_t* q) {
+    double a2 = 0.0, sx = 0.0, sy = 0.0, r2 = 0.0;
+    for (int k = 0; k < 4; ++k) { q->x[k] = v[2 * k]; q->y[k] = v[2 * k + 1]; sx += v[2 * k]; sy += v[2 * k + 1]; }
+    for (int k = 0; k < 4; ++k) {
+        int n = (k + 1) & 3;
+        a2 += q->x[k] * q->y[n] - q->x[n] * q->y[k];
+    }
+    q->area = 0.5 * a2; q->cx = 0.25 * sx; q->cy = 0.25 * sy;
+    for (int k = 0; k < 4; ++k) {
+        double dx = q->x[k] - q->cx, dy = q->y[k] - q->cy;
+        if (dx * dx + dy * dy > r2) r2 = dx * dx + dy * dy;
+    }
+    q->r = sqrt(r2);
+}
+
+void oracle_quad_iou_pairwise(const double* q1, int64_t n, const double* q2, int64_t m, double* out) {
+    rquad_t* Q2 = (rquad_t*)malloc((size_t)(m > 0 ? m : 1) * sizeof(rquad_t));
+    for (int64_t j = 0; j < m; ++j) quad_from_corners(q2 + 8 * j, &Q2[j]);
+    for (int64_t i = 0; i < n; ++i) {
+        rquad_t A; quad_from_corners(q1 + 8 * i, &A);
+        for (int64_t j = 0; j < m; ++j) out[i * m + j] = quad_iou(&A, &Q2[j]);
+    }
+    free(Q2);
+}
+
 /* nms_rotbb control flow.  majority <= 0 means None.  Returns the number kept. */
 int64_t oracle_nms_rot(const float* boxes, const float* scores, int64_t n, double thr,
                        int64_t majority, int64_t* keep) {

@@ -232,3 +232,41 @@ def test_header_is_plain_c(tmp_path):
                 ['g++', '-std=c++17', '-Wall', '-Werror', '-fsyntax-only', '-x', 'c++']):
         res = subprocess.run(cmd + ['-I', inc, str(src)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         assert res.returncode == 0, res.stdout
+
+
+def test_reference_copy_and_dropin_graft():
+    """oracle/fetch_ref.py's copy is byte-identical to the manifest, the reference imports from it with the three
+    third-party stand-ins, and dropin.install() completes the mirror with what lies outside the hot path (tracklets,
+    drawing) from the reference's own utils/structures.py.  No compute."""
+    from oracle import fetch_ref, refload
+    if os.path.isdir(fetch_ref.SRC):
+        fetch_ref.fetch()
+    if not refload.available():
+        pytest.skip('oracle/_ref absent and /root/reference not present')
+    assert fetch_ref.verify()
+    saved_path = list(sys.path)
+    try:
+        refload.activate(fresh=True)
+        from mydetection_b200 import dropin, structures
+        dropin.install()
+        import importlib
+        general = importlib.import_module('models.general')
+        assert general.__file__.startswith(refload.ROOT) and general.ImageObjects is structures.ImageObjects
+        assert importlib.import_module('api.detection').ImageObjects is structures.ImageObjects
+        st = importlib.import_module('utils.structures')
+        assert st is structures and st.OnlineTracklet.__module__ == 'utils._structures_reference'
+        assert st.KFTracklet is sys.modules['utils._structures_reference'].KFTracklet
+        for name in ('draw_on_np', 'category_filter_', 'mask_to_bbox_', 'to_json', 'bboxes_to_original_', 'sort_by_score_'):
+            assert callable(getattr(structures.ImageObjects, name))
+        objs = structures.ImageObjects(torch.rand(5, 4), torch.tensor([0, 3, 3, 7, 1]), scores=torch.rand(5))
+        objs.category_filter_([3, 1])
+        assert objs.cats.tolist() == [3, 3, 1] and len(objs.scores) == 3
+        import numpy as np
+        im = np.zeros((64, 64, 3), dtype=np.uint8)
+        structures.ImageObjects(torch.tensor([[32., 32., 20., 10.]]), torch.tensor([0]), scores=torch.tensor([0.9])).draw_on_np(im)
+        assert im.any()
+        tr = st.OnlineTracklet(0, objs[0], obj_id=1)       # isinstance check against the class in use
+        assert len(tr) == 1
+    finally:
+        refload.deactivate()
+        sys.path[:] = saved_path
