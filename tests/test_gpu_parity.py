@@ -3,10 +3,12 @@
 Bars (BASELINE.json north_star):
   * integer / index results (class_idx, kept indices, masks) bit-exact, except where a float
     that feeds a comparison lies inside the stated band of its threshold;
-  * decoded coordinates and scores within 1e-5 relative in fp32.  Box coordinates that are
-    differences of image-scale numbers (FCOS w = x2 - x1 ...) additionally get an absolute floor of
-    2 ulp of the image extent, because a 1-ulp difference between CUDA expf and the CPU's exp is
-    amplified by that cancellation (DESIGN.md "tolerances").
+  * decoded coordinates and scores within 1e-5 relative in fp32, PURE relative for every YOLO / RAPiD / Retina /
+    YOLOv5 box and every score.  Only values that are differences of larger numbers (FCOS w = x2 - x1, the
+    angle sigmoid*360 - 180 near 0, YOLOv5's 2*sigmoid - 0.5 in the first row / column) additionally get an absolute
+    floor of 2 ulp of the operands' magnitude, because a 1-ulp difference between CUDA expf and the CPU's exp is
+    amplified by that cancellation (DESIGN.md "tolerances"); each such call names its cancellation.  The largest
+    error seen per quantity is printed at the end of the session (conftest.py).
 """
 import numpy as np
 import pytest
@@ -23,12 +25,30 @@ def dev():
     return torch.device('cuda:0')
 
 
-def close(got, ref, extent, what):
+OBSERVED = {}      # what -> (max relative error over |ref| > 1e-30, max absolute error); printed by conftest at session end
+
+
+def close(got, ref, extent, what, cancel=None):
+    """|got - ref| <= 1e-5 * |ref|: the north star's bar, pure relative.  Only where the decoded value is a DIFFERENCE of
+    larger numbers -- so that a last-bit difference between CUDA expf / sigmoid and the CPU's is amplified by
+    cancellation -- an absolute floor of 2 ulp of `extent` (the magnitude of the operands) is added, and the call site
+    says which cancellation (`cancel='...'`)."""
     got, ref = got.detach().cpu().double(), ref.double()
-    atol = 2 * float(np.spacing(np.float32(extent)))
+    atol = 2 * float(np.spacing(np.float32(extent))) if cancel else 0.0
     err = (got - ref).abs()
+    nz = ref.abs() > 1e-30
+    rel = float((err[nz] / ref.abs()[nz]).max()) if bool(nz.any()) else 0.0
+    prev = OBSERVED.get(what, (0.0, 0.0))
+    OBSERVED[what] = (max(prev[0], rel), max(prev[1], float(err.max()) if err.numel() else 0.0))
     bad = err > (RTOL * ref.abs() + atol)
-    assert not bad.any(), f'{what}: {int(bad.sum())} of {bad.numel()} outside tolerance, max err {float(err.max()):.3e}'
+    assert not bad.any(), (f'{what}: {int(bad.sum())} of {bad.numel()} outside tolerance, max abs err {float(err.max()):.3e}, '
+                           f'max rel err {rel:.3e}')
+
+
+FCOS_W = 'FCOS: w = x2 - x1, cx = (x1 + x2) / 2 of image-scale clamped corners'
+ANGLE = 'angle = (sigmoid * 2 pi - pi) / pi * 180 (sigmoid * 360 - 180): cancels near 0 degrees'
+UV5_XY = 'YOLOv5: (2 sigmoid - 0.5 + g) cancels near sigmoid = 0.25 in the first row / column'
+CORNERS = 'corners = centre +- v -+ h with last-bit differences in sinf / cosf'
 
 
 def cls_match(got_cls, raw_cls_logits, ref_cls, what):
@@ -92,7 +112,7 @@ def test_decode_rapid_golden(golden):
         box, cls, score = run_dense(ops.KIND_RAPID, raws, (8, 16, 32), anchors, (96, 128))
         rb, rc, rs = od.merge_levels(refs)
         close(box[..., :4], rb[..., :4], 128, tag + ' bbox')
-        close(box[..., 4], rb[..., 4], 180, tag + ' angle')
+        close(box[..., 4], rb[..., 4], 180, tag + ' angle', cancel=ANGLE)
         close(score, rs, 1, tag + ' score')
         if nc:
             cls_match(cls, torch.cat([r['class'].reshape(2, -1, nc) for r in raws], 1), rc, tag + ' cls')
@@ -110,7 +130,7 @@ def test_decode_fcos_golden(golden):
         refs.append((T(g[f'fcos{li}_bbox']), T(g[f'fcos{li}_cls']), T(g[f'fcos{li}_score'])))
     box, cls, score = run_dense(ops.KIND_FCOS, raws, (8, 16, 32, 64, 128), None, (256, 384))
     rb, rc, rs = od.merge_levels(refs)
-    close(box, rb, 384, 'fcos bbox')
+    close(box, rb, 384, 'fcos bbox', cancel=FCOS_W)
     close(score, rs, 1, 'fcos score')
     cls_match(cls, torch.cat([r['class'].reshape(2, -1, 6) for r in raws], 1), rc, 'fcos cls')
     # FCOS v1 reads the centerness head under the key 'center'
@@ -127,12 +147,13 @@ def test_decode_retina_uv5_golden(golden):
         box, cls, score = run_dense(ops.KIND_RETINA, [raw], (16,), [g[f'{tag}_anchors'].tolist()], (96, 128))
         close(box[..., :4], T(g[f'{tag}_bbox'])[..., :4], 128, tag + ' bbox')
         if tag == 'retina_rot':
-            close(box[..., 4], T(g[f'{tag}_bbox'])[..., 4], 180, tag + ' angle')
+            close(box[..., 4], T(g[f'{tag}_bbox'])[..., 4], 180, tag + ' angle', cancel=ANGLE)
         close(score, T(g[f'{tag}_score']), 1, tag + ' score')
         cls_match(cls, raw['class'].reshape(2, -1, 4), T(g[f'{tag}_cls']), tag + ' cls')
     raw = yolo_views(T(g['uv5_in']), 3, 4, 5)
     box, cls, score = run_dense(ops.KIND_UV5, [raw], (8,), [level_anchors(YOLO_ANCHORS, 0).tolist()], (96, 128))
-    close(box, T(g['uv5_bbox']), 128, 'uv5 bbox')
+    close(box[..., 2:], T(g['uv5_bbox'])[..., 2:], 128, 'uv5 wh')
+    close(box[..., :2], T(g['uv5_bbox'])[..., :2], 128, 'uv5 xy', cancel=UV5_XY)
     close(score, T(g['uv5_score']), 1, 'uv5 score')
     cls_match(cls, raw['class'].reshape(2, -1, 5), T(g['uv5_cls']), 'uv5 cls')
 
@@ -300,7 +321,7 @@ def test_detect_end_to_end_vs_oracle(golden):
         k = int(out['count'][b])
         got = out['idx'][b, :k].cpu().long()
         assert k == want.numel() and torch.equal(got, want)
-        close(out['box'][b, :k], ref[0][b][want], 384, 'e2e box')
+        close(out['box'][b, :k], ref[0][b][want], 384, 'e2e box', cancel=FCOS_W)
         close(out['score'][b, :k], ref[2][b][want], 1, 'e2e score')
         assert torch.equal(out['cls'][b, :k].cpu(), ref[1][b][want])
 
