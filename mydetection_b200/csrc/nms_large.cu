@@ -49,7 +49,16 @@ struct LargeWs {          // carved out of the caller's workspace
     int words;                  // ceil(n/64)
     // appended last, so that every field above keeps its offset (and the kernels that take this struct their code)
     int fx_cap;                 // entries per image of fx_list
-    fx::Entry* fx_list;         // B*fx_cap  non-empty mask words of an image (experimental fixed-point sweep)
+    fx::Entry* fx_list;         // B*fx_cap  non-empty mask words of an image (fixed-point sweep)
+    // rotated path, broad phase / narrow phase split (rot_broad_kernel, rot_narrow_kernel)
+    float4* cull4;              // B*n      (cx, cy, circumscribed radius, area) in spatial order
+    float4* hull4;              // B*n      axis-aligned hull (x0, y0, x1, y1) of the corners, spatial order
+    float4* hull16;             // B*n16    hull of 16 consecutive spatial positions (n16 = ceil(n/16))
+    float4* hull32;             // B*n32    hull of 32 consecutive spatial positions
+    unsigned* pairs;            // B*pair_cap  candidate pairs (lower position << 16 | higher position) that reach the clip
+    int* pair_count;            // B        entries appended (may exceed pair_cap: the image then takes the tile kernel)
+    int pair_cap;
+    int n16, n32;
 };
 
 static size_t carve(LargeWs& w, void* base, int batch, int n, bool rot) {
@@ -76,6 +85,16 @@ static size_t carve(LargeWs& w, void* base, int batch, int n, bool rot) {
     const size_t o_adjb = take(sp ? (size_t)batch * w.words * kTile * w.aw * 8 : 0);
     w.fx_cap = sp ? 4 * n : 0;                      // last in the layout: everything before keeps its offset
     const size_t o_fx = take((size_t)batch * w.fx_cap * sizeof(fx::Entry));
+    const bool bp = sp && rot;                      // broad / narrow phase buffers of the rotated path
+    w.n16 = (n + 15) / 16; w.n32 = (n + 31) / 32;
+    {
+        const long long all = (long long)n * (n - 1) / 2, want = 128ll * n;     // 128 partners per box before the tile kernel takes over
+        w.pair_cap = bp ? (int)(all < want ? all : want) : 0;
+        if (w.pair_cap < 1) w.pair_cap = bp ? 1 : 0;
+    }
+    const size_t o_cull = take(bp ? bn * 16 : 0), o_h4 = take(bp ? bn * 16 : 0);
+    const size_t o_h16 = take(bp ? (size_t)batch * w.n16 * 16 : 0), o_h32 = take(bp ? (size_t)batch * w.n32 * 16 : 0);
+    const size_t o_pairs = take((size_t)batch * w.pair_cap * 4), o_pcnt = take(bp ? (size_t)batch * 4 : 0);
     if (base) {
         char* p = static_cast<char*>(base);
         w.keys = (unsigned long long*)(p + o_keys); w.order = (int*)(p + o_order); w.m = (int*)(p + o_m);
@@ -92,6 +111,9 @@ static size_t carve(LargeWs& w, void* base, int batch, int n, bool rot) {
         w.diag_all = (unsigned long long*)(p + o_diag);
         w.adj_blk = (unsigned long long*)(p + o_adjb);
         w.fx_list = (fx::Entry*)(p + o_fx);
+        w.cull4 = (float4*)(p + o_cull); w.hull4 = (float4*)(p + o_h4);
+        w.hull16 = (float4*)(p + o_h16); w.hull32 = (float4*)(p + o_h32);
+        w.pairs = (unsigned*)(p + o_pairs); w.pair_count = (int*)(p + o_pcnt);
     }
     return off;
 }
@@ -643,6 +665,8 @@ __global__ void __launch_bounds__(kTile) spatial_gather_kernel(GatherParams P, c
             rot_box_hull(q);
             w.rbox[row] = q;
             x0 = q.x0; y0 = q.y0; x1 = q.x1; y1 = q.y1;
+            w.cull4[row] = make_float4(q.cx, q.cy, q.r, 0.5f * fabsf(q.area2));
+            w.hull4[row] = make_float4(q.x0, q.y0, q.x1, q.y1);
         } else {
             const float v0 = bx[0], v1 = bx[1], v2 = bx[2], v3 = bx[3];
             float4 c4;
@@ -662,11 +686,15 @@ __global__ void __launch_bounds__(kTile) spatial_gather_kernel(GatherParams P, c
         w.spos_of_rank[(long long)b * P.n + r] = spos;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = 1; o < 32; o <<= 1) {
         x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o));
         x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
         c_lo = min(c_lo, __shfl_xor_sync(0xffffffffu, c_lo, o)); c_hi = max(c_hi, __shfl_xor_sync(0xffffffffu, c_hi, o));
+        if (ROT && o == 8 && (t & 15) == 0 && tile * kTile + (t & ~15) < mb)      // groups of 16 positions are complete here
+            w.hull16[(long long)b * w.n16 + tile * 4 + (t >> 4)] = make_float4(x0 - 1e-2f, y0 - 1e-2f, x1 + 1e-2f, y1 + 1e-2f);
     }
+    if (ROT && (t & 31) == 0 && tile * kTile + t < mb)
+        w.hull32[(long long)b * w.n32 + tile * 2 + (t >> 5)] = make_float4(x0 - 1e-2f, y0 - 1e-2f, x1 + 1e-2f, y1 + 1e-2f);
     if ((t & 31) == 0) { part[t >> 5] = make_float4(x0, y0, x1, y1); cpart[t >> 5] = make_int2(c_lo, c_hi); }
     __syncthreads();
     if (t == 0 && tile * kTile < mb) {
@@ -738,8 +766,12 @@ __global__ void __launch_bounds__(kTile) mask_aabb_spatial_kernel(LargeWs w, con
 // grid (row tile ti, chunk of column tiles, image).  Unordered tile pairs ti <= tj are visited once; a hit
 // sets the bit in the row of the higher-scored box with a global atomicOr (hits are rare); the mask is
 // zeroed beforehand.  Cull / queue / drain exactly as mask_rot_kernel.
-__global__ void __launch_bounds__(kTile) mask_rot_spatial_kernel(LargeWs w, const int* m, int n, double thr_d, int ge) {
+// only_overflowed != 0: the launch backs up the broad / narrow phase kernels below and handles just the images whose
+// pair list overflowed (pair_count > pair_cap); every other CTA leaves at once.
+__global__ void __launch_bounds__(kTile) mask_rot_spatial_kernel(LargeWs w, const int* m, int n, double thr_d, int ge,
+                                                                 int only_overflowed) {
     const int ti = blockIdx.x, cc = blockIdx.y, b = blockIdx.z;
+    if (only_overflowed && w.pair_count[b] <= w.pair_cap) return;
     const int T = (n + kTile - 1) / kTile;
     const int tj_lo = max(ti, cc * kColChunk), tj_hi = min(T, (cc + 1) * kColChunk);
     if (tj_lo >= tj_hi) return;
@@ -843,6 +875,140 @@ __global__ void __launch_bounds__(kTile) mask_rot_spatial_kernel(LargeWs w, cons
     }
     __syncthreads();
     drain(qn);
+}
+
+// ---------------------------------------------------------------------------- rotated mask: broad phase + narrow phase
+// The tile kernel above spends its time waiting, not computing (ncu, round 1: 35 % of the warp slots active, 11 % of the
+// samples on the CTA barrier in front of the queue drain, 15 % in the serial walk over the circle survivors that fetches
+// every candidate's hull from L2).  Split:
+//   broad  : ONE WARP per row tile of 32 spatial positions, no CTA barrier anywhere.  The lanes test the hulls of 32
+//            column sub-tiles (16 positions each) at a time against the row tile's hull; for every overlapping sub-tile
+//            the cull data (centre, radius, area) AND the hulls of its 16 boxes are staged in the warp's shared memory with
+//            one 16-byte load per lane, every lane runs 16 branch-free circle + area-ratio tests for its row, and the
+//            survivors go through the hull-overlap bound (shared memory, no L2 round trip) into a warp-private queue kept
+//            with ballots (no atomics).  The queue is appended to the image's pair list with one global atomic per ~512 pairs.
+//   narrow : one thread per listed pair: polygon clip (float32 in box-local coordinates, float64 re-check within 1e-3 of
+//            the threshold -- rot_overlaps, unchanged) and the bit for the row of the higher-ranked box.  Every lane busy,
+//            no queue, no barrier.
+// 32 x 16 tiles cut the circle tests per 10 000-box image from 22 M (64 x 64 tiles) to 13 M (scripts/rot_mask_workload.py).
+// A pair list that overflows (more than 128 partners per box on average) marks its image for the tile kernel.
+constexpr int kBroadWarps = 4;
+constexpr int kBroadQueue = 1024;          // entries per warp; flushed above kBroadQueue - 512 (a sub-tile adds at most 512)
+
+__global__ void __launch_bounds__(kBroadWarps * 32) rot_broad_kernel(LargeWs w, const int* m, int n, float thr_f) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.y;
+    const int R = blockIdx.x * kBroadWarps + warp;
+    const int mb = m[b];
+    if (R * 32 >= mb) return;                       // warps are independent: no CTA-wide barrier below
+    __shared__ float4 s_col[kBroadWarps][2][32];    // [0,16): cull data, [16,32): hulls of the column sub-tile
+    __shared__ unsigned s_queue[kBroadWarps][kBroadQueue];
+    const long long base = (long long)b * n;
+    const int n16 = (mb + 15) >> 4;
+    const int p = R * 32 + lane;
+    const bool have = p < mb;
+    float4 mc = make_float4(3.0e18f, 3.0e18f, 0.f, 0.f), mh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (have) { mc = w.cull4[base + p]; mh = w.hull4[base + p]; }
+    const float mr = mc.z * 1.00001f + 1e-3f, ma = mc.w;
+    const float4 rh = w.hull32[(long long)b * w.n32 + R];
+    unsigned* queue = s_queue[warp];
+    unsigned* pairs = w.pairs + (long long)b * w.pair_cap;
+    int qn = 0;                                     // warp-uniform
+    int buf = 0;
+
+    auto flush = [&]() {
+        int at = 0;
+        if (lane == 0) at = atomicAdd(&w.pair_count[b], qn);
+        at = __shfl_sync(0xffffffffu, at, 0);
+        for (int e = lane; e < qn; e += 32)
+            if (at + e < w.pair_cap) pairs[at + e] = queue[e];
+        __syncwarp();
+        qn = 0;
+    };
+
+#pragma unroll 1
+    for (int cbase = 2 * R; cbase < n16; cbase += 32) {
+        const int Cl = cbase + lane;
+        bool ov = false;
+        if (Cl < n16) {
+            const float4 h = w.hull16[(long long)b * w.n16 + Cl];
+            ov = !(h.x > rh.z || rh.x > h.z || h.y > rh.w || rh.y > h.w);
+        }
+        unsigned tiles = __ballot_sync(0xffffffffu, ov);
+#pragma unroll 1
+        while (tiles) {
+            const int C = cbase + __ffs(tiles) - 1;
+            tiles &= tiles - 1;
+            {
+                const int q = C * 16 + (lane & 15);
+                float4 v = (lane < 16) ? make_float4(-3.0e18f, -3.0e18f, 0.f, 0.f) : make_float4(3.0e18f, 3.0e18f, -3.0e18f, -3.0e18f);
+                if (q < mb) v = (lane < 16) ? w.cull4[base + q] : w.hull4[base + q];
+                s_col[warp][buf][lane] = v;
+            }
+            __syncwarp();
+            unsigned pass = 0u;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float4 c = s_col[warp][buf][j];
+                const float dx = mc.x - c.x, dy = mc.y - c.y, rr = fmaf(c.z, 1.00001f, mr);
+                // circle test AND area-ratio bound (IoU <= min / max of the two areas), branch-free, as in the tile kernel
+                const bool ok = (fmaf(dx, dx, dy * dy) <= rr * rr) & (fminf(ma, c.w) * 1.0001f >= thr_f * fmaxf(ma, c.w));
+                pass |= (ok ? 1u : 0u) << j;
+            }
+            {   // each unordered pair once: only partners at a higher spatial position
+                const int d = p - C * 16;           // partner j qualifies iff j > d
+                if (!have || d >= 15) pass = 0u;
+                else if (d >= 0) pass &= ~0u << (d + 1);
+            }
+#pragma unroll 1
+            while (__any_sync(0xffffffffu, pass != 0u)) {
+                bool push = false;
+                unsigned code = 0u;
+                if (pass) {
+                    const int j = __ffs(pass) - 1;
+                    pass &= pass - 1;
+                    const float4 qh = s_col[warp][buf][16 + j];
+                    const float oa = s_col[warp][buf][j].w;
+                    const float ix = fminf(mh.z, qh.z) - fmaxf(mh.x, qh.x);
+                    const float iy = fminf(mh.w, qh.w) - fmaxf(mh.y, qh.y);
+                    if (ix > -1e-3f && iy > -1e-3f) {
+                        const float ub = (ix + 2e-3f) * (iy + 2e-3f);
+                        push = !(ub * 1.0001f < thr_f * (ma + oa - ub));
+                    }
+                    code = ((unsigned)p << 16) | (unsigned)(C * 16 + j);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, push);
+                if (push) queue[qn + __popc(bal & ((1u << lane) - 1u))] = code;
+                qn += __popc(bal);
+            }
+            buf ^= 1;
+            if (qn > kBroadQueue - 512) { __syncwarp(); flush(); }
+        }
+    }
+    __syncwarp();
+    if (qn) flush();
+}
+
+__global__ void __launch_bounds__(256) rot_narrow_kernel(LargeWs w, const int* m, int n, double thr_d, int ge) {
+    const int b = blockIdx.y;
+    const int cnt = w.pair_count[b];
+    if (cnt > w.pair_cap) return;                   // overflowed: the tile kernel redoes this image
+    const long long base = (long long)b * n;
+    const unsigned* pairs = w.pairs + (long long)b * w.pair_cap;
+    unsigned* mask32 = reinterpret_cast<unsigned*>(w.mask);
+    const bool ge_mode = ge != 0;
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < cnt; e += gridDim.x * 256) {
+        const unsigned code = pairs[e];
+        const int pa = (int)(code >> 16), pb = (int)(code & 0xffffu);           // spatial positions, pa < pb
+        const RotBox A = w.rbox[base + pa];
+        const RotBox B = w.rbox[base + pb];
+        if (rot_overlaps(A, B, thr_d, ge_mode)) {
+            const bool a_first = w.rank_of_spos[base + pa] < w.rank_of_spos[base + pb];
+            const int row = a_first ? pa : pb, col = a_first ? pb : pa;           // the higher-scored box suppresses
+            atomicOr(&mask32[((base + row) * w.words + (col >> 6)) * 2 + ((col >> 5) & 1)], 1u << (col & 31));
+            const int trow = row >> 6, tcol = col >> 6;
+            atomicOr(&w.tile_adj[((long long)b * w.words + trow) * w.aw + (tcol >> 6)], 1ull << (tcol & 63));
+        }
+    }
 }
 
 // The 64 boxes of a score block sit at arbitrary spatial positions: gather their mutual suppression bits
@@ -1244,13 +1410,24 @@ int run_large(const LargeArgs& A, void* workspace, size_t workspace_bytes, cudaS
         const dim3 mgrid(tiles, (tiles + kColChunk - 1) / kColChunk, B);
         if (A.rot) {
             spatial_gather_kernel<true><<<dim3(tiles, B), kTile, 0, st>>>(G, w.keys, w.order, w.m, w);
-            mask_rot_spatial_kernel<<<mgrid, kTile, 0, st>>>(w, w.m, n, A.thr, A.ge);
+            const char* tenv = getenv("MYDET_ROT_MASK_TILES");        // =1: the single tile kernel (A/B tests, profiling)
+            if (tenv && tenv[0] == '1') {
+                mask_rot_spatial_kernel<<<mgrid, kTile, 0, st>>>(w, w.m, n, A.thr, A.ge, 0);
+            } else {
+                MYDET_CUDA(cudaMemsetAsync(w.pair_count, 0, sizeof(int) * (size_t)B, st));
+                rot_broad_kernel<<<dim3((w.n32 + kBroadWarps - 1) / kBroadWarps, B), kBroadWarps * 32, 0, st>>>(w, w.m, n, (float)A.thr);
+                const int nb = (int)(((long long)w.pair_cap / 8 + 255) / 256);        // ~8 pairs per thread when the list is full
+                rot_narrow_kernel<<<dim3(nb < 1 ? 1 : (nb > 592 ? 592 : nb), B), 256, 0, st>>>(w, w.m, n, A.thr, A.ge);
+                mask_rot_spatial_kernel<<<mgrid, kTile, 0, st>>>(w, w.m, n, A.thr, A.ge, 1);
+            }
         } else {
             spatial_gather_kernel<false><<<dim3(tiles, B), kTile, 0, st>>>(G, w.keys, w.order, w.m, w);
             mask_aabb_spatial_kernel<<<mgrid, kTile, 0, st>>>(w, w.m, n, float_at_or_below(A.thr));
         }
-        const char* fxenv = getenv("MYDET_SWEEP_FIXPOINT");       // experimental, not yet run on a GPU: off unless asked for
-        if (fxenv && fxenv[0] == '1') {
+        // parallel fixed-point sweep (sweep_fixpoint.cuh) by default since round 2 (rotated 10 k boxes: 63.8 -> 48.8 us per
+        // image, dense scene @1536: 1030 -> 301 us); MYDET_SWEEP_FIXPOINT=0 selects the serial block sweep (A/B tests)
+        const char* fxenv = getenv("MYDET_SWEEP_FIXPOINT");
+        if (!(fxenv && fxenv[0] == '0')) {
             const size_t smem2 = smem + (size_t)w.words * sizeof(unsigned long long);
             const int attr2 = (int)smem2 > 48 * 1024 ? (int)smem2 : 48 * 1024;
             MYDET_CUDA(cudaFuncSetAttribute(sweep_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, attr2));

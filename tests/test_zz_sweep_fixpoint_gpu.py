@@ -1,4 +1,4 @@
-"""GPU tests of the EXPERIMENTAL fixed-point sweep (sweep_kernel<2>, MYDET_SWEEP_FIXPOINT=1).
+"""GPU tests of the fixed-point sweep (sweep_kernel<2>) and of the broad / narrow phase rotated mask against the round-1 kernels.
 
 STATUS: green on a B200 in the round-1 driver run (GPUTEST_r01.json); hard tests since round 2.  The phases the kernel
 runs between its barriers are also verified on the CPU (tests/test_sweep_fixpoint_host.py).  Each test runs the block
@@ -12,13 +12,17 @@ import torch
 pytestmark = [pytest.mark.gpu]
 
 
-class fixpoint_sweep:
-    """The C library reads MYDET_SWEEP_FIXPOINT at every large-N call."""
+class legacy_path:
+    """The round-1 kernels: serial block sweep (MYDET_SWEEP_FIXPOINT=0) and the single tile kernel of the rotated mask
+    (MYDET_ROT_MASK_TILES=1).  The C library reads both variables at every large-N call; the defaults since round 2 are
+    the fixed-point sweep and the broad / narrow phase split."""
     def __enter__(self):
-        os.environ['MYDET_SWEEP_FIXPOINT'] = '1'
+        os.environ['MYDET_SWEEP_FIXPOINT'] = '0'
+        os.environ['MYDET_ROT_MASK_TILES'] = '1'
 
     def __exit__(self, *exc):
         os.environ.pop('MYDET_SWEEP_FIXPOINT', None)
+        os.environ.pop('MYDET_ROT_MASK_TILES', None)
 
 
 def rotated_boxes(gen, batch, n, span):
@@ -32,12 +36,14 @@ def test_rotated_nms_same_result_and_votes():
     from oracle import iou as oi
     gen = torch.Generator().manual_seed(41)
     dev = torch.device('cuda', 0)
-    for n, span in ((3000, 700.0), (10000, 1024.0), (1100, 120.0)):      # the last one: heavy overlap, long suppression lists
+    # (1100, 120): heavy overlap, long suppression lists; (2000, 60): nearly every pair overlaps, so the pair list of the
+    # broad phase overflows (> 128 partners per box) and the tile kernel takes the image over
+    for n, span in ((3000, 700.0), (10000, 1024.0), (1100, 120.0), (2000, 60.0)):
         b, s = rotated_boxes(gen, 3, n, span)
         counts = torch.tensor([n, n - 37, n // 2], dtype=torch.int32)
-        ref = ops.nms_rot(b.to(dev), s.to(dev), 0.45, counts=counts.to(dev), want_votes=True)
-        with fixpoint_sweep():
-            got = ops.nms_rot(b.to(dev), s.to(dev), 0.45, counts=counts.to(dev), want_votes=True)
+        with legacy_path():
+            ref = ops.nms_rot(b.to(dev), s.to(dev), 0.45, counts=counts.to(dev), want_votes=True)
+        got = ops.nms_rot(b.to(dev), s.to(dev), 0.45, counts=counts.to(dev), want_votes=True)
         torch.cuda.synchronize()
         assert torch.equal(ref[1], got[1])
         for i in range(3):
@@ -60,9 +66,9 @@ def test_dense_scene_same_result(img, batch):
         t[:, 4] = torch.randn(batch, n, n, generator=gen) * 1.5 + 2.0
         raws.append({k: v[:, 0].to(dev) for k, v in yolo_head_views(t, 1, 4, 1).items()})
     ls = ops.LevelSet(raws, (8, 16, 32))
-    ref = ops.detect(ops.KIND_FCOS, ls, (img, img), 0.005, 0.45, topk=None)
-    with fixpoint_sweep():
-        got = ops.detect(ops.KIND_FCOS, ls, (img, img), 0.005, 0.45, topk=None)
+    with legacy_path():
+        ref = ops.detect(ops.KIND_FCOS, ls, (img, img), 0.005, 0.45, topk=None)
+    got = ops.detect(ops.KIND_FCOS, ls, (img, img), 0.005, 0.45, topk=None)
     torch.cuda.synchronize()
     assert torch.equal(ref['count'], got['count']) and int(got['status'].abs().sum()) == 0
     for b in range(batch):
