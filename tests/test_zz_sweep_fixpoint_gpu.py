@@ -36,9 +36,9 @@ def test_rotated_nms_same_result_and_votes():
     from oracle import iou as oi
     gen = torch.Generator().manual_seed(41)
     dev = torch.device('cuda', 0)
-    # (1100, 120): heavy overlap, long suppression lists; (2000, 60): nearly every pair overlaps, so the pair list of the
-    # broad phase overflows (> 128 partners per box) and the tile kernel takes the image over
-    for n, span in ((3000, 700.0), (10000, 1024.0), (1100, 120.0), (2000, 60.0)):
+    # (1100, 120): heavy overlap, long suppression lists; (3000, 40): nearly every pair overlaps, so the pair list of the
+    # broad phase overflows (> 256 listed partners per box) and the tile kernel takes the image over
+    for n, span in ((3000, 700.0), (10000, 1024.0), (1100, 120.0), (3000, 40.0)):
         b, s = rotated_boxes(gen, 3, n, span)
         counts = torch.tensor([n, n - 37, n // 2], dtype=torch.int32)
         with legacy_path():
