@@ -15,6 +15,12 @@
  *   - Return value: 0 = ok; > 0 = a cudaError_t; < 0 = one of the MYDET_ERR_* codes.
  *   - Strides are in ELEMENTS, so the permuted NCHW views the reference heads hand to the
  *     det layers (models/rpns.py:29-41, :175-189) are consumed in place, without a copy.
+ *   - Alignment: arrays of 4-float boxes (boxes / out_box of mydet_postprocess with n_param == 4, cand_box of
+ *     mydet_decode_compact, a / b / gt of the IoU entry points) move as 128-bit vectors and must be 16-byte
+ *     aligned -- a violation returns MYDET_ERR_INVALID, it never faults on the device.  Every other pointer
+ *     needs only the alignment of its element type (dense-decode outputs fall back to scalar stores).
+ *     Workspaces: 256 bytes.  Anything torch allocates satisfies all of this unless it is a view with an odd
+ *     storage offset.
  *   - Tie policy (the reference leaves it open): wherever scores are ranked,
  *     equal scores are ordered by ascending candidate index.
  */

@@ -58,6 +58,8 @@ static int postprocess_impl(const float* boxes, const float* scores, const void*
         return 0;
     }
     MYDET_REQUIRE(boxes && scores && cls && out_box && out_score && out_cls && out_idx, "NULL tensor pointer");
+    MYDET_REQUIRE(n_param != 4 || ((reinterpret_cast<uintptr_t>(boxes) | reinterpret_cast<uintptr_t>(out_box)) & 15) == 0,
+                  "boxes and out_box must be 16-byte aligned (4-parameter boxes move as 128-bit vectors)");
     const int K = effective_k(n_per_image, topk);
     if (K <= MYDET_SMALL_K) {
         PPParams P;

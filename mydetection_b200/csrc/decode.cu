@@ -311,7 +311,7 @@ __device__ __forceinline__ void decode_unit(const DecodeParams& P, const LevelDe
                 for (int p = 0; p < 5; ++p)
                     if (p < n_par) ob[j * n_par + p] = box[j][p];
         }
-        if (VEC == 4 && ((reinterpret_cast<uintptr_t>(os) & 15) == 0)) {
+        if (VEC == 4 && ((reinterpret_cast<uintptr_t>(os) & 15) == 0) && ((reinterpret_cast<uintptr_t>(oc) & 15) == 0)) {
             *reinterpret_cast<float4*>(os) = make_float4(score[0], score[1 % VEC], score[2 % VEC], score[3 % VEC]);
             reinterpret_cast<longlong2*>(oc)[0] = make_longlong2(best_c[0], best_c[1 % VEC]);
             reinterpret_cast<longlong2*>(oc)[1] = make_longlong2(best_c[2 % VEC], best_c[3 % VEC]);
@@ -456,6 +456,8 @@ int decode_compact_impl(int kind, const mydet_level_t* levels, int n_levels, int
     if (rc) return rc;
     MYDET_REQUIRE(cand_box && cand_score && cand_cls && cand_idx && cand_count && capacity > 0,
                   "compact decode: NULL output or capacity <= 0");
+    MYDET_REQUIRE(n_param != 4 || (reinterpret_cast<uintptr_t>(cand_box) & 15) == 0,
+                  "compact decode: cand_box must be 16-byte aligned (4-parameter boxes are stored as 128-bit vectors)");
     P.thr = conf_thres;
     P.cand_box = cand_box; P.cand_score = cand_score; P.cand_cls = cand_cls; P.cand_idx = cand_idx;
     P.cand_count = cand_count; P.capacity = capacity;

@@ -69,8 +69,11 @@ __device__ __forceinline__ T clip_area(const float* ax, const float* ay, const f
         for (int k = 0; k < n; ++k) {
             const int k2 = (k + 1 == n) ? 0 : k + 1;
             const T dq = sgn * (ex * (py[k2] - ey0) - ey * (px[k2] - ex0));
-            if (dp >= (T)0) { qx[m] = px[k]; qy[m] = py[k]; ++m; }
-            if ((dp >= (T)0) != (dq >= (T)0)) {
+            // a convex quad clipped by 4 half planes has <= 8 vertices in exact arithmetic; rounding can make an
+            // intermediate polygon non-convex (near-collinear vertices) and produce a 9th: it is dropped, never
+            // written past the arrays (oracle/rotiou.c applies the same rule)
+            if (dp >= (T)0 && m < 8) { qx[m] = px[k]; qy[m] = py[k]; ++m; }
+            if ((dp >= (T)0) != (dq >= (T)0) && m < 8) {
                 const T t = dp / (dp - dq);
                 qx[m] = px[k] + t * (px[k2] - px[k]);
                 qy[m] = py[k] + t * (py[k2] - py[k]);
@@ -78,7 +81,7 @@ __device__ __forceinline__ T clip_area(const float* ax, const float* ay, const f
             }
             dp = dq;
         }
-        n = m < 8 ? m : 8;
+        n = m;
 #pragma unroll 1
         for (int k = 0; k < n; ++k) { px[k] = qx[k]; py[k] = qy[k]; }
     }

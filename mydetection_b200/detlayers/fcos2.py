@@ -5,7 +5,10 @@ from .. import ops
 from ._base import decode_level, pack_labels, stage_raw
 
 
-_THR_CACHE = {}   # (id(labels), img_size, batch, max_gt) -> thresholds of the forward pass in progress
+# Thresholds of the forward pass in progress: at most ONE entry, written by level 0 and read by the later levels of
+# the same pass.  The entry holds a strong reference to the labels list it was computed for (so its id cannot be
+# recycled) and is only honoured when that very object comes back with the same geometry / layer configuration.
+_THR_CACHE = {}
 
 
 def _check_shapes(raw, img_size, stride, n_cls):
@@ -95,14 +98,19 @@ class FCOS_ATSS_Layer(torch.nn.Module):
         max_gt = gt_box.shape[1]
         # the adaptive threshold of a GT is level independent: the first level's call computes it, the
         # other levels of the same forward pass (same labels list) reuse it
-        key = (id(labels), tuple(img_size), n_b, max_gt)
-        thr = _THR_CACHE.get(key)
+        key = (tuple(img_size), n_b, max_gt, str(t_ltrb.device), int(self.topk),
+               tuple(self.strides_all), tuple(float(a) for a in self.anchors_all))
+        thr = None
+        if self.level_i > 0:                          # level 0 always recomputes: a pass that stopped early leaves nothing behind
+            ent = _THR_CACHE.get('pass')
+            if ent is not None and ent[0] is labels and ent[1] == key:
+                thr = ent[2]
         out = ops.atss_assign(t_ltrb, self.level_i, self.strides_all, self.anchors_all, img_size,
                               gt_box, gt_cls, counts, self.topk, self.ignore_thre,
                               self.n_cls, thr=thr)
         _THR_CACHE.clear()
         if self.level_i + 1 < len(self.strides_all):
-            _THR_CACHE[key] = out['thr']
+            _THR_CACHE['pass'] = (labels, key, out['thr'])
         return out
 
     def forward(self, raw, img_size, labels=None):

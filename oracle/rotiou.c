@@ -70,8 +70,9 @@ static double quad_iou(const rquad_t* A, const rquad_t* B) {
                 int k2 = (k + 1 == n) ? 0 : k + 1;
                 double dp = sgn * (ex * (py[k] - ay) - ey * (px[k] - ax));
                 double dq = sgn * (ex * (py[k2] - ay) - ey * (px[k2] - ax));
-                if (dp >= 0.0) { qx[m] = px[k]; qy[m] = py[k]; ++m; }
-                if ((dp >= 0.0) != (dq >= 0.0)) {
+                /* <= 8 vertices in exact arithmetic; a 9th born of rounding is dropped (as rotgeom.cuh does) */
+                if (dp >= 0.0 && m < 8) { qx[m] = px[k]; qy[m] = py[k]; ++m; }
+                if ((dp >= 0.0) != (dq >= 0.0) && m < 8) {
                     double t = dp / (dp - dq);
                     qx[m] = px[k] + t * (px[k2] - px[k]);
                     qy[m] = py[k] + t * (py[k2] - py[k]);
