@@ -390,6 +390,14 @@ class Runner:
         self.comm = torch.cuda.Stream(dev) if world > 1 else None
         self.exchange_mode, P = 'none', 4
         no_ex = args.no_exchange or not exchange
+        if world == 1 and getattr(args, 'local_exchange', False):
+            # diagnostic: the fused exchange and its protocol against a LOCAL gathered buffer (one rank = producer and
+            # consumer): isolates what the flags, the fence and the consumer kernels cost, without NVLink
+            peers = [pl.PeerExchange(BATCH, TOPK, P, dev, local_only=True) for _ in range(N_ROTATE)]
+            self.protocol = not args.no_protocol
+            for bc, ex in zip(self.bound, peers):
+                bc.bind_exchange(ex, protocol=self.protocol)
+            self.exchange_mode = 'p2p_local_buffer_diagnostic' + ('+seq_ack_protocol' if self.protocol else '')
         if world > 1 and no_ex:
             self.exchange_mode = 'none (diagnostic: detections stay on their rank)'
         if world > 1 and not no_ex:
@@ -397,9 +405,12 @@ class Runner:
             if not args.nccl_exchange:
                 try:   # fused exchange: the post-process kernel stores its rows into every rank's buffer (NVLink)
                     peers = [pl.PeerExchange(BATCH, TOPK, P, dev) for _ in range(N_ROTATE)]
+                    self.protocol = not args.no_protocol
                     for bc, ex in zip(self.bound, peers):
-                        bc.bind_exchange(ex)
-                    self.exchange_mode = 'p2p_store_fused_in_postprocess'
+                        bc.bind_exchange(ex, protocol=self.protocol, multicast=not args.no_multicast)
+                    self.multicast = bool(self.bound[0].exchange_multicast)
+                    self.exchange_mode = ('p2p_store_fused_in_postprocess' + ('+nvls_multicast' if self.multicast else '+unicast')
+                                          + ('+seq_ack_protocol' if self.protocol else ''))
                 except Exception as e:  # symmetric memory not available on this box: keep the NCCL exchange
                     if rank == 0:
                         sys.stderr.write(f'[bench] peer-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL\n')
@@ -411,6 +422,10 @@ class Runner:
             self.gathered = [torch.empty(world * self.pk[0].numel(), dtype=torch.float32, device=dev) for _ in range(N_ROTATE)]
         self.fused = self.exchange_mode.startswith('p2p')
         self.nccl = self.exchange_mode == 'nccl_all_gather'
+        self.protocol = self.fused and getattr(self, 'protocol', False)
+        # the consumer of the gathered detections: tiny kernels, high priority so that they are not queued behind a
+        # grid-filling decode
+        self.s_con = torch.cuda.Stream(dev, priority=-1) if self.protocol else None
         self.done = [torch.cuda.Event() for _ in range(N_ROTATE)]
         self.sent = [None] * N_ROTATE     # exchange of buffer j finished (its out/packed buffers may be overwritten)
         self.P = P
@@ -418,6 +433,26 @@ class Runner:
     # ---- one eager step
     def pp_launch(self, bc):
         return bc.launch_postprocess_scatter() if self.fused else bc.launch_postprocess()
+
+    def consume(self, bc, after=None):
+        """Exchange protocol on: this rank's consumer of the gathered detections -- a device-side wait until every
+        rank has published the step (no host barrier, no cross-process stream dependency), a snapshot of the counts,
+        then the acknowledgement that lets the producers overwrite the buffer.  Runs on its own stream beside the
+        next steps' kernels; the producers' back-pressure is the only thing that couples it to them."""
+        if not self.protocol:
+            return
+        cur = torch.cuda.current_stream()
+        ev = after
+        if ev is None:
+            ev = torch.cuda.Event()
+            ev.record(cur)
+        with torch.cuda.stream(self.s_con):
+            self.s_con.wait_event(ev)
+            if self.args.consumer == 'fused':
+                bc.exchange.consume_counts()
+            else:
+                bc.exchange.wait()
+                bc.exchange.release()
 
     def nccl_exchange(self, i):
         """The path's only exchange as one all-gather of the packed detections, on a side
@@ -441,6 +476,7 @@ class Runner:
         if ev:
             ev[1].record()
         self.pp_launch(bc)
+        self.consume(bc)
         if self.nccl:
             self.nccl_exchange(i)
 
@@ -454,7 +490,7 @@ class Runner:
         bound = bound or self.bound
         dev = self.dev
         if not hasattr(self, 's_cap'):
-            self.s_cap, self.s_pp = torch.cuda.Stream(dev), torch.cuda.Stream(dev, priority=-1)
+            self.s_cap, self.s_pp = torch.cuda.Stream(dev), torch.cuda.Stream(dev, priority=self.args.pp_priority)
             self.s_dec = [self.s_cap] + [torch.cuda.Stream(dev) for _ in range(N_ROTATE - 1)]
         s_cap, s_pp, s_dec = self.s_cap, self.s_pp, self.s_dec[:n_dec]
         g = torch.cuda.CUDAGraph()
@@ -478,10 +514,13 @@ class Runner:
                         e2 = torch.cuda.Event()
                         e2.record(s_pp)
                         pp_ev.append(e2)
+                    self.consume(bound[j], after=e2)
             for s in s_dec[1:]:
                 s_cap.wait_stream(s)
             if with_pp:
                 s_cap.wait_stream(s_pp)
+                if self.protocol:
+                    s_cap.wait_stream(self.s_con)
         return g
 
     def measure(self, steps, warmup, repeats):
@@ -496,6 +535,8 @@ class Runner:
             self.step(i)
         if self.comm is not None:
             torch.cuda.current_stream().wait_stream(self.comm)
+        if self.protocol:
+            torch.cuda.current_stream().wait_stream(self.s_con)
         self.barrier()
         if pipelined:
             pipe_graph = self.capture_pipeline(chunk, n_dec)
@@ -524,6 +565,8 @@ class Runner:
                     self.step(i, (dec_a[i], dec_b[i]))
                 if self.comm is not None:
                     torch.cuda.current_stream().wait_stream(self.comm)
+                if self.protocol:
+                    torch.cuda.current_stream().wait_stream(self.s_con)
             ev1.record()
             self.barrier()
             ms = ev0.elapsed_time(ev1)
@@ -572,12 +615,20 @@ class Runner:
         bc = self.bound[0]
         bc.launch_decode()
         self.pp_launch(bc)
+        if self.protocol:            # the consumer's snapshot is taken behind the device-side wait, before any barrier
+            self.consume(bc)
+            torch.cuda.current_stream().wait_stream(self.s_con)
         ref = pl.gather_detections(bc.out)
         self.barrier()
         want_rows, want_counts = pl.unpack_gathered(ref, self.world, BATCH, TOPK, self.P)
         got_rows, got_counts = bc.exchange.views() if self.fused else (want_rows, want_counts)
         live = torch.arange(TOPK, device=dev)[None, :] < want_counts[:, None]
         good = torch.equal(got_counts, want_counts) and torch.equal(got_rows[live], want_rows[live])
+        if self.protocol:
+            ex = bc.exchange
+            good = good and torch.equal(ex.counts_snapshot, want_counts) and int(ex.wait_status) == 0
+            late = sum(int((b.out['status'] & 16).sum()) for b in self.bound)
+            good = good and late == 0
         flag = torch.tensor([1 if good else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         return bool(flag.item())
@@ -719,7 +770,7 @@ def run_gpu(args, wl):
     clocks = sampler.stop(*m['wall']) if sampler else None
     # the timed launches left their detections in the output buffers: check them against the oracle (rank 0)
     parity = check_against_oracle(wl, run.batches[0][0], run.bound[0].out) if rank == 0 else None
-    exchange_mode, nccl = run.exchange_mode, run.nccl
+    exchange_mode, nccl, run_protocol = run.exchange_mode, run.nccl, run.protocol
     exchange_ok = run.verify_exchange() if (world > 1 and not exchange_mode.startswith('none')) else None
     e2e = run.e2e(max(3, min(steps, 50)))
     dec_only_ms, lone_ms, cand = run.decode_only() if rank == 0 else (None, None, None)
@@ -745,6 +796,7 @@ def run_gpu(args, wl):
 
     if rank == 0:
         mode = 'cuda_graph_pipelined' if m['pipelined'] else 'eager'
+        per_step = 3 if nccl else ((3 if args.consumer == 'fused' else 4) if run_protocol else 2)
         line = {'metric': wl.metric, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': warmup,
                 'ms_per_step': ms / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'f32', 'data': 'synthetic', 'config': wl.config(world),
@@ -753,8 +805,9 @@ def run_gpu(args, wl):
                 'roofline': decode_roofline(wl, ms / steps, m['pipelined'], m.get('decode_event_ms'), dec_only_ms, lone_ms, cand),
                 'e2e': e2e, 'matches_oracle': parity['ok'], 'parity': parity,
                 # kernels of libmydet launched inside the timed regions: decode + post-process per step (+ the pack kernel
-                # in front of an NCCL exchange), over all `repeats` regions
-                'gpu_launches': (3 if nccl else 2) * steps * repeats, 'gpu_launches_per_step': 3 if nccl else 2,
+                # in front of an NCCL exchange; + the consumer's wait and release kernels under the exchange protocol),
+                # over all `repeats` regions
+                'gpu_launches': per_step * steps * repeats, 'gpu_launches_per_step': per_step,
                 'exchange': exchange_mode, 'exchange_verified': exchange_ok, 'launch_mode': mode, 'clocks': clocks}
         if ge10k is not None:
             line['ge10k'] = ge10k
@@ -782,8 +835,16 @@ def main():
     ap.add_argument('--pipe-steps', type=int, default=96,
                     help='max steps per pipelined CUDA graph (the pipeline drains once per graph)')
     ap.add_argument('--decode-streams', type=int, default=2, help='pipelined mode: streams the decode launches alternate on')
+    ap.add_argument('--pp-priority', type=int, default=-1, help='pipelined mode: priority of the post-process stream (-1 = high)')
     ap.add_argument('--nccl-exchange', action='store_true', help='N>1: use the NCCL all-gather instead of peer stores')
     ap.add_argument('--no-exchange', action='store_true', help='N>1 diagnostic: skip the detections exchange')
+    ap.add_argument('--local-exchange', action='store_true',
+                    help='N=1 diagnostic: run the fused exchange (and its protocol) against a local gathered buffer')
+    ap.add_argument('--consumer', default='fused', choices=['fused', 'two-kernel'],
+                    help='exchange protocol: the consumer is one wait+snapshot+ack launch [default] or a wait and a release launch')
+    ap.add_argument('--no-multicast', action='store_true', help='N>1: unicast peer stores even where an NVLS multicast mapping exists')
+    ap.add_argument('--no-protocol', action='store_true',
+                    help='N>1: no sequence flags / acknowledgements / consumer kernels (the round-1 behaviour: rows only)')
     ap.add_argument('--no-rot', action='store_true', help='skip the rotated-NMS side metric')
     ap.add_argument('--no-flow', action='store_true', help='skip the drop-in call-sequence leg')
     ap.add_argument('--no-ge10k', action='store_true', help='skip the 768 x 768 (12 276 candidates/image) sub-record')

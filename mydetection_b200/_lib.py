@@ -8,7 +8,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libmydet.so')
+LIB_PATH = os.environ.get('MYDET_LIB') or os.path.join(HERE, 'libmydet.so')   # MYDET_LIB: developer A/B runs of a variant build
 
 MAX_LEVELS = 8
 MAX_ANCHORS = 16
@@ -47,6 +47,13 @@ SIGNATURES = {
     'mydet_postprocess_scatter': (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_f32,
                                           c_int, c_f64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_sz,
                                           ctypes.POINTER(c_vp), c_int, c_i64, c_i64, c_int, c_vp]),
+    'mydet_postprocess_exchange': (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_f32,
+                                           c_int, c_f64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_sz,
+                                           ctypes.POINTER(c_vp), c_int, c_vp, c_int, c_i64, c_i64, c_int, c_int, c_vp]),
+    'mydet_exchange_buffer_bytes': (c_sz, [c_i64, c_int, c_int]),
+    'mydet_exchange_wait': (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
+    'mydet_exchange_release': (c_int, [ctypes.POINTER(c_vp), c_int, c_vp, c_int, c_i64, c_int, c_int, c_vp]),
+    'mydet_exchange_consume_counts': (c_int, [ctypes.POINTER(c_vp), c_int, c_vp, c_int, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
     'mydet_detect_workspace_bytes': (c_sz, [c_int, c_i64, c_int, c_int]),
     'mydet_detect': (c_int, [c_int, ctypes.POINTER(Level), c_int, c_int, c_int, c_int, c_f32, c_f32, c_f32, c_int,
                              c_f64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),

@@ -37,11 +37,16 @@ static int postprocess_impl(const float* boxes, const float* scores, const void*
                             double nms_thres, float* out_box, float* out_score, int64_t* out_cls,
                             int32_t* out_idx, int32_t* out_count, int32_t* status, int out_cap,
                             void* workspace, size_t workspace_bytes, void* const* peers, int n_peers,
-                            int64_t peer_row0, int64_t peer_rows_total, int pp_flags, void* stream) {
+                            int64_t peer_row0, int64_t peer_rows_total, int pp_flags, void* stream,
+                            void* peer_mc = nullptr, int peer_self = 0, int peer_protocol = 0) {
     cudaStream_t st = (cudaStream_t)stream;
     MYDET_REQUIRE(n_peers >= 0 && n_peers <= 8, "n_peers must be in [0,8]");
     MYDET_REQUIRE(n_peers == 0 || (peers && peer_row0 >= 0 && peer_row0 + batch <= peer_rows_total),
                   "bad peer buffer description");
+    MYDET_REQUIRE(!peer_protocol || (n_peers > 0 && peer_self >= 0 && peer_self < n_peers),
+                  "the exchange protocol needs the peer buffers and this rank's index among them");
+    MYDET_REQUIRE(!peer_mc || n_peers > 0, "a multicast buffer without peer buffers");
+    MYDET_REQUIRE((reinterpret_cast<uintptr_t>(peer_mc) & 15) == 0, "the multicast buffer must be 16-byte aligned");
     MYDET_REQUIRE(batch >= 0 && n_per_image >= 0 && pitch >= n_per_image, "bad batch / n_per_image / pitch");
     MYDET_REQUIRE(n_param == 4 || n_param == 5, "n_param must be 4 or 5");
     MYDET_REQUIRE(box_format == MYDET_BOX_CXCYWH || box_format == MYDET_BOX_X1Y1X2Y2, "unknown box format");
@@ -74,6 +79,7 @@ static int postprocess_impl(const float* boxes, const float* scores, const void*
         P.peer_vec = (n_peers > 0 && ((long long)out_cap * (n_param + 2)) % 4 == 0) ? 1 : 0;
         for (int q = 0; q < n_peers; ++q)
             if (reinterpret_cast<uintptr_t>(peers[q]) & 15) P.peer_vec = 0;
+        P.peer_mc = static_cast<float*>(peer_mc); P.peer_self = peer_self; P.peer_protocol = peer_protocol ? 1 : 0;
         P.consume = consume; P.force_scan = (pp_flags & MYDET_PP_FORCE_SCAN) ? 1 : 0;
         return launch_postprocess_small(P, batch, st);
     }
@@ -106,6 +112,20 @@ MYDET_API int mydet_postprocess_scatter(const float* boxes, const float* scores,
                             box_format, conf_thres, topk, nms_thres, out_box, out_score, out_cls, out_idx, out_count,
                             status, out_cap, workspace, workspace_bytes, peer_bufs, n_peers, image_offset, images_total,
                             flags, stream);
+}
+
+MYDET_API int mydet_postprocess_exchange(const float* boxes, const float* scores, const void* cls, int cls_is_i64,
+                                         const int32_t* src_idx, int32_t* counts, int batch, int64_t pitch,
+                                         int n_per_image, int n_param, int box_format, float conf_thres, int topk,
+                                         double nms_thres, float* out_box, float* out_score, int64_t* out_cls,
+                                         int32_t* out_idx, int32_t* out_count, int32_t* status, int out_cap,
+                                         void* workspace, size_t workspace_bytes, void* const* peer_bufs, int n_peers,
+                                         void* multicast_buf, int self_index, int64_t image_offset, int64_t images_total,
+                                         int protocol, int flags, void* stream) {
+    return postprocess_impl(boxes, scores, cls, cls_is_i64, src_idx, counts, batch, pitch, n_per_image, n_param,
+                            box_format, conf_thres, topk, nms_thres, out_box, out_score, out_cls, out_idx, out_count,
+                            status, out_cap, workspace, workspace_bytes, peer_bufs, n_peers, image_offset, images_total,
+                            flags, stream, multicast_buf, self_index, protocol);
 }
 
 // ---- whole path: candidate buffers live in the workspace

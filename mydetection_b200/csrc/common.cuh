@@ -49,9 +49,19 @@ constexpr int kNumSMs = 148;  // B200
 // Streaming 128-bit load: read-only path, do not allocate in L1 (every logit is read once).
 __device__ __forceinline__ float4 ld_stream_v4(const float* p) {
     float4 r;
+#ifdef MYDET_DECODE_EVICT_FIRST
+    // the logits are read exactly once: mark their L2 lines evict-first, so that the candidates the decode writes (and
+    // the post-process reads back a few microseconds later) are what stays in the 126 MB L2
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p), "l"(pol));
+#else
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
                  : "l"(p));
+#endif
     return r;
 }
 __device__ __forceinline__ float ld_stream(const float* p) {
@@ -75,6 +85,34 @@ __device__ __forceinline__ float key_float(uint32_t k) {
     uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
     return __uint_as_float(u);
 }
+
+// ---- system-scope flag accesses and NVLS multicast stores of the fused detections exchange (exchange.cu, stage E of
+// the post-process kernel).  A multimem.st is a store to the multicast mapping of a buffer: the NVSwitch replicates it
+// into the copy of every GPU bound to the multicast object.
+__device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_st_v4(float4* p, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void multimem_st_u32(unsigned* p, unsigned v) {
+    asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_st_release_u32(unsigned* p, unsigned v) {
+    asm volatile("multimem.st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+constexpr long long kExchangeSpinCycles = 2000000000LL;   // ~1 s at 1.9 GHz: a flag wait gives up after this, it never hangs
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ unsigned lanemask_lt() {

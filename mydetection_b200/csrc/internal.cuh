@@ -31,10 +31,30 @@ struct PPParams {
     long long peer_row0;        // first image row of this rank inside the gathered buffer
     long long peer_rows_total;  // images in the gathered buffer (all ranks)
     int peer_vec;               // image blocks of the gathered buffers are 16-byte aligned: coalesced vector stores
+    float* peer_mc;             // multicast mapping of the same buffer (NVLS): ONE store reaches every rank; NULL = unicast loop
+    int peer_protocol;          // sequence flags + back-pressure (include/mydet.h: exchange protocol)
+    int peer_self;              // index of this rank's own buffer in peer[] (its flags are read locally)
     int consume;                // zero counts[b] once it has been read
     int force_scan;             // skip the sampled front end of the select (tests)
 };
 int launch_postprocess_small(const PPParams& P, int batch, cudaStream_t st);
+
+// Gathered-detections buffer of the fused exchange, in 32-bit words (include/mydet.h):
+//   float rows[images_total][out_cap][P+2]; int32 counts[images_total];                      (the data)
+//   uint32 seq[images_total]   -- written by the image's producer AFTER its rows and count: how often the image was published
+//   uint32 ack[8]              -- ack[q], written by consumer rank q into EVERY rank's copy: how many publications q has consumed
+//   uint32 want                -- local only: publications this rank's consumer has waited for so far
+// seq / ack start on 16-byte boundaries.
+struct ExchangeLayout { long long counts_off, seq_off, ack_off, want_off, total_words; };
+__host__ __device__ inline ExchangeLayout exchange_layout(long long images_total, int out_cap, int n_param) {
+    ExchangeLayout L;
+    L.counts_off = images_total * out_cap * (n_param + 2);
+    L.seq_off = (L.counts_off + images_total + 3) & ~3LL;
+    L.ack_off = L.seq_off + ((images_total + 3) & ~3LL);
+    L.want_off = L.ack_off + 8;
+    L.total_words = L.want_off + 8;
+    return L;
+}
 
 // nms_large.cu
 struct LargeArgs {

@@ -66,7 +66,13 @@ __host__ __device__ inline size_t pp_mask_bytes(int kpad) {
 constexpr int kClassBins = MYDET_MAX_CLASS_ID + 1;   // 4096
 constexpr int kHistBins = 2 * kPPThreads;            // sample histogram of the front end
 
-__global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const PPParams P) {
+// 48 registers per thread (no spills), not the 62 the compiler takes when it may: a 1024-thread CTA then leaves a quarter
+// of the SM's register file free, so two CTAs of the bandwidth-bound decode kernel of the NEXT step stay resident on each
+// of the 64 SMs a post-process launch occupies.  Measured in the pipelined bench step: 33.3 -> 31.2 us (profiles/r2_history.md).
+#ifndef MYDET_PP_MAXNREG
+#define MYDET_PP_MAXNREG 48
+#endif
+__global__ void __maxnreg__(MYDET_PP_MAXNREG) postprocess_small_kernel(const PPParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -104,6 +110,7 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
     int* uidx = reinterpret_cast<int*>(sarea);                                              // ... and candidate numbers (both die before (B2))
     __shared__ unsigned long long s_prefix;
     __shared__ int s_need, s_done, s_nsel, s_total, s_flags, s_bucket, s_ucount, s_top, s_nvalid;
+    __shared__ unsigned s_seq;      // exchange protocol: the sequence number this launch publishes for the image
 
     int n = P.n_per_image;
     int flags = 0;
@@ -935,6 +942,24 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
             wtot[lane] = incl - v;
             if (lane == 31) wtot[32] = incl;
         }
+        // exchange protocol (back-pressure): the image's rows may only be overwritten once every consumer has acknowledged
+        // the previous publication of this image slot.  One lane of the last warp polls the LOCAL ack words while warp 0
+        // builds the prefix; the acks have normally arrived long ago.  Bounded: a consumer that never acknowledges costs
+        // ~1 s once and raises status bit 16 instead of hanging the GPU.
+        if (P.n_peers > 0 && P.peer_protocol && tid == kPPThreads - 32) {
+            const ExchangeLayout XL = exchange_layout(P.peer_rows_total, P.out_cap, P.n_param);
+            const unsigned* own = reinterpret_cast<const unsigned*>(P.peer[P.peer_self]);
+            const unsigned prev = ld_relaxed_sys(own + XL.seq_off + P.peer_row0 + b);
+            const long long t0 = clock64();
+            bool late = false;
+            for (int q = 0; q < P.n_peers && !late; ++q)
+                while ((int)(ld_acquire_sys(own + XL.ack_off + q) - prev) < 0) {
+                    if (clock64() - t0 > kExchangeSpinCycles) { late = true; break; }
+                    __nanosleep(64);
+                }
+            s_seq = prev + 1u;
+            if (late) atomicOr(&s_flags, 16);
+        }
         __syncthreads();
         int nk = wtot[32];
         float* stage = reinterpret_cast<float*>(mask);      // packed rows for the vector peer stores (mask is dead)
@@ -973,9 +998,10 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
                             else { o[4] = sc; o[5] = (float)cl; }
                         } else {
                             const long long grow = ((P.peer_row0 + b) * P.out_cap + pos) * np2;
+                            const int nq = P.peer_mc ? 1 : P.n_peers;          // multicast mapping: one store reaches every rank
 #pragma unroll 1
-                            for (int q = 0; q < P.n_peers; ++q) {
-                                float* o = P.peer[q] + grow;
+                            for (int q = 0; q < nq; ++q) {
+                                float* o = (P.peer_mc ? P.peer_mc : P.peer[q]) + grow;
                                 o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
                                 if (P.n_param == 5) { o[4] = ang; o[5] = sc; o[6] = (float)cl; }
                                 else { o[4] = sc; o[5] = (float)cl; }
@@ -994,20 +1020,48 @@ __global__ void __launch_bounds__(kPPThreads, 1) postprocess_small_kernel(const 
             const long long img0 = (P.peer_row0 + b) * (long long)P.out_cap * np2;   // 16-byte aligned (host check)
             const float4* sv4 = reinterpret_cast<const float4*>(stage);
 #pragma unroll 1
-            for (int i = tid; i < nvec; i += kPPThreads) {
-                const float4 val = sv4[i];
+            if (P.peer_mc) {
+                // NVLS: the buffer's multicast address -- the switch replicates ONE 16-byte store into every rank's copy
+                // (own copy included), instead of n_peers unicast stores per vector (~1.8 us per peer and step)
+                for (int i = tid; i < nvec; i += kPPThreads) multimem_st_v4(reinterpret_cast<float4*>(P.peer_mc + img0) + i, sv4[i]);
+            } else {
 #pragma unroll 1
-                for (int q = 0; q < P.n_peers; ++q) reinterpret_cast<float4*>(P.peer[q] + img0)[i] = val;
+                for (int i = tid; i < nvec; i += kPPThreads) {
+                    const float4 val = sv4[i];
+#pragma unroll 1
+                    for (int q = 0; q < P.n_peers; ++q) reinterpret_cast<float4*>(P.peer[q] + img0)[i] = val;
+                }
             }
         }
+        if (P.n_peers > 0 && P.peer_protocol) __syncthreads();    // every row store of the CTA is ordered before thread 0's release below
         if (tid == 0) {
             if (nk > P.out_cap) { nk = P.out_cap; flags |= 2; }
             P.out_count[b] = nk;
             if (P.status) P.status[b] = flags | s_flags;
             if (P.consume && P.counts) P.counts[b] = 0;   // every thread read it before the first barrier
-            for (int q = 0; q < P.n_peers; ++q) {
-                int* counts_q = reinterpret_cast<int*>(P.peer[q] + P.peer_rows_total * P.out_cap * (P.n_param + 2));
-                counts_q[P.peer_row0 + b] = nk;
+            if (P.n_peers > 0) {
+                const ExchangeLayout XL = exchange_layout(P.peer_rows_total, P.out_cap, P.n_param);
+                const long long row = P.peer_row0 + b;
+                const int nq = P.peer_mc ? 1 : P.n_peers;
+                for (int q = 0; q < nq; ++q) {
+                    int* base = reinterpret_cast<int*>(P.peer_mc ? P.peer_mc : P.peer[q]);
+                    if (P.peer_mc) multimem_st_u32(reinterpret_cast<unsigned*>(base + XL.counts_off + row), (unsigned)nk);
+                    else base[XL.counts_off + row] = nk;
+                }
+                if (P.peer_protocol) {
+                    // publication: rows and count first, then -- release at system scope, cumulative over the barrier above --
+                    // the image's sequence number, which a consumer kernel acquires (mydet_exchange_wait)
+                    // (the release store orders every earlier store of the CTA -- cumulativity through the barrier -- so no
+                    // separate fence.sc is issued: it cost a second ~1 us drain per CTA)
+#ifdef MYDET_EXCH_FENCE
+                    __threadfence_system();
+#endif
+                    for (int q = 0; q < nq; ++q) {
+                        unsigned* base = reinterpret_cast<unsigned*>(P.peer_mc ? P.peer_mc : P.peer[q]);
+                        if (P.peer_mc) multimem_st_release_u32(base + XL.seq_off + row, s_seq);
+                        else st_release_sys(base + XL.seq_off + row, s_seq);
+                    }
+                }
             }
         }
     }

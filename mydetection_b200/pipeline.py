@@ -88,22 +88,29 @@ class BoundCall:
             _lib.check(rc, 'mydet_postprocess')
         return self.out
 
-    def bind_exchange(self, exchange):
+    def bind_exchange(self, exchange, protocol=False, multicast=True):
         """Fuse the multi-GPU exchange into the post-process kernel: detections are stored straight
-        into every rank's gathered buffer (peer memory) by the kernel's output stage."""
+        into every rank's gathered buffer (peer memory) by the kernel's output stage.
+        multicast: use the buffer's NVLS multicast mapping when the exchange has one (one store per vector instead of
+        one per peer).  protocol: publish per-image sequence numbers and wait for the consumers' acknowledgements
+        before overwriting (include/mydet.h); every rank must then consume each step with exchange.wait() ... release()."""
+        import ctypes
         o = self.out
         B, K, P = o['box'].shape
         if exchange.batch != B or exchange.cap != K or exchange.n_param != P:
             raise ValueError('exchange buffer geometry does not match the bound call')
-        self._scatter_args = self._pp_args + (exchange.peer_array, exchange.world, exchange.rank * B,
-                                              exchange.world * B)
+        mc = ctypes.c_void_p(exchange.multicast_ptr if (multicast and exchange.multicast_ptr) else None)
+        self._scatter_args = self._pp_args + (exchange.peer_array, exchange.world, mc, exchange.rank, exchange.rank * B,
+                                              exchange.world * B, 1 if protocol else 0)
         self.exchange = exchange
+        self.exchange_multicast = bool(mc.value)
+        self.exchange_protocol = bool(protocol)
         return self
 
     def launch_postprocess_scatter(self):
-        rc = self._L.mydet_postprocess_scatter(*self._scatter_args, *self._consume_args, self._stream())
+        rc = self._L.mydet_postprocess_exchange(*self._scatter_args, *self._consume_args, self._stream())
         if rc:
-            _lib.check(rc, 'mydet_postprocess_scatter')
+            _lib.check(rc, 'mydet_postprocess_exchange')
         return self.out
 
     def capture(self):
@@ -157,15 +164,18 @@ def unpack(out, to_cpu=True):
 # --------------------------------------------------------------------------------------- multi-GPU
 class PeerExchange:
     """Gathered-detections buffer of every rank, mapped into this process (torch symmetric memory over
-    CUDA IPC / NVLink), for the fused exchange of mydet_postprocess_scatter.
+    CUDA IPC / NVLink, plus its NVLS multicast mapping where the fabric offers one), for the fused exchange of
+    mydet_postprocess_exchange.
 
-    Layout per rank: float32 rows[world*batch][cap][P+2] followed by int32 counts[world*batch].
-    `peers` may be given explicitly (a list of device pointers) -- with a single entry pointing at a local
-    tensor this degenerates to "pack into one buffer" and is how the layout is unit-tested on one GPU."""
+    Layout per rank (include/mydet.h): float32 rows[world*batch][cap][P+2], int32 counts[world*batch], then the
+    protocol words (sequence numbers per image, acknowledgements per rank).
+    `local_only` builds a one-rank exchange on a plain local tensor -- "pack into one buffer" -- which is how the
+    layout and the protocol are unit-tested on one GPU."""
 
     def __init__(self, batch, cap, n_param, device, group=None, local_only=False):
         import ctypes
         self.batch, self.cap, self.n_param = batch, cap, n_param
+        self.multicast_ptr = 0
         if local_only:
             self.world, self.rank = 1, 0
             self.buffer = torch.zeros(self.numel(1), dtype=torch.float32, device=device)
@@ -178,11 +188,24 @@ class PeerExchange:
             self.buffer = symm.empty(self.numel(self.world), dtype=torch.float32, device=device)
             self.buffer.zero_()
             self.handle = symm.rendezvous(self.buffer, group if group is not None else dist.group.WORLD)
-            ptrs = [int(p) for p in self.handle.buffer_ptrs]
+            off = int(getattr(self.handle, 'offset', 0) or 0)       # of this tensor inside its symmetric allocation
+            ptrs = [int(p) + off for p in self.handle.buffer_ptrs]
+            try:
+                mc = int(self.handle.multicast_ptr or 0)
+                self.multicast_ptr = mc + off if mc else 0
+            except Exception:        # symmetric memory without multicast support
+                self.multicast_ptr = 0
+            torch.cuda.synchronize(device)
+            dist.barrier(group)      # every copy is zeroed before any rank publishes into it
+        self.images_total = self.world * batch
         self.peer_array = (ctypes.c_void_p * len(ptrs))(*ptrs)
+        self._mc = ctypes.c_void_p(self.multicast_ptr or None)
+        self.wait_status = torch.zeros(1, dtype=torch.int32, device=device)
+        self.counts_snapshot = torch.zeros(self.images_total, dtype=torch.int32, device=device)
 
     def numel(self, world):
-        return world * self.batch * (self.cap * (self.n_param + 2) + 1)
+        nbytes = _lib.lib().mydet_exchange_buffer_bytes(world * self.batch, self.cap, self.n_param)
+        return nbytes // 4
 
     def views(self):
         """(rows (world*batch, cap, P+2) f32, counts (world*batch,) i32) views of the local gathered buffer."""
@@ -191,6 +214,33 @@ class PeerExchange:
         rows = self.buffer[:n_rows].view(n_img, self.cap, self.n_param + 2)
         counts = self.buffer[n_rows:n_rows + n_img].view(torch.int32)
         return rows, counts
+
+    # consumer side of the protocol: wait() ... kernels reading views()[0] on the same stream ... release()
+    def wait(self):
+        """Device-side wait (no host involvement) until every image of every rank carries the next publication;
+        snapshots the counts into self.counts_snapshot.  self.wait_status becomes 1 if the bounded wait expired."""
+        rc = _lib.lib().mydet_exchange_wait(ops._ptr(self.buffer), self.images_total, self.cap, self.n_param,
+                                            ops._ptr(self.counts_snapshot), ops._ptr(self.wait_status),
+                                            torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, 'mydet_exchange_wait')
+        return self.counts_snapshot
+
+    def consume_counts(self, multicast=True):
+        """wait() + release() in one launch, for a consumer that needs only the counts of the step."""
+        rc = _lib.lib().mydet_exchange_consume_counts(self.peer_array, self.world, self._mc if multicast else None, self.rank,
+                                                      self.images_total, self.cap, self.n_param,
+                                                      ops._ptr(self.counts_snapshot), ops._ptr(self.wait_status),
+                                                      torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, 'mydet_exchange_consume_counts')
+        return self.counts_snapshot
+
+    def release(self, multicast=True):
+        """Acknowledge the publication the last wait() returned: its rows may now be overwritten by the producers."""
+        rc = _lib.lib().mydet_exchange_release(self.peer_array, self.world, self._mc if multicast else None, self.rank,
+                                               self.images_total, self.cap, self.n_param,
+                                               torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, 'mydet_exchange_release')
+
 
 def shard_range(n_images, rank, world):
     """Contiguous block of ceil(n/world) images per rank."""

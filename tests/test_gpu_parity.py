@@ -472,6 +472,65 @@ def test_fused_exchange_layout_single_gpu(golden, topk):
         assert n > 0 and torch.equal(rows[b, :n], want_rows[b, :n])
 
 
+def test_exchange_protocol_single_gpu(golden):
+    """The exchange protocol on one GPU (one rank = producer and consumer of a local buffer): five publications in
+    a row with wait / release between them and NO host synchronisation inside the loop; the consumer's snapshot of
+    step s must hold step s's detections (inputs alternate between two batches).  Then back-pressure: a second
+    publication without the consumer's acknowledgement must not hang -- the bounded wait expires and status bit 16
+    is raised -- and a wait for a publication that never comes reports its own time-out."""
+    from mydetection_b200 import pipeline as pl
+    g = golden('decode')
+    d = dev()
+    strides = (8, 16, 32, 64, 128)
+    raws_a = [{k: v.to(d) for k, v in efdet_views(T(g[f'fcos{li}_bbox_in']), T(g[f'fcos{li}_cls_in'])).items()} for li in range(5)]
+    raws_b = [{k: v.flip(0) for k, v in r.items()} for r in raws_a]              # the two images swapped
+    pipe = pl.DetectionPipeline('FCOS2', strides, 6, (256, 384), 0.05, 0.5, 512)
+    ex = pl.PeerExchange(2, 512, 4, d, local_only=True)
+    calls = [pipe.bind(raws_a).bind_exchange(ex, protocol=True), pipe.bind(raws_b).bind_exchange(ex, protocol=True)]
+    snaps = []
+    for s in range(5):
+        bc = calls[s % 2]
+        bc.launch_decode()
+        bc.launch_postprocess_scatter()
+        counts = ex.wait().clone()
+        rows = ex.views()[0].clone()                 # the consumer's read, stream-ordered behind the wait
+        ex.release()
+        snaps.append((rows, counts, ex.wait_status.clone(), bc.out['status'].clone()))
+    torch.cuda.synchronize()
+    want = []
+    for bc in calls:
+        bc.launch_decode()
+        out = bc.launch_postprocess()
+        torch.cuda.synchronize()
+        want.append(pl.unpack_gathered(pl.pack_detections(out), 1, 2, 512, 4))
+    for s, (rows, counts, wst, pst) in enumerate(snaps):
+        w_rows, w_counts = want[s % 2]
+        assert int(wst) == 0 and int((pst & 16).sum()) == 0
+        assert torch.equal(counts, w_counts)
+        for b in range(2):
+            assert torch.equal(rows[b, :int(counts[b])], w_rows[b, :int(counts[b])])
+    assert int(want[0][1][0]) != int(want[0][1][1]), 'the two images must differ for the alternation to prove anything'
+    for s in (5, 6):                                 # the one-launch consumer (wait + snapshot + acknowledgement)
+        bc = calls[s % 2]
+        bc.launch_decode(); bc.launch_postprocess_scatter()
+        counts = ex.consume_counts().clone()
+        torch.cuda.synchronize()
+        assert torch.equal(counts, want[s % 2][1]) and int(ex.wait_status) == 0 and int((bc.out['status'] & 16).sum()) == 0
+    # back-pressure, bounded: the next publication is never acknowledged, so the one after it has to give up waiting
+    import time
+    calls[0].launch_decode(); calls[0].launch_postprocess_scatter()
+    torch.cuda.synchronize()
+    assert int((calls[0].out['status'] & 16).sum()) == 0
+    t0 = time.perf_counter()
+    calls[1].launch_decode(); calls[1].launch_postprocess_scatter()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    assert int((calls[1].out['status'] & 16).min()) == 16 and 0.2 < dt < 10.0, dt
+    ex.wait(); ex.release(); ex.wait(); ex.release(); ex.wait()      # those two publications are there, a further one never comes
+    torch.cuda.synchronize()
+    assert int(ex.wait_status) == 1
+
+
 # ------------------------------------------------------------------------------------- IoU / rotated
 def test_bboxes_iou_bit_exact(golden):
     from mydetection_b200 import ops
