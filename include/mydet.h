@@ -256,6 +256,13 @@ int mydet_iou_aabb_rowmax(const float* a, int64_t a_batch_stride, int64_t a_pitc
 int mydet_iou_rot_pairwise(const float* a, int64_t n, const float* b, int64_t k, double* out,
                            void* stream);
 
+/* The matching IoU of a whole CEPDOF evaluation in one launch: CEPDOFeval.computeIoU (utils/evaluation/cepdof.py:67-99)
+ * is called once per (image, category) and each call builds a small dt x gt matrix with the evaluator's own iou_rle
+ * (:210-243).  segments: DEVICE array of n_segments x 5 int64 {a0, na, b0, nb, out0}: rows a[a0..a0+na) against columns
+ * b[b0..b0+nb), written row-major at out + out0; out0 must be the running sum of na*nb (non-decreasing), total its end. */
+int mydet_iou_rot_segments(const float* a, const float* b, const int64_t* segments, int n_segments, int64_t total,
+                           double* out, void* stream);
+
 /* Format helpers of utils/bbox_ops.py, kept because callers outside the path use the names.
  * cxcywh_to_x1y1x2y2 (:309-316): rows of n_param >= 4 floats, columns 4.. are copied through.
  * xywha2vertex (:137-172): rows (cx,cy,w,h,RADIANS) with n_param >= 5 -> out (N,4,2) tl,tr,br,bl. */

@@ -87,6 +87,34 @@ __global__ void __launch_bounds__(kIouCols) iou_rot_kernel(const float* __restri
     }
 }
 
+// Many small rotated-IoU matrices in ONE launch: the matching IoU of a whole evaluation (CEPDOFeval.computeIoU is
+// called once per (image, category), utils/evaluation/cepdof.py:67-99 -- thousands of tiny dt x gt problems).
+// Segment s: rows a[seg[s].a0 .. +na), columns b[seg[s].b0 .. +nb), row-major output at out + seg[s].out0.
+// One thread per output element; the segment of an element is found by binary search in the out0 prefix.
+__global__ void __launch_bounds__(256) iou_rot_segments_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                               const long long* __restrict__ seg, int n_seg,
+                                                               long long total, double* __restrict__ out) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    int lo = 0, hi = n_seg - 1;                      // last segment whose out0 <= e (out0 is non-decreasing)
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (seg[(long long)mid * 5 + 4] <= e) lo = mid; else hi = mid - 1;
+    }
+    const long long* sg = seg + (long long)lo * 5;
+    const long long nb = sg[3], local = e - sg[4];
+    const long long r = local / nb, c = local - r * nb;
+    const float* pa = a + (sg[0] + r) * 5;
+    const float* pb = b + (sg[2] + c) * 5;
+    float va[5] = {pa[0], pa[1], pa[2], pa[3], pa[4]}, vb[5] = {pb[0], pb[1], pb[2], pb[3], pb[4]};
+    float ax[4], ay[4], bx[4], by[4], ra, rb;
+    make_rot_box(va, ax, ay, ra);
+    make_rot_box(vb, bx, by, rb);
+    const double dx = (double)va[0] - (double)vb[0], dy = (double)va[1] - (double)vb[1];
+    const double rr = (double)ra + (double)rb + 1e-3;
+    out[e] = (dx * dx + dy * dy <= rr * rr) ? rot_iou_f64(ax, ay, bx, by) : 0.0;
+}
+
 // Row-wise max / arg-max of the bboxes_iou matrix, batched, WITHOUT materialising it: what every training
 // branch does next with that matrix (`bboxes_iou(...).max(dim=1)`: yolov3.py:106-107 and :94-95, fcos2.py:104-106,
 // retinanet.py:106-107).  One thread per row box; the image's GT boxes are staged in shared memory (corners
@@ -221,6 +249,17 @@ MYDET_API int mydet_iou_rot_pairwise(const float* a, int64_t n, const float* b, 
     MYDET_REQUIRE(grid.y <= 65535, "too many rows for one launch");
     iou_rot_kernel<<<grid, kIouCols, 0, (cudaStream_t)stream>>>(a, n, b, k, out);
     return launch_status("iou_rot_kernel");
+}
+
+MYDET_API int mydet_iou_rot_segments(const float* a, const float* b, const int64_t* segments, int n_segments, int64_t total,
+                                     double* out, void* stream) {
+    MYDET_REQUIRE(n_segments >= 0 && total >= 0, "negative size");
+    if (n_segments == 0 || total == 0) return 0;
+    MYDET_REQUIRE(a && b && segments && out, "NULL tensor pointer");
+    MYDET_REQUIRE(total <= 0x7fffffffLL * 256, "too many pairs for one launch");
+    iou_rot_segments_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        a, b, reinterpret_cast<const long long*>(segments), n_segments, total, out);
+    return launch_status("iou_rot_segments_kernel");
 }
 
 MYDET_API int mydet_iou_aabb_rowmax(const float* a, int64_t a_batch_stride, int64_t a_pitch, int64_t n, const float* gt,

@@ -81,6 +81,9 @@ def install():
     # importing `models` runs models/registry.py, whose det-layer imports are lazy (inside the function)
     models_pkg = _parent('models')
     models_pkg.detlayers = detlayers
+    # the evaluator's matching IoU (utils/evaluation/cepdof.py): patched when that module is importable here
+    from . import evaluation
+    evaluation.install_cepdof()
     return {'utils.bbox_ops': bbox_ops, 'utils.structures': structures, 'models.detlayers': detlayers}
 
 

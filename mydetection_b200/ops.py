@@ -326,6 +326,24 @@ def iou_rot(a, b):
     return out
 
 
+def iou_rot_segments(a, b, segments):
+    """Many small rotated-IoU matrices in one launch (mydet_iou_rot_segments).  a (Na,5), b (Nb,5) degrees;
+    segments: int64 (S,4) rows {a0, na, b0, nb} (host or device).  Returns (flat f64 tensor, out0 list): matrix s is
+    flat[out0[s] : out0[s] + na*nb].view(na, nb)."""
+    a = _dev(a, torch.float32, 'a').contiguous()
+    b = _dev(b, torch.float32, 'b').contiguous()
+    seg = torch.as_tensor(segments, dtype=torch.int64).reshape(-1, 4).cpu()
+    sizes = seg[:, 1] * seg[:, 3]
+    out0 = torch.cumsum(sizes, 0) - sizes
+    total = int(sizes.sum())
+    seg5 = torch.cat([seg, out0[:, None]], dim=1).contiguous().to(a.device)
+    out = torch.empty(max(total, 1), dtype=torch.float64, device=a.device)
+    with torch.cuda.device(a.device):
+        rc = _lib.lib().mydet_iou_rot_segments(_ptr(a), _ptr(b), _ptr(seg5), seg5.shape[0], total, _ptr(out), _stream())
+    _lib.check(rc, 'mydet_iou_rot_segments')
+    return out[:total], out0.tolist()
+
+
 # --------------------------------------------------------------------------------------- ATSS
 def fcos_assign(t_ltrb, stride, img_hw, gt_box, gt_cls, gt_count, center_region, anch_min, anch_max, ignore_thres, n_cls):
     """FCOSLayer's targets of one level (mydet_fcos_assign).  Same tensors as atss_assign (no 'thr')."""

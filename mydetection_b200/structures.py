@@ -13,6 +13,30 @@ from . import _lib, ops
 
 TOPK_CAP = 512  # utils/structures.py:99-101
 
+# The reference post-processes a batch one image at a time (models/general.py:78-84 builds one ImageObjects per row of
+# the level-concatenated (B,N,.) tensors, api/detection.py:172 / examples call post_process on each).  Each of those
+# per-image tensors is a VIEW of the batch tensor, and the view metadata says which row it is -- so the first image's
+# post_process runs ONE mydet_postprocess launch (and one device-to-host copy) for the whole batch, and the other
+# images of the same batch take their rows from that result: no launch, no synchronisation.  One entry: the batch in
+# flight.  It holds strong references to the three batch tensors (their addresses cannot be recycled while it lives)
+# and is only honoured for the same tensors at the same version counters and the same thresholds.
+_BATCH = {}
+
+
+def _row_of_batch(t):
+    """(batch tensor, row) when `t` is row `row` of a contiguous CUDA batch tensor (what iterating / unbinding /
+    indexing dim 0 yields), else None."""
+    base = t._base
+    if base is None or not t.is_cuda or base.dim() != t.dim() + 1 or tuple(base.shape[1:]) != tuple(t.shape):
+        return None
+    per = t.numel()
+    if per == 0 or base.shape[0] < 2 or not (t.is_contiguous() and base.is_contiguous()):
+        return None
+    off = t.storage_offset() - base.storage_offset()
+    if off % per or not 0 <= off // per < base.shape[0]:
+        return None
+    return base, off // per
+
 
 def _cuda_device():
     if not torch.cuda.is_available():
@@ -106,11 +130,20 @@ class ImageObjects():
             raise NotImplementedError()
         if len(self) == 0:
             return self                      # structures.py:120-121
+        hit = self._run_batched(conf_thres, nms_thres, topk) if topk else None    # the un-capped nms() stays per image
+        if hit is not None:
+            return hit
         home = self.bboxes.device
         dev = home if home.type == 'cuda' else _cuda_device()
         out = ops.postprocess(self.bboxes.detach().to(dev)[None], self.scores.detach().to(dev, torch.float32)[None],
                               self.cats.to(dev)[None], conf_thres, nms_thres, topk=topk, box_format=self._bb_format)
         n, status = (int(v) for v in torch.stack([out['count'][0], out['status'][0]]).tolist())  # one D2H sync
+        self._check_status(status)
+        return ImageObjects(out['box'][0, :n], out['cls'][0, :n], None, out['score'][0, :n], self._bb_format,
+                            img_hw=self.img_hw), out['idx'][0, :n]
+
+    @staticmethod
+    def _check_status(status):
         if status & 1:
             raise _lib.MydetError(f'category ids must lie in [0, {_lib.MAX_CLASS_ID}]')
         if status & (2 | 4):   # cannot happen through this wrapper (out_cap and counts are derived from the input); never silent
@@ -118,13 +151,45 @@ class ImageObjects():
         if status & 8:
             import warnings
             warnings.warn('more than 2^20 candidates in one image: equal scores are ordered by the low 20 bits of the index')
-        return ImageObjects(out['box'][0, :n], out['cls'][0, :n], None, out['score'][0, :n], self._bb_format,
-                            img_hw=self.img_hw), out['idx'][0, :n]
+
+    def _run_batched(self, conf_thres, nms_thres, topk, to_cpu=False):
+        """This image as a row of its batch (see _BATCH): one launch per batch instead of one per image."""
+        if self.bboxes.requires_grad or self.scores.requires_grad:
+            return None
+        rows = [_row_of_batch(t) for t in (self.bboxes, self.scores, self.cats)]
+        if any(r is None for r in rows) or len({r[1] for r in rows}) != 1 or self.scores.dtype != torch.float32:
+            return None
+        (bb, b), (sc, _), (ct, _) = rows
+        if not (bb.shape[0] == sc.shape[0] == ct.shape[0]):
+            return None
+        key = (bb.data_ptr(), sc.data_ptr(), ct.data_ptr(), bb._version, sc._version, ct._version, tuple(bb.shape),
+               float(conf_thres), float(nms_thres), topk, self._bb_format)
+        ent = _BATCH.get('entry')
+        if ent is None or ent['key'] != key:
+            out = ops.postprocess(bb.detach(), sc.detach(), ct, conf_thres, nms_thres, topk=topk, box_format=self._bb_format)
+            meta = torch.stack([out['count'], out['status']]).cpu()               # the batch's one synchronisation
+            ent = {'key': key, 'hold': (bb, sc, ct), 'out': out, 'count': meta[0].tolist(), 'status': meta[1].tolist(), 'host': None}
+            _BATCH['entry'] = ent
+        n = ent['count'][b]
+        self._check_status(ent['status'][b])
+        src = ent['out']
+        if to_cpu:
+            if ent['host'] is None:            # one device-to-host copy of the batch's rows, cut to the longest image
+                m = max(ent['count'] + [1])
+                ent['host'] = {k: src[k][:, :m].cpu() for k in ('box', 'cls', 'score', 'idx')}
+            src = ent['host']
+        # clones: the caller owns its result (bboxes_to_original_ edits it in place), the cached batch stays intact
+        return ImageObjects(src['box'][b, :n].clone(), src['cls'][b, :n].clone(), None, src['score'][b, :n].clone(),
+                            self._bb_format, img_hw=self.img_hw), src['idx'][b, :n].clone()
 
     def post_process(self, conf_thres, nms_thres):
         '''Confidence threshold + top-512 + per-class NMS (utils/structures.py:92-106).
         Like the reference, the result lives on the CPU.'''
-        res = self._run(conf_thres, nms_thres, TOPK_CAP)
+        res = None
+        if len(self) and self.masks is None and self.scores is not None and self._bb_format in ops.BOX_FORMATS:
+            res = self._run_batched(conf_thres, nms_thres, TOPK_CAP, to_cpu=True)
+        if res is None:
+            res = self._run(conf_thres, nms_thres, TOPK_CAP)
         if res is self:
             return self
         dts, _ = res

@@ -49,6 +49,27 @@ def _have(name):
         return False
 
 
+class _MiniParams:
+    """The fields of pycocotools.cocoeval.Params that CEPDOFeval touches (defaults of the published class)."""
+    def __init__(self, iouType='bbox'):
+        self.iouType, self.useCats, self.maxDets = iouType, 1, [1, 10, 100]
+        self.imgIds, self.catIds = [], []
+        self.iouThrs = np.linspace(.5, 0.95, 10)
+        self.areaRngLbl = ['all', 'small', 'medium', 'large']
+
+
+class _MiniCOCOeval:
+    """Stand-in base class for CEPDOFeval when pycocotools is absent: `evaluate()` up to and including the IoU table
+    (`self.ious[(imgId, catId)] = self.computeIoU(imgId, catId)`, as the published COCOeval.evaluate does); matching
+    and accumulation are third-party code outside the path and are not restated."""
+    def evaluate(self):
+        p = self.params
+        p.imgIds, p.catIds = list(np.unique(p.imgIds)), list(np.unique(p.catIds))
+        self._prepare()
+        cat_ids = p.catIds if p.useCats else [-1]
+        self.ious = {(i, c): self.computeIoU(i, c) for i in p.imgIds for c in cat_ids}
+
+
 def install_stubs():
     """Stand-ins for pycocotools / matplotlib / fvcore -- only for those that are really absent."""
     if not _have('pycocotools'):
@@ -68,7 +89,7 @@ def install_stubs():
         mask = _mod('pycocotools.mask', frPyObjects=fr, iou=iou)
         _mod('pycocotools', mask=mask)
         _mod('pycocotools.coco', COCO=object)
-        _mod('pycocotools.cocoeval', COCOeval=object)
+        _mod('pycocotools.cocoeval', COCOeval=_MiniCOCOeval, Params=_MiniParams)
     if not _have('matplotlib'):
         plt = _mod('matplotlib.pyplot')
         _mod('matplotlib', pyplot=plt)

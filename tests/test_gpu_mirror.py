@@ -299,6 +299,58 @@ def test_one_stage_forward_flow(golden):
         assert torch.equal(out.cats, ref[1][b][want])
 
 
+def test_post_process_is_batched_behind_the_per_image_calls(golden, monkeypatch):
+    """The reference's per-image post_process loop (models/general.py:78-84, api/detection.py:172) on the mirror costs
+    ONE mydet_postprocess launch per batch: rows of a batch tensor are recognised by their view metadata.  Same results
+    as the per-image path; a different threshold, an in-place edit of the batch tensor or of a returned result must
+    not be served from the cached batch."""
+    from mydetection_b200 import detlayers, ops, structures
+    from mydetection_b200.structures import ImageObjects
+    g = golden('decode')
+    strides = [8, 16, 32, 64, 128]
+    cfg = {'model.pred_layer': 'FCOS2', 'model.fcos.anchors': [0, 64, 128, 256, 512, 100000000],
+           'model.fpn.out_strides': strides, 'general.num_class': 6, 'model.fcos2.ignored_threshold': 0.7,
+           'general.pred_bbox_format': 'cxcywh'}
+    raws = [efdet_views(T(g[f'fcos{li}_bbox_in']), T(g[f'fcos{li}_cls_in'])) for li in range(5)]
+    layers = [detlayers.get_det_layer(cfg)(level_i=i, cfg=cfg) for i in range(5)]
+    dts_all = [layers[i]({k: v.cuda() for k, v in raws[i].items()}, (256, 384), None)[0] for i in range(5)]
+    bbs = torch.cat([d['bbox'] for d in dts_all], dim=1)
+    cls_idx = torch.cat([d['class_idx'] for d in dts_all], dim=1)
+    scores = torch.cat([d['score'] for d in dts_all], dim=1)
+    calls = []
+    real = ops.postprocess
+    monkeypatch.setattr(ops, 'postprocess', lambda *a, **k: (calls.append(a[0].shape[0]), real(*a, **k))[1])
+
+    def loop(conf, nms):
+        objs = [ImageObjects(bboxes=b, cats=c, scores=s_, bb_format='cxcywh', img_hw=(256, 384))
+                for b, c, s_ in zip(bbs, cls_idx, scores)]                   # general.py:78-84
+        return [o.post_process(conf, nms) for o in objs]
+
+    def alone(b, conf, nms):      # the same image as a tensor of its own: per-image path
+        o = ImageObjects(bboxes=bbs[b].clone(), cats=cls_idx[b].clone(), scores=scores[b].clone(), bb_format='cxcywh')
+        return o.post_process(conf, nms)
+
+    structures._BATCH.clear()
+    got = loop(0.05, 0.5)
+    assert calls == [2], calls                                                # one launch for the batch of 2
+    for b in range(2):
+        want = alone(b, 0.05, 0.5)
+        assert not got[b].bboxes.is_cuda and len(got[b]) == len(want) > 0
+        assert torch.equal(got[b].bboxes, want.bboxes) and torch.equal(got[b].scores, want.scores) and torch.equal(got[b].cats, want.cats)
+    calls.clear()
+    got[0].bboxes.mul_(0.0)                                                   # the caller edits ITS result in place ...
+    again = loop(0.05, 0.5)
+    assert calls == [] and float(again[0].bboxes.abs().sum()) > 0             # ... the cached batch is intact, no new launch
+    other = loop(0.3, 0.5)
+    assert calls == [2] and len(other[0]) < len(again[0])                     # another threshold: recomputed
+    calls.clear()
+    scores[1].mul_(0.5)                                                       # the batch tensor changes: version counter
+    changed = loop(0.3, 0.5)
+    assert calls == [2]
+    want = alone(1, 0.3, 0.5)
+    assert len(changed[1]) == len(want) and torch.equal(changed[1].scores, want.scores)
+
+
 def test_cepdof_matching_iou(golden):
     """CEPDOFeval.computeIoU (dt x gt rotated IoU, stable score order, maxDets cap)."""
     from mydetection_b200 import evaluation

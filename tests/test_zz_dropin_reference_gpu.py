@@ -187,3 +187,59 @@ def test_reference_alone_vs_reference_on_dropin_same_box(ref, name):
         assert torch.equal(got.cats, want.cats)
         assert torch.allclose(got.scores, want.scores, rtol=1e-5, atol=0)
         assert torch.allclose(got.bboxes, want.bboxes, rtol=1e-5, atol=atol)
+
+
+def test_cepdof_evaluator_on_dropin(ref, monkeypatch):
+    """utils/evaluation/cepdof.py of the reference, unedited, under dropin.install(): `CEPDOFeval(...).evaluate()` builds
+    its IoU table through the patched computeIoU -- ONE mydet_iou_rot_segments launch for all (image, category) pairs
+    -- and the table equals what the unpatched evaluator computes pair by pair (its raster replaced by the oracle's
+    exact clipping, refload's stand-in): same keys, same shapes, same empties, values within 1e-6."""
+    import copy
+    rng = np.random.RandomState(3)
+    images = [{'id': i, 'height': 1024, 'width': 1024} for i in range(1, 13)]
+    cats = [{'id': 1}, {'id': 2}, {'id': 5}]
+    anns, dts = [], []
+    for im in images:
+        for c in cats:
+            n_gt = int(rng.randint(0, 7)) if im['id'] != 4 else 0
+            for _ in range(n_gt):
+                box = [*rng.uniform(100, 900, 2), *rng.uniform(20, 160, 2), rng.uniform(-90, 90)]
+                anns.append({'image_id': im['id'], 'category_id': c['id'], 'bbox': [float(v) for v in box]})
+                for _ in range(int(rng.randint(0, 4))):       # detections near the GT, tied scores included
+                    d = [box[0] + rng.randn() * 8, box[1] + rng.randn() * 8, box[2] * rng.uniform(0.8, 1.2),
+                         box[3] * rng.uniform(0.8, 1.2), box[4] + rng.randn() * 12]
+                    dts.append({'image_id': im['id'], 'category_id': c['id'], 'bbox': [float(v) for v in d],
+                                'score': float(np.round(rng.uniform(0, 1), 1))})
+    for _ in range(130):                                       # one crowded pair: more than maxDets detections
+        dts.append({'image_id': 2, 'category_id': 1, 'bbox': [float(v) for v in (*rng.uniform(100, 900, 2), 60., 30., rng.uniform(-90, 90))],
+                    'score': float(rng.uniform(0, 1))})
+    gt_json = {'images': images, 'categories': cats, 'annotations': anns}
+
+    import utils.evaluation.cepdof as cep_ref                  # the reference alone (stand-in raster = exact clipping)
+    assert cep_ref.__file__.startswith(ref.ROOT)
+    ev_ref = cep_ref.CEPDOFeval(copy.deepcopy(gt_json), copy.deepcopy(dts))
+    ev_ref.evaluate()
+
+    ref.activate(fresh=True)
+    from mydetection_b200 import dropin, evaluation, ops
+    dropin.install()
+    import utils.evaluation.cepdof as cep
+    assert cep.__file__.startswith(ref.ROOT) and cep.iou_rle is evaluation.iou_rle
+    launches = []
+    real = ops.iou_rot_segments
+    monkeypatch.setattr(ops, 'iou_rot_segments', lambda *a, **k: (launches.append(1), real(*a, **k))[1])
+    ev = cep.CEPDOFeval(copy.deepcopy(gt_json), copy.deepcopy(dts))
+    ev.evaluate()
+    assert launches == [1]
+    assert set(ev.ious) == set(ev_ref.ious) and len(ev.ious) == 36
+    worst = 0.0
+    for key, want in ev_ref.ious.items():
+        got = ev.ious[key]
+        if isinstance(want, list):
+            assert isinstance(got, list) and got == []
+            continue
+        assert got.shape == want.shape and got.dtype == np.float64, key
+        if want.size:
+            worst = max(worst, float(np.abs(got - want).max()))
+    assert ev.ious[(2, 1)].shape[0] == 100                     # maxDets cap after the stable score sort
+    assert worst < 1e-6, worst
