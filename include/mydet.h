@@ -259,9 +259,11 @@ int mydet_iou_rot_pairwise(const float* a, int64_t n, const float* b, int64_t k,
 /* The matching IoU of a whole CEPDOF evaluation in one launch: CEPDOFeval.computeIoU (utils/evaluation/cepdof.py:67-99)
  * is called once per (image, category) and each call builds a small dt x gt matrix with the evaluator's own iou_rle
  * (:210-243).  segments: DEVICE array of n_segments x 5 int64 {a0, na, b0, nb, out0}: rows a[a0..a0+na) against columns
- * b[b0..b0+nb), written row-major at out + out0; out0 must be the running sum of na*nb (non-decreasing), total its end. */
-int mydet_iou_rot_segments(const float* a, const float* b, const int64_t* segments, int n_segments, int64_t total,
-                           double* out, void* stream);
+ * b[b0..b0+nb), written row-major at out + out0; out0 must be the running sum of na*nb (non-decreasing), total its end.
+ * boxes_are_f64 != 0: a / b are float64 (N,5) and the corners are built in float64, as the evaluator's numpy code does
+ * with the JSON's Python floats (:181-207, :232-236); 0: float32 boxes and corners, as iou_rle of utils/bbox_ops.py. */
+int mydet_iou_rot_segments(const void* a, const void* b, int boxes_are_f64, const int64_t* segments, int n_segments,
+                           int64_t total, double* out, void* stream);
 
 /* Format helpers of utils/bbox_ops.py, kept because callers outside the path use the names.
  * cxcywh_to_x1y1x2y2 (:309-316): rows of n_param >= 4 floats, columns 4.. are copied through.
@@ -303,6 +305,29 @@ int mydet_fcos_assign(const float* t_ltrb, const int64_t t_stride[4], int batch,
                       int n_cls, uint8_t* positive, uint8_t* ignored, float* target_ltrb,
                       float* target_conf, float* target_cls, void* workspace, size_t workspace_bytes,
                       void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Tracklets of rotated boxes, batched.  Replaces the per-object numpy Kalman filters of
+ * utils/kalman_filter.py:77-142 (RotBBoxKalmanFilter) as driven by utils/structures.py:447-529 (KFTracklet.__init__,
+ * predict, update, likelihood): all tracklets of a frame advance in one launch, float64 like the reference.
+ *   x (N,10), P (N,10,10) f64: state (cx, cy, w, h, angle in [0,180), velocities) and covariance; score (N) f64 and
+ *   pred_count (N) i32 (predictions since the last update) may be NULL.
+ *   noise       HOST array of 26 doubles: 10 initial, 10 process, 5 measurement standard deviations, score momentum
+ *               (structures.py:458-461, :471)
+ *   initiate    boxes (N,5) -> x, P (the four size-like components and their velocities scaled by w*h), pred_count = 0
+ *   predict     out_boxes (N,5) or NULL: the predicted boxes (angle NOT wrapped, as KFTracklet.predict returns it)
+ *   update      meas (N,5), meas_score (N) or NULL, has (N) u8 or NULL (= all): tracklets without a measurement are left
+ *               untouched and get a zero row in out_boxes
+ *   likelihood  cand (M,5) -> out (N,M): the Gaussian density of every candidate under every tracklet (:519-528)
+ * The association IoU between predicted tracklet boxes and detections is mydet_iou_rot_pairwise. */
+int mydet_kf_initiate(const double* boxes, int n, const double* noise, double* x, double* P, int32_t* pred_count,
+                      void* stream);
+int mydet_kf_predict(double* x, double* P, double* score, int32_t* pred_count, int n, const double* noise,
+                     double* out_boxes, void* stream);
+int mydet_kf_update(double* x, double* P, double* score, int32_t* pred_count, const double* meas,
+                    const double* meas_score, const uint8_t* has, int n, const double* noise, double* out_boxes,
+                    void* stream);
+int mydet_kf_likelihood(const double* x, const double* P, int n, const double* cand, int m, double* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Image pre-processing in front of the model.  Replaces, for a batch of equally

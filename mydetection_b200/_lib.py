@@ -63,7 +63,7 @@ SIGNATURES = {
     'mydet_iou_aabb_pairwise': (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp]),
     'mydet_iou_aabb_rowmax': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     'mydet_iou_rot_pairwise': (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
-    'mydet_iou_rot_segments': (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_vp]),
+    'mydet_iou_rot_segments': (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_vp, c_vp]),
     'mydet_cxcywh_to_x1y1x2y2': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     'mydet_xywha2vertex': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     'mydet_atss_workspace_bytes': (c_sz, [c_int, c_int]),
@@ -72,6 +72,10 @@ SIGNATURES = {
                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),
     'mydet_fcos_assign': (c_int, [c_vp, ctypes.POINTER(c_i64), c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int,
                                   c_f32, c_f32, c_f32, c_f32, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'mydet_kf_initiate': (c_int, [c_vp, c_int, ctypes.POINTER(c_f64), c_vp, c_vp, c_vp, c_vp]),
+    'mydet_kf_predict': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, ctypes.POINTER(c_f64), c_vp, c_vp]),
+    'mydet_kf_update': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, ctypes.POINTER(c_f64), c_vp, c_vp]),
+    'mydet_kf_likelihood': (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp]),
     'mydet_preprocess_workspace_bytes': (c_sz, [c_int, c_int, c_int, c_int, c_int]),
     'mydet_preprocess': (c_int, [c_vp, c_int, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_vp, c_vp, c_sz, c_vp]),

@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(kIouCols) iou_rot_kernel(const float* __restri
 // called once per (image, category), utils/evaluation/cepdof.py:67-99 -- thousands of tiny dt x gt problems).
 // Segment s: rows a[seg[s].a0 .. +na), columns b[seg[s].b0 .. +nb), row-major output at out + seg[s].out0.
 // One thread per output element; the segment of an element is found by binary search in the out0 prefix.
-__global__ void __launch_bounds__(256) iou_rot_segments_kernel(const float* __restrict__ a, const float* __restrict__ b,
+template <typename C>
+__global__ void __launch_bounds__(256) iou_rot_segments_kernel(const C* __restrict__ a, const C* __restrict__ b,
                                                                const long long* __restrict__ seg, int n_seg,
                                                                long long total, double* __restrict__ out) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -104,10 +105,10 @@ __global__ void __launch_bounds__(256) iou_rot_segments_kernel(const float* __re
     const long long* sg = seg + (long long)lo * 5;
     const long long nb = sg[3], local = e - sg[4];
     const long long r = local / nb, c = local - r * nb;
-    const float* pa = a + (sg[0] + r) * 5;
-    const float* pb = b + (sg[2] + c) * 5;
-    float va[5] = {pa[0], pa[1], pa[2], pa[3], pa[4]}, vb[5] = {pb[0], pb[1], pb[2], pb[3], pb[4]};
-    float ax[4], ay[4], bx[4], by[4], ra, rb;
+    const C* pa = a + (sg[0] + r) * 5;
+    const C* pb = b + (sg[2] + c) * 5;
+    C va[5] = {pa[0], pa[1], pa[2], pa[3], pa[4]}, vb[5] = {pb[0], pb[1], pb[2], pb[3], pb[4]};
+    C ax[4], ay[4], bx[4], by[4], ra, rb;
     make_rot_box(va, ax, ay, ra);
     make_rot_box(vb, bx, by, rb);
     const double dx = (double)va[0] - (double)vb[0], dy = (double)va[1] - (double)vb[1];
@@ -251,14 +252,20 @@ MYDET_API int mydet_iou_rot_pairwise(const float* a, int64_t n, const float* b, 
     return launch_status("iou_rot_kernel");
 }
 
-MYDET_API int mydet_iou_rot_segments(const float* a, const float* b, const int64_t* segments, int n_segments, int64_t total,
-                                     double* out, void* stream) {
+MYDET_API int mydet_iou_rot_segments(const void* a, const void* b, int boxes_are_f64, const int64_t* segments, int n_segments,
+                                     int64_t total, double* out, void* stream) {
     MYDET_REQUIRE(n_segments >= 0 && total >= 0, "negative size");
     if (n_segments == 0 || total == 0) return 0;
     MYDET_REQUIRE(a && b && segments && out, "NULL tensor pointer");
     MYDET_REQUIRE(total <= 0x7fffffffLL * 256, "too many pairs for one launch");
-    iou_rot_segments_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        a, b, reinterpret_cast<const long long*>(segments), n_segments, total, out);
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    const long long* sg = reinterpret_cast<const long long*>(segments);
+    if (boxes_are_f64)
+        iou_rot_segments_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const double*>(a), static_cast<const double*>(b),
+                                                                                sg, n_segments, total, out);
+    else
+        iou_rot_segments_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const float*>(a), static_cast<const float*>(b),
+                                                                               sg, n_segments, total, out);
     return launch_status("iou_rot_segments_kernel");
 }
 

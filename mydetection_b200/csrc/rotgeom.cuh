@@ -39,7 +39,21 @@ __device__ __forceinline__ void make_rot_box(const float* b, float* x, float* y,
     r = 0.5f * sqrtf(b[2] * b[2] + b[3] * b[3]);
 }
 
-__device__ __forceinline__ double signed_area2_f64(const float* x, const float* y) {
+// The evaluator's variant (utils/evaluation/cepdof.py:181-207, :232-236): boxes are Python floats, the corners are built
+// with numpy in float64 -- degree * pi / 180, then c +/- verti -/+ hori in double.
+__device__ __forceinline__ void make_rot_box(const double* b, double* x, double* y, double& r) {
+    const double rad = b[4] * 3.14159265358979323846 / 180.0;
+    const double s = sin(rad), c = cos(rad);
+    const double vx = (b[3] / 2) * s, vy = -(b[3] / 2) * c, hx = (b[2] / 2) * c, hy = (b[2] / 2) * s;
+    x[0] = b[0] + vx - hx; y[0] = b[1] + vy - hy;
+    x[1] = b[0] + vx + hx; y[1] = b[1] + vy + hy;
+    x[2] = b[0] - vx + hx; y[2] = b[1] - vy + hy;
+    x[3] = b[0] - vx - hx; y[3] = b[1] - vy - hy;
+    r = 0.5 * sqrt(b[2] * b[2] + b[3] * b[3]);
+}
+
+template <typename C>
+__device__ __forceinline__ double signed_area2_f64(const C* x, const C* y) {
     double a2 = 0.0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -52,9 +66,9 @@ __device__ __forceinline__ double signed_area2_f64(const float* x, const float* 
 // Intersection area of convex quads A and B (B's orientation given by sgn), arithmetic in T.
 // (ox, oy) is subtracted from every corner first: exact in float32 for nearby boxes, and it keeps
 // the float32 variant's rounding error relative to the box size instead of the image size.
-template <typename T>
-__device__ __forceinline__ T clip_area(const float* ax, const float* ay, const float* bx, const float* by,
-                                       T sgn, float ox, float oy) {
+template <typename T, typename C = float>
+__device__ __forceinline__ T clip_area(const C* ax, const C* ay, const C* bx, const C* by,
+                                       T sgn, C ox, C oy) {
     T px[8], py[8], qx[8], qy[8];
     int n = 4;
 #pragma unroll
@@ -96,11 +110,12 @@ __device__ __forceinline__ T clip_area(const float* ax, const float* ay, const f
 }
 
 // Exact (float64) IoU, same operation order as oracle/rotiou.c::quad_iou.
-__device__ __forceinline__ double rot_iou_f64(const float* ax, const float* ay, const float* bx, const float* by) {
+template <typename C>
+__device__ __forceinline__ double rot_iou_f64(const C* ax, const C* ay, const C* bx, const C* by) {
     const double a2A = signed_area2_f64(ax, ay), a2B = signed_area2_f64(bx, by);
     const double areaA = 0.5 * fabs(a2A), areaB = 0.5 * fabs(a2B);
     double inter = 0.0;
-    if (areaA > 0.0 && areaB > 0.0) inter = clip_area<double>(ax, ay, bx, by, a2B >= 0.0 ? 1.0 : -1.0, 0.f, 0.f);
+    if (areaA > 0.0 && areaB > 0.0) inter = clip_area<double, C>(ax, ay, bx, by, a2B >= 0.0 ? 1.0 : -1.0, (C)0, (C)0);
     const double uni = areaA + areaB - inter;
     return uni > 0.0 ? inter / uni : 0.0;
 }

@@ -54,8 +54,28 @@ def last_writer(lin, n_cells):
     return winner[lin] == order
 
 
+def periodic_angle_loss(name):
+    """models/losses.py:7-98 get_angle_loss(name, reduction='sum'): the angle difference is folded into
+    [-pi/2, pi/2) (a box rotated by 180 degrees is the same box) before the L1 / L2 / smooth-L1 (beta 0.4) penalty."""
+    import numpy as np
+
+    def fold(pred, gt):
+        return torch.remainder(pred - gt - np.pi / 2, np.pi) - np.pi / 2
+
+    if name == 'Periodic_L1':
+        return lambda p, g: torch.abs(fold(p, g)).sum()
+    if name == 'Periodic_L2':
+        return lambda p, g: (fold(p, g) ** 2).sum()
+    if name == 'Periodic_smoothL1':
+        def sl1(p, g, beta=0.4):
+            n = torch.abs(fold(p, g))
+            return torch.where(n < beta, 0.5 * n ** 2 / beta, n - 0.5 * beta).sum()
+        return sl1
+    raise NotImplementedError()
+
+
 def no_training(name):
     raise NotImplementedError(
         f'{name}: training-time target assignment is outside the post-processing hot path '
-        '(SURVEY.md section 8f, rank 2); the YOLO, FCOS2, FCOS2-ATSS, RetinaNet and RAPiD layers implement '
+        '(SURVEY.md section 8f, rank 2); the YOLO, Ultralytics, FCOS2, FCOS2-ATSS, RetinaNet and RAPiD layers implement '
         'forward(..., labels)')

@@ -3,15 +3,22 @@ import torch
 import torch.nn.functional as tnf
 
 from .. import ops
-from ._base import decode_level, pack_labels, stage_raw
+from ._base import decode_level, pack_labels, periodic_angle_loss, stage_raw
 
 
 class RetinaLayer(torch.nn.Module):
     '''RetinaNet anchor-delta layer (reference: models/detlayers/retinanet.py:12-160).
-    Test mode: decode.  Training mode ('cxcywh' boxes): the anchor-to-GT matching `bboxes_iou(anchors, gt).max(dim=1)`
+    Test mode: decode.  Training mode: the anchor-to-GT matching `bboxes_iou(anchors, gt).max(dim=1)`
     (:106-107) runs on the device for the whole batch without its matrix (mydet_iou_aabb_rowmax, one shared anchor
     set); targets and the loss follow from it with elementwise ops (:108-152).  Like the reference, training mode
-    returns (None, loss).'''
+    returns (None, loss).
+    Rotated boxes ('cxcywhd'): the matching uses the first four box parameters (:106), the angle target is the matched
+    GT's angle in radians (:133-136) and the periodic angle loss is added at the positives (:151-154).  The reference
+    itself cannot construct this variant at HEAD -- its __init__ imports `.losses` from the detlayers package (:36; the
+    module lives one level up) and reads a config key no config defines ('model.angle.loss_name') -- so the loss name is taken
+    from 'model.angle.loss_name' or, failing that, 'model.angle.loss_angle' (the key the configs do have), and the branch
+    is pinned to the reference's unmodified forward() run on a layer whose three rotated attributes were set by hand
+    (tests/golden/train_retina_rot.npz).'''
     def __init__(self, level_i: int, cfg: dict):
         super().__init__()
         stride = cfg['model.fpn.out_strides'][level_i]
@@ -26,6 +33,8 @@ class RetinaLayer(torch.nn.Module):
         self.n_cls = cfg['general.num_class']
         self.pred_bbox_format = cfg['general.pred_bbox_format']
         self.n_bbparam = cfg['general.bbox_param']
+        if self.pred_bbox_format == 'cxcywhd':
+            self.loss_angle = periodic_angle_loss(cfg.get('model.angle.loss_name', cfg.get('model.angle.loss_angle', 'Periodic_L1')))
         self.loss_str = ''
 
     def anchor_boxes(self, img_size, n_h, n_w, device):
@@ -47,14 +56,16 @@ class RetinaLayer(torch.nn.Module):
         if labels is None:
             preds = decode_level(ops.KIND_RETINA, raw, self.stride, img_size, self.anchor_wh.tolist(), keys=('bbox', 'class'))
             return preds, None
-        if self.pred_bbox_format != 'cxcywh':
-            raise NotImplementedError('RetinaLayer training with rotated boxes (needs models.losses.get_angle_loss)')
+        if self.pred_bbox_format not in ('cxcywh', 'cxcywhd'):
+            raise NotImplementedError()
+        rotated = self.pred_bbox_format == 'cxcywhd'
         assert isinstance(labels, list) and len(labels) == n_b
         staged = stage_raw(raw, ('bbox', 'class'), detach=False)
         t_xywh, cls_logits = staged['bbox'], staged['class']
         dev = t_xywh.device
         anch = self.anchor_boxes(img_size, n_h, n_w, dev)
-        gt_box, gt_cls, counts = pack_labels(labels, 4, dev)
+        gt_full, gt_cls, counts = pack_labels(labels, 5 if rotated else 4, dev)
+        gt_box = gt_full[..., :4].contiguous()
         iou_with_gt, gt_idx = ops.iou_rowmax(anch.reshape(-1, 4), gt_box, counts)              # :106-107, whole batch
         iou_with_gt, gt_idx = iou_with_gt.view(n_b, n_a, n_h, n_w), gt_idx.view(n_b, n_a, n_h, n_w)
         has_gt = (counts > 0).view(n_b, 1, 1, 1)
@@ -80,6 +91,12 @@ class RetinaLayer(torch.nn.Module):
         # loss (:137-152): smooth-L1 (fvcore's, beta 0.1) at the positives, BCE on the penalised cells
         err = torch.abs(t_xywh[m_pos][:, 0:4] - tgt_xywh[m_pos])
         loss_xywh = torch.where(err < 0.1, 0.5 * err.pow(2) / 0.1, err - 0.05).sum()
+        if rotated:
+            tgt_angle = gt_full[bi, gsel][..., 4] / 180 * np.pi                               # :133-136, radians
+            self.targets['tgt_angle'] = tgt_angle
+            if bool(m_pos.any()):
+                p_angle = torch.sigmoid(t_xywh[m_pos][:, 4]) * 2 * np.pi - np.pi              # :152
+                loss_xywh = loss_xywh + self.loss_angle(p_angle, tgt_angle[m_pos])             # :153-154
         loss_cls = tnf.binary_cross_entropy_with_logits(cls_logits[penalty], tgt_cls[penalty], reduction='sum')
         loss = (loss_xywh + loss_cls) / n_b
         total_pos, total = int(m_pos.sum()), int((counts > 0).sum()) * n_a * n_h * n_w

@@ -25,10 +25,9 @@ def iou_rle(boxes1, boxes2, img_size=2048):
     b2 = np.array(boxes2, dtype=np.float64).reshape(-1, 5)
     if b1.shape[0] == 0 or b2.shape[0] == 0:
         return np.zeros((b1.shape[0], b2.shape[0]))
-    dev = _cuda_device()
-    t1 = torch.from_numpy(b1).to(dev, torch.float32)
-    t2 = torch.from_numpy(b2).to(dev, torch.float32)
-    return ops.iou_rot(t1, t2).cpu().numpy()
+    dev = _cuda_device()                      # float64 boxes and corners, as the evaluator's numpy code (cepdof.py:232-236)
+    flat, _ = ops.iou_rot_segments(torch.from_numpy(b1).to(dev), torch.from_numpy(b2).to(dev), [(0, b1.shape[0], 0, b2.shape[0])])
+    return flat.cpu().numpy().reshape(b1.shape[0], b2.shape[0])
 
 
 def compute_iou(dts, gts, max_dets=100, img_size=2048):
@@ -64,8 +63,8 @@ def compute_iou_all(dts_by_key, gts_by_key, keys, max_dets=100):
     if not live:
         return res
     dev = _cuda_device()
-    a = torch.tensor(np.array(a_rows, dtype=np.float64).reshape(-1, 5), dtype=torch.float32)
-    b = torch.tensor(np.array(b_rows, dtype=np.float64).reshape(-1, 5), dtype=torch.float32)
+    a = torch.tensor(np.array(a_rows, dtype=np.float64).reshape(-1, 5), dtype=torch.float64)     # float64 end to end,
+    b = torch.tensor(np.array(b_rows, dtype=np.float64).reshape(-1, 5), dtype=torch.float64)     # like the evaluator's numpy
     if a.shape[0] == 0 or b.shape[0] == 0:
         flat, out0 = np.zeros(0), [0] * len(segs)
     else:

@@ -330,8 +330,9 @@ def iou_rot_segments(a, b, segments):
     """Many small rotated-IoU matrices in one launch (mydet_iou_rot_segments).  a (Na,5), b (Nb,5) degrees;
     segments: int64 (S,4) rows {a0, na, b0, nb} (host or device).  Returns (flat f64 tensor, out0 list): matrix s is
     flat[out0[s] : out0[s] + na*nb].view(na, nb)."""
-    a = _dev(a, torch.float32, 'a').contiguous()
-    b = _dev(b, torch.float32, 'b').contiguous()
+    f64 = a.dtype == torch.float64            # float64 boxes: corners in float64 too (the evaluator's numpy arithmetic)
+    a = _dev(a, torch.float64 if f64 else torch.float32, 'a').contiguous()
+    b = _dev(b, torch.float64 if f64 else torch.float32, 'b').contiguous()
     seg = torch.as_tensor(segments, dtype=torch.int64).reshape(-1, 4).cpu()
     sizes = seg[:, 1] * seg[:, 3]
     out0 = torch.cumsum(sizes, 0) - sizes
@@ -339,7 +340,7 @@ def iou_rot_segments(a, b, segments):
     seg5 = torch.cat([seg, out0[:, None]], dim=1).contiguous().to(a.device)
     out = torch.empty(max(total, 1), dtype=torch.float64, device=a.device)
     with torch.cuda.device(a.device):
-        rc = _lib.lib().mydet_iou_rot_segments(_ptr(a), _ptr(b), _ptr(seg5), seg5.shape[0], total, _ptr(out), _stream())
+        rc = _lib.lib().mydet_iou_rot_segments(_ptr(a), _ptr(b), 1 if f64 else 0, _ptr(seg5), seg5.shape[0], total, _ptr(out), _stream())
     _lib.check(rc, 'mydet_iou_rot_segments')
     return out[:total], out0.tolist()
 

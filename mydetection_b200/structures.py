@@ -257,3 +257,5 @@ COCO_CATEGORY_IDS = ([*range(1, 12), *range(13, 26), 27, 28, *range(31, 45), *ra
                       148, 149, 151, 154, 155, 156, 159, 161, 166, 168, 171, *range(175, 179), 180, 181,
                       *range(184, 201)])
 assert len(COCO_CATEGORY_IDS) == 133
+
+from .tracking import TrackletBank  # noqa: E402,F401  batched counterpart of the reference's KFTracklet (utils/structures.py:447-529)

@@ -144,3 +144,28 @@ def nms_rot(boxes, scores, nms_thres=0.45, majority=None):
 def deg2rad_f32(deg):
     """degrees -> radians the way iou_rle does it (bbox_ops.py:88-89), float32."""
     return deg * math.pi / 180
+
+
+def iou_rot_f64(boxes1, boxes2):
+    """The EVALUATOR's rotated IoU (utils/evaluation/cepdof.py:210-243): boxes are float64 (lists of Python floats), the
+    corners are built with numpy in float64 (:181-207), and the two polygons go to pycocotools -- here, as everywhere,
+    to the exact clipping of oracle/rotiou.c.  Returns np.array[M, N] float64."""
+    import ctypes
+    import numpy as np
+    b1 = np.array(boxes1, dtype=np.float64).reshape(-1, 5)
+    b2 = np.array(boxes2, dtype=np.float64).reshape(-1, 5)
+    if b1.shape[0] == 0 or b2.shape[0] == 0:
+        return np.zeros((b1.shape[0], b2.shape[0]))
+
+    def vertices(box):
+        rad = box[:, 4] * np.pi / 180
+        center, w, h = box[:, 0:2], box[:, 2], box[:, 3]
+        verti = np.stack([(h / 2) * np.sin(rad), -(h / 2) * np.cos(rad)], axis=1)
+        hori = np.stack([(w / 2) * np.cos(rad), (w / 2) * np.sin(rad)], axis=1)
+        return np.ascontiguousarray(np.concatenate([center + verti - hori, center + verti + hori, center - verti + hori,
+                                                    center - verti - hori], axis=1))
+    a, b = vertices(b1), vertices(b2)
+    out = np.empty((a.shape[0], b.shape[0]), dtype=np.float64)
+    f64p = ctypes.POINTER(ctypes.c_double)
+    lib().oracle_quad_iou_pairwise(a.ctypes.data_as(f64p), a.shape[0], b.ctypes.data_as(f64p), b.shape[0], out.ctypes.data_as(f64p))
+    return out

@@ -113,9 +113,11 @@ def retina_anchors(img_hw, stride, anchor_wh):
     return torch.cat([a_cx.expand(n_a, n_h, n_w, 1), a_cy.expand(n_a, n_h, n_w, 1), a_wh.expand(n_a, n_h, n_w, 2)], dim=-1)
 
 
-def retina_targets_and_loss(t_xywh, cls_logits, gts, img_hw, stride, anchor_wh, pos_thres, neg_thres):
+def retina_targets_and_loss(t_xywh, cls_logits, gts, img_hw, stride, anchor_wh, pos_thres, neg_thres, angle_loss=None):
     """RetinaLayer's training branch for 'cxcywh' boxes and ONE class (the reference's squeeze(-1), :125, supports
     nothing else) -- retinanet.py:84-160.  t_xywh (B,nA,nH,nW,4), cls_logits (B,nA,nH,nW,1).
+    angle_loss: None for 'cxcywh'; 'Periodic_L1' | 'Periodic_L2' | 'Periodic_smoothL1' (models/losses.py:18-98) for
+    'cxcywhd' boxes: t_xywh then has 5 columns, GT boxes 5, and the angle part of :133-136, :151-154 is added.
     Returns (per-image list of dict(M_pos, M_neg, gt_idx, tgt_xywh, tgt_cls, cls_penalty_mask) or None, loss, pos)."""
     import math
     import torch.nn.functional as tnf
@@ -144,7 +146,19 @@ def retina_targets_and_loss(t_xywh, cls_logits, gts, img_hw, stride, anchor_wh, 
         penalty = need_higher | need_lower
         if int(m_pos.sum()) > 0:                                               # fvcore.nn.smooth_l1_loss, beta 0.1
             n = torch.abs(t_xywh[b][m_pos][:, 0:4] - tgt_xywh[m_pos, :])
-            loss_xywh = loss_xywh + torch.where(n < 0.1, 0.5 * n ** 2 / 0.1, n - 0.05).sum()
+            im_loss = torch.where(n < 0.1, 0.5 * n ** 2 / 0.1, n - 0.05).sum()
+            if angle_loss is not None:
+                tgt_angle = g[..., 4] / 180 * math.pi                           # :136
+                p_angle = torch.sigmoid(t_xywh[b][m_pos][:, 4]) * 2 * math.pi - math.pi     # :152
+                d = torch.remainder(p_angle - tgt_angle[m_pos] - math.pi / 2, math.pi) - math.pi / 2
+                if angle_loss == 'Periodic_L1':
+                    im_loss = im_loss + torch.abs(d).sum()
+                elif angle_loss == 'Periodic_L2':
+                    im_loss = im_loss + (d ** 2).sum()
+                else:
+                    a = torch.abs(d)
+                    im_loss = im_loss + torch.where(a < 0.4, 0.5 * a ** 2 / 0.4, a - 0.5 * 0.4).sum()
+            loss_xywh = loss_xywh + im_loss
         loss_cls = loss_cls + tnf.binary_cross_entropy_with_logits(cls_logits[b, penalty], tgt_cls[penalty], reduction='sum')
         per_image.append({'M_pos': m_pos, 'M_neg': m_neg, 'gt_idx': gt_idx, 'tgt_xywh': tgt_xywh, 'tgt_cls': tgt_cls,
                           'cls_penalty_mask': penalty})
@@ -202,3 +216,56 @@ def rapid_targets(p_xywha, conf_logits, gts, img_hw, stride, anchors_all, indice
             weighted[b, ta, tj, ti] = 2 - gt_bb[2] * gt_bb[3] / (img_hw[0] * img_hw[1])
     return {'PositiveMask': pos, 'IgnoredMask': ign, 'TargetXYWH': t_xywh, 'TargetAngle': t_angle, 'TargetConf': t_conf,
             'TargetCls': t_cls, 'weighted': weighted}
+
+
+def uv5_targets_and_loss(t_bbox, conf_logits, cls_logits, p_bbox, gts, stride, anchors_all, indices, n_cls, conf_target, negative_thres):
+    """Training branch of DetectLayer, models/detlayers/uv5.py:115-224, with the reference's per-image / per-GT loops.
+    t_bbox (B,nA,nH,nW,4) logits, p_bbox (B, nA*nH*nW, 4) decoded boxes, gts: list of (boxes (n,4), cats (n,)).
+    Returns dict(TargetConf, IgnoredMask | None, loss, valid_gt_num)."""
+    import torch.nn.functional as tnf
+    bce = tnf.binary_cross_entropy_with_logits
+    n_b, n_a, n_h, n_w = t_bbox.shape[:4]
+    anchors_all = torch.tensor(anchors_all, dtype=torch.float32)
+    ind = torch.tensor(indices).long()
+    anchors = anchors_all[ind, :]
+    anch_00wh_all = torch.zeros(len(anchors_all), 4)
+    anch_00wh_all[:, 2:4] = anchors_all
+    tgt_conf = torch.zeros(n_b, n_a, n_h, n_w, 1)
+    ignored = torch.zeros(n_b, n_a, n_h, n_w, dtype=torch.bool) if conf_target == 'zero-one' else None
+    loss_xy = loss_wh = loss_cls = 0
+    valid = 0
+    for b, (gt_bboxes, gt_cls_idx) in enumerate(gts):
+        if gt_bboxes.shape[0] == 0:                                            # :131-133
+            continue
+        for gt_bb, gt_c in zip(gt_bboxes, gt_cls_idx):
+            g00 = gt_bb.clone()
+            g00[0:2] = 0
+            a_all = torch.argmax(bboxes_iou(g00, anch_00wh_all), dim=1).squeeze().item()   # :141-143
+            if not (ind == a_all).any():
+                continue
+            ta = a_all % n_a
+            ti, tj = (gt_bb[0] / stride).long(), (gt_bb[1] / stride).long()
+            valid += 1
+            tb = t_bbox[b, ta, tj, ti]
+            loss_xy = loss_xy + bce(tb[:2], ((gt_bb[:2] / stride) % 1 + 0.5) / 2, reduction='sum')        # :161-163
+            loss_wh = loss_wh + bce(tb[2:4], torch.sqrt(gt_bb[2:4] / anchors[ta, :]) / 2, reduction='sum')  # :164-166
+            if n_cls > 0:
+                tc = cls_logits[b, ta, tj, ti]
+                tgt = torch.zeros_like(tc)
+                tgt[..., gt_c] = 1
+                loss_cls = loss_cls + bce(tc, tgt)                              # :178 (mean over the classes)
+            if conf_target == 'zero-one':
+                tgt_conf[b, ta, tj, ti] = 1
+        iou_with_gt, _ = bboxes_iou(p_bbox[b], gt_bboxes).max(dim=1)           # :186-190
+        if conf_target == 'IoU':
+            tgt_conf[b] = iou_with_gt.view(n_a, n_h, n_w, 1)
+        else:
+            ignored[b] = (iou_with_gt > negative_thres).view(n_a, n_h, n_w)
+    if conf_target == 'IoU':
+        loss_conf = bce(conf_logits, tgt_conf, reduction='sum')
+    else:
+        pos = tgt_conf.squeeze(-1).bool()
+        pen = pos | (~ignored)
+        loss_conf = bce(conf_logits[pen], tgt_conf[pen], reduction='sum')
+    loss = (loss_xy + loss_wh + loss_conf + loss_cls) / n_b
+    return {'TargetConf': tgt_conf, 'IgnoredMask': ignored, 'loss': loss, 'valid_gt_num': valid}

@@ -458,6 +458,83 @@ def gen_train():
     save('train', **out)
 
 
+def gen_train_uv5():
+    """Training branch of the Ultralytics / YOLOv5 layer (models/detlayers/uv5.py:92-224) of the unmodified reference:
+    both confidence targets ('zero-one' with the ignore mask, 'IoU'), three levels, three images (one without GT)."""
+    from models.detlayers.uv5 import DetectLayer
+    from utils.structures import ImageObjects
+    gen = torch.Generator().manual_seed(1011)
+    img_hw, n_cls, counts = (256, 320), 5, [9, 0, 4]
+    out, labels = {}, []
+    for b, n in enumerate(counts):
+        bx, ct = _random_gt(gen, n, img_hw, n_cls, 10.0, 330.0) if n else (torch.zeros(0, 4), torch.zeros(0, dtype=torch.int64))
+        if b == 0:
+            bx[-1, 2:4] = torch.tensor([300.0, 270.0])
+            bx[-2, 2:4] = torch.tensor([150.0, 180.0])
+            bx[1, 0:2] = bx[0, 0:2] + 1.0                          # two GTs in one cell: both contribute to the loss
+            bx[1, 2:4] = bx[0, 2:4] * 1.05
+        labels.append(ImageObjects(bx, ct, bb_format='cxcywh', img_hw=img_hw))
+        out[f'gt{b}_boxes'], out[f'gt{b}_cats'] = bx, ct
+    for mode in ('zero-one', 'IoU'):
+        cfg = {'model.detect.anchors': YOLO_ANCHORS, 'model.detect.anchor_indices': IDX3, 'model.fpn.out_strides': [8, 16, 32],
+               'general.num_class': n_cls, 'model.detect.sample_selection': 'best', 'model.detect.confidence_target': mode,
+               'model.detect.negative_threshold': 0.3, 'model.detect.loss_bbox': 'smooth_L1', 'general.pred_bbox_format': 'cxcywh'}
+        tag = 'zo' if mode == 'zero-one' else 'iou'
+        for li, s in enumerate(cfg['model.fpn.out_strides']):
+            store, raw = head_views(gen, len(counts), 3, img_hw[0] // s, img_hw[1] // s, 4, n_cls, conf_mu=-1.0)
+            layer = DetectLayer(li, cfg)
+            (_, loss), g = _grab_forward(layer, ['TargetConf', 'IgnoredMask'], raw, img_hw, labels)
+            out[f'{tag}{li}_in'] = store['nchw']
+            out[f'{tag}{li}_loss'] = loss
+            out[f'{tag}{li}_assigned'] = torch.tensor(int(layer._assigned_num))
+            out[f'{tag}{li}_loss_str'] = np.array(layer.loss_str)
+            out.update({f'{tag}{li}_{k}': v for k, v in g.items()})
+            print('uv5', mode, li, layer.loss_str)
+    save('train_uv5', **out)
+
+
+def gen_train_retina_rot():
+    """RetinaLayer.forward(raw, img_size, labels) with ROTATED boxes (retinanet.py:84-160, angle part :133-136, :151-154).
+    At HEAD the reference cannot construct this variant: __init__ does `from .losses import get_angle_loss` (:36) inside
+    the detlayers package (the module is models/losses.py) and reads 'model.angle.loss_name', a key no config has.  The
+    layer is therefore built with the 'cxcywh' config and the three attributes __init__ would have set are assigned by
+    hand (pred_bbox_format, n_bbparam, loss_angle = models.losses.get_angle_loss(name, 'sum')); forward() itself runs
+    unmodified."""
+    from models.detlayers.retinanet import RetinaLayer
+    from models.losses import get_angle_loss
+    from utils.structures import ImageObjects
+    gen = torch.Generator().manual_seed(1013)
+    img_hw, counts, strides = (256, 320), [7, 0, 5], [8, 16, 32, 64, 128]
+    rcfg = {'model.fpn.out_strides': strides, 'model.retina.anchor.base': 4, 'model.retina.anchor.scales': [1, 1.26, 1.5874],
+            'model.retina.anchor.ratios': [[1, 1], [1.4, 0.7], [0.7, 1.4]], 'model.retina.anchor.positive_threshold': 0.5,
+            'model.retina.anchor.negative_threshold': 0.4, 'general.num_class': 1, 'general.pred_bbox_format': 'cxcywh',
+            'general.bbox_param': 4}
+    out, labels = {}, []
+    for b, n in enumerate(counts):
+        bx = torch.zeros(n, 5)
+        if n:
+            bx[:, :4], _ = _random_gt(gen, n, img_hw, 1, 20.0, 200.0)
+            bx[:, 4] = torch.rand(n, generator=gen) * 180 - 90
+        labels.append(ImageObjects(bx, torch.zeros(n, dtype=torch.int64), bb_format='cxcywhd', img_hw=img_hw))
+        out[f'gt{b}_boxes'] = bx
+    for name in ('Periodic_L1', 'Periodic_smoothL1'):
+        for li in (1, 2, 3):
+            s = strides[li]
+            n_h, n_w = img_hw[0] // s, img_hw[1] // s
+            bb = torch.randn(len(counts), 9 * 5, n_h, n_w, generator=gen) * 0.3
+            cc = torch.randn(len(counts), 9 * 1, n_h, n_w, generator=gen) * 3.0
+            raw = {'bbox': bb.view(len(counts), 9, 5, n_h, n_w).permute(0, 1, 3, 4, 2),
+                   'class': cc.view(len(counts), 9, 1, n_h, n_w).permute(0, 1, 3, 4, 2)}
+            layer = RetinaLayer(li, rcfg)
+            layer.pred_bbox_format, layer.n_bbparam, layer.loss_angle = 'cxcywhd', 5, get_angle_loss(name, reduction='sum')
+            (_, loss), _ = _grab_forward(layer, ['M_pos'], raw, img_hw, labels)
+            out[f'{name}{li}_bbox_in'], out[f'{name}{li}_cls_in'] = bb, cc
+            out[f'{name}{li}_loss'] = loss
+            out[f'{name}{li}_loss_str'] = np.array(layer.loss_str)
+            print('retina rot', name, li, layer.loss_str)
+    save('train_retina_rot', **out)
+
+
 def gen_preprocess():
     """Detector._preprocess_pil + tvf.to_tensor + format_tensor_img (api/detection.py:158-162, :177-205) of the unmodified
     reference on small seeded uint8 images: every pre-processing name x every input format, up- and down-scaling."""
@@ -491,6 +568,45 @@ def gen_preprocess():
         cases.append(f'{name}|{size}|{div}|{code}')
     out['cases'] = np.array(cases)
     save('preprocess', **out)
+
+
+def gen_tracking():
+    """the tracklet state machine of utils/structures.py:447-529 (KFTracklet) on top of
+    utils/kalman_filter.py:77-142 (RotBBoxKalmanFilter), run UNMODIFIED for 12 tracklets over 8 frames: predict every
+    frame, update when the tracklet has a measurement, likelihood of 6 candidate boxes under every tracklet.
+    The reference writes `np.bool`, which NumPy >= 1.24 no longer has: the alias is restored for the run (the only
+    accommodation; no reference file is touched)."""
+    import_reference()
+    if not hasattr(np, 'bool'):
+        np.bool = bool
+    from utils.structures import KFTracklet
+    rng = np.random.RandomState(77)
+    n_t, n_f, n_c = 12, 8, 6
+    init = np.concatenate([rng.uniform(100, 900, (n_t, 2)), rng.uniform(20, 120, (n_t, 2)), rng.uniform(-200, 400, (n_t, 1))], axis=1)
+    init_score = rng.uniform(0.2, 1.0, n_t)
+    tracks = [KFTracklet(init[i].copy(), float(init_score[i]), object_id=i, img_hw=(1024, 1024)) for i in range(n_t)]
+    meas = np.zeros((n_f, n_t, 5)); meas_score = np.zeros((n_f, n_t)); has = np.zeros((n_f, n_t), dtype=bool)
+    cand = np.zeros((n_f, n_c, 5))
+    out = {k: [] for k in ('pred', 'upd', 'x', 'P', 'score', 'feasible', 'lik')}
+    truth = init.copy()
+    for f in range(n_f):
+        pred = np.stack([t.predict() for t in tracks])
+        truth[:, :2] += rng.randn(n_t, 2) * 3
+        truth[:, 4] += rng.randn(n_t) * 4
+        has[f] = rng.rand(n_t) < 0.7
+        meas[f] = truth + np.concatenate([rng.randn(n_t, 4) * 1.5, rng.randn(n_t, 1) * 3 + 180 * rng.randint(-1, 2, (n_t, 1))], axis=1)
+        meas_score[f] = rng.uniform(0.1, 1.0, n_t)
+        cand[f] = np.concatenate([truth[:n_c, :4] + rng.randn(n_c, 4) * 2, (truth[:n_c, 4:] % 180) + rng.randn(n_c, 1) * 2], axis=1)
+        lik = np.stack([t.likelihood(cand[f]) for t in tracks])
+        upd = np.zeros((n_t, 5))
+        for i, t in enumerate(tracks):
+            if has[f, i]:
+                upd[i] = t.update(meas[f, i].copy(), float(meas_score[f, i]))
+        out['pred'].append(pred); out['upd'].append(upd); out['lik'].append(lik)
+        out['x'].append(np.stack([t.kf.x for t in tracks])); out['P'].append(np.stack([t.kf.P for t in tracks]))
+        out['score'].append(np.array([t.score for t in tracks])); out['feasible'].append(np.array([t.is_feasible() for t in tracks]))
+    save('tracking', init=init, init_score=init_score, meas=meas, meas_score=meas_score, has=has, cand=cand,
+         **{k: np.stack(v) for k, v in out.items()})
 
 
 def _build_reference_model(cfg):
@@ -639,6 +755,9 @@ if __name__ == '__main__':
     gen_atss()
     gen_train()
     gen_preprocess()
+    gen_tracking()
+    gen_train_uv5()
+    gen_train_retina_rot()
     for cfg_name in ('yolov3_80', 'rapid', 'd1_fcs2'):
         gen_fullmodel(cfg_name)
     gen_fullmodel_atss()

@@ -193,7 +193,7 @@ def test_cepdof_evaluator_on_dropin(ref, monkeypatch):
     """utils/evaluation/cepdof.py of the reference, unedited, under dropin.install(): `CEPDOFeval(...).evaluate()` builds
     its IoU table through the patched computeIoU -- ONE mydet_iou_rot_segments launch for all (image, category) pairs
     -- and the table equals what the unpatched evaluator computes pair by pair (its raster replaced by the oracle's
-    exact clipping, refload's stand-in): same keys, same shapes, same empties, values within 1e-6."""
+    exact clipping, refload's stand-in): same keys, same shapes, same empties, values within 1e-9 (float64 throughout)."""
     import copy
     rng = np.random.RandomState(3)
     images = [{'id': i, 'height': 1024, 'width': 1024} for i in range(1, 13)]
@@ -242,4 +242,4 @@ def test_cepdof_evaluator_on_dropin(ref, monkeypatch):
         if want.size:
             worst = max(worst, float(np.abs(got - want).max()))
     assert ev.ious[(2, 1)].shape[0] == 100                     # maxDets cap after the stable score sort
-    assert worst < 1e-6, worst
+    assert worst < 1e-9, worst                                  # float64 boxes and corners on both sides
