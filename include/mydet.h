@@ -256,6 +256,16 @@ int mydet_iou_aabb_rowmax(const float* a, int64_t a_batch_stride, int64_t a_pitc
 int mydet_iou_rot_pairwise(const float* a, int64_t n, const float* b, int64_t k, double* out,
                            void* stream);
 
+/* iou_rle the way the reference computes it (utils/bbox_ops.py:84-96): both polygons rasterised on a canvas_h x
+ * canvas_w canvas with pycocotools' polygon rule (maskApi.c rleFrPoly: 5x sub-sampled integer boundary walk, a pixel column
+ * changes value where the walk crosses its sub-column 2|3 line) and IoU = common pixels / united pixels (rleIou).  The
+ * library is not available here; the algorithm is restated in oracle/raster.c, pinned to run-length encodings derived by
+ * hand, and this entry point reproduces that restatement bit for bit.  a (N,5), b (K,5) degrees -> out (N,K) f64.
+ * Workspace: mydet_iou_raster_workspace_bytes(n, k, canvas_w) = one (lo, hi) run per box and pixel column. */
+size_t mydet_iou_raster_workspace_bytes(int64_t n, int64_t k, int canvas_w);
+int mydet_iou_raster_pairwise(const float* a, int64_t n, const float* b, int64_t k, int canvas_h, int canvas_w,
+                              double* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* The matching IoU of a whole CEPDOF evaluation in one launch: CEPDOFeval.computeIoU (utils/evaluation/cepdof.py:67-99)
  * is called once per (image, category) and each call builds a small dt x gt matrix with the evaluator's own iou_rle
  * (:210-243).  segments: DEVICE array of n_segments x 5 int64 {a0, na, b0, nb, out0}: rows a[a0..a0+na) against columns

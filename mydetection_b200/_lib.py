@@ -63,6 +63,8 @@ SIGNATURES = {
     'mydet_iou_aabb_pairwise': (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp]),
     'mydet_iou_aabb_rowmax': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     'mydet_iou_rot_pairwise': (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
+    'mydet_iou_raster_workspace_bytes': (c_sz, [c_i64, c_i64, c_int]),
+    'mydet_iou_raster_pairwise': (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),
     'mydet_iou_rot_segments': (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_vp, c_vp]),
     'mydet_cxcywh_to_x1y1x2y2': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     'mydet_xywha2vertex': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),

@@ -7,6 +7,8 @@ Without a CUDA device these functions raise -- there is no CPU implementation he
 """
 from math import pi
 
+import os
+
 import torch
 
 from . import _lib, ops
@@ -37,8 +39,11 @@ def bboxes_iou(bboxes_a, bboxes_b, xyxy=False):
 def iou_rle(boxes1, boxes2, bb_format='cxcywhd', **kwargs):
     """IoU between rotated boxes (N,5) x (M,5) -> (N,M) float64; utils/bbox_ops.py:52-100.
 
-    The reference rasterises the polygons with pycocotools on an `img_hw` canvas; this computes the
-    exact intersection area of the same polygons, so `img_hw` / `img_size` are accepted and unused.
+    The reference rasterises the polygons with pycocotools on an `img_hw` canvas (default 2048 x 2048, :84-85).
+    Default here: the EXACT intersection area of the same polygons (`img_hw` accepted and unused).  `raster=True`
+    (or MYDET_IOU_RASTER=1 in the environment) selects the raster route instead -- pycocotools' polygon rule restated
+    (oracle/raster.c, pinned to hand-derived run-length encodings; the library itself is not available to check
+    against) and evaluated on the device, on the `img_hw` canvas exactly as the reference reads that keyword.
     """
     assert type(boxes1) == type(boxes2)
     assert bb_format == 'cxcywhd'
@@ -52,7 +57,10 @@ def iou_rle(boxes1, boxes2, bb_format='cxcywhd', **kwargs):
     if boxes2.dim() == 1:
         boxes2 = boxes2.unsqueeze(0)
     assert boxes1.shape[1] == boxes2.shape[1] == 5
-    ious = ops.iou_rot(_stage(boxes1), _stage(boxes2))
+    if kwargs.get('raster', os.environ.get('MYDET_IOU_RASTER') == '1'):
+        ious = ops.iou_raster(_stage(boxes1), _stage(boxes2), kwargs.get('img_hw', 2048))     # :84-85
+    else:
+        ious = ops.iou_rot(_stage(boxes1), _stage(boxes2))
     if kwargs.get('return_numpy', False):
         return ious.cpu().numpy()
     return ious.to(device=device)

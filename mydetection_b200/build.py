@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libmydet.so')
-SOURCES = ['api.cu', 'decode.cu', 'postprocess_small.cu', 'nms_large.cu', 'iou.cu', 'atss.cu', 'preprocess.cu', 'exchange.cu', 'kalman.cu']
+SOURCES = ['api.cu', 'decode.cu', 'postprocess_small.cu', 'nms_large.cu', 'iou.cu', 'atss.cu', 'preprocess.cu', 'exchange.cu', 'kalman.cu', 'raster.cu']
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',   # B200 only: no other arch, no PTX fallback
     '-O3', '-std=c++17', '-lineinfo',

@@ -14,6 +14,7 @@
 #include "internal.cuh"
 #include "rotgeom.cuh"
 #include "sweep_fixpoint.cuh"
+#include <stdlib.h>
 
 namespace mydet {
 
@@ -60,7 +61,18 @@ struct LargeWs {          // carved out of the caller's workspace
     int* pair_count;            // B        entries appended (may exceed pair_cap: the image then takes the tile kernel)
     int pair_cap;
     int n16, n32;
+    // entry list of the fixed-point sweep, appended to by the mask kernels themselves: the thread whose atomicOr turns a
+    // 32-bit mask half-word non-zero records (row, half-word index) -- exactly one entry per non-empty half-word, so
+    // the sweep no longer walks the adjacency map of every row to find them (75 of its 100 us at 10 000 boxes)
+    int* fx_count;              // B
 };
+// record the first bit of a mask half-word in the image's entry list (entries beyond the capacity are dropped: the
+// count still says so, and the sweep then falls back to the adjacency walk)
+__device__ __forceinline__ void fx_note(const LargeWs& w, int b, int row, int half, unsigned old) {
+    if (old != 0u || w.fx_cap == 0) return;
+    const int at = atomicAdd(&w.fx_count[b], 1);
+    if (at < w.fx_cap) { fx::Entry& e = w.fx_list[(long long)b * w.fx_cap + at]; e.row = row; e.word = half; }
+}
 
 static size_t carve(LargeWs& w, void* base, int batch, int n, bool rot) {
     size_t off = 0;
@@ -96,6 +108,7 @@ static size_t carve(LargeWs& w, void* base, int batch, int n, bool rot) {
     const size_t o_cull = take(bp ? bn * 16 : 0), o_h4 = take(bp ? bn * 16 : 0), o_ax = take(bp ? bn * 16 : 0);
     const size_t o_h16 = take(bp ? (size_t)batch * w.n16 * 16 : 0), o_h32 = take(bp ? (size_t)batch * w.n32 * 16 : 0);
     const size_t o_pairs = take((size_t)batch * w.pair_cap * 4), o_pcnt = take(bp ? (size_t)batch * 4 : 0);
+    const size_t o_fxc = take(sp ? (size_t)batch * 4 : 0);
     if (base) {
         char* p = static_cast<char*>(base);
         w.keys = (unsigned long long*)(p + o_keys); w.order = (int*)(p + o_order); w.m = (int*)(p + o_m);
@@ -115,6 +128,7 @@ static size_t carve(LargeWs& w, void* base, int batch, int n, bool rot) {
         w.cull4 = (float4*)(p + o_cull); w.hull4 = (float4*)(p + o_h4); w.axes4 = (float4*)(p + o_ax);
         w.hull16 = (float4*)(p + o_h16); w.hull32 = (float4*)(p + o_h32);
         w.pairs = (unsigned*)(p + o_pairs); w.pair_count = (int*)(p + o_pcnt);
+        w.fx_count = (int*)(p + o_fxc);
     }
     return off;
 }
@@ -331,6 +345,121 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_reg16k_kernel(const unsi
     else sort_reg16k_body<false>(kb, ob, invb, n, skeys, spay);
 }
 
+// LSD radix sort, one CTA per image (n <= 16 384), for keys whose low 20 bits ARE the element's slot and whose
+// initial order is slot order ("payload in key": Morton keys always, score keys when no src_idx remaps the tie
+// index).  A stable sort then only has to look at the bits above the tie field: 4 passes of 8 bits over the 32-bit score
+// (or Morton) field, plus 2 passes of 6 bits over the class field when any key has a class -- 4 to 6 passes with three
+// barriers each, where the bitonic network above needs 105 compare-exchange stages (153 us at 16 384 keys).
+// Keys live in registers in WARP-STRIPED order (round r of warp w, lane l: element 512 w + 32 r + l -- 1024 E per
+// round for E < 16), so that within a warp, round after round, lane after lane is index order: the rank of a key among
+// the equal digits before it = the warp's running count of that digit (one shared-memory word per warp and digit,
+// updated by the leader of each __match_any_sync group) + its position inside the group; an exclusive scan of the
+// 256 x 32 counters in (digit, warp) order turns that into the global rank, and the keys are scattered through shared
+// memory.  Invalid keys (~0) have the largest digit in every pass and stay at the end.
+constexpr int kRadixPitch = 257;                 // counters [warp][digit], padded: conflict-free for both access patterns
+template <int E>
+__global__ void __launch_bounds__(kSortThreads, 1) sort_radix_kernel(const unsigned long long* keys, int* order, int* inv,
+                                                                     const unsigned long long* keys2, int* order2, int n, int B) {
+    extern __shared__ unsigned long long skeys[];                      // 1024 E keys, then the counters
+    unsigned* cnt = reinterpret_cast<unsigned*>(skeys + 1024 * E);     // 32 x 257
+    __shared__ unsigned s_warp_tot[32];
+    __shared__ unsigned s_cls_or;
+    const bool second = (int)blockIdx.x >= B;
+    const int b = second ? blockIdx.x - B : blockIdx.x;
+    const unsigned long long* kb = (second ? keys2 : keys) + (long long)b * n;
+    int* ob = (second ? order2 : order) + (long long)b * n;
+    int* invb = (inv && !second) ? inv + (long long)b * n : nullptr;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const int base = warp * (32 * E) + lane;                           // element of round r: base + 32 r
+    unsigned long long k[E];
+    unsigned cls_or = 0;
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const int g = base + 32 * r;
+        k[r] = (g < n) ? kb[g] : ~0ull;
+        if (k[r] != ~0ull) cls_or |= (unsigned)(k[r] >> 52);
+    }
+    if (tid == 0) s_cls_or = 0;
+    __syncthreads();
+    cls_or = __reduce_or_sync(0xffffffffu, cls_or);
+    if (lane == 0 && cls_or) atomicOr(&s_cls_or, cls_or);
+    __syncthreads();
+    const int n_pass = s_cls_or ? 6 : 4;
+#pragma unroll 1
+    for (int pass = 0; pass < n_pass; ++pass) {
+        const int shift = pass < 4 ? 20 + 8 * pass : 52 + 6 * (pass - 4);
+        const unsigned dmask = pass < 4 ? 255u : 63u;
+        for (int i = tid; i < 32 * kRadixPitch; i += kSortThreads) cnt[i] = 0u;
+        __syncthreads();
+        unsigned pre2[E / 2];                                          // 16-bit ranks, two per register (64-register budget)
+        unsigned* mycnt = cnt + warp * kRadixPitch;
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+            const unsigned d = (unsigned)(k[r] >> shift) & dmask;
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            const int leader = __ffs(peers) - 1;
+            unsigned old = 0;
+            if (lane == leader) { old = mycnt[d]; mycnt[d] = old + __popc(peers); }
+            old = __shfl_sync(0xffffffffu, old, leader);
+            const unsigned pr = old + __popc(peers & lt);
+            if (r & 1) pre2[r >> 1] |= pr << 16; else pre2[r >> 1] = pr;
+            __syncwarp();
+        }
+        __syncthreads();
+        // exclusive scan over the counters in (digit major, warp minor) order: thread t owns digit t/4, warps 8 (t%4) .. +8
+        {
+            const int d = tid >> 2, w0 = (tid & 3) * 8;
+            unsigned v[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { v[j] = cnt[(w0 + j) * kRadixPitch + d]; sum += v[j]; }
+            unsigned incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            if (lane == 31) s_warp_tot[warp] = incl;
+            __syncthreads();
+            if (warp == 0) {
+                const unsigned t0 = s_warp_tot[lane];
+                unsigned wi = t0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+                s_warp_tot[lane] = wi - t0;
+            }
+            __syncthreads();
+            unsigned run = s_warp_tot[warp] + incl - sum;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { cnt[(w0 + j) * kRadixPitch + d] = run; run += v[j]; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+            const unsigned d = (unsigned)(k[r] >> shift) & dmask;
+            skeys[mycnt[d] + ((pre2[r >> 1] >> (16 * (r & 1))) & 0xffffu)] = k[r];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < E; ++r) k[r] = skeys[base + 32 * r];
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const int g = base + 32 * r;
+        if (g < n && k[r] != ~0ull) {
+            const int slot = (int)(k[r] & 0xfffffull);
+            ob[g] = slot;
+            if (invb) invb[slot] = g;
+        }
+    }
+}
+template <int E>
+static int launch_sort_radix(const unsigned long long* keys, int* order, int* inv, const unsigned long long* keys2, int* order2,
+                             int n, int B, cudaStream_t st) {
+    const size_t smem = (size_t)1024 * E * 8 + (size_t)32 * kRadixPitch * 4;
+    MYDET_CUDA(cudaFuncSetAttribute(sort_radix_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sort_radix_kernel<E><<<keys2 ? 2 * B : B, kSortThreads, smem, st>>>(keys, order, inv, keys2, order2, n, B);
+    return launch_status("sort_radix_kernel");
+}
+
 // Sort for larger images (16 384 < n <= 2^20): the same bitonic network split over CTAs.  16 384-key chunks
 // are sorted / merged in shared memory (strides < 16 384), the few stages with longer strides are
 // compare-exchanges in global memory.  Replaces the O(n^2) all-pairs rank kernel (2.3e9 compares at 48 k).
@@ -410,10 +539,20 @@ static int sort_big(const unsigned long long* keys, int* order, int n, int B, La
     return launch_status("sort_big kernels");
 }
 
+static bool sort_force_bitonic() {            // developer A/B switch (tests compare both sorts)
+    const char* e = getenv("MYDET_SORT_BITONIC");
+    return e && e[0] == '1';
+}
 // order[b][rank] = index of the rank-th smallest key of image b (invalid keys ~0 are left out); inv (optional)
 // = its inverse.  keys2 / order2 (optional): a second key array of the same shape, sorted alongside.
 static int sort_keys(const unsigned long long* keys, int* order, int* inv, const unsigned long long* keys2, int* order2,
                      int n, int B, LargeWs& w, cudaStream_t st, bool pik1 = false) {
+    if (n <= kSortMaxN && n > 1024 && pik1 && !sort_force_bitonic()) {
+        if (n <= 2048) return launch_sort_radix<2>(keys, order, inv, keys2, order2, n, B, st);
+        if (n <= 4096) return launch_sort_radix<4>(keys, order, inv, keys2, order2, n, B, st);
+        if (n <= 8192) return launch_sort_radix<8>(keys, order, inv, keys2, order2, n, B, st);
+        return launch_sort_radix<16>(keys, order, inv, keys2, order2, n, B, st);
+    }
     if (n <= kSortMaxN) {
         int npad = 64;
         while (npad < n) npad <<= 1;
@@ -755,7 +894,7 @@ __global__ void __launch_bounds__(kTile) mask_aabb_spatial_kernel(LargeWs w, con
                                           : iou_corners(c4.x, c4.y, c4.z, c4.w, carea[buf][j], a.x, a.y, a.z, a.w, aarea);
                 if (ovr > thr_f) {
                     const int row = a_first ? r : pb, col = a_first ? pb : r;
-                    atomicOr(&mask32[((base + row) * w.words + (col >> 6)) * 2 + ((col >> 5) & 1)], 1u << (col & 31));
+                    fx_note(w, b, row, col >> 5, atomicOr(&mask32[((base + row) * w.words + (col >> 6)) * 2 + ((col >> 5) & 1)], 1u << (col & 31)));
                     const int trow = row >> 6, tcol = col >> 6;
                     atomicOr(&w.tile_adj[((long long)b * w.words + trow) * w.aw + (tcol >> 6)], 1ull << (tcol & 63));
                 }
@@ -801,7 +940,7 @@ __device__ __forceinline__ void mask_rot_tile(const LargeWs& w, int mb, int n, i
             if (rot_overlaps(A, B, thr_d, ge_mode)) {
                 const bool a_first = w.rank_of_spos[base + pa] < w.rank_of_spos[base + pb];
                 const int row = a_first ? pa : pb, col = a_first ? pb : pa;           // the higher-scored box suppresses
-                atomicOr(&mask32[((base + row) * w.words + (col >> 6)) * 2 + ((col >> 5) & 1)], 1u << (col & 31));
+                fx_note(w, b, row, col >> 5, atomicOr(&mask32[((base + row) * w.words + (col >> 6)) * 2 + ((col >> 5) & 1)], 1u << (col & 31)));
                 const int trow = row >> 6, tcol = col >> 6;
                 atomicOr(&w.tile_adj[((long long)b * w.words + trow) * w.aw + (tcol >> 6)], 1ull << (tcol & 63));
             }
@@ -1087,7 +1226,7 @@ __global__ void __launch_bounds__(kNarrowThreads) rot_narrow_kernel(LargeWs w, c
             if (rot_overlaps(A, B, thr_d, ge_mode)) {
                 const bool a_first = w.rank_of_spos[base + pa] < w.rank_of_spos[base + pb];
                 const int row = a_first ? pa : pb, col = a_first ? pb : pa;           // the higher-scored box suppresses
-                atomicOr(&mask32[((base + row) * w.words + (col >> 6)) * 2 + ((col >> 5) & 1)], 1u << (col & 31));
+                fx_note(w, b, row, col >> 5, atomicOr(&mask32[((base + row) * w.words + (col >> 6)) * 2 + ((col >> 5) & 1)], 1u << (col & 31)));
                 const int trow = row >> 6, tcol = col >> 6;
                 atomicOr(&w.tile_adj[((long long)b * w.words + trow) * w.aw + (tcol >> 6)], 1ull << (tcol & 63));
             }
@@ -1174,16 +1313,14 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(LargeWs w, const i
         unsigned long long* keep = diag + kTile;             // w.words more (the launch sizes the buffer for it)
         const fx::View V{mask, w.tile_adj + (long long)b * w.words * w.aw, w.spos_of_rank + base_n, mb, w.words, w.aw};
         fx::Entry* list = w.fx_list + (long long)b * w.fx_cap;
-        __shared__ int s_entries;
-        if (tid == 0) s_entries = 0;
         fx::phase_init(V, keep, removed, keptw, w.words, tid, kSweepThreads);
-        __syncthreads();
-        fx::phase_build_list(V, list, w.fx_cap, &s_entries, tid, kSweepThreads);
-        __syncthreads();
-        const int n_entries = s_entries;
+        // the mask kernels recorded every non-empty 32-bit half-word of the image (fx_note); fetch their bits once
+        const int n_entries = w.fx_count[b];
         const bool use_list = n_entries <= w.fx_cap;            // else: walk the adjacency map every round
+        if (use_list) fx::phase_fill_list32(reinterpret_cast<const unsigned*>(mask), w.words, list, n_entries, tid, kSweepThreads);
+        __syncthreads();
         for (;;) {
-            if (use_list) fx::phase_scatter_list(list, n_entries, keep, removed, tid, kSweepThreads);
+            if (use_list) fx::phase_scatter_list32(list, n_entries, keep, removed, tid, kSweepThreads);
             else fx::phase_scatter(V, keep, removed, tid, kSweepThreads);
             __syncthreads();
             if (!__syncthreads_or(fx::phase_update(V, keep, removed, w.words, tid, kSweepThreads))) break;
@@ -1386,29 +1523,28 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(LargeWs w, const i
         s_prefix_total = acc;
     }
     __syncthreads();
-    int pos = chunk_sum[tid];
+    // one thread per RANK (not per 64-rank word: that was <= 64 dependent load-store pairs in a row per thread, ~30 us
+    // of latency at 10 000 boxes): output position = kept ranks before this one
     const int* order = w.order + (long long)b * n;
-    for (int k = 0; k < per; ++k) {
-        const int wd = tid * per + k;
-        if (wd >= words) break;
-        unsigned long long kw = keptw[wd];
-        while (kw) {
-            const int j = __ffsll((long long)kw) - 1;
-            kw &= kw - 1;
-            const int i = order[wd * kTile + j];
-            if (E.keep64) {
-                E.keep64[(long long)b * E.pitch + pos] = i;
-                w.rowpos[(long long)b * n + wd * kTile + j] = pos;
-            } else if (pos < E.out_cap) {
-                const long long orow = (long long)b * E.out_cap + pos;
-                const long long irow = (long long)b * E.pitch + i;
-                for (int p = 0; p < E.n_param; ++p) E.out_box[orow * E.n_param + p] = E.boxes[irow * E.n_param + p];
-                E.out_score[orow] = E.scores[irow];
-                E.out_cls[orow] = E.cls ? (E.cls_is_i64 ? reinterpret_cast<const long long*>(E.cls)[irow]
-                                                        : (long long)reinterpret_cast<const int*>(E.cls)[irow]) : 0ll;
-                E.out_idx[orow] = E.src_idx ? E.src_idx[irow] : i;
-            }
-            ++pos;
+    for (int r = tid; r < mb; r += kSweepThreads) {
+        const int wd = r >> 6, j = r & 63;
+        const unsigned long long kw = keptw[wd];
+        if (!((kw >> j) & 1ull)) continue;
+        const int c = wd / per;
+        int pos = chunk_sum[c] + __popcll(kw & ((1ull << j) - 1ull));
+        for (int k = c * per; k < wd; ++k) pos += __popcll(keptw[k]);
+        const int i = order[r];
+        if (E.keep64) {
+            E.keep64[(long long)b * E.pitch + pos] = i;
+            w.rowpos[(long long)b * n + r] = pos;
+        } else if (pos < E.out_cap) {
+            const long long orow = (long long)b * E.out_cap + pos;
+            const long long irow = (long long)b * E.pitch + i;
+            for (int p = 0; p < E.n_param; ++p) E.out_box[orow * E.n_param + p] = E.boxes[irow * E.n_param + p];
+            E.out_score[orow] = E.scores[irow];
+            E.out_cls[orow] = E.cls ? (E.cls_is_i64 ? reinterpret_cast<const long long*>(E.cls)[irow]
+                                                    : (long long)reinterpret_cast<const int*>(E.cls)[irow]) : 0ll;
+            E.out_idx[orow] = E.src_idx ? E.src_idx[irow] : i;
         }
     }
     if (tid == 0) {
@@ -1491,6 +1627,7 @@ int run_large(const LargeArgs& A, void* workspace, size_t workspace_bytes, cudaS
     if (spatial) {
         MYDET_CUDA(cudaMemsetAsync(w.mask, 0, (size_t)B * n * w.words * sizeof(unsigned long long), st));
         MYDET_CUDA(cudaMemsetAsync(w.tile_adj, 0, (size_t)B * w.words * w.aw * 8, st));
+        MYDET_CUDA(cudaMemsetAsync(w.fx_count, 0, sizeof(int) * (size_t)B, st));
         const dim3 mgrid(tiles, (tiles + kColChunk - 1) / kColChunk, B);
         if (A.rot) {
             spatial_gather_kernel<true><<<dim3(tiles, B), kTile, 0, st>>>(G, w.keys, w.order, w.m, w);

@@ -142,6 +142,22 @@ FX_HD void phase_scatter_list(const Entry* list, int n_entries, const unsigned l
     }
 }
 
+// Entries recorded by the mask kernels: `word` is a 32-bit HALF-word index of the row (column >> 5).  Fetch the bits
+// once (the mask is final when the sweep starts).   (barrier after)
+FX_HD void phase_fill_list32(const unsigned* mask32, int words_total, Entry* list, int n_entries, int tid, int nt) {
+    for (int e = tid; e < n_entries; e += nt)
+        list[e].bits = mask32[(long long)list[e].row * (2 * words_total) + list[e].word];
+}
+// One round over that list.   (barrier before and after)
+FX_HD void phase_scatter_list32(const Entry* list, int n_entries, const unsigned long long* keep, unsigned long long* removed,
+                                int tid, int nt) {
+    for (int e = tid; e < n_entries; e += nt) {
+        const Entry x = list[e];
+        if ((keep[x.row >> 6] >> (x.row & 63)) & 1ull)
+            or_bits(removed, x.word >> 1, (x.word & 1) ? (x.bits << 32) : x.bits);
+    }
+}
+
 // keep = valid & ~removed; removed is cleared for the next round.  Returns whether this thread changed a word.
 // (barrier before; the caller ORs the return values over the CTA, which is also the barrier after)
 FX_HD int phase_update(const View& V, unsigned long long* keep, unsigned long long* removed, int n_words, int tid, int nt) {

@@ -326,6 +326,21 @@ def iou_rot(a, b):
     return out
 
 
+def iou_raster(a, b, canvas_hw=(2048, 2048)):
+    """Rasterised rotated IoU (mydet_iou_raster_pairwise): the reference's pycocotools route, restated.  a (N,5), b (K,5)
+    degrees -> (N,K) float64 on a canvas_hw canvas."""
+    a = _dev(a, torch.float32, 'boxes1').contiguous()
+    b = _dev(b, torch.float32, 'boxes2').contiguous()
+    h, w = (int(canvas_hw), int(canvas_hw)) if isinstance(canvas_hw, int) else (int(canvas_hw[0]), int(canvas_hw[1]))
+    out = torch.zeros(a.shape[0], b.shape[0], dtype=torch.float64, device=a.device)
+    L = _lib.lib()
+    ws = _workspace(L.mydet_iou_raster_workspace_bytes(a.shape[0], b.shape[0], w), a.device)
+    with torch.cuda.device(a.device):
+        rc = L.mydet_iou_raster_pairwise(_ptr(a), a.shape[0], _ptr(b), b.shape[0], h, w, _ptr(out), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, 'mydet_iou_raster_pairwise')
+    return out
+
+
 def iou_rot_segments(a, b, segments):
     """Many small rotated-IoU matrices in one launch (mydet_iou_rot_segments).  a (Na,5), b (Nb,5) degrees;
     segments: int64 (S,4) rows {a0, na, b0, nb} (host or device).  Returns (flat f64 tensor, out0 list): matrix s is

@@ -26,6 +26,8 @@ def lib():
         L.oracle_argsort_desc_stable.argtypes = [f32p, i64, i64p]
         L.oracle_rot_iou_pairwise.restype = None
         L.oracle_rot_iou_pairwise.argtypes = [f32p, i64, f32p, i64, f64p]
+        L.oracle_raster_rle.restype = ctypes.c_int64
+        L.oracle_raster_rle.argtypes = [f64p, i64, i64, i64, ctypes.POINTER(ctypes.c_uint32), i64]
         L.oracle_raster_iou_pairwise.restype = None
         L.oracle_raster_iou_pairwise.argtypes = [f64p, i64, f64p, i64, i64, i64, f64p]
         L.oracle_quad_iou_pairwise.restype = None
@@ -169,3 +171,15 @@ def iou_rot_f64(boxes1, boxes2):
     f64p = ctypes.POINTER(ctypes.c_double)
     lib().oracle_quad_iou_pairwise(a.ctypes.data_as(f64p), a.shape[0], b.ctypes.data_as(f64p), b.shape[0], out.ctypes.data_as(f64p))
     return out
+
+
+def raster_rle(xy, h, w):
+    """Run lengths (alternating 0-runs / 1-runs, column major) of the polygon xy = [x0, y0, x1, y1, ...] on an h x w
+    canvas, by oracle/raster.c (the restated rleFrPoly)."""
+    import ctypes
+    import numpy as np
+    pts = np.ascontiguousarray(np.asarray(xy, dtype=np.float64))
+    out = np.zeros(4096, dtype=np.uint32)
+    m = lib().oracle_raster_rle(pts.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), pts.size // 2, int(h), int(w),
+                                out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), out.size)
+    return out[:m].tolist()

@@ -99,6 +99,15 @@ static double rle_iou(const uint32_t* A, long ka, const uint32_t* B, long kb) {
     return inter / uni;
 }
 
+/* run lengths of one polygon (k points), for the known-answer tests; returns the number of runs (written up to cap) */
+int64_t oracle_raster_rle(const double* xy, int64_t k, int64_t h, int64_t w, uint32_t* out, int64_t cap) {
+    uint32_t* r;
+    const long m = rle_from_poly(xy, (long)k, (long)h, (long)w, &r);
+    for (long j = 0; j < m && j < cap; j++) out[j] = r[j];
+    free(r);
+    return m;
+}
+
 /* corners1 (n, 8), corners2 (m, 8): x,y of the 4 vertices; out (n, m) */
 void oracle_raster_iou_pairwise(const double* c1, int64_t n, const double* c2, int64_t m, int64_t h, int64_t w, double* out) {
     uint32_t** r2 = (uint32_t**)malloc(sizeof(uint32_t*) * (m > 0 ? m : 1));

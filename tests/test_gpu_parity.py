@@ -602,3 +602,73 @@ def test_atss_golden(golden):
                                 thr=out['thr'])
         for k in ('PositiveMask', 'IgnoredMask', 'TargetConf', 'TargetCls', 'TargetLTRB'):
             assert torch.equal(again[k], out[k]), (li, k)
+
+
+@pytest.mark.parametrize('n', [1025, 3000, 8192, 10000, 16384])
+def test_radix_sort_equals_bitonic_sort(n, monkeypatch):
+    """The one-CTA LSD radix sort of the large-N path (score order and Morton order, n in (1024, 16384]) against the
+    bitonic network it replaces (MYDET_SORT_BITONIC=1) and against the oracle: identical kept indices, in identical order,
+    for rotated NMS (single class: 4 passes) and class-aware axis-aligned NMS (6 passes), with heavy score ties."""
+    from mydetection_b200 import ops
+    from oracle import iou as oi, postprocess as opp
+    d = dev()
+    gen = torch.Generator().manual_seed(n)
+    rb = torch.cat([torch.rand(2, n, 2, generator=gen) * 700, torch.rand(2, n, 2, generator=gen) * 50 + 10,
+                    torch.rand(2, n, 1, generator=gen) * 180 - 90], dim=2)
+    rs = (torch.rand(2, n, generator=gen) * 200).round() / 200                       # ~50 boxes per score value: ties by index
+    counts = torch.tensor([n, n - 37], dtype=torch.int32)
+    keep, cnt = ops.nms_rot(rb.to(d), rs.to(d), 0.45, counts=counts.to(d))
+    monkeypatch.setenv('MYDET_SORT_BITONIC', '1')
+    keep_b, cnt_b = ops.nms_rot(rb.to(d), rs.to(d), 0.45, counts=counts.to(d))
+    monkeypatch.delenv('MYDET_SORT_BITONIC')
+    assert torch.equal(cnt, cnt_b)
+    for b in range(2):
+        c = int(cnt[b])
+        assert torch.equal(keep[b, :c], keep_b[b, :c])
+    want = oi.nms_rot(rb[1, :n - 37], rs[1, :n - 37], 0.45)
+    assert int(cnt[1]) == want.numel() and torch.equal(keep[1, :int(cnt[1])].cpu(), want)
+    # class-aware axis-aligned NMS without a cap: the large path with class bits in the keys
+    cls = torch.randint(0, 7, (2, n), generator=gen)
+    out = ops.postprocess(rb[..., :4].contiguous().to(d), rs.to(d), cls.to(d), -1.0, 0.5, topk=None)
+    monkeypatch.setenv('MYDET_SORT_BITONIC', '1')
+    out_b = ops.postprocess(rb[..., :4].contiguous().to(d), rs.to(d), cls.to(d), -1.0, 0.5, topk=None)
+    monkeypatch.delenv('MYDET_SORT_BITONIC')
+    assert torch.equal(out['count'], out_b['count'])
+    c0 = int(out['count'][0])
+    assert torch.equal(out['idx'][0, :c0], out_b['idx'][0, :c0])
+    want = opp.post_process(rb[0, :, :4], cls[0], rs[0], -1.0, 0.5, 'cxcywh', None)
+    assert c0 == want.numel() and torch.equal(out['idx'][0, :c0].cpu().long(), want)
+
+
+@pytest.mark.parametrize('canvas,lo,hi,n', [(2048, 6, 250, 400), (2048, 0.3, 12, 400), (96, 4, 60, 300), ((70, 130), 2, 90, 300)])
+def test_raster_iou_bit_exact_vs_oracle(canvas, lo, hi, n):
+    """mydet_iou_raster_pairwise (closed-form column runs) against oracle/raster.c (the restated pycocotools boundary
+    walk + RLE merge): bit-exact, on the reference's 2048 canvas, for sub-pixel boxes, and on small canvases that clip
+    the boxes on every side; also through the mirror's iou_rle(..., raster=True, img_hw=...)."""
+    from mydetection_b200 import ops, bbox_ops
+    from oracle import iou as oi
+    h, w = (canvas, canvas) if isinstance(canvas, int) else canvas
+    gen = torch.Generator().manual_seed(int(h + 10 * hi))
+    bx = torch.cat([torch.rand(n, 1, generator=gen) * (w + 20) - 10, torch.rand(n, 1, generator=gen) * (h + 20) - 10,
+                    torch.rand(n, 2, generator=gen) * (hi - lo) + lo, torch.rand(n, 1, generator=gen) * 360 - 180], dim=1)
+    if canvas == 2048:                                                   # clustered: plenty of overlapping pairs
+        bx[:, :2] = torch.rand(n, 2, generator=gen) * (400 if hi > 100 else 40) + 800
+    a, b = bx[:n // 2], bx[n // 2:]
+    # the oracle helper takes a square canvas; call the C function for the rectangular one
+    import ctypes
+    rad = bx.clone()
+    rad[:, 4] = oi.deg2rad_f32(rad[:, 4])
+    cs = np.ascontiguousarray(oi.xywha2vertex(rad).reshape(-1, 8).double().numpy())
+    want = np.empty((n // 2, n - n // 2))
+    f64p = ctypes.POINTER(ctypes.c_double)
+    oi.lib().oracle_raster_iou_pairwise(cs[:n // 2].ctypes.data_as(f64p), n // 2, cs[n // 2:].ctypes.data_as(f64p), n - n // 2,
+                                        h, w, want.ctypes.data_as(f64p))
+    got = ops.iou_raster(a.to(dev()), b.to(dev()), (h, w)).cpu().numpy()
+    assert (want > 0).sum() > 20
+    assert np.array_equal(got, want), (np.abs(got - want).max(), int((got != want).sum()))
+    via = bbox_ops.iou_rle(a, b, raster=True, img_hw=(h, w))
+    assert not via.is_cuda and np.array_equal(via.numpy(), want)
+    exact = bbox_ops.iou_rle(a, b).numpy()
+    big = want > 0.3
+    if canvas == 2048 and hi > 100 and big.any():                        # un-clipped boxes of ordinary size: the raster follows the exact IoU
+        assert np.abs(exact - want)[big].max() < 0.08

@@ -360,3 +360,33 @@ def test_retina_rotated_training_oracle_vs_reference(golden):
             ref = float(g[f'{name}{li}_loss'])
             assert abs(float(loss) - ref) <= 1e-6 * max(1.0, abs(ref)), (name, li, float(loss), ref)
             assert f'pos {pos}/' in str(g[f'{name}{li}_loss_str'])
+
+
+def test_raster_known_answers():
+    """oracle/raster.c (pycocotools' rleFrPoly + rleIou restated; the library is not in this image) against run-length
+    encodings DERIVED BY HAND from the published algorithm -- X = (int)(5x + .5); walk every edge along its major axis;
+    the mask toggles where the walk steps from sub-column 5c+2 to 5c+3, at row ceil((v + .5)/5 - .5) of the smaller
+    sub-row v; sorted column-major positions, differences = run lengths (zeros first).
+      A  rectangle (1,1)-(4,3), 5 x 6 canvas: top edge v=5 -> row 1 at columns 1,2,3; bottom edge v=15 -> row 3:
+         positions 6,8,11,13,16,18 then 30                                       -> 6,2,3,2,3,2,12
+      B  diamond (3,1),(5,3),(3,5),(1,3), 7 x 7: slopes +-1, the four edges cross columns 3,4 / 4,3 / 2,1 / 1,2 at rows
+         1,2 / 3,4 / 4,3 / 2,1: positions 9,10,15,18,22,25,30,31 then 49          -> 9,1,5,3,4,3,5,1,18  (8 pixels = its area)
+      C  0.8 x 4.8 box (2.3,0.6)-(3.1,5.4), 7 x 6: X = 12..16 crosses only 12|13 (column 2); v=3 -> row 1, v=27 -> row 5
+                                                                                 -> 15,4,23
+      D  0.6-wide box (2.7,1)-(3.3,4): X = 14..17 steps over no 5c+2|5c+3 line     -> 42  (empty mask)
+      E  parallelogram (1,1),(2,1),(4,5),(3,5), 7 x 6 (slope 1/2, y-major edges): right edge crosses 12|13 at t=5
+         (v=9 -> row 2) and 17|18 at t=15 (v=19 -> row 4); left edge 12|13 at v=19 -> row 4 and 7|8 at v=9 -> row 2;
+         top v=5 -> (1,1); bottom v=25 -> (3,5): positions 8,9,16,18,25,26 then 42 -> 8,1,7,2,7,1,16  (4 pixels = its area)"""
+    assert oi.raster_rle([1, 1, 4, 1, 4, 3, 1, 3], 5, 6) == [6, 2, 3, 2, 3, 2, 12]
+    assert oi.raster_rle([3, 1, 5, 3, 3, 5, 1, 3], 7, 7) == [9, 1, 5, 3, 4, 3, 5, 1, 18]
+    assert oi.raster_rle([2.3, 0.6, 3.1, 0.6, 3.1, 5.4, 2.3, 5.4], 7, 6) == [15, 4, 23]
+    assert oi.raster_rle([2.7, 1, 3.3, 1, 3.3, 4, 2.7, 4], 7, 6) == [42]
+    assert oi.raster_rle([1, 1, 2, 1, 4, 5, 3, 5], 7, 6) == [8, 1, 7, 2, 7, 1, 16]
+    # rleIou on two of them: rectangle A (6 px) and rectangle (2,1)-(5,4) (9 px) share columns 2,3 x rows 1,2
+    import ctypes
+    c1 = np.array([[1, 1, 4, 1, 4, 3, 1, 3]], dtype=np.float64)
+    c2 = np.array([[2, 1, 5, 1, 5, 4, 2, 4], [2.7, 1, 3.3, 1, 3.3, 4, 2.7, 4]], dtype=np.float64)
+    out = np.empty((1, 2))
+    f64p = ctypes.POINTER(ctypes.c_double)
+    oi.lib().oracle_raster_iou_pairwise(c1.ctypes.data_as(f64p), 1, c2.ctypes.data_as(f64p), 2, 6, 7, out.ctypes.data_as(f64p))
+    assert out.tolist() == [[4 / 11, 0.0]]
