@@ -1313,22 +1313,50 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(LargeWs w, const i
         unsigned long long* keep = diag + kTile;             // w.words more (the launch sizes the buffer for it)
         const fx::View V{mask, w.tile_adj + (long long)b * w.words * w.aw, w.spos_of_rank + base_n, mb, w.words, w.aw};
         fx::Entry* list = w.fx_list + (long long)b * w.fx_cap;
+#ifdef MYDET_SWEEP_PROFILE
+        long long fxt[5]; int fx_rounds = 0;
+        fxt[0] = clock64();
+#endif
         fx::phase_init(V, keep, removed, keptw, w.words, tid, kSweepThreads);
         // the mask kernels recorded every non-empty 32-bit half-word of the image (fx_note); fetch their bits once
         const int n_entries = w.fx_count[b];
         const bool use_list = n_entries <= w.fx_cap;            // else: walk the adjacency map every round
-        if (use_list) fx::phase_fill_list32(reinterpret_cast<const unsigned*>(mask), w.words, list, n_entries, tid, kSweepThreads);
+        // up to 16 entries per thread stay in registers for all rounds; longer lists are re-read from memory every round
+        const bool in_regs = use_list && n_entries <= fx::kRegEntries * kSweepThreads;
+        unsigned long long ent[fx::kRegEntries];
+        if (in_regs) {
+#pragma unroll
+            for (int k = 0; k < fx::kRegEntries; ++k) ent[k] = 0ull;
+            fx::phase_load_entries32(reinterpret_cast<const unsigned*>(mask), w.words, list, n_entries, ent, tid, kSweepThreads);
+        } else if (use_list) {
+            fx::phase_fill_list32(reinterpret_cast<const unsigned*>(mask), w.words, list, n_entries, tid, kSweepThreads);
+        }
         __syncthreads();
+#ifdef MYDET_SWEEP_PROFILE
+        fxt[1] = clock64();
+#endif
         for (;;) {
-            if (use_list) fx::phase_scatter_list32(list, n_entries, keep, removed, tid, kSweepThreads);
+            if (in_regs) fx::phase_scatter_entries32(ent, keep, removed);
+            else if (use_list) fx::phase_scatter_list32(list, n_entries, keep, removed, tid, kSweepThreads);
             else fx::phase_scatter(V, keep, removed, tid, kSweepThreads);
             __syncthreads();
+#ifdef MYDET_SWEEP_PROFILE
+            ++fx_rounds;
+#endif
             if (!__syncthreads_or(fx::phase_update(V, keep, removed, w.words, tid, kSweepThreads))) break;
         }
+#ifdef MYDET_SWEEP_PROFILE
+        fxt[2] = clock64();
+#endif
         fx::phase_to_rank(V, keep, keptw, tid, kSweepThreads);
         __syncthreads();
         for (int i = tid; i < words; i += kSweepThreads) w.kept[(long long)b * w.words + i] = keptw[i];
         __syncthreads();
+#ifdef MYDET_SWEEP_PROFILE
+        fxt[3] = clock64();
+        if (tid == 0 && b == 0) printf("fixpoint sweep (cycles): init+fill %lld  rounds(%d, %d entries) %lld  to_rank %lld\n",
+                                       fxt[1] - fxt[0], fx_rounds, n_entries, fxt[2] - fxt[1], fxt[3] - fxt[2]);
+#endif
     } else if (SPATIAL) {
         // Software-pipelined: the data of block t+1 (positions, adjacency rows, gathered diagonal words) does
         // not depend on the removed vector, so it is loaded while thread 0 resolves block t.
@@ -1526,27 +1554,44 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(LargeWs w, const i
     // one thread per RANK (not per 64-rank word: that was <= 64 dependent load-store pairs in a row per thread, ~30 us
     // of latency at 10 000 boxes): output position = kept ranks before this one
     const int* order = w.order + (long long)b * n;
-    for (int r = tid; r < mb; r += kSweepThreads) {
-        const int wd = r >> 6, j = r & 63;
-        const unsigned long long kw = keptw[wd];
-        if (!((kw >> j) & 1ull)) continue;
-        const int c = wd / per;
-        int pos = chunk_sum[c] + __popcll(kw & ((1ull << j) - 1ull));
-        for (int k = c * per; k < wd; ++k) pos += __popcll(keptw[k]);
-        const int i = order[r];
-        if (E.keep64) {
-            E.keep64[(long long)b * E.pitch + pos] = i;
-            w.rowpos[(long long)b * n + r] = pos;
-        } else if (pos < E.out_cap) {
-            const long long orow = (long long)b * E.out_cap + pos;
-            const long long irow = (long long)b * E.pitch + i;
-            for (int p = 0; p < E.n_param; ++p) E.out_box[orow * E.n_param + p] = E.boxes[irow * E.n_param + p];
-            E.out_score[orow] = E.scores[irow];
-            E.out_cls[orow] = E.cls ? (E.cls_is_i64 ? reinterpret_cast<const long long*>(E.cls)[irow]
-                                                    : (long long)reinterpret_cast<const int*>(E.cls)[irow]) : 0ll;
-            E.out_idx[orow] = E.src_idx ? E.src_idx[irow] : i;
+    constexpr int kEmitBatch = 4;                          // independent order[] loads in flight per thread
+    for (int r0 = tid; r0 < mb; r0 += kSweepThreads * kEmitBatch) {
+        int idx[kEmitBatch], posv[kEmitBatch];
+#pragma unroll
+        for (int u = 0; u < kEmitBatch; ++u) {
+            const int r = r0 + u * kSweepThreads;
+            idx[u] = -1; posv[u] = 0;
+            if (r >= mb) continue;
+            const int wd = r >> 6, j = r & 63;
+            const unsigned long long kw = keptw[wd];
+            if (!((kw >> j) & 1ull)) continue;
+            const int c = wd / per;
+            int pos = chunk_sum[c] + __popcll(kw & ((1ull << j) - 1ull));
+            for (int k = c * per; k < wd; ++k) pos += __popcll(keptw[k]);
+            posv[u] = pos;
+            idx[u] = order[r];
+        }
+#pragma unroll
+        for (int u = 0; u < kEmitBatch; ++u) {
+            const int i = idx[u], pos = posv[u], r = r0 + u * kSweepThreads;
+            if (i < 0) continue;
+            if (E.keep64) {
+                E.keep64[(long long)b * E.pitch + pos] = i;
+                w.rowpos[(long long)b * n + r] = pos;
+            } else if (pos < E.out_cap) {
+                const long long orow = (long long)b * E.out_cap + pos;
+                const long long irow = (long long)b * E.pitch + i;
+                for (int p = 0; p < E.n_param; ++p) E.out_box[orow * E.n_param + p] = E.boxes[irow * E.n_param + p];
+                E.out_score[orow] = E.scores[irow];
+                E.out_cls[orow] = E.cls ? (E.cls_is_i64 ? reinterpret_cast<const long long*>(E.cls)[irow]
+                                                        : (long long)reinterpret_cast<const int*>(E.cls)[irow]) : 0ll;
+                E.out_idx[orow] = E.src_idx ? E.src_idx[irow] : i;
+            }
         }
     }
+#ifdef MYDET_SWEEP_PROFILE
+    if (tid == 0 && b == 0) printf("sweep emit done at clock %lld\n", clock64());
+#endif
     if (tid == 0) {
         int total = s_prefix_total;
         if (!E.keep64 && total > E.out_cap) { total = E.out_cap; if (E.status) atomicOr(E.status + b, 2); }

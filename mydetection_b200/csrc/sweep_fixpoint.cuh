@@ -172,10 +172,45 @@ FX_HD int phase_update(const View& V, unsigned long long* keep, unsigned long lo
 }
 
 // Survivors by score rank (the order the emit stage walks).   (barrier before and after)
+// The positions of kBatch ranks are loaded before any of them is used: one CTA works on the image, so a loop of
+// dependent load -> test -> atomic would pay one memory latency per rank.
 FX_HD void phase_to_rank(const View& V, const unsigned long long* keep, unsigned long long* kept_by_rank, int tid, int nt) {
-    for (int r = tid; r < V.mb; r += nt) {
-        const int p = V.spos_of_rank[r];
-        if ((keep[p >> 6] >> (p & 63)) & 1ull) or_bits(kept_by_rank, r >> 6, 1ull << (r & 63));
+    for (int r0 = tid; r0 < V.mb; r0 += nt * kBatch) {
+        int p[kBatch];
+        for (int j = 0; j < kBatch; ++j) { const int r = r0 + j * nt; p[j] = (r < V.mb) ? V.spos_of_rank[r] : -1; }
+        for (int j = 0; j < kBatch; ++j) {
+            const int r = r0 + j * nt;
+            if (p[j] >= 0 && ((keep[p[j] >> 6] >> (p[j] & 63)) & 1ull)) or_bits(kept_by_rank, r >> 6, 1ull << (r & 63));
+        }
+    }
+}
+
+// Register-resident entry list of the device sweep: (row : 16 | half-word : 16 | bits : 32) per entry, kRegEntries per
+// thread, loaded ONCE (entry coordinates first, then the mask bits, each as a batch of independent loads) -- the rounds
+// then touch shared memory only.  Rows < 65 536 on this path (spatial ordering is used up to 65 536 boxes).
+constexpr int kRegEntries = 16;
+FX_HD void phase_load_entries32(const unsigned* mask32, int words_total, const Entry* list, int n_entries,
+                                unsigned long long (&ent)[kRegEntries], int tid, int nt) {
+    int row[kRegEntries], half[kRegEntries];
+    for (int k = 0; k < kRegEntries; ++k) {
+        const int e = tid + k * nt;
+        row[k] = (e < n_entries) ? list[e].row : -1;
+        half[k] = (e < n_entries) ? list[e].word : 0;
+    }
+    for (int k = 0; k < kRegEntries; ++k) {
+        unsigned bits = 0u;
+        if (row[k] >= 0) bits = mask32[(long long)row[k] * (2 * words_total) + half[k]];
+        ent[k] = (row[k] >= 0 && bits) ? (((unsigned long long)row[k] << 48) | ((unsigned long long)half[k] << 32) | bits) : 0ull;
+    }
+}
+FX_HD void phase_scatter_entries32(const unsigned long long (&ent)[kRegEntries], const unsigned long long* keep,
+                                   unsigned long long* removed) {
+    for (int k = 0; k < kRegEntries; ++k) {
+        const unsigned long long x = ent[k];
+        if (!x) continue;
+        const int row = (int)(x >> 48), half = (int)((x >> 32) & 0xffffu);
+        if ((keep[row >> 6] >> (row & 63)) & 1ull)
+            or_bits(removed, half >> 1, (half & 1) ? ((x & 0xffffffffull) << 32) : (x & 0xffffffffull));
     }
 }
 
