@@ -451,6 +451,7 @@ class Runner:
             if self.args.consumer == 'fused':
                 bc.exchange.consume_counts()
             else:
+                bc.exchange.publish()
                 bc.exchange.wait()
                 bc.exchange.release()
 
@@ -796,7 +797,7 @@ def run_gpu(args, wl):
 
     if rank == 0:
         mode = 'cuda_graph_pipelined' if m['pipelined'] else 'eager'
-        per_step = 3 if nccl else ((3 if args.consumer == 'fused' else 4) if run_protocol else 2)
+        per_step = 3 if nccl else ((3 if args.consumer == 'fused' else 5) if run_protocol else 2)
         line = {'metric': wl.metric, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': warmup,
                 'ms_per_step': ms / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'f32', 'data': 'synthetic', 'config': wl.config(world),
@@ -841,7 +842,7 @@ def main():
     ap.add_argument('--local-exchange', action='store_true',
                     help='N=1 diagnostic: run the fused exchange (and its protocol) against a local gathered buffer')
     ap.add_argument('--consumer', default='fused', choices=['fused', 'two-kernel'],
-                    help='exchange protocol: the consumer is one wait+snapshot+ack launch [default] or a wait and a release launch')
+                    help='exchange protocol: publish+wait+snapshot+ack in one launch [default] or as three launches')
     ap.add_argument('--no-multicast', action='store_true', help='N>1: unicast peer stores even where an NVLS multicast mapping exists')
     ap.add_argument('--no-protocol', action='store_true',
                     help='N>1: no sequence flags / acknowledgements / consumer kernels (the round-1 behaviour: rows only)')

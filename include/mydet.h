@@ -166,11 +166,10 @@ int mydet_postprocess_scatter(const float* boxes, const float* scores, const voi
  * not only a benchmark.  Buffer of every rank (mydet_exchange_buffer_bytes bytes, 16-byte aligned, zeroed once by its
  * owner before the first use, followed by one barrier):
  *     float  rows[images_total][out_cap][P+2];  int32 counts[images_total];      as for mydet_postprocess_scatter
- *     uint32 seq[images_total]   how often image i has been PUBLISHED: written by its producer after the image's rows
- *                                and count, with release semantics at system scope
+ *     uint32 seq[images_total]   how often image i has been PUBLISHED (release semantics at system scope)
  *     uint32 ack[8]              ack[q]: how many publications consumer rank q has CONSUMED; rank q writes it into every
  *                                rank's copy (mydet_exchange_release)
- *     uint32 want[2]             local bookkeeping of this rank's consumer
+ *     uint32 want[8], prod[images_total]   local bookkeeping of this rank's consumer / producer
  *   multicast_buf  the multicast mapping of the same symmetric buffer (cuMulticast* / torch symmetric memory
  *                  `multicast_ptr`), or NULL.  With it every row vector, count and flag is ONE multimem.st that the
  *                  NVSwitch replicates into all copies (the own one included); without it the kernel stores to each
@@ -178,14 +177,16 @@ int mydet_postprocess_scatter(const float* boxes, const float* scores, const voi
  *   self_index     index of this rank's own buffer in peer_bufs (its flags are polled locally)
  *   protocol != 0  producer: before it overwrites image slot i for the k-th time it waits (polling LOCAL memory) until
  *                  ack[q] >= k-1 for every rank q -- back-pressure, so a fast producer never overwrites rows a slow
- *                  consumer is still reading; after the stores it publishes seq[i] = k.  The wait is bounded (~1 s);
- *                  if it expires the image is stored anyway and status bit 16 is raised.  EVERY rank must then
- *                  consume every publication: mydet_exchange_wait (device-side acquire wait on the local copy until all
- *                  images_total images carry publication number consumed+1; optional snapshot of the counts; status
+ *                  consumer is still reading.  The wait is bounded (~1 s); if it expires the image is stored anyway and
+ *                  status bit 16 is raised.  The kernel itself does not publish: mydet_exchange_publish, next on the same
+ *                  stream, sets seq[i] = k for this rank's images (one fence and a few flag stores after the kernel
+ *                  boundary, instead of a system-scope drain at the end of each of the kernel's CTAs).  EVERY rank must
+ *                  then consume every publication: mydet_exchange_wait (device-side acquire wait on the local copy until
+ *                  all images_total images carry publication number consumed+1; optional snapshot of the counts; status
  *                  word: 1 = timed out), the consumer's own kernels reading rows on the same stream, then
- *                  mydet_exchange_release (ack into every copy).  Nothing here involves the host or a stream
- *                  dependency between processes; all state lives in the buffer, so the calls can sit in a replayed
- *                  CUDA graph.
+ *                  mydet_exchange_release (ack into every copy).  mydet_exchange_consume_counts is publish + wait +
+ *                  snapshot + release in one launch.  Nothing here involves the host or a stream dependency between
+ *                  processes; all state lives in the buffer, so the calls can sit in a replayed CUDA graph.
  *   protocol == 0  rows / counts only, as mydet_postprocess_scatter. */
 size_t mydet_exchange_buffer_bytes(int64_t images_total, int out_cap, int n_param);
 int mydet_postprocess_exchange(const float* boxes, const float* scores, const void* cls, int cls_is_i64,
@@ -196,15 +197,18 @@ int mydet_postprocess_exchange(const float* boxes, const float* scores, const vo
                                void* workspace, size_t workspace_bytes, void* const* peer_bufs, int n_peers,
                                void* multicast_buf, int self_index, int64_t image_offset, int64_t images_total,
                                int protocol, int flags, void* stream);
+int mydet_exchange_publish(void* const* peer_bufs, int n_peers, void* multicast_buf, int self_index, int64_t image_offset,
+                           int batch, int64_t images_total, int out_cap, int n_param, void* stream);
 int mydet_exchange_wait(void* local_buf, int64_t images_total, int out_cap, int n_param, int32_t* counts_out,
                         int32_t* status, void* stream);
 int mydet_exchange_release(void* const* peer_bufs, int n_peers, void* multicast_buf, int self_index,
                            int64_t images_total, int out_cap, int n_param, void* stream);
-/* mydet_exchange_wait + mydet_exchange_release in ONE launch, for a consumer that needs only the per-image counts of
+/* mydet_exchange_publish (this rank's images [image_offset, image_offset + batch); batch 0 = nothing to publish) +
+ * mydet_exchange_wait + mydet_exchange_release in ONE launch, for a consumer that needs only the per-image counts of
  * the step (snapshotted into counts_out before the acknowledgement goes out). */
 int mydet_exchange_consume_counts(void* const* peer_bufs, int n_peers, void* multicast_buf, int self_index,
-                                  int64_t images_total, int out_cap, int n_param, int32_t* counts_out,
-                                  int32_t* status, void* stream);
+                                  int64_t image_offset, int batch, int64_t images_total, int out_cap, int n_param,
+                                  int32_t* counts_out, int32_t* status, void* stream);
 
 /* Whole path in one call: decode_compact + postprocess (what api/detection.py:168-172 does per
  * image, here for the batch).  Workspace: mydet_detect_workspace_bytes(...). */

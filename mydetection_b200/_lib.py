@@ -53,7 +53,8 @@ SIGNATURES = {
     'mydet_exchange_buffer_bytes': (c_sz, [c_i64, c_int, c_int]),
     'mydet_exchange_wait': (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
     'mydet_exchange_release': (c_int, [ctypes.POINTER(c_vp), c_int, c_vp, c_int, c_i64, c_int, c_int, c_vp]),
-    'mydet_exchange_consume_counts': (c_int, [ctypes.POINTER(c_vp), c_int, c_vp, c_int, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
+    'mydet_exchange_publish': (c_int, [ctypes.POINTER(c_vp), c_int, c_vp, c_int, c_i64, c_int, c_i64, c_int, c_int, c_vp]),
+    'mydet_exchange_consume_counts': (c_int, [ctypes.POINTER(c_vp), c_int, c_vp, c_int, c_i64, c_int, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
     'mydet_detect_workspace_bytes': (c_sz, [c_int, c_i64, c_int, c_int]),
     'mydet_detect': (c_int, [c_int, ctypes.POINTER(Level), c_int, c_int, c_int, c_int, c_f32, c_f32, c_f32, c_int,
                              c_f64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),

@@ -41,18 +41,23 @@ int launch_postprocess_small(const PPParams& P, int batch, cudaStream_t st);
 
 // Gathered-detections buffer of the fused exchange, in 32-bit words (include/mydet.h):
 //   float rows[images_total][out_cap][P+2]; int32 counts[images_total];                      (the data)
-//   uint32 seq[images_total]   -- written by the image's producer AFTER its rows and count: how often the image was published
+//   uint32 seq[images_total]   -- how often image i has been PUBLISHED: written, with release semantics at system scope, by
+//                                 the publish step that follows the producing kernel on its stream (mydet_exchange_publish
+//                                 or the prologue of mydet_exchange_consume_counts) -- NOT by the producing kernel
+//                                 itself, whose CTAs would each end in a system-scope drain of their peer stores
 //   uint32 ack[8]              -- ack[q], written by consumer rank q into EVERY rank's copy: how many publications q has consumed
-//   uint32 want                -- local only: publications this rank's consumer has waited for so far
-// seq / ack start on 16-byte boundaries.
-struct ExchangeLayout { long long counts_off, seq_off, ack_off, want_off, total_words; };
+//   uint32 want[8]             -- local only: publications this rank's consumer has waited for so far
+//   uint32 prod[images_total]  -- local only: how often the producing kernel has WRITTEN image i (its own rows only)
+// seq / ack / prod start on 16-byte boundaries.
+struct ExchangeLayout { long long counts_off, seq_off, ack_off, want_off, prod_off, total_words; };
 __host__ __device__ inline ExchangeLayout exchange_layout(long long images_total, int out_cap, int n_param) {
     ExchangeLayout L;
     L.counts_off = images_total * out_cap * (n_param + 2);
     L.seq_off = (L.counts_off + images_total + 3) & ~3LL;
     L.ack_off = L.seq_off + ((images_total + 3) & ~3LL);
     L.want_off = L.ack_off + 8;
-    L.total_words = L.want_off + 8;
+    L.prod_off = L.want_off + 8;
+    L.total_words = L.prod_off + ((images_total + 3) & ~3LL);
     return L;
 }
 

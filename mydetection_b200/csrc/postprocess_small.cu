@@ -949,7 +949,7 @@ __global__ void __maxnreg__(MYDET_PP_MAXNREG) postprocess_small_kernel(const PPP
         if (P.n_peers > 0 && P.peer_protocol && tid == kPPThreads - 32) {
             const ExchangeLayout XL = exchange_layout(P.peer_rows_total, P.out_cap, P.n_param);
             const unsigned* own = reinterpret_cast<const unsigned*>(P.peer[P.peer_self]);
-            const unsigned prev = ld_relaxed_sys(own + XL.seq_off + P.peer_row0 + b);
+            const unsigned prev = own[XL.prod_off + P.peer_row0 + b];      // written by this image's CTA of the previous launch
             const long long t0 = clock64();
             bool late = false;
             for (int q = 0; q < P.n_peers && !late; ++q)
@@ -1033,7 +1033,6 @@ __global__ void __maxnreg__(MYDET_PP_MAXNREG) postprocess_small_kernel(const PPP
                 }
             }
         }
-        if (P.n_peers > 0 && P.peer_protocol) __syncthreads();    // every row store of the CTA is ordered before thread 0's release below
         if (tid == 0) {
             if (nk > P.out_cap) { nk = P.out_cap; flags |= 2; }
             P.out_count[b] = nk;
@@ -1049,18 +1048,10 @@ __global__ void __maxnreg__(MYDET_PP_MAXNREG) postprocess_small_kernel(const PPP
                     else base[XL.counts_off + row] = nk;
                 }
                 if (P.peer_protocol) {
-                    // publication: rows and count first, then -- release at system scope, cumulative over the barrier above --
-                    // the image's sequence number, which a consumer kernel acquires (mydet_exchange_wait)
-                    // (the release store orders every earlier store of the CTA -- cumulativity through the barrier -- so no
-                    // separate fence.sc is issued: it cost a second ~1 us drain per CTA)
-#ifdef MYDET_EXCH_FENCE
-                    __threadfence_system();
-#endif
-                    for (int q = 0; q < nq; ++q) {
-                        unsigned* base = reinterpret_cast<unsigned*>(P.peer_mc ? P.peer_mc : P.peer[q]);
-                        if (P.peer_mc) multimem_st_release_u32(base + XL.seq_off + row, s_seq);
-                        else st_release_sys(base + XL.seq_off + row, s_seq);
-                    }
+                    // the image has been written once more.  Its PUBLICATION (seq, release at system scope) is left to the
+                    // publish step that follows this kernel on the stream: a release here would end every CTA in a
+                    // system-scope drain of its peer stores (~1 us per CTA with the SM's registers and shared memory held)
+                    reinterpret_cast<unsigned*>(P.peer[P.peer_self])[XL.prod_off + row] = s_seq;
                 }
             }
         }

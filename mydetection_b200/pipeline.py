@@ -215,6 +215,15 @@ class PeerExchange:
         counts = self.buffer[n_rows:n_rows + n_img].view(torch.int32)
         return rows, counts
 
+    # producer side: after launch_postprocess_scatter(), on the same stream
+    def publish(self, multicast=True):
+        """Publish the step the post-process kernel just wrote (this rank's images): sequence numbers with release
+        semantics, after the kernel boundary.  consume_counts() includes it."""
+        rc = _lib.lib().mydet_exchange_publish(self.peer_array, self.world, self._mc if multicast else None, self.rank,
+                                               self.rank * self.batch, self.batch, self.images_total, self.cap, self.n_param,
+                                               torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, 'mydet_exchange_publish')
+
     # consumer side of the protocol: wait() ... kernels reading views()[0] on the same stream ... release()
     def wait(self):
         """Device-side wait (no host involvement) until every image of every rank carries the next publication;
@@ -226,9 +235,9 @@ class PeerExchange:
         return self.counts_snapshot
 
     def consume_counts(self, multicast=True):
-        """wait() + release() in one launch, for a consumer that needs only the counts of the step."""
+        """publish() + wait() + release() in one launch, for a consumer that needs only the counts of the step."""
         rc = _lib.lib().mydet_exchange_consume_counts(self.peer_array, self.world, self._mc if multicast else None, self.rank,
-                                                      self.images_total, self.cap, self.n_param,
+                                                      self.rank * self.batch, self.batch, self.images_total, self.cap, self.n_param,
                                                       ops._ptr(self.counts_snapshot), ops._ptr(self.wait_status),
                                                       torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, 'mydet_exchange_consume_counts')

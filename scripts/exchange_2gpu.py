@@ -61,6 +61,7 @@ def main():
             torch.cuda._sleep(3_000_000)              # ~1.5 ms: this rank falls behind as producer AND consumer
         bc.launch_decode()
         bc.launch_postprocess_scatter()
+        ex.publish(multicast=use_mc)
         snap_status[s, 0].copy_((bc.out['status'] & 16).max())
         counts = ex.wait()
         if (s + 2 * rank) % 7 == 0:

@@ -492,6 +492,7 @@ def test_exchange_protocol_single_gpu(golden):
         bc = calls[s % 2]
         bc.launch_decode()
         bc.launch_postprocess_scatter()
+        ex.publish()                                 # after the kernel boundary: the producer kernel itself never fences
         counts = ex.wait().clone()
         rows = ex.views()[0].clone()                 # the consumer's read, stream-ordered behind the wait
         ex.release()
@@ -518,11 +519,11 @@ def test_exchange_protocol_single_gpu(golden):
         assert torch.equal(counts, want[s % 2][1]) and int(ex.wait_status) == 0 and int((bc.out['status'] & 16).sum()) == 0
     # back-pressure, bounded: the next publication is never acknowledged, so the one after it has to give up waiting
     import time
-    calls[0].launch_decode(); calls[0].launch_postprocess_scatter()
+    calls[0].launch_decode(); calls[0].launch_postprocess_scatter(); ex.publish()
     torch.cuda.synchronize()
     assert int((calls[0].out['status'] & 16).sum()) == 0
     t0 = time.perf_counter()
-    calls[1].launch_decode(); calls[1].launch_postprocess_scatter()
+    calls[1].launch_decode(); calls[1].launch_postprocess_scatter(); ex.publish()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     assert int((calls[1].out['status'] & 16).min()) == 16 and 0.2 < dt < 10.0, dt
