@@ -21,6 +21,13 @@
  *     needs only the alignment of its element type (dense-decode outputs fall back to scalar stores).
  *     Workspaces: 256 bytes.  Anything torch allocates satisfies all of this unless it is a view with an odd
  *     storage offset.
+ *   - Persistent workspaces.  The large-N NMS (more than MYDET_SMALL_K survivors, and mydet_nms_rot) keeps an
+ *     n x ceil(n/64)-word suppression matrix per image in its workspace: 12.6 MB at 10 000 boxes, 293 MB at 48 384 --
+ *     sparse, but it must start all-zero, and clearing it costs more than any kernel of the path.  A caller that passes
+ *     the SAME workspace buffer, for the SAME (batch, n_per_image, entry point), to every call may hand it over zeroed
+ *     once (cudaMemset of the whole buffer) and set MYDET_PP_WS_CLEAN / workspace_clean: the library then skips the
+ *     wholesale clear and, as its last step, zeroes exactly the words the call set, so the buffer is clean again for the
+ *     next call.  Without the flag every call clears the matrix itself and makes no assumption about the buffer.
  *   - Tie policy (the reference leaves it open): wherever scores are ranked,
  *     equal scores are ordered by ascending candidate index.
  */
@@ -43,6 +50,7 @@ extern "C" {
 
 #define MYDET_PP_CONSUME 1           /* mydet_postprocess flags                            */
 #define MYDET_PP_FORCE_SCAN 2
+#define MYDET_PP_WS_CLEAN 4          /* persistent workspace in its clean state (see "persistent workspaces")  */
 
 enum {
     MYDET_OK = 0,
@@ -136,6 +144,7 @@ int mydet_decode_compact(int kind, const mydet_level_t* levels, int n_levels, in
  *            every score with radix passes, as it does on its own when a front end cannot decide: heavy
  *            ties, a misleading sample); results are identical either way -- the flag exists so that tests
  *            can prove that.
+ *            MYDET_PP_WS_CLEAN: the workspace is persistent and clean (conventions at the top); large-N path only.
  * Workspace: mydet_postprocess_workspace_bytes(...) bytes, 256-byte aligned. */
 size_t mydet_postprocess_workspace_bytes(int batch, int n_per_image, int topk);
 int mydet_postprocess(const float* boxes, const float* scores, const void* cls, int cls_is_i64,
@@ -219,6 +228,14 @@ int mydet_detect(int kind, const mydet_level_t* levels, int n_levels, int batch,
                  int32_t* out_idx, int32_t* out_count, int32_t* status, int out_cap,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* mydet_detect on a persistent workspace (see the conventions at the top): workspace_clean != 0 = the buffer was zeroed
+ * once and has only been used by this entry point with this geometry since. */
+int mydet_detect_ws(int kind, const mydet_level_t* levels, int n_levels, int batch, int n_cls,
+                    int n_param, float img_h, float img_w, float conf_thres, int topk,
+                    double nms_thres, float* out_box, float* out_score, int64_t* out_cls,
+                    int32_t* out_idx, int32_t* out_count, int32_t* status, int out_cap,
+                    void* workspace, size_t workspace_bytes, int workspace_clean, void* stream);
+
 /* Pack the detections of a batch into ONE float32 buffer for the multi-GPU exchange:
  * packed[(b*out_cap + k)*(P+2) + 0..P-1] = box, [+P] = score, [+P+1] = (float)class, followed by
  * batch floats holding the bit patterns of the int32 counts.  Size: batch*(out_cap*(P+2) + 1) floats. */
@@ -240,6 +257,12 @@ int mydet_nms_rot(const float* boxes, const float* scores, const int32_t* counts
                   int64_t pitch, int n_per_image, double thr, int ge_mode, int64_t* keep,
                   int32_t* keep_count, int32_t* votes, void* workspace, size_t workspace_bytes,
                   void* stream);
+
+/* mydet_nms_rot on a persistent workspace (see the conventions at the top). */
+int mydet_nms_rot_ws(const float* boxes, const float* scores, const int32_t* counts, int batch,
+                     int64_t pitch, int n_per_image, double thr, int ge_mode, int64_t* keep,
+                     int32_t* keep_count, int32_t* votes, void* workspace, size_t workspace_bytes,
+                     int workspace_clean, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Pairwise IoU matrices. */

@@ -58,9 +58,12 @@ SIGNATURES = {
     'mydet_detect_workspace_bytes': (c_sz, [c_int, c_i64, c_int, c_int]),
     'mydet_detect': (c_int, [c_int, ctypes.POINTER(Level), c_int, c_int, c_int, c_int, c_f32, c_f32, c_f32, c_int,
                              c_f64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),
+    'mydet_detect_ws': (c_int, [c_int, ctypes.POINTER(Level), c_int, c_int, c_int, c_int, c_f32, c_f32, c_f32, c_int,
+                                c_f64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_sz, c_int, c_vp]),
     'mydet_pack_detections': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp]),
     'mydet_nms_rot_workspace_bytes': (c_sz, [c_int, c_int]),
     'mydet_nms_rot': (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_f64, c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'mydet_nms_rot_ws': (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_f64, c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_int, c_vp]),
     'mydet_iou_aabb_pairwise': (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp]),
     'mydet_iou_aabb_rowmax': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     'mydet_iou_rot_pairwise': (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),

@@ -87,6 +87,7 @@ static int postprocess_impl(const float* boxes, const float* scores, const void*
     LargeArgs A{boxes, scores, cls, cls_is_i64, src_idx, counts, batch, pitch, n_per_image, n_param, box_format,
                 conf_thres, topk, nms_thres, 0, false, out_box, out_score, reinterpret_cast<long long*>(out_cls),
                 out_idx, out_count, status, out_cap, nullptr, nullptr};
+    A.ws_clean = (pp_flags & MYDET_PP_WS_CLEAN) != 0;
     return run_large(A, workspace, workspace_bytes, st);
 }
 
@@ -153,10 +154,10 @@ MYDET_API size_t mydet_detect_workspace_bytes(int batch, int64_t n_total, int n_
     return carve_detect(w, nullptr, 0, batch, n_total, n_param, topk);
 }
 
-MYDET_API int mydet_detect(int kind, const mydet_level_t* levels, int n_levels, int batch, int n_cls, int n_param,
-                           float img_h, float img_w, float conf_thres, int topk, double nms_thres, float* out_box,
-                           float* out_score, int64_t* out_cls, int32_t* out_idx, int32_t* out_count, int32_t* status,
-                           int out_cap, void* workspace, size_t workspace_bytes, void* stream) {
+static int detect_impl(int kind, const mydet_level_t* levels, int n_levels, int batch, int n_cls, int n_param,
+                       float img_h, float img_w, float conf_thres, int topk, double nms_thres, float* out_box,
+                       float* out_score, int64_t* out_cls, int32_t* out_idx, int32_t* out_count, int32_t* status,
+                       int out_cap, void* workspace, size_t workspace_bytes, int pp_flags, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     MYDET_REQUIRE(levels && n_levels >= 1 && n_levels <= MYDET_MAX_LEVELS, "n_levels must be in [1,%d]", MYDET_MAX_LEVELS);
     int64_t n_total = 0;
@@ -174,7 +175,24 @@ MYDET_API int mydet_detect(int kind, const mydet_level_t* levels, int n_levels, 
     // the decode already applied conf_thres; the post-process sees only survivors
     return mydet_postprocess(w.box, w.score, w.cls, 0, w.idx, w.count, batch, n_total, (int)n_total, n_param,
                              MYDET_BOX_CXCYWH, -INFINITY, topk, nms_thres, out_box, out_score, out_cls, out_idx,
-                             out_count, status, out_cap, w.rest, w.rest_bytes, /*flags=*/0, st);
+                             out_count, status, out_cap, w.rest, w.rest_bytes, pp_flags, st);
+}
+
+MYDET_API int mydet_detect(int kind, const mydet_level_t* levels, int n_levels, int batch, int n_cls, int n_param,
+                           float img_h, float img_w, float conf_thres, int topk, double nms_thres, float* out_box,
+                           float* out_score, int64_t* out_cls, int32_t* out_idx, int32_t* out_count, int32_t* status,
+                           int out_cap, void* workspace, size_t workspace_bytes, void* stream) {
+    return detect_impl(kind, levels, n_levels, batch, n_cls, n_param, img_h, img_w, conf_thres, topk, nms_thres, out_box, out_score,
+                       out_cls, out_idx, out_count, status, out_cap, workspace, workspace_bytes, 0, stream);
+}
+
+MYDET_API int mydet_detect_ws(int kind, const mydet_level_t* levels, int n_levels, int batch, int n_cls, int n_param,
+                              float img_h, float img_w, float conf_thres, int topk, double nms_thres, float* out_box,
+                              float* out_score, int64_t* out_cls, int32_t* out_idx, int32_t* out_count, int32_t* status,
+                              int out_cap, void* workspace, size_t workspace_bytes, int workspace_clean, void* stream) {
+    return detect_impl(kind, levels, n_levels, batch, n_cls, n_param, img_h, img_w, conf_thres, topk, nms_thres, out_box, out_score,
+                       out_cls, out_idx, out_count, status, out_cap, workspace, workspace_bytes,
+                       workspace_clean ? MYDET_PP_WS_CLEAN : 0, stream);
 }
 
 namespace mydet {
@@ -211,9 +229,9 @@ MYDET_API size_t mydet_nms_rot_workspace_bytes(int batch, int n_per_image) {
     return large_workspace_bytes(batch, n_per_image, true);
 }
 
-MYDET_API int mydet_nms_rot(const float* boxes, const float* scores, const int32_t* counts, int batch, int64_t pitch,
-                            int n_per_image, double thr, int ge_mode, int64_t* keep, int32_t* keep_count,
-                            int32_t* votes, void* workspace, size_t workspace_bytes, void* stream) {
+static int nms_rot_impl(const float* boxes, const float* scores, const int32_t* counts, int batch, int64_t pitch,
+                        int n_per_image, double thr, int ge_mode, int64_t* keep, int32_t* keep_count,
+                        int32_t* votes, void* workspace, size_t workspace_bytes, int ws_clean, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     MYDET_REQUIRE(batch >= 0 && n_per_image >= 0 && pitch >= n_per_image, "bad batch / n_per_image / pitch");
     MYDET_REQUIRE(n_per_image <= MYDET_MAX_CANDIDATES, "more than %d boxes per image", MYDET_MAX_CANDIDATES);
@@ -224,5 +242,20 @@ MYDET_API int mydet_nms_rot(const float* boxes, const float* scores, const int32
     LargeArgs A{boxes, scores, nullptr, 0, nullptr, counts, batch, pitch, n_per_image, 5, MYDET_BOX_CXCYWH,
                 -INFINITY, 0, thr, ge_mode, true, nullptr, nullptr, nullptr, nullptr, keep_count, nullptr, 0,
                 reinterpret_cast<long long*>(keep), votes};
+    A.ws_clean = ws_clean != 0;
     return run_large(A, workspace, workspace_bytes, st);
+}
+
+MYDET_API int mydet_nms_rot(const float* boxes, const float* scores, const int32_t* counts, int batch, int64_t pitch,
+                            int n_per_image, double thr, int ge_mode, int64_t* keep, int32_t* keep_count,
+                            int32_t* votes, void* workspace, size_t workspace_bytes, void* stream) {
+    return nms_rot_impl(boxes, scores, counts, batch, pitch, n_per_image, thr, ge_mode, keep, keep_count, votes, workspace,
+                        workspace_bytes, 0, stream);
+}
+
+MYDET_API int mydet_nms_rot_ws(const float* boxes, const float* scores, const int32_t* counts, int batch, int64_t pitch,
+                               int n_per_image, double thr, int ge_mode, int64_t* keep, int32_t* keep_count,
+                               int32_t* votes, void* workspace, size_t workspace_bytes, int workspace_clean, void* stream) {
+    return nms_rot_impl(boxes, scores, counts, batch, pitch, n_per_image, thr, ge_mode, keep, keep_count, votes, workspace,
+                        workspace_bytes, workspace_clean, stream);
 }

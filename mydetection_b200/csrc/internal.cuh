@@ -68,6 +68,7 @@ struct LargeArgs {
     float* out_box; float* out_score; long long* out_cls; int* out_idx; int* out_count; int* status; int out_cap;
     long long* keep64;
     int* votes;
+    bool ws_clean = false;   // persistent workspace: the bit matrix is clean on entry and is left clean (no wholesale memset)
 };
 int run_large(const LargeArgs& A, void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t large_workspace_bytes(int batch, int n, bool rot);

@@ -96,7 +96,7 @@ static size_t carve(LargeWs& w, void* base, int batch, int n, bool rot) {
     const size_t o_adj = take(sp ? (size_t)batch * w.words * w.aw * 8 : 0);
     const size_t o_diag = take(sp ? (size_t)batch * w.words * kTile * 8 : 0);
     const size_t o_adjb = take(sp ? (size_t)batch * w.words * kTile * w.aw * 8 : 0);
-    w.fx_cap = sp ? 4 * n : 0;                      // last in the layout: everything before keeps its offset
+    w.fx_cap = sp ? 16 * n : 0;                     // entries (16 B each) per image: 16 non-empty half-words per row on average
     const size_t o_fx = take((size_t)batch * w.fx_cap * sizeof(fx::Entry));
     const bool bp = sp && rot;                      // broad / narrow phase buffers of the rotated path
     w.n16 = (n + 15) / 16; w.n32 = (n + 31) / 32;
@@ -1635,6 +1635,24 @@ __global__ void votes_kernel(LargeWs w, const int* m, int n, int* votes, long lo
     if (best_q >= 0) atomicAdd(votes + (long long)b * pitch + w.rowpos[base + best_q], 1);
 }
 
+// Leaves the bit matrix of every image all-zero again (persistent workspaces, LargeArgs::ws_clean): the half-words the mask
+// kernels recorded, or -- when the list overflowed -- the whole matrix of that image.
+__global__ void __launch_bounds__(256) mask_cleanup_kernel(LargeWs w, int n) {
+    const int b = blockIdx.y;
+    const int cnt = w.fx_count[b];
+    unsigned* mask32 = reinterpret_cast<unsigned*>(w.mask + (long long)b * n * w.words);
+    const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cnt <= w.fx_cap) {
+        const fx::Entry* list = w.fx_list + (long long)b * w.fx_cap;
+        for (long long e = t0; e < cnt; e += stride) mask32[(long long)list[e].row * (2 * w.words) + list[e].word] = 0u;
+    } else {
+        uint4* m4 = reinterpret_cast<uint4*>(mask32);                  // n * words * 8 bytes: a multiple of 16 (256-byte aligned base)
+        const long long total = (long long)n * w.words / 2;
+        for (long long i = t0; i < total; i += stride) m4[i] = make_uint4(0u, 0u, 0u, 0u);
+        if ((((long long)n * w.words) & 1) && t0 == 0) w.mask[(long long)b * n * w.words + (long long)n * w.words - 1] = 0ull;
+    }
+}
+
 // ---------------------------------------------------------------------------- host orchestration
 int run_large(const LargeArgs& A, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     LargeWs w;
@@ -1670,7 +1688,11 @@ int run_large(const LargeArgs& A, void* workspace, size_t workspace_bytes, cudaS
     MYDET_REQUIRE(smem <= 200 * 1024, "too many candidates per image for the sweep kernel");
     const int smem_attr = (int)smem > 48 * 1024 ? (int)smem : 48 * 1024;
     if (spatial) {
-        MYDET_CUDA(cudaMemsetAsync(w.mask, 0, (size_t)B * n * w.words * sizeof(unsigned long long), st));
+        // the bit matrix (8 n ceil(n/64) bytes per image: 12.6 MB at 10 000 boxes, 293 MB at 48 384) is sparse -- a few
+        // thousand non-zero words -- and clearing it costs more than any kernel of the path.  A caller that keeps the
+        // workspace between calls (ws_clean) gets it back clean: mask_cleanup_kernel, last in the pipeline, zeroes exactly
+        // the half-words this call set (the entry list again), so no call after the first clears the matrix wholesale.
+        if (!A.ws_clean) MYDET_CUDA(cudaMemsetAsync(w.mask, 0, (size_t)B * n * w.words * sizeof(unsigned long long), st));
         MYDET_CUDA(cudaMemsetAsync(w.tile_adj, 0, (size_t)B * w.words * w.aw * 8, st));
         MYDET_CUDA(cudaMemsetAsync(w.fx_count, 0, sizeof(int) * (size_t)B, st));
         const dim3 mgrid(tiles, (tiles + kColChunk - 1) / kColChunk, B);
@@ -1719,6 +1741,7 @@ int run_large(const LargeArgs& A, void* workspace, size_t workspace_bytes, cudaS
         MYDET_CUDA(cudaMemsetAsync(A.votes, 0, sizeof(int) * (size_t)B * (size_t)A.pitch, st));
         votes_kernel<<<dim3((n + 127) / 128, B), 128, 0, st>>>(w, w.m, n, A.votes, A.pitch, spatial ? 1 : 0);
     }
+    if (spatial && A.ws_clean) mask_cleanup_kernel<<<dim3(32, B), 256, 0, st>>>(w, n);
     return launch_status("large NMS pipeline");
 }
 

@@ -4,6 +4,7 @@ PyTorch is used here only for device memory, the current stream and dtype/shape 
 result is produced by the hand-written CUDA kernels of libmydet.so.  CPU tensors are rejected --
 there is no fallback path.
 """
+import collections
 import ctypes
 
 import torch
@@ -35,6 +36,29 @@ def _ptr(t):
 
 def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# Persistent workspaces of the large-N NMS (include/mydet.h, "persistent workspaces"): zeroed once, handed to the library
+# with the clean flag, returned clean -- the n x ceil(n/64) suppression matrix is then never cleared wholesale again.
+# Keyed by everything that fixes the buffer's layout AND by the stream (two streams must not share a buffer); a few
+# entries, least recently used out first.
+_PERSISTENT = collections.OrderedDict()
+_PERSISTENT_MAX = 6
+
+
+def _persistent_workspace(key, nbytes, device):
+    ws = _PERSISTENT.pop(key, None)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+    _PERSISTENT[key] = ws
+    while len(_PERSISTENT) > _PERSISTENT_MAX:
+        _PERSISTENT.popitem(last=False)
+    return ws
+
+
+def release_workspaces():
+    """Drop the cached persistent workspaces (they hold device memory between calls)."""
+    _PERSISTENT.clear()
 
 
 # --------------------------------------------------------------------------------------- levels
@@ -212,10 +236,13 @@ def detect(kind, levels: LevelSet, img_hw, conf_thres, nms_thres, topk=512, out=
     return out
 
 
-def detect_workspace(levels: LevelSet, topk=512):
+def detect_workspace(levels: LevelSet, topk=512, zeroed=False):
+    """zeroed=True: a persistent workspace in its clean state, for mydet_detect_ws(..., workspace_clean=1)."""
     k = int(topk) if topk else 0
-    return _workspace(_lib.lib().mydet_detect_workspace_bytes(levels.batch, levels.n_total, levels.n_param, k),
-                      levels.device)
+    nbytes = _lib.lib().mydet_detect_workspace_bytes(levels.batch, levels.n_total, levels.n_param, k)
+    if zeroed:
+        return torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=levels.device)
+    return _workspace(nbytes, levels.device)
 
 
 # --------------------------------------------------------------------------------------- rotated NMS / IoU
@@ -252,24 +279,33 @@ def nms_rot(boxes, scores, thr, ge=True, counts=None, want_votes=False, chunks=N
         chunks = 2 if (B >= 4 and n >= 2048) else 1
     chunks = max(1, min(int(chunks), B))
     bounds = [(B * c // chunks, B * (c + 1) // chunks) for c in range(chunks)]
-    wss = [_workspace(L.mydet_nms_rot_workspace_bytes(hi - lo, n), dev) for lo, hi in bounds]
+    def ws_key(lo, hi, ci, stream):
+        return ('nms_rot', dev.index, hi - lo, n, ci, stream.cuda_stream)
 
-    def call(lo, hi, ws, stream):
+    def call(lo, hi, ci, stream):
+        # one persistent workspace per (geometry, chunk, stream): clean on entry, left clean by the library
+        key = ws_key(lo, hi, ci, stream)
+        ws = _persistent_workspace(key, L.mydet_nms_rot_workspace_bytes(hi - lo, n), dev)
         sub = lambda t: _ptr(t[lo:hi]) if t is not None else _ptr(None)
-        rc = L.mydet_nms_rot(sub(boxes), sub(scores), sub(counts), hi - lo, n, n, float(thr), 1 if ge else 0,
-                             sub(keep), sub(cnt), sub(votes), _ptr(ws), ws.numel(), ctypes.c_void_p(stream.cuda_stream))
-        _lib.check(rc, 'mydet_nms_rot')
+        rc = L.mydet_nms_rot_ws(sub(boxes), sub(scores), sub(counts), hi - lo, n, n, float(thr), 1 if ge else 0,
+                                sub(keep), sub(cnt), sub(votes), _ptr(ws), ws.numel(), 1, ctypes.c_void_p(stream.cuda_stream))
+        if rc:
+            _PERSISTENT.pop(key, None)             # its state is unknown now
+        _lib.check(rc, 'mydet_nms_rot_ws')
 
     with torch.cuda.device(dev):
         main = torch.cuda.current_stream()
         if chunks == 1:
-            call(0, B, wss[0], main)
+            call(0, B, 0, main)
         else:
+            sides = _side_streams(dev, chunks)
+            for ci, ((lo, hi), side) in enumerate(zip(bounds, sides)):       # a new buffer is zeroed on `main`, BEFORE the fork
+                _persistent_workspace(ws_key(lo, hi, ci, side), L.mydet_nms_rot_workspace_bytes(hi - lo, n), dev)
             fork = torch.cuda.Event()
             fork.record(main)
-            for (lo, hi), ws, side in zip(bounds, wss, _side_streams(dev, chunks)):
+            for ci, ((lo, hi), side) in enumerate(zip(bounds, sides)):
                 side.wait_event(fork)
-                call(lo, hi, ws, side)
+                call(lo, hi, ci, side)
                 main.wait_stream(side)
     return (keep, cnt, votes) if want_votes else (keep, cnt)
 

@@ -28,7 +28,9 @@ class BoundCall:
         k = int(pipe.topk) if pipe.topk else 0
         cap = min(k, ls.n_total) if k > 0 else ls.n_total
         self.out = ops._alloc_dets(ls.batch, max(cap, 1), ls.n_param, dev)
-        self.workspace = ops.detect_workspace(ls, pipe.topk)
+        # the bound call owns its workspace for its whole life: persistent and clean (include/mydet.h), so the large-N
+        # path never clears its suppression matrix wholesale after the first launch
+        self.workspace = ops.detect_workspace(ls, pipe.topk, zeroed=True)
         B, N, P = ls.batch, ls.n_total, ls.n_param
         self.cand = {'box': torch.empty(B, N, P, dtype=torch.float32, device=dev),
                      'score': torch.empty(B, N, dtype=torch.float32, device=dev),
@@ -47,7 +49,7 @@ class BoundCall:
         self._detect_args = (pipe.kind, ls.array, ls.n_levels, B, ls.n_cls, P, img_h, img_w, pipe.conf_thres, k,
                              pipe.nms_thres, ptr(o['box']), ptr(o['score']), ptr(o['cls']), ptr(o['idx']),
                              ptr(o['count']), ptr(o['status']), o['box'].shape[1], ptr(self.workspace),
-                             self.workspace.numel())
+                             self.workspace.numel(), 1)
         self._decode_args = (pipe.kind, ls.array, ls.n_levels, B, ls.n_cls, P, img_h, img_w, pipe.conf_thres,
                              ptr(c['box']), ptr(c['score']), ptr(c['cls']), ptr(c['idx']), ptr(c['count']), N, clean)
         self._pp_args = (ptr(c['box']), ptr(c['score']), ptr(c['cls']), 0, ptr(c['idx']), ptr(c['count']), B, N, N, P,
@@ -63,9 +65,9 @@ class BoundCall:
 
     def launch(self):
         """decode + threshold + top-k + NMS: one C call (mydet_detect), asynchronous."""
-        rc = self._L.mydet_detect(*self._detect_args, self._stream())
+        rc = self._L.mydet_detect_ws(*self._detect_args, self._stream())
         if rc:
-            _lib.check(rc, 'mydet_detect')
+            _lib.check(rc, 'mydet_detect_ws')
         return self.out
 
     # stage-wise entry points: the same two kernels as launch(), exposed so that bench.py can put

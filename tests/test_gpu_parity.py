@@ -673,3 +673,45 @@ def test_raster_iou_bit_exact_vs_oracle(canvas, lo, hi, n):
     big = want > 0.3
     if canvas == 2048 and hi > 100 and big.any():                        # un-clipped boxes of ordinary size: the raster follows the exact IoU
         assert np.abs(exact - want)[big].max() < 0.08
+
+
+def test_persistent_workspace_is_left_clean():
+    """The large-N NMS on a persistent workspace (ops.nms_rot caches one per geometry; mydet_nms_rot_ws with
+    workspace_clean=1): the suppression matrix is never cleared wholesale after the first call, each call zeroes what it
+    set.  Different inputs of one geometry, one after the other -- sparse, then so dense that the entry list overflows
+    (whole-matrix cleanup path), then sparse again -- must each equal the oracle; a stale bit would suppress a box."""
+    from mydetection_b200 import ops
+    from oracle import iou as oi
+    d = dev()
+    n = 2000
+    gen = torch.Generator().manual_seed(5)
+
+    def boxes(spread):
+        return torch.cat([torch.rand(1, n, 2, generator=gen) * spread + 100, torch.rand(1, n, 2, generator=gen) * 40 + 20,
+                          torch.rand(1, n, 1, generator=gen) * 180 - 90], dim=2)
+
+    ops.release_workspaces()
+    for spread in (900.0, 900.0, 25.0, 900.0, 300.0):
+        rb, rs = boxes(spread), torch.rand(1, n, generator=gen)
+        keep, cnt = ops.nms_rot(rb.to(d), rs.to(d), 0.3)
+        want = oi.nms_rot(rb[0], rs[0], 0.3)
+        assert int(cnt[0]) == want.numel() and torch.equal(keep[0, :int(cnt[0])].cpu(), want), spread
+    assert len(ops._PERSISTENT) == 1
+    # the same through a bound pipeline call (mydet_detect_ws): un-capped single-class scenes, launched repeatedly
+    from mydetection_b200 import pipeline as pl
+    from oracle import decode as od, postprocess as opp
+    raws_cpu = []
+    for s_ in (8, 16):
+        m = 256 // s_
+        t = torch.randn(1, 6, m, m, generator=gen) * 0.5
+        t[:, 4] = torch.randn(1, m, m, generator=gen) * 1.5 + 2.0
+        raws_cpu.append({k: v[:, 0] for k, v in yolo_views(t, 1, 4, 1).items()})
+    pipe = pl.DetectionPipeline('FCOS2', (8, 16), 1, (256, 256), 0.005, 0.3, None)
+    bc = pipe.bind([{k: v.to(d) for k, v in r.items()} for r in raws_cpu])
+    ref = od.merge_levels([od.decode_fcos(r, s_, (256, 256)) for r, s_ in zip(raws_cpu, (8, 16))])
+    want = opp.post_process(ref[0][0], ref[1][0], ref[2][0], 0.005, 0.3, 'cxcywh', None)
+    for _ in range(3):
+        out = bc.launch()
+        torch.cuda.synchronize()
+        c = int(out['count'][0])
+        assert c == want.numel() and torch.equal(out['idx'][0, :c].cpu().long(), want)
