@@ -21,8 +21,9 @@ else:
     _lib.LIB_PATH = LIBP
     dev = torch.device('cuda', 0)
     gen = torch.Generator(device=dev).manual_seed(2000)
-    _, raws, _ = bench.make_batch(gen, dev)
-    pipe = pl.DetectionPipeline('FCOS2', bench.STRIDES, bench.N_CLS, (bench.IMG, bench.IMG), bench.CONF_THRES,
+    wl = bench.Workload(640, 2.0)
+    raws, _ = wl.make_batch(gen, dev)
+    pipe = pl.DetectionPipeline('FCOS2', bench.STRIDES, bench.N_CLS, (wl.img, wl.img), bench.CONF_THRES,
                                 bench.NMS_THRES, bench.TOPK)
     bc = pipe.bind(raws)
     for _ in range(3):
