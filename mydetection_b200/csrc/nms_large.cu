@@ -65,6 +65,11 @@ struct LargeWs {          // carved out of the caller's workspace
     // 32-bit mask half-word non-zero records (row, half-word index) -- exactly one entry per non-empty half-word, so
     // the sweep no longer walks the adjacency map of every row to find them (75 of its 100 us at 10 000 boxes)
     int* fx_count;              // B
+    // lazy narrow phase of the rotated path (rot_filter_kernel / rot_clip_kernel)
+    unsigned* pairs2;           // B*pair_cap  the listed pairs that survive the oriented-extent bound
+    int* pair2_count;           // B
+    unsigned char* lz_high;     // B*n  by spatial position: some surviving pair has a higher-scored partner for this box
+    unsigned char* lz_dead;     // B*n  by spatial position: overlapped (>= thr) by a ROOT (a box with lz_high == 0)
 };
 // record the first bit of a mask half-word in the image's entry list (entries beyond the capacity are dropped: the
 // count still says so, and the sweep then falls back to the adjacency walk)
@@ -109,6 +114,8 @@ static size_t carve(LargeWs& w, void* base, int batch, int n, bool rot) {
     const size_t o_h16 = take(bp ? (size_t)batch * w.n16 * 16 : 0), o_h32 = take(bp ? (size_t)batch * w.n32 * 16 : 0);
     const size_t o_pairs = take((size_t)batch * w.pair_cap * 4), o_pcnt = take(bp ? (size_t)batch * 4 : 0);
     const size_t o_fxc = take(sp ? (size_t)batch * 4 : 0);
+    const size_t o_p2 = take((size_t)batch * w.pair_cap * 4), o_p2c = take(bp ? (size_t)batch * 4 : 0);
+    const size_t o_lzh = take(bp ? bn : 0), o_lzd = take(bp ? bn : 0);
     if (base) {
         char* p = static_cast<char*>(base);
         w.keys = (unsigned long long*)(p + o_keys); w.order = (int*)(p + o_order); w.m = (int*)(p + o_m);
@@ -129,6 +136,8 @@ static size_t carve(LargeWs& w, void* base, int batch, int n, bool rot) {
         w.hull16 = (float4*)(p + o_h16); w.hull32 = (float4*)(p + o_h32);
         w.pairs = (unsigned*)(p + o_pairs); w.pair_count = (int*)(p + o_pcnt);
         w.fx_count = (int*)(p + o_fxc);
+        w.pairs2 = (unsigned*)(p + o_p2); w.pair2_count = (int*)(p + o_p2c);
+        w.lz_high = (unsigned char*)(p + o_lzh); w.lz_dead = (unsigned char*)(p + o_lzd);
     }
     return off;
 }
@@ -1171,7 +1180,15 @@ __device__ __forceinline__ float oriented_overlap_bound(const float4 ca, const f
 constexpr int kNarrowThreads = 256;
 constexpr int kNarrowPer = 4;                       // listed pairs per thread and round
 
-__global__ void __launch_bounds__(kNarrowThreads) rot_narrow_kernel(LargeWs w, const int* m, int n, double thr_d, int ge) {
+// An image takes the lazy (root-first) narrow phase below when its boxes have many listed partners -- clustered detector
+// output -- and the one-pass kernel otherwise (14 partners per box on the bench workload: the two extra passes over the
+// list would cost more than the skipped clips save).  Decided on the device from the broad phase's pair count.
+constexpr int kLazyPartners = 32;
+__device__ __forceinline__ bool rot_image_is_lazy(const LargeWs& w, const int* m, int b, int lazy_mode) {
+    return lazy_mode == 2 || (lazy_mode == 1 && w.pair_count[b] > kLazyPartners * m[b]);
+}
+
+__device__ __forceinline__ void rot_narrow_body(const LargeWs& w, const int* m, int n, double thr_d, int ge) {
     const int b = blockIdx.y, tid = threadIdx.x;
     const int cnt = w.pair_count[b];
     if (cnt > w.pair_cap) return;                   // overflowed: the tile kernel redoes this image
@@ -1226,6 +1243,141 @@ __global__ void __launch_bounds__(kNarrowThreads) rot_narrow_kernel(LargeWs w, c
             if (rot_overlaps(A, B, thr_d, ge_mode)) {
                 const bool a_first = w.rank_of_spos[base + pa] < w.rank_of_spos[base + pb];
                 const int row = a_first ? pa : pb, col = a_first ? pb : pa;           // the higher-scored box suppresses
+                fx_note(w, b, row, col >> 5, atomicOr(&mask32[((base + row) * w.words + (col >> 6)) * 2 + ((col >> 5) & 1)], 1u << (col & 31)));
+                const int trow = row >> 6, tcol = col >> 6;
+                atomicOr(&w.tile_adj[((long long)b * w.words + trow) * w.aw + (tcol >> 6)], 1ull << (tcol & 63));
+            }
+        }
+    }
+}
+
+// ---- lazy narrow phase.  Detector output is clustered: an object draws hundreds of mutually overlapping boxes, of which
+// greedy NMS keeps one or two -- yet the kernel above clips EVERY listed pair (1.25 M polygon clips per image for 40
+// objects x 250 boxes, 73 % of the whole rotated NMS).  Most of those pairs cannot matter: a box that a certainly-kept box
+// suppresses is never kept itself, so its row of the suppression matrix is never read, and its column is already decided.
+//   filter : the oriented-extent bound on every listed pair (stage 1 of the kernel above); survivors are compacted into a
+//            second list and mark their LOWER-scored box "has a higher-scored partner".  Boxes without the mark are ROOTS:
+//            nothing that could suppress them exists, greedy NMS keeps them.
+//   clip<0>: pairs whose higher-scored box is a root: clip, set the bit, mark the lower box DEAD on overlap.
+//   clip<1>: the remaining pairs, except those with a dead member: a dead higher box never suppresses (it is not kept), a
+//            dead lower box is already removed by its root's bit.  The fixed point of the reduced matrix is the greedy set.
+// 40 x 250 clustered boxes: 1.25 M -> ~0.1 M clips per image.
+__device__ __forceinline__ void rot_filter_body(const LargeWs& w, const int* m, int n, double thr_d) {
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int cnt = w.pair_count[b];
+    if (cnt > w.pair_cap) return;                   // overflowed: the tile kernel redoes this image
+    const long long base = (long long)b * n;
+    const unsigned* pairs = w.pairs + (long long)b * w.pair_cap;
+    unsigned* out = w.pairs2 + (long long)b * w.pair_cap;
+    const float thr_f = (float)thr_d;
+    __shared__ unsigned s_q[kNarrowThreads * kNarrowPer];
+    __shared__ int s_n, s_at;
+    constexpr int kChunk = kNarrowThreads * kNarrowPer;
+    for (int c0 = blockIdx.x * kChunk; c0 < cnt; c0 += gridDim.x * kChunk) {       // block-uniform
+        __syncthreads();
+        if (tid == 0) s_n = 0;
+        __syncthreads();
+        unsigned code[kNarrowPer];
+        float4 ca[kNarrowPer], cb[kNarrowPer], xa[kNarrowPer], xb[kNarrowPer];
+#pragma unroll
+        for (int u = 0; u < kNarrowPer; ++u) {
+            const int e = c0 + u * kNarrowThreads + tid;
+            code[u] = (e < cnt) ? pairs[e] : 0xffffffffu;
+        }
+#pragma unroll
+        for (int u = 0; u < kNarrowPer; ++u) {
+            const bool live = code[u] != 0xffffffffu;
+            const int pa = live ? (int)(code[u] >> 16) : 0, pb = live ? (int)(code[u] & 0xffffu) : 0;
+            ca[u] = w.cull4[base + pa]; cb[u] = w.cull4[base + pb];
+            xa[u] = w.axes4[base + pa]; xb[u] = w.axes4[base + pb];
+        }
+#pragma unroll
+        for (int u = 0; u < kNarrowPer; ++u) {
+            const float ub = oriented_overlap_bound(ca[u], xa[u], cb[u], xb[u]);
+            const bool drop = ub * 1.001f + 1e-2f < thr_f * (ca[u].w + cb[u].w - ub);     // same slack as rot_narrow_kernel
+            const bool keep = code[u] != 0xffffffffu && !drop;
+            if (keep) {
+                const int pa = (int)(code[u] >> 16), pb = (int)(code[u] & 0xffffu);
+                const bool a_first = w.rank_of_spos[base + pa] < w.rank_of_spos[base + pb];
+                w.lz_high[base + (a_first ? pb : pa)] = 1;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            int at = 0;
+            if ((tid & 31) == 0 && bal) at = atomicAdd(&s_n, __popc(bal));
+            at = __shfl_sync(0xffffffffu, at, 0);
+            if (keep) s_q[at + __popc(bal & ((1u << (tid & 31)) - 1u))] = code[u];
+        }
+        __syncthreads();
+        const int total = s_n;
+        if (tid == 0 && total) s_at = atomicAdd(&w.pair2_count[b], total);
+        __syncthreads();
+        for (int e = tid; e < total; e += kNarrowThreads) out[s_at + e] = s_q[e];
+    }
+}
+
+// lazy_mode: 0 = one-pass narrow phase for every image, 1 = per image by its pair count, 2 = lazy for every image
+__global__ void __launch_bounds__(kNarrowThreads) rot_narrow_kernel(LargeWs w, const int* m, int n, double thr_d, int ge, int lazy_mode) {
+    if (rot_image_is_lazy(w, m, blockIdx.y, lazy_mode)) rot_filter_body(w, m, n, thr_d);
+    else rot_narrow_body(w, m, n, thr_d, ge);
+}
+
+template <int PHASE>
+__global__ void __launch_bounds__(kNarrowThreads) rot_clip_kernel(LargeWs w, const int* m, int n, double thr_d, int ge, int lazy_mode) {
+    const int b = blockIdx.y, tid = threadIdx.x;
+    if (w.pair_count[b] > w.pair_cap || !rot_image_is_lazy(w, m, b, lazy_mode)) return;
+    const int cnt = w.pair2_count[b];
+    const long long base = (long long)b * n;
+    const unsigned* pairs = w.pairs2 + (long long)b * w.pair_cap;
+    unsigned* mask32 = reinterpret_cast<unsigned*>(w.mask);
+    const bool ge_mode = ge != 0;
+    __shared__ unsigned s_q[kNarrowThreads * kNarrowPer];
+    __shared__ int s_n;
+    constexpr int kChunk = kNarrowThreads * kNarrowPer;
+    for (int c0 = blockIdx.x * kChunk; c0 < cnt; c0 += gridDim.x * kChunk) {       // block-uniform
+        __syncthreads();
+        if (tid == 0) s_n = 0;
+        __syncthreads();
+        // (1) which pairs does this phase own?  code in the queue: higher-scored position << 16 | lower-scored position
+        unsigned code[kNarrowPer];
+        int ra[kNarrowPer], rb[kNarrowPer];
+#pragma unroll
+        for (int u = 0; u < kNarrowPer; ++u) {
+            const int e = c0 + u * kNarrowThreads + tid;
+            code[u] = (e < cnt) ? pairs[e] : 0xffffffffu;
+        }
+#pragma unroll
+        for (int u = 0; u < kNarrowPer; ++u) {
+            const bool live = code[u] != 0xffffffffu;
+            ra[u] = live ? w.rank_of_spos[base + (code[u] >> 16)] : 0;
+            rb[u] = live ? w.rank_of_spos[base + (code[u] & 0xffffu)] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < kNarrowPer; ++u) {
+            bool own = false;
+            unsigned ordered = 0u;
+            if (code[u] != 0xffffffffu) {
+                const int pa = (int)(code[u] >> 16), pb = (int)(code[u] & 0xffffu);
+                const int hi = ra[u] < rb[u] ? pa : pb, lo = ra[u] < rb[u] ? pb : pa;
+                const bool root = w.lz_high[base + hi] == 0;
+                own = PHASE == 0 ? root : (!root && !w.lz_dead[base + hi] && !w.lz_dead[base + lo]);
+                ordered = ((unsigned)hi << 16) | (unsigned)lo;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, own);
+            int at = 0;
+            if ((tid & 31) == 0 && bal) at = atomicAdd(&s_n, __popc(bal));
+            at = __shfl_sync(0xffffffffu, at, 0);
+            if (own) s_q[at + __popc(bal & ((1u << (tid & 31)) - 1u))] = ordered;
+        }
+        __syncthreads();
+        // (2) polygon clip, every lane busy
+        const int total = s_n;
+        for (int e = tid; e < total; e += kNarrowThreads) {
+            const unsigned cd = s_q[e];
+            const int row = (int)(cd >> 16), col = (int)(cd & 0xffffu);           // the higher-scored box suppresses
+            const RotBox A = w.rbox[base + min(row, col)];
+            const RotBox B = w.rbox[base + max(row, col)];                        // operand order of rot_narrow_kernel: lower position first
+            if (rot_overlaps(A, B, thr_d, ge_mode)) {
+                if (PHASE == 0) w.lz_dead[base + col] = 1;
                 fx_note(w, b, row, col >> 5, atomicOr(&mask32[((base + row) * w.words + (col >> 6)) * 2 + ((col >> 5) & 1)], 1u << (col & 31)));
                 const int trow = row >> 6, tcol = col >> 6;
                 atomicOr(&w.tile_adj[((long long)b * w.words + trow) * w.aw + (tcol >> 6)], 1ull << (tcol & 63));
@@ -1706,7 +1858,23 @@ int run_large(const LargeArgs& A, void* workspace, size_t workspace_bytes, cudaS
                 rot_broad_kernel<<<dim3((w.n32 + kBroadWarps - 1) / kBroadWarps, B), kBroadWarps * 32, 0, st>>>(w, w.m, n, (float)A.thr);
                 // a CTA takes 1024 listed pairs per round; 148 CTAs per image cover the typical list (~14 pairs per box) in one
                 const int nb = (int)(((long long)w.pair_cap + kNarrowThreads * kNarrowPer - 1) / (kNarrowThreads * kNarrowPer));
-                rot_narrow_kernel<<<dim3(nb < 1 ? 1 : (nb > 148 ? 148 : nb), B), kNarrowThreads, 0, st>>>(w, w.m, n, A.thr, A.ge);
+                const dim3 ngrid(nb < 1 ? 1 : (nb > 148 ? 148 : nb), B);
+                // developer A/B switch MYDET_ROT_LAZY: 0 = clip every listed pair, 2 = lazy for every image; default 1 = per image
+                const char* lzenv = getenv("MYDET_ROT_LAZY");
+                const int lazy_mode = (lzenv && lzenv[0] >= '0' && lzenv[0] <= '2') ? lzenv[0] - '0' : 1;
+                if (lazy_mode == 0) {
+                    rot_narrow_kernel<<<ngrid, kNarrowThreads, 0, st>>>(w, w.m, n, A.thr, A.ge, 0);
+                } else {
+                    // pair2_count, lz_high, lz_dead are carved one after the other: one memset
+                    MYDET_CUDA(cudaMemsetAsync(w.pair2_count, 0, (size_t)((char*)w.lz_dead - (char*)w.pair2_count) + (size_t)B * n, st));
+                    rot_narrow_kernel<<<ngrid, kNarrowThreads, 0, st>>>(w, w.m, n, A.thr, A.ge, lazy_mode);
+                    // the two clip passes are empty launches for every image that is not lazy: a grid of ~8 CTAs per SM over the
+                    // batch (grid-stride inside) keeps those cheap and still fills the GPU for the images that are
+                    int cg = 1184 / (B < 1 ? 1 : B);
+                    cg = cg < 8 ? 8 : (cg > (int)ngrid.x ? (int)ngrid.x : cg);
+                    rot_clip_kernel<0><<<dim3(cg, B), kNarrowThreads, 0, st>>>(w, w.m, n, A.thr, A.ge, lazy_mode);
+                    rot_clip_kernel<1><<<dim3(cg, B), kNarrowThreads, 0, st>>>(w, w.m, n, A.thr, A.ge, lazy_mode);
+                }
                 mask_rot_overflow_kernel<<<148 * 16, kTile, 0, st>>>(w, w.m, n, B, A.thr, A.ge);
             }
         } else {

@@ -715,3 +715,35 @@ def test_persistent_workspace_is_left_clean():
         torch.cuda.synchronize()
         c = int(out['count'][0])
         assert c == want.numel() and torch.equal(out['idx'][0, :c].cpu().long(), want)
+
+
+@pytest.mark.parametrize('spread', [4.0, 12.0, 400.0])
+def test_lazy_narrow_phase_equals_full_and_oracle(spread, monkeypatch):
+    """The root-first narrow phase of rotated NMS (pairs with a member that a certainly-kept box suppresses are never
+    clipped) against clipping every listed pair (MYDET_ROT_LAZY=0) and against the oracle: identical kept indices and
+    votes -- on tight clusters (most boxes die at their root), loose clusters (chains: a dead box must not suppress) and
+    scattered boxes (few roots)."""
+    from mydetection_b200 import ops
+    from oracle import iou as oi
+    d = dev()
+    gen = torch.Generator().manual_seed(int(spread))
+    n_obj, per = 12, 250
+    n = n_obj * per
+    obj = torch.rand(2, n_obj, 1, 2, generator=gen) * 800 + 100
+    xy = (obj + torch.randn(2, n_obj, per, 2, generator=gen) * spread).reshape(2, n, 2)
+    wh = (torch.rand(2, n_obj, 1, 2, generator=gen) * 80 + 30 + torch.randn(2, n_obj, per, 2, generator=gen) * 3).reshape(2, n, 2).abs() + 4
+    ang = (torch.rand(2, n_obj, 1, 1, generator=gen) * 180 - 90 + torch.randn(2, n_obj, per, 1, generator=gen) * 8).reshape(2, n, 1)
+    rb, rs = torch.cat([xy, wh, ang], dim=2), torch.rand(2, n, generator=gen)
+    keep, cnt, votes = ops.nms_rot(rb.to(d), rs.to(d), 0.45, want_votes=True)        # default: lazy per image, by its pair count
+    for mode in ('0', '2'):                                                          # never lazy / always lazy
+        monkeypatch.setenv('MYDET_ROT_LAZY', mode)
+        keep_f, cnt_f, votes_f = ops.nms_rot(rb.to(d), rs.to(d), 0.45, want_votes=True)
+        monkeypatch.delenv('MYDET_ROT_LAZY')
+        assert torch.equal(cnt, cnt_f)
+        for b in range(2):
+            c = int(cnt[b])
+            assert torch.equal(keep[b, :c], keep_f[b, :c]) and torch.equal(votes[b, :c], votes_f[b, :c]), (mode, b)
+    for b in range(2):
+        c = int(cnt[b])
+        want = oi.nms_rot(rb[b], rs[b], 0.45)
+        assert c == want.numel() and torch.equal(keep[b, :c].cpu(), want), (spread, b)
