@@ -8,8 +8,10 @@
 //                           (vertical pass first for images more than 100x taller than wide: Pillow's own rule)
 //   final_kernel            the other pass + zero padding + /255 + normalisation / channel order -> float32 planes,
 //                           each thread produces 4 consecutive pixels of a row and writes three 16-byte vectors
-// Bandwidth-bound byte work: no tensor cores, no shared-memory staging (the taps of neighbouring threads overlap
-// and are served by L1; the intermediate of a 1080p frame is 2 MB and stays in L2).
+// Byte work, bound by instruction issue (ncu: 74-85 % issue-active), not by HBM: no tensor cores; no shared-memory
+// staging -- a variant that staged each CTA's source span with coalesced word loads was measured SLOWER (682 vs 486 us
+// per 64 x 1080p batch: 207 k small CTAs with two barriers each; the taps of neighbouring threads are served by L1 anyway).
+// Per-pixel float work is a 768-entry table (format_lut_entry), index splitting is 32-bit.
 // All arithmetic lives in preprocess_core.cuh (host/device), which tests compile for the host and compare with
 // Pillow and the reference bit for bit.
 #include "internal.cuh"
@@ -35,9 +37,12 @@ __global__ void final_kernel(Geometry G, const uint8_t* __restrict__ img, long l
                              const int* __restrict__ bounds_h, const int* __restrict__ kk_h,
                              const int* __restrict__ bounds_v, const int* __restrict__ kk_v, float* __restrict__ dst,
                              int quads_per_row, long long total_quads, int vec_ok) {
+    __shared__ float s_lut[768];                       // to_tensor + format_tensor_img of every byte value, per plane
+    for (int v = threadIdx.x; v < 256; v += blockDim.x) format_lut_entry(v, G.format, s_lut);
+    __syncthreads();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < total_quads)
-        final_item(G, i, img, image_stride, row_pitch, bounds_h, kk_h, bounds_v, kk_v, dst, quads_per_row, vec_ok);
+        final_item(G, i, img, image_stride, row_pitch, bounds_h, kk_h, bounds_v, kk_v, dst, quads_per_row, vec_ok, s_lut);
 }
 
 }  // namespace pre

@@ -83,6 +83,9 @@ MYDET_HD void resample_h_pixel(const uint8_t* src_row, const int* bounds_h, cons
     const int* k = kk_h + (long long)xx * ksize_h;
     int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
     const uint8_t* p = src_row + 3ll * x0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 4                                      // the byte loads of four taps in flight before the first multiply-add
+#endif
     for (int t = 0; t < n; ++t) {
         const int w = k[t];
         s0 += (int)p[3 * t + 0] * w;
@@ -99,6 +102,9 @@ MYDET_HD void resample_v_pixel(const uint8_t* tmp, long long row_pitch, const in
     const int* k = kk_v + (long long)yy * ksize_v;
     int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
     const uint8_t* p = tmp + (long long)y0 * row_pitch + 3ll * x;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 4
+#endif
     for (int t = 0; t < n; ++t) {
         const int w = k[t];
         s0 += (int)p[0] * w;
@@ -125,6 +131,22 @@ MYDET_HD void format_pixel(const uint8_t* rgb, int format, float* out3) {
     }
 }
 
+// The same through a table: plane c of a pixel depends only on ONE source byte (channel c, or 2 - c for the BGR format),
+// so lut[c * 256 + v] = format_pixel of the grey pixel (v, v, v), plane c, is bit for bit what format_pixel computes --
+// and replaces three IEEE divisions by 255 plus the normalisation per pixel by three table reads.
+MYDET_HD void format_lut_entry(int v, int format, float* lut) {
+    const uint8_t rgb[3] = {(uint8_t)v, (uint8_t)v, (uint8_t)v};
+    float o[3];
+    format_pixel(rgb, format, o);
+    lut[v] = o[0]; lut[256 + v] = o[1]; lut[512 + v] = o[2];
+}
+MYDET_HD void format_pixel_lut(const uint8_t* rgb, int format, const float* lut, float* out3) {
+    const bool bgr = !(format == kFormatRGB1 || format == kFormatRGB1Norm);
+    out3[0] = lut[rgb[bgr ? 2 : 0]];
+    out3[1] = lut[256 + rgb[1]];
+    out3[2] = lut[512 + rgb[bgr ? 0 : 2]];
+}
+
 // Geometry of one call, shared by the kernels and the harness.
 struct Geometry {
     int in_h, in_w;            // source image
@@ -141,7 +163,7 @@ struct Geometry {
 // 3 * rs_w bytes after a horizontal first pass, rows of 3 * in_w bytes after a vertical one (G.v_first) -- or, when
 // G.direct, the source image (rows of src_row_pitch bytes).
 MYDET_HD void final_pixel(const Geometry& G, const uint8_t* img, long long row_pitch, const int* bounds_h, const int* kk_h,
-                          const int* bounds_v, const int* kk_v, int y, int x, float* out3) {
+                          const int* bounds_v, const int* kk_v, int y, int x, float* out3, const float* lut = nullptr) {
     uint8_t rgb[3] = {0, 0, 0};                                   // the zero padding of tvf.pad(fill=0)
     const int ry = y - G.top, rx = x - G.left;
     if (ry >= 0 && ry < G.rs_h && rx >= 0 && rx < G.rs_w) {
@@ -154,7 +176,25 @@ MYDET_HD void final_pixel(const Geometry& G, const uint8_t* img, long long row_p
             resample_v_pixel(img, row_pitch, bounds_v, kk_v, G.ksize_v, ry, rx, rgb);
         }
     }
-    format_pixel(rgb, G.format, out3);
+    if (lut) format_pixel_lut(rgb, G.format, lut, out3);
+    else format_pixel(rgb, G.format, out3);
+}
+
+// (column, row, image) of linear work item i of a (batch, rows, cols) space, x fastest.  32-bit arithmetic whenever the
+// index fits: a 64-bit divide is ~100 instructions, and every item starts with two of them.
+MYDET_HD void split_index(long long i, int cols, int rows, int* x, int* y, long long* b) {
+    if (i <= 0x7fffffffLL) {
+        const unsigned u = (unsigned)i, row = u / (unsigned)cols;
+        *x = (int)(u - row * (unsigned)cols);
+        const unsigned bb = row / (unsigned)rows;
+        *y = (int)(row - bb * (unsigned)rows);
+        *b = (long long)bb;
+    } else {
+        *x = (int)(i % cols);
+        const long long row = i / cols;
+        *y = (int)(row % rows);
+        *b = row / rows;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -178,10 +218,9 @@ MYDET_HD void first_item(const Geometry& G, long long i, const uint8_t* src, lon
                          long long src_row_pitch, const int* bounds_h, const int* kk_h, const int* bounds_v,
                          const int* kk_v, uint8_t* tmp) {
     const int cols = G.v_first ? G.in_w : G.rs_w, rows = G.v_first ? G.rs_h : G.in_h;
-    const int x = (int)(i % cols);
-    const long long row = i / cols;                           // b * rows + y
-    const int y = (int)(row % rows);
-    const long long b = row / rows;
+    int x, y;
+    long long b;
+    split_index(i, cols, rows, &x, &y, &b);
     const uint8_t* image = src + b * src_image_stride;
     uint8_t px[3];
     if (G.v_first) resample_v_pixel(image, src_row_pitch, bounds_v, kk_v, G.ksize_v, y, x, px);
@@ -205,11 +244,10 @@ MYDET_HD void store4(float* p, float a, float b, float c, float d) {
 // vec_ok: out_w % 4 == 0 and dst 16-byte aligned, so each plane takes one 16-byte store.
 MYDET_HD void final_item(const Geometry& G, long long i, const uint8_t* img, long long image_stride,
                          long long row_pitch, const int* bounds_h, const int* kk_h, const int* bounds_v, const int* kk_v,
-                         float* dst, int quads_per_row, int vec_ok) {
-    const int q = (int)(i % quads_per_row);
-    const long long row = i / quads_per_row;                  // b * out_h + y
-    const int y = (int)(row % G.out_h);
-    const long long b = row / G.out_h;
+                         float* dst, int quads_per_row, int vec_ok, const float* lut = nullptr) {
+    int q, y;
+    long long b;
+    split_index(i, quads_per_row, G.out_h, &q, &y, &b);
     const uint8_t* im = img + b * image_stride;
     const long long plane = (long long)G.out_h * G.out_w;
     float* o = dst + b * 3 * plane + (long long)y * G.out_w;
@@ -220,7 +258,7 @@ MYDET_HD void final_item(const Geometry& G, long long i, const uint8_t* img, lon
 #endif
     for (int k = 0; k < 4; ++k) {
         v[k][0] = v[k][1] = v[k][2] = 0.f;
-        if (x0 + k < G.out_w) final_pixel(G, im, row_pitch, bounds_h, kk_h, bounds_v, kk_v, y, x0 + k, v[k]);
+        if (x0 + k < G.out_w) final_pixel(G, im, row_pitch, bounds_h, kk_h, bounds_v, kk_v, y, x0 + k, v[k], lut);
     }
     if (vec_ok && x0 + 3 < G.out_w) {
         for (int c = 0; c < 3; ++c) store4(o + c * plane + x0, v[0][c], v[1][c], v[2][c], v[3][c]);

@@ -37,9 +37,11 @@ int main(int argc, char** argv) {
     memset(dst, 0xff, dst_count * sizeof(float));            // NaN pattern: every element must be overwritten
     const Geometry& G = P.G;
     const int vec_ok = (out_w % 4 == 0 && ((uintptr_t)dst & 15) == 0) ? 1 : 0;      // as mydet_preprocess decides
+    float lut[768];                                           // as final_kernel builds it in shared memory
+    for (int v = 0; v < 256; ++v) format_lut_entry(v, G.format, lut);
     if (G.direct) {
         for (long long i = 0; i < P.n_final_items; ++i)
-            final_item(G, i, src, image_stride, row_pitch, nullptr, nullptr, nullptr, nullptr, dst, P.quads_per_row, vec_ok);
+            final_item(G, i, src, image_stride, row_pitch, nullptr, nullptr, nullptr, nullptr, dst, P.quads_per_row, vec_ok, lut);
     } else {
         int* bounds_h = (int*)(ws + P.off_bounds_h);
         int* kk_h = (int*)(ws + P.off_kk_h);
@@ -51,7 +53,7 @@ int main(int argc, char** argv) {
         for (long long i = 0; i < P.n_first_items; ++i)
             first_item(G, i, src, image_stride, row_pitch, bounds_h, kk_h, bounds_v, kk_v, tmp);
         for (long long i = 0; i < P.n_final_items; ++i)
-            final_item(G, i, tmp, P.tmp_image_stride, P.tmp_row_pitch, bounds_h, kk_h, bounds_v, kk_v, dst, P.quads_per_row, vec_ok);
+            final_item(G, i, tmp, P.tmp_image_stride, P.tmp_row_pitch, bounds_h, kk_h, bounds_v, kk_v, dst, P.quads_per_row, vec_ok, lut);
     }
     f = fopen(argv[2], "wb");
     if (!f || fwrite(dst, sizeof(float), dst_count, f) != dst_count) { fprintf(stderr, "cannot write %s\n", argv[2]); return 5; }
