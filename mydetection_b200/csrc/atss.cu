@@ -48,6 +48,18 @@ __device__ __forceinline__ float iou_cxcywh(float acx, float acy, float aw, floa
     return __fdiv_rn(inter, __fsub_rn(__fadd_rn(__fmul_rn(aw, ah), __fmul_rn(bw, bh)), inter));
 }
 
+// The same, for callers that only compare the result with a NON-NEGATIVE threshold (or take a maximum that is then so
+// compared): boxes that do not overlap give +-0 (or NaN for degenerate boxes) whatever the union is -- never above such a
+// threshold -- so the multiply / divide tail is skipped for them (the vast majority of anchor-GT and cell-GT pairs).
+__device__ __forceinline__ float iou_cxcywh_or_zero(float acx, float acy, float aw, float ah, float bcx, float bcy, float bw, float bh) {
+    const float ahw = __fmul_rn(aw, 0.5f), ahh = __fmul_rn(ah, 0.5f), bhw = __fmul_rn(bw, 0.5f), bhh = __fmul_rn(bh, 0.5f);
+    const float tlx = fmaxf(__fsub_rn(acx, ahw), __fsub_rn(bcx, bhw)), tly = fmaxf(__fsub_rn(acy, ahh), __fsub_rn(bcy, bhh));
+    const float brx = fminf(__fadd_rn(acx, ahw), __fadd_rn(bcx, bhw)), bry = fminf(__fadd_rn(acy, ahh), __fadd_rn(bcy, bhh));
+    if (!(tlx < brx && tly < bry)) return 0.0f;
+    const float inter = __fmul_rn(__fsub_rn(brx, tlx), __fsub_rn(bry, tly));         // en == 1
+    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(__fmul_rn(aw, ah), __fmul_rn(bw, bh)), inter));
+}
+
 __global__ void atss_prepare_kernel(const float* gt_box, const long long* gt_cls, const int* gt_count, int max_gt, AtssWs w) {
     extern __shared__ float s_area[];
     const int b = blockIdx.x;
@@ -102,19 +114,45 @@ __global__ void atss_threshold_kernel(AtssGeom G, const int* gt_count, int max_g
         const int n_cand = w_rows * w_cols;
         float last_d = -1.0f;
         int last_i = -1;
+        auto cand = [&](int q, float& d, int& i) {             // q-th cell of the window: squared distance of its centre, flat index
+            const int wr = q / w_cols;
+            const int row = r_lo + wr, col = c_lo + (q - wr * w_cols);
+            i = row * n_w + col;
+            const float ax = __fadd_rn(__fmul_rn((float)col, fs), half);
+            const float ay = __fadd_rn(__fmul_rn((float)row, fs), half);
+            const float dx = __fsub_rn(gt.x, ax), dy = __fsub_rn(gt.y, ay);
+            d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));                            // :396
+        };
+        // the 11 x 11 window is at most 4 cells per lane: their (distance, index) pairs are computed ONCE and the k
+        // selection rounds run on registers (they used to recompute every distance, with an integer division, every round)
+        constexpr int kPerLane = 4;
+        const bool in_regs = n_cand <= 32 * kPerLane;
+        float cd[kPerLane];
+        int ci[kPerLane];
+#pragma unroll
+        for (int u = 0; u < kPerLane; ++u) {
+            cd[u] = INFINITY; ci[u] = 0x7fffffff;
+            if (in_regs && lane + 32 * u < n_cand) cand(lane + 32 * u, cd[u], ci[u]);
+        }
         for (int round = 0; round < G.k; ++round) {
             float best_d = INFINITY;
             int best_i = 0x7fffffff;
-            for (int q = lane; q < n_cand; q += 32) {
-                const int wr = q / w_cols;
-                const int row = r_lo + wr, col = c_lo + (q - wr * w_cols);
-                const int i = row * n_w + col;
-                const float ax = __fadd_rn(__fmul_rn((float)col, fs), half);
-                const float ay = __fadd_rn(__fmul_rn((float)row, fs), half);
-                const float dx = __fsub_rn(gt.x, ax), dy = __fsub_rn(gt.y, ay);
-                const float d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));           // :396
-                const bool after_last = d > last_d || (d == last_d && i > last_i);
-                if (after_last && (d < best_d || (d == best_d && i < best_i))) { best_d = d; best_i = i; }
+            if (in_regs) {
+#pragma unroll
+                for (int u = 0; u < kPerLane; ++u) {
+                    const float d = cd[u];
+                    const int i = ci[u];
+                    const bool after_last = d > last_d || (d == last_d && i > last_i);
+                    if (after_last && (d < best_d || (d == best_d && i < best_i))) { best_d = d; best_i = i; }
+                }
+            } else {
+                for (int q = lane; q < n_cand; q += 32) {
+                    float d;
+                    int i;
+                    cand(q, d, i);
+                    const bool after_last = d > last_d || (d == last_d && i > last_i);
+                    if (after_last && (d < best_d || (d == best_d && i < best_i))) { best_d = d; best_i = i; }
+                }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -208,19 +246,21 @@ __global__ void __launch_bounds__(kAssignThreads) assign_kernel(AssignParams P, 
 
     float best_iou = -INFINITY;
     bool positive = false;
+    const bool skip_disjoint = P.ignore_thres >= 0.f;      // else a disjoint pair's IoU of 0 could exceed the threshold: keep the full formula
     float4 ltrb = make_float4(0.f, 0.f, 0.f, 0.f);
     float* cls_row = P.target_cls + ((long long)b * n_hw + cell) * P.n_cls;
     for (int g = 0; g < n_gt; ++g) {
         const float4 gt = s_gt[g];
-        best_iou = fmaxf(best_iou, iou_cxcywh(pcx, pcy, pw, ph, gt.x, gt.y, gt.z, gt.w));   // :306-307
+        best_iou = fmaxf(best_iou, skip_disjoint ? iou_cxcywh_or_zero(pcx, pcy, pw, ph, gt.x, gt.y, gt.z, gt.w)
+                                                 : iou_cxcywh(pcx, pcy, pw, ph, gt.x, gt.y, gt.z, gt.w));   // :306-307
         const float hw = __fmul_rn(gt.z, 0.5f), hh = __fmul_rn(gt.w, 0.5f);                  // :408-414, cr = 1
         const float tl = __fsub_rn(gx, __fsub_rn(gt.x, hw)), tt = __fsub_rn(gy, __fsub_rn(gt.y, hh));
         const float tr = __fsub_rn(__fadd_rn(gt.x, hw), gx), tb = __fsub_rn(__fadd_rn(gt.y, hh), gy);
         bool pos;
         if (ATSS) {
             const bool inside = tl > 0.f && tt > 0.f && tr > 0.f && tb > 0.f;                // :321
-            const float iou = iou_cxcywh(gx, gy, P.side, P.side, gt.x, gt.y, gt.z, gt.w);    // :329
-            pos = inside && iou > s_thr[g];                                                  // :330-331
+            // :329-331: the anchor IoU only where the cell lies inside the GT (the result is ANDed with `inside`)
+            pos = inside && iou_cxcywh(gx, gy, P.side, P.side, gt.x, gt.y, gt.z, gt.w) > s_thr[g];
         } else {
             // _xywh_to_xyxy(bb, cr): c -/+ (w * cr) / 2                                        :408-414
             const float chw = __fmul_rn(__fmul_rn(gt.z, P.center_region), 0.5f), chh = __fmul_rn(__fmul_rn(gt.w, P.center_region), 0.5f);
