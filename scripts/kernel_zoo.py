@@ -3,7 +3,7 @@ one JSON line per section with CUDA-event timings, the stated bound and the achi
 
     python scripts/kernel_zoo.py                 # all sections, timed (events, warm-up, L2-sized rotation where it matters)
     python scripts/kernel_zoo.py --once rot      # ONE un-timed invocation of a section: the command ncu wraps
-Sections: rot, rot1 (single image), rotclu, atss, fcos, rowmax, iou, iourot, dense, pre, decode_yolo, decode_rapid
+Sections: rot, rotbench (bench.py's rotated workload), rot1 (single image), rotclu, atss, fcos, rowmax, iou, iourot, dense, pre, decode_yolo, decode_rapid
 """
 import json
 import os
@@ -63,6 +63,15 @@ def sec_rot(clustered=False, B=32):
     us = timed(lambda i: ops.nms_rot(sets[i % 2][0], sets[i % 2][1], 0.45), iters=6)
     emit(('rotclu' if clustered else 'rot') + ('' if B == 32 else str(B)), workload=f'{B} images x {n} rotated boxes' + (' (40 objects x 250 boxes)' if clustered else ''),
          us_per_batch=us, us_per_image=us / B, bound='ALU / latency (pairwise)', algorithmic_pairs_per_s=B * n * (n - 1) / 2 / us * 1e6)
+
+
+def sec_rotbench():
+    """bench.py's own rotated workload: the best 10 000 of 64 512 RAPiD candidates @1024 per image."""
+    import bench
+    rb, rs = bench.rapid_boxes(DEV, 32, 10000)
+    us = timed(lambda i: ops.nms_rot(rb, rs, 0.45), iters=6)
+    emit('rotbench', workload='32 images x the best 10000 of 64512 RAPiD candidates @1024', us_per_batch=us, us_per_image=us / 32,
+         bound='ALU / latency (pairwise)', algorithmic_pairs_per_s=32 * 10000 * 9999 / 2 / us * 1e6)
 
 
 def sec_atss(fcos=False):
@@ -183,7 +192,7 @@ def sec_decode(kind):
          note='eager launch + a 4-byte-per-image memset; the lone-launch ramp is included')
 
 
-SECTIONS = {'rot': sec_rot, 'rot1': lambda: sec_rot(False, 1), 'rotclu': lambda: sec_rot(True), 'atss': sec_atss, 'fcos': lambda: sec_atss(True), 'rowmax': sec_rowmax,
+SECTIONS = {'rot': sec_rot, 'rotbench': sec_rotbench, 'rot1': lambda: sec_rot(False, 1), 'rotclu': lambda: sec_rot(True), 'atss': sec_atss, 'fcos': lambda: sec_atss(True), 'rowmax': sec_rowmax,
             'iou': sec_iou, 'iourot': lambda: sec_iou(True), 'dense': sec_dense, 'pre': sec_pre,
             'decode_yolo': lambda: sec_decode('yolo'), 'decode_rapid': lambda: sec_decode('rapid')}
 
