@@ -1,4 +1,5 @@
-"""Small end-to-end case for compute-sanitizer (racecheck / memcheck): every kernel family once."""
+"""Small end-to-end case, every kernel family once: written for compute-sanitizer (racecheck / memcheck; round 1 ran it
+clean) -- the tool is closed on the round-2 GPU pool, where this still serves as a crash / launch-error smoke."""
 import os
 import sys
 
@@ -45,6 +46,35 @@ tg = ops.fcos_assign(raws[0]['bbox'], 8, img, b2[:, :7].contiguous() * 0.4, c2[:
 n3 = 8300
 b3 = torch.cat([b2[:1, :n3, :2], b2[:1, :n3, 2:] * 0.3 + 2, (torch.rand(1, n3, 1, generator=g) * 180 - 90).to(d)], 2).contiguous()
 keep3, cnt3 = ops.nms_rot(b3, s2[:1, :n3].contiguous(), 0.45)
+# round 2: exchange protocol (publish / wait / release / fused consumer), lazy narrow phase on clustered boxes (forced and
+# by pair count), persistent workspace reuse, raster IoU, segmented evaluator IoU, tracklets, ATSS assignment
+import os
+ex = pl.PeerExchange(2, 128, 4, d, local_only=True)
+bc2 = pl.DetectionPipeline('FCOS2', strides, 5, img, 0.05, 0.5, 128).bind(raws).bind_exchange(ex, protocol=True)
+for _ in range(2):
+    bc2.launch_decode(); bc2.launch_postprocess_scatter(); ex.publish(); ex.wait(); ex.release()
+    bc2.launch_decode(); bc2.launch_postprocess_scatter(); ex.consume_counts()
+obj = torch.rand(2, 6, 1, 2, generator=g) * 300 + 50
+cl = torch.cat([(obj + torch.randn(2, 6, 250, 2, generator=g) * 5).reshape(2, 1500, 2), torch.rand(2, 1500, 2, generator=g) * 30 + 30,
+                torch.rand(2, 1500, 1, generator=g) * 180 - 90], 2).to(d)
+for mode in ('2', None):
+    if mode:
+        os.environ['MYDET_ROT_LAZY'] = mode
+    else:
+        os.environ.pop('MYDET_ROT_LAZY', None)
+    keep4, cnt4 = ops.nms_rot(cl, scores, 0.3)
+    keep4, cnt4 = ops.nms_rot(cl, scores, 0.3)                       # second call on the persistent workspace
+ras = ops.iou_raster(rb[0, :200], rb[1, :100], (320, 400))
+seg, _ = ops.iou_rot_segments(rb[0, :300].double(), rb[1, :300].double(), [(0, 100, 0, 50), (100, 0, 50, 20), (100, 200, 70, 230)])
+from mydetection_b200 import tracking
+tb = tracking.TrackletBank(rb[0, :50].double(), scores[0, :50].double(), img_hw=(400, 400))
+tb.predict(); lik = tb.likelihood(rb[1, :20].double()); tb.update(rb[1, :50].double(), scores[1, :50].double(), has=(scores[0, :50] > 0.5))
+gtb = (b2[:, :30, :4] * 0.5 + 10).contiguous()
+thr = None
+for li in range(3):                                                  # three levels: the two coarsest of this tiny image have < 9 anchors
+    thr = ops.atss_assign(raws[li]['bbox'], li, list(strides[:3]), [24., 48., 96.], img, gtb, c2[:, :30].contiguous() % 5,
+                          torch.tensor([30, 12], dtype=torch.int32, device=d), 9, 0.7, 5, thr=thr)['thr']
 torch.cuda.synchronize()
+print('round 2 ok', cnt4.tolist(), float(ras.max()), float(seg.max()), float(lik.max()), float(thr.max()))
 print('ok', out['count'].tolist(), big['count'].tolist(), cnt.tolist(), float(iou.max()), [f['count'].tolist() for f in front],
       bc.out['count'].tolist(), float(mx.max()), int(tg['PositiveMask'].sum()), cnt3.tolist())
