@@ -3,7 +3,7 @@
 # exported to CSV pages on the box and deleted (gpurun_out/ is capped at 64 MiB).
 mkdir -p gpurun_out
 python scripts/kernel_zoo.py > gpurun_out/zoo.jsonl 2>gpurun_out/zoo.err; echo "zoo rc=$?"
-for sec in rot rot1 rotclu atss fcos rowmax iou iourot dense pre decode_yolo decode_rapid; do
+for sec in rot rotbench rot1 rotclu atss fcos rowmax iou iourot dense pre decode_yolo decode_rapid; do
   ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_$sec.csv python scripts/kernel_zoo.py --once $sec > gpurun_out/ncu_l_$sec.log 2>&1
 done
 full() {   # name, launch cap, command...
@@ -13,7 +13,9 @@ full() {   # name, launch cap, command...
   python scripts/hot_lines.py gpurun_out/full_$name.ncu-rep > gpurun_out/hot_$name.txt 2>/dev/null
   rm -f gpurun_out/full_$name.ncu-rep
 }
-full rot 16 python scripts/kernel_zoo.py --once rot
+full rot 24 python scripts/kernel_zoo.py --once rot
+full rotbench 24 python scripts/kernel_zoo.py --once rotbench
+full rotclu 24 python scripts/kernel_zoo.py --once rotclu
 full atss 16 python scripts/kernel_zoo.py --once atss
 full fcos 4 python scripts/kernel_zoo.py --once fcos
 full rowmax 2 python scripts/kernel_zoo.py --once rowmax

@@ -20,6 +20,8 @@ COLS = [('gpu__time_duration.sum', 'us'), ('launch__grid_size', 'grid'), ('launc
         ('smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio', 'stall barrier')]
 BOUND = {
     'rot': 'rotated NMS, 32 images x 10 000 boxes (2 chunks of 16): pairwise ALU / latency; unit = IoU pair, 4.9995e7 algorithmic pairs per image',
+    'rotbench': 'rotated NMS on bench.py\'s own workload (the best 10 000 of 64 512 RAPiD candidates @1024 per image, boxes of 18-250 px), 32 images',
+    'rotclu': 'rotated NMS on detector-like clusters (40 objects x 250 mutually overlapping boxes per image), 32 images: the lazy narrow phase (rot_narrow = filter, rot_clip<0>, rot_clip<1>)',
     'atss': 'ATSS targets, batch 64 @640, 100 GT/image, 5 levels: HBM write of the dense target maps (86 floats + 2 mask bytes per cell) + ALU for 852 500 anchor-GT tests per image',
     'fcos': 'FCOS2 targets (central-region rule), same shapes as ATSS: HBM write of the target maps',
     'rowmax': 'IoU row-max, 64 x 25 575 boxes vs 100 GT: ALU (100 IoUs per 28 bytes moved)',
