@@ -1,4 +1,5 @@
-// Parallel fixed-point sweep for the large-N NMS (EXPERIMENTAL, opt-in: MYDET_SWEEP_FIXPOINT=1).
+// Parallel fixed-point sweep for the large-N NMS (the default since round 2; MYDET_SWEEP_FIXPOINT=0 selects the serial block
+// sweep for A/B tests).
 //
 // The greedy NMS result is the unique fixed point of
 //     keep[i] = valid[i] and not any(keep[j] and M[j, i] for j ranked above i)

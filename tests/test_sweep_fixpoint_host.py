@@ -1,5 +1,5 @@
-"""CPU-only test of the EXPERIMENTAL fixed-point sweep (sweep_kernel<2> of nms_large.cu, opt-in with
-MYDET_SWEEP_FIXPOINT=1, not yet run on a GPU).
+"""CPU-only test of the fixed-point sweep (sweep_kernel<2> of nms_large.cu, the default sweep of the large-N NMS;
+its GPU counterparts are tests/test_zz_sweep_fixpoint_gpu.py and every large-N parity test).
 
 tests/host_harness/sweep_fixpoint_host.cpp runs the phases of csrc/sweep_fixpoint.cuh -- the code the kernel executes
 between its barriers -- on the CPU under AddressSanitizer.  Suppression matrices are built here in the spatial layout
