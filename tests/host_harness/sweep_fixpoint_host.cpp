@@ -53,6 +53,40 @@ int main(int argc, char** argv) {
         if (!changed) break;
     }
     for (int t = 0; t < nt; ++t) phase_to_rank(V, keep, keptw, t, nt);
+    // The path the library takes since the mask kernels record their own entries (fx_note): one entry per non-empty 32-bit
+    // half-word, (row, half-word index), here collected by scanning the matrix (in reverse, as "any order").  Both ways of
+    // consuming it -- entries filled in memory, entries packed into per-thread registers -- must give the survivors above.
+    {
+        const unsigned* mask32 = (const unsigned*)mask;
+        std::vector<Entry> l32;
+        for (long long i = (long long)mb * words_total * 2 - 1; i >= 0; --i)
+            if (mask32[i]) { Entry e; e.row = (int)(i / (2 * words_total)); e.word = (int)(i % (2 * words_total)); e.bits = 0; l32.push_back(e); }
+        const int n32 = (int)l32.size();
+        Entry* lp = n32 ? l32.data() : list;
+        std::vector<unsigned long long> keep2(words_total), removed2(words_total), kept2(words_total);
+        for (int variant = 0; variant < 2; ++variant) {
+            const bool in_regs = variant == 1;
+            if (in_regs && n32 > kRegEntries * nt) break;
+            for (int t = 0; t < nt; ++t) phase_init(V, keep2.data(), removed2.data(), kept2.data(), words_total, t, nt);
+            std::vector<unsigned long long> regs((size_t)nt * kRegEntries, 0ull);
+            for (int t = 0; t < nt; ++t) {
+                if (in_regs) phase_load_entries32(mask32, words_total, lp, n32, *(unsigned long long (*)[kRegEntries])&regs[(size_t)t * kRegEntries], t, nt);
+                else phase_fill_list32(mask32, words_total, lp, n32, t, nt);
+            }
+            for (;;) {
+                for (int t = 0; t < nt; ++t) {
+                    if (in_regs) phase_scatter_entries32(*(unsigned long long (*)[kRegEntries])&regs[(size_t)t * kRegEntries], keep2.data(), removed2.data());
+                    else phase_scatter_list32(lp, n32, keep2.data(), removed2.data(), t, nt);
+                }
+                int changed = 0;
+                for (int t = 0; t < nt; ++t) changed |= phase_update(V, keep2.data(), removed2.data(), words_total, t, nt);
+                if (!changed) break;
+            }
+            for (int t = 0; t < nt; ++t) phase_to_rank(V, keep2.data(), kept2.data(), t, nt);
+            for (int i = 0; i < words_total; ++i)
+                if (kept2[i] != keptw[i]) { fprintf(stderr, "entry-list variant %d differs at word %d\n", variant, i); return 6; }
+        }
+    }
     f = fopen(argv[2], "wb");
     const int head[3] = {rounds, entries, use_list ? 1 : 0};
     if (!f || fwrite(head, sizeof(int), 3, f) != 3 || fwrite(keptw, 8, words_total, f) != (size_t)words_total) return 5;
