@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_big_chunk_kernel(unsigne
             for (int t = tid; t < (kChunk >> 1); t += kSortThreads) {
                 const int lo = 2 * t - (t & (stride - 1));
                 const int hi = lo + stride;
-                const bool up = ((gbase + lo) & size) == 0;
+                const bool up = (((first == 2 ? 0 : gbase) + lo) & size) == 0;     // first == 2: every chunk ascending (rank merge)
                 const unsigned long long a = skeys[lo], d = skeys[hi];
                 if ((a > d) == up) {
                     skeys[lo] = d; skeys[hi] = a;
@@ -540,19 +540,53 @@ __global__ void invert_kernel(const int* order, const int* m, int* inv, int n) {
     if (r < m[b]) inv[(long long)b * n + order[(long long)b * n + r]] = r;
 }
 
+// Merge of the sorted 16 384-key chunks of an image BY RANKING: keys are unique (their tie field is), so the final
+// position of an element is its index inside its own chunk plus, for every other chunk, the number of keys below it --
+// one binary search per other chunk (the chunks of an image are 128 KB each and sit in L2).  Replaces the log2(chunks)
+// bitonic merge steps, each of which was a full pass of the shared-memory chunk kernel plus the long-stride global
+// stages (48 384 boxes: 3 chunk-kernel launches of ~130 us per key array -> 1 + this kernel).
+__global__ void __launch_bounds__(256) sort_big_rank_kernel(const unsigned long long* __restrict__ bk, const int* __restrict__ bp,
+                                                            int* __restrict__ order, int n, int npad) {
+    const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npad) return;
+    const unsigned long long* gk = bk + (long long)b * npad;
+    const unsigned long long key = gk[i];
+    if (key == ~0ull) return;                                   // padding / invalid: left out of the order
+    const int chunks = npad / kChunk, mine = i / kChunk;
+    int rank = i - mine * kChunk;
+    for (int c = 0; c < chunks; ++c) {
+        if (c == mine) continue;
+        const unsigned long long* ck = gk + (long long)c * kChunk;
+        int lo = 0, hi = kChunk;                                // first index with ck[idx] >= key  (= keys below `key`)
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (ck[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        rank += lo;
+    }
+    if (rank < n) order[(long long)b * n + rank] = bp[(long long)b * npad + i];
+}
+
 static int sort_big(const unsigned long long* keys, int* order, int n, int B, LargeWs& w, cudaStream_t st) {
     int npad = 2 * kChunk;
     while (npad < n) npad <<= 1;
     const int chunks = npad / kChunk;
     MYDET_CUDA(cudaFuncSetAttribute(sort_big_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kChunk * 12)));
     sort_big_load_kernel<<<dim3((npad + 255) / 256, B), 256, 0, st>>>(keys, w.bk, w.bp, n, npad);
-    sort_big_chunk_kernel<<<dim3(chunks, B), kSortThreads, (size_t)kChunk * 12, st>>>(w.bk, w.bp, npad, 0, 1);
-    for (int size = 2 * kChunk; size <= npad; size <<= 1) {
-        for (int stride = size >> 1; stride >= kChunk; stride >>= 1)
-            sort_big_global_kernel<<<dim3((npad / 2 + 255) / 256, B), 256, 0, st>>>(w.bk, w.bp, npad, size, stride);
-        sort_big_chunk_kernel<<<dim3(chunks, B), kSortThreads, (size_t)kChunk * 12, st>>>(w.bk, w.bp, npad, size, 0);
+    const char* menv = getenv("MYDET_SORT_BIG_MERGE");          // developer A/B switch: 1 = the bitonic merge steps
+    const bool bitonic_merge = menv && menv[0] == '1';
+    // first = 1: chunks alternate ascending / descending (a bitonic sequence for the merge steps); 2: all ascending
+    sort_big_chunk_kernel<<<dim3(chunks, B), kSortThreads, (size_t)kChunk * 12, st>>>(w.bk, w.bp, npad, 0, bitonic_merge ? 1 : 2);
+    if (bitonic_merge) {
+        for (int size = 2 * kChunk; size <= npad; size <<= 1) {
+            for (int stride = size >> 1; stride >= kChunk; stride >>= 1)
+                sort_big_global_kernel<<<dim3((npad / 2 + 255) / 256, B), 256, 0, st>>>(w.bk, w.bp, npad, size, stride);
+            sort_big_chunk_kernel<<<dim3(chunks, B), kSortThreads, (size_t)kChunk * 12, st>>>(w.bk, w.bp, npad, size, 0);
+        }
+        sort_big_store_kernel<<<dim3((n + 255) / 256, B), 256, 0, st>>>(w.bk, w.bp, order, n, npad);
+    } else {
+        sort_big_rank_kernel<<<dim3((npad + 255) / 256, B), 256, 0, st>>>(w.bk, w.bp, order, n, npad);
     }
-    sort_big_store_kernel<<<dim3((n + 255) / 256, B), 256, 0, st>>>(w.bk, w.bp, order, n, npad);
     return launch_status("sort_big kernels");
 }
 

@@ -747,3 +747,30 @@ def test_lazy_narrow_phase_equals_full_and_oracle(spread, monkeypatch):
         c = int(cnt[b])
         want = oi.nms_rot(rb[b], rs[b], 0.45)
         assert c == want.numel() and torch.equal(keep[b, :c].cpu(), want), (spread, b)
+
+
+@pytest.mark.parametrize('n', [16385, 40000])
+def test_rank_merge_sort_equals_bitonic_merge(n, monkeypatch):
+    """Large-N sort above 16 384 candidates: sorted 16 384-key chunks merged by ranking (binary searches) against the
+    bitonic merge steps it replaces (MYDET_SORT_BIG_MERGE=1) and against the oracle -- un-capped single-class NMS with
+    heavy score ties, counts below the capacity on the second image."""
+    from mydetection_b200 import ops
+    from oracle import postprocess as opp
+    d = dev()
+    gen = torch.Generator().manual_seed(n)
+    bx = torch.cat([torch.rand(2, n, 2, generator=gen) * 1500, torch.rand(2, n, 2, generator=gen) * 24 + 6], dim=2)
+    sc = (torch.rand(2, n, generator=gen) * 500).round() / 500
+    cls = torch.zeros(2, n, dtype=torch.int64)
+    counts = torch.tensor([n, n - 4097], dtype=torch.int32)
+    out = ops.postprocess(bx.to(d), sc.to(d), cls.to(d), -1.0, 0.5, topk=None, counts=counts.to(d))
+    monkeypatch.setenv('MYDET_SORT_BIG_MERGE', '1')
+    out_b = ops.postprocess(bx.to(d), sc.to(d), cls.to(d), -1.0, 0.5, topk=None, counts=counts.to(d))
+    monkeypatch.delenv('MYDET_SORT_BIG_MERGE')
+    assert torch.equal(out['count'], out_b['count'])
+    for b in range(2):
+        c = int(out['count'][b])
+        assert torch.equal(out['idx'][b, :c], out_b['idx'][b, :c])
+    m = int(counts[1])
+    want = opp.post_process(bx[1, :m], cls[1, :m], sc[1, :m], -1.0, 0.5, 'cxcywh', None)
+    c = int(out['count'][1])
+    assert c == want.numel() and torch.equal(out['idx'][1, :c].cpu().long(), want)
