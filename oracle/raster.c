@@ -25,8 +25,8 @@ static int cmp_u32(const void* a, const void* b) {
 static long rle_from_poly(const double* xy, long k, long h, long w, uint32_t** out) {
     const double scale = 5.0;
     long j, m = 0;
-    int* x = (int*)malloc(sizeof(int) * (k + 1));
-    int* y = (int*)malloc(sizeof(int) * (k + 1));
+    int* x = (int*)calloc((size_t)k + 1, sizeof(int));
+    int* y = (int*)calloc((size_t)k + 1, sizeof(int));
     for (j = 0; j < k; j++) x[j] = (int)(scale * xy[j * 2 + 0] + .5);
     x[k] = x[0];
     for (j = 0; j < k; j++) y[j] = (int)(scale * xy[j * 2 + 1] + .5);
