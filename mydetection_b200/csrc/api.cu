@@ -51,7 +51,7 @@ static int postprocess_impl(const float* boxes, const float* scores, const void*
     MYDET_REQUIRE(n_param == 4 || n_param == 5, "n_param must be 4 or 5");
     MYDET_REQUIRE(box_format == MYDET_BOX_CXCYWH || box_format == MYDET_BOX_X1Y1X2Y2, "unknown box format");
     MYDET_REQUIRE(n_per_image <= MYDET_MAX_CANDIDATES, "more than %d candidates per image", MYDET_MAX_CANDIDATES);
-    MYDET_REQUIRE(out_count && (batch == 0 || out_cap > 0), "NULL out_count or out_cap <= 0");
+    MYDET_REQUIRE(batch == 0 || (out_count && out_cap > 0), "NULL out_count or out_cap <= 0");
     const int consume = pp_flags & MYDET_PP_CONSUME;
     MYDET_REQUIRE(!consume || counts, "consume needs counts");
     if (batch == 0) return 0;
@@ -235,8 +235,8 @@ static int nms_rot_impl(const float* boxes, const float* scores, const int32_t* 
     cudaStream_t st = (cudaStream_t)stream;
     MYDET_REQUIRE(batch >= 0 && n_per_image >= 0 && pitch >= n_per_image, "bad batch / n_per_image / pitch");
     MYDET_REQUIRE(n_per_image <= MYDET_MAX_CANDIDATES, "more than %d boxes per image", MYDET_MAX_CANDIDATES);
-    MYDET_REQUIRE(keep_count, "NULL keep_count");
     if (batch == 0) return 0;
+    MYDET_REQUIRE(keep_count, "NULL keep_count");
     if (n_per_image == 0) { MYDET_CUDA(cudaMemsetAsync(keep_count, 0, sizeof(int32_t) * (size_t)batch, st)); return 0; }
     MYDET_REQUIRE(boxes && scores && keep, "NULL tensor pointer");
     LargeArgs A{boxes, scores, nullptr, 0, nullptr, counts, batch, pitch, n_per_image, 5, MYDET_BOX_CXCYWH,

@@ -275,6 +275,8 @@ def nms_rot(boxes, scores, thr, ge=True, counts=None, want_votes=False, chunks=N
     cnt = torch.zeros(B, dtype=torch.int32, device=dev)
     votes = torch.empty(B, max(n, 1), dtype=torch.int32, device=dev) if want_votes else None
     L = _lib.lib()
+    if B == 0:
+        return (keep, cnt, votes) if want_votes else (keep, cnt)
     if chunks is None:
         chunks = 2 if (B >= 4 and n >= 2048) else 1
     chunks = max(1, min(int(chunks), B))

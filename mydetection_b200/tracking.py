@@ -64,7 +64,7 @@ class TrackletBank:
     def update(self, boxes, scores, has=None):
         """KFTracklet.update (structures.py:487-503) for the tracklets with has[i] (default: all).  boxes (N,5), scores (N).
         Returns the updated boxes (N,5); rows without a measurement are zero and keep their predicted `bbox`."""
-        if int(self.pred_count.min()) <= 0 and len(self):
+        if len(self) and int(self.pred_count.min()) <= 0:
             raise AssertionError('Please call predict() before update()')        # structures.py:489
         boxes = torch.as_tensor(boxes, dtype=torch.float64).reshape(-1, 5).to(self.device).contiguous()
         scores = torch.as_tensor(scores, dtype=torch.float64).reshape(-1).to(self.device).contiguous()
