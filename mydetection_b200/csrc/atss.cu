@@ -41,11 +41,11 @@ static size_t carve_atss(AtssWs& w, void* base, int batch, int max_gt) {
 // bboxes_iou(a, b, xyxy=False) for one pair, cxcywh inputs.
 __device__ __forceinline__ float iou_cxcywh(float acx, float acy, float aw, float ah, float bcx, float bcy, float bw, float bh) {
     const float ahw = __fmul_rn(aw, 0.5f), ahh = __fmul_rn(ah, 0.5f), bhw = __fmul_rn(bw, 0.5f), bhh = __fmul_rn(bh, 0.5f);
-    const float tlx = fmaxf(__fsub_rn(acx, ahw), __fsub_rn(bcx, bhw)), tly = fmaxf(__fsub_rn(acy, ahh), __fsub_rn(bcy, bhh));
-    const float brx = fminf(__fadd_rn(acx, ahw), __fadd_rn(bcx, bhw)), bry = fminf(__fadd_rn(acy, ahh), __fadd_rn(bcy, bhh));
+    const float tlx = fmax_nan(__fsub_rn(acx, ahw), __fsub_rn(bcx, bhw)), tly = fmax_nan(__fsub_rn(acy, ahh), __fsub_rn(bcy, bhh));
+    const float brx = fmin_nan(__fadd_rn(acx, ahw), __fadd_rn(bcx, bhw)), bry = fmin_nan(__fadd_rn(acy, ahh), __fadd_rn(bcy, bhh));
     const float en = (tlx < brx && tly < bry) ? 1.0f : 0.0f;
     const float inter = __fmul_rn(__fmul_rn(__fsub_rn(brx, tlx), __fsub_rn(bry, tly)), en);
-    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(__fmul_rn(aw, ah), __fmul_rn(bw, bh)), inter));
+    return iou_from_parts(inter, __fadd_rn(__fmul_rn(aw, ah), __fmul_rn(bw, bh)));
 }
 
 // The same, for callers that only compare the result with a NON-NEGATIVE threshold (or take a maximum that is then so
@@ -53,8 +53,8 @@ __device__ __forceinline__ float iou_cxcywh(float acx, float acy, float aw, floa
 // threshold -- so the multiply / divide tail is skipped for them (the vast majority of anchor-GT and cell-GT pairs).
 __device__ __forceinline__ float iou_cxcywh_or_zero(float acx, float acy, float aw, float ah, float bcx, float bcy, float bw, float bh) {
     const float ahw = __fmul_rn(aw, 0.5f), ahh = __fmul_rn(ah, 0.5f), bhw = __fmul_rn(bw, 0.5f), bhh = __fmul_rn(bh, 0.5f);
-    const float tlx = fmaxf(__fsub_rn(acx, ahw), __fsub_rn(bcx, bhw)), tly = fmaxf(__fsub_rn(acy, ahh), __fsub_rn(bcy, bhh));
-    const float brx = fminf(__fadd_rn(acx, ahw), __fadd_rn(bcx, bhw)), bry = fminf(__fadd_rn(acy, ahh), __fadd_rn(bcy, bhh));
+    const float tlx = fmax_nan(__fsub_rn(acx, ahw), __fsub_rn(bcx, bhw)), tly = fmax_nan(__fsub_rn(acy, ahh), __fsub_rn(bcy, bhh));
+    const float brx = fmin_nan(__fadd_rn(acx, ahw), __fadd_rn(bcx, bhw)), bry = fmin_nan(__fadd_rn(acy, ahh), __fadd_rn(bcy, bhh));
     if (!(tlx < brx && tly < bry)) return 0.0f;
     const float inter = __fmul_rn(__fsub_rn(brx, tlx), __fsub_rn(bry, tly));         // en == 1
     return __fdiv_rn(inter, __fsub_rn(__fadd_rn(__fmul_rn(aw, ah), __fmul_rn(bw, bh)), inter));
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(kAssignThreads) assign_kernel(AssignParams P, 
     float* cls_row = P.target_cls + ((long long)b * n_hw + cell) * P.n_cls;
     for (int g = 0; g < n_gt; ++g) {
         const float4 gt = s_gt[g];
-        best_iou = fmaxf(best_iou, skip_disjoint ? iou_cxcywh_or_zero(pcx, pcy, pw, ph, gt.x, gt.y, gt.z, gt.w)
+        best_iou = fmax_nan(best_iou, skip_disjoint ? iou_cxcywh_or_zero(pcx, pcy, pw, ph, gt.x, gt.y, gt.z, gt.w)
                                                  : iou_cxcywh(pcx, pcy, pw, ph, gt.x, gt.y, gt.z, gt.w));   // :306-307
         const float hw = __fmul_rn(gt.z, 0.5f), hh = __fmul_rn(gt.w, 0.5f);                  // :408-414, cr = 1
         const float tl = __fsub_rn(gx, __fsub_rn(gt.x, hw)), tt = __fsub_rn(gy, __fsub_rn(gt.y, hh));
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(kAssignThreads) assign_kernel(AssignParams P, 
             const float chw = __fmul_rn(__fmul_rn(gt.z, P.center_region), 0.5f), chh = __fmul_rn(__fmul_rn(gt.w, P.center_region), 0.5f);
             const bool centre = gx > __fsub_rn(gt.x, chw) && gx < __fadd_rn(gt.x, chw) &&
                                 gy > __fsub_rn(gt.y, chh) && gy < __fadd_rn(gt.y, chh);      // :123-124
-            const float mx = fmaxf(fmaxf(tl, tt), fmaxf(tr, tb));                            // :126
+            const float mx = fmax_nan(fmax_nan(tl, tt), fmax_nan(tr, tb));                            // :126
             pos = centre && P.anch_min < mx && mx < P.anch_max;                              // :127-129
         }
         if (pos) {

@@ -114,6 +114,10 @@ __device__ __forceinline__ void multimem_st_release_u32(unsigned* p, unsigned v)
 }
 constexpr long long kExchangeSpinCycles = 2000000000LL;   // ~1 s at 1.9 GHz: a flag wait gives up after this, it never hangs
 
+// torch.max / torch.min (and Tensor.max(dim)) propagate NaN; fmaxf / fminf return the other operand.  One FMNMX either way.
+__device__ __forceinline__ float fmax_nan(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float fmin_nan(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
@@ -132,6 +136,32 @@ __device__ __forceinline__ float iou_corners(float ax1, float ay1, float ax2, fl
     float inter = __fmul_rn(w, h);
     float uni = __fsub_rn(__fadd_rn(aarea, barea), inter);
     return __fdiv_rn(inter, uni);
+}
+
+// inter / (area_a + area_b - inter), bboxes_iou :49, without the divide where its result is known: a zero numerator
+// (+-0: a disjoint pair) over area_a + area_b > 0 (also +inf) gives that same signed zero.  This is not a micro-optimisation:
+// a zero numerator sends the IEEE divide down its slow path (a subroutine of ~50 instructions), and anchor-vs-GT
+// matrices are almost entirely disjoint pairs -- 16 384 x 8 192: 284 -> 160 us with a third of the pairs disjoint,
+// 282 -> 118 us with nearly all of them (scripts/iou_variants.py).  The test is per lane: a warp-uniform vote that
+// lets all lanes divide when one must runs the slow path for the whole warp again (297 us).
+__device__ __forceinline__ float iou_from_parts(float inter, float area_sum) {
+    if (inter == 0.0f && area_sum > 0.0f) return inter;
+    return __fdiv_rn(inter, __fsub_rn(area_sum, inter));
+}
+
+// iou_corners(...) > thr without the divide where the answer is known: inter == 0 gives 0, -0 or NaN, none of which is
+// above a non-negative threshold.  (Not a micro-optimisation: a zero numerator sends the IEEE divide down its slow path,
+// a subroutine of ~50 instructions, and in NMS nearly every pair is disjoint.)
+__device__ __forceinline__ bool iou_corners_gt(float ax1, float ay1, float ax2, float ay2, float aarea,
+                                               float bx1, float by1, float bx2, float by2, float barea, float thr) {
+    float xx1 = fmaxf(ax1, bx1), yy1 = fmaxf(ay1, by1);
+    float xx2 = fminf(ax2, bx2), yy2 = fminf(ay2, by2);
+    float w = fmaxf(0.0f, __fsub_rn(xx2, xx1));
+    float h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
+    float inter = __fmul_rn(w, h);
+    if (inter == 0.0f && thr >= 0.0f) return false;
+    float uni = __fsub_rn(__fadd_rn(aarea, barea), inter);
+    return __fdiv_rn(inter, uni) > thr;
 }
 
 #endif  // __CUDACC__

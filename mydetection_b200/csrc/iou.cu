@@ -14,12 +14,15 @@ namespace mydet {
 constexpr int kIouCols = 128;
 constexpr int kIouRows = 32;
 
+// V columns per thread: V = 4 writes one 128-bit vector per row (k % 4 == 0 and a 16-byte aligned `out`), and the row
+// box read from shared memory serves 4 pairs; V = 1 is the general case.
+template <int V>
 __global__ void __launch_bounds__(kIouCols) iou_aabb_kernel(const float* __restrict__ a, long long n,
                                                            const float* __restrict__ b, long long k, int xyxy,
                                                            float* __restrict__ out) {
     __shared__ float4 lo_hi_a[kIouRows];   // tl.x tl.y br.x br.y of the row boxes
     __shared__ float area_a[kIouRows];
-    const long long col = (long long)blockIdx.x * kIouCols + threadIdx.x;
+    const long long col = ((long long)blockIdx.x * kIouCols + threadIdx.x) * V;
     const long long row0 = (long long)blockIdx.y * kIouRows;
     if (threadIdx.x < kIouRows && row0 + threadIdx.x < n) {
         const float4 v = reinterpret_cast<const float4*>(a)[row0 + threadIdx.x];
@@ -33,27 +36,37 @@ __global__ void __launch_bounds__(kIouCols) iou_aabb_kernel(const float* __restr
         }
     }
     __syncthreads();
-    if (col >= k) return;
-    const float4 vb = reinterpret_cast<const float4*>(b)[col];
-    float4 cb;
-    float area_b;
-    if (xyxy) {
-        cb = vb;
-        area_b = __fmul_rn(__fsub_rn(vb.z, vb.x), __fsub_rn(vb.w, vb.y));
-    } else {
-        const float hw = __fmul_rn(vb.z, 0.5f), hh = __fmul_rn(vb.w, 0.5f);
-        cb = make_float4(__fsub_rn(vb.x, hw), __fsub_rn(vb.y, hh), __fadd_rn(vb.x, hw), __fadd_rn(vb.y, hh));
-        area_b = __fmul_rn(vb.z, vb.w);
+    if (col >= k) return;                  // V == 4: k % 4 == 0, so a thread has all of its columns or none
+    float4 cb[V];
+    float area_b[V];
+#pragma unroll
+    for (int c = 0; c < V; ++c) {
+        const float4 vb = reinterpret_cast<const float4*>(b)[col + c];
+        if (xyxy) {
+            cb[c] = vb;
+            area_b[c] = __fmul_rn(__fsub_rn(vb.z, vb.x), __fsub_rn(vb.w, vb.y));
+        } else {
+            const float hw = __fmul_rn(vb.z, 0.5f), hh = __fmul_rn(vb.w, 0.5f);
+            cb[c] = make_float4(__fsub_rn(vb.x, hw), __fsub_rn(vb.y, hh), __fadd_rn(vb.x, hw), __fadd_rn(vb.y, hh));
+            area_b[c] = __fmul_rn(vb.z, vb.w);
+        }
     }
     const int rows = (int)min((long long)kIouRows, n - row0);
-#pragma unroll 4
+#pragma unroll 2
     for (int r = 0; r < rows; ++r) {
         const float4 ca = lo_hi_a[r];
-        const float tlx = fmaxf(ca.x, cb.x), tly = fmaxf(ca.y, cb.y);
-        const float brx = fminf(ca.z, cb.z), bry = fminf(ca.w, cb.w);
-        const float en = (tlx < brx && tly < bry) ? 1.0f : 0.0f;                            // :47
-        const float inter = __fmul_rn(__fmul_rn(__fsub_rn(brx, tlx), __fsub_rn(bry, tly)), en);  // :48
-        out[(row0 + r) * k + col] = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a[r], area_b), inter));  // :49
+        const float aa = area_a[r];
+        float res[V];
+#pragma unroll
+        for (int c = 0; c < V; ++c) {
+            const float tlx = fmax_nan(ca.x, cb[c].x), tly = fmax_nan(ca.y, cb[c].y);
+            const float brx = fmin_nan(ca.z, cb[c].z), bry = fmin_nan(ca.w, cb[c].w);
+            const float en = (tlx < brx && tly < bry) ? 1.0f : 0.0f;                            // :47
+            const float inter = __fmul_rn(__fmul_rn(__fsub_rn(brx, tlx), __fsub_rn(bry, tly)), en);  // :48
+            res[c] = iou_from_parts(inter, __fadd_rn(aa, area_b[c]));                           // :49
+        }
+        if (V == 4) *reinterpret_cast<float4*>(out + (row0 + r) * k + col) = make_float4(res[0], res[1], res[2], res[3 % V]);
+        else out[(row0 + r) * k + col] = res[0];
     }
 }
 
@@ -169,11 +182,11 @@ __global__ void __launch_bounds__(kRowmaxThreads) iou_rowmax_kernel(const float*
 #pragma unroll 4
             for (int i = 0; i < cnt; ++i) {
                 const float4 cb = s_box[i];
-                const float tlx = fmaxf(ca.x, cb.x), tly = fmaxf(ca.y, cb.y);
-                const float brx = fminf(ca.z, cb.z), bry = fminf(ca.w, cb.w);
+                const float tlx = fmax_nan(ca.x, cb.x), tly = fmax_nan(ca.y, cb.y);
+                const float brx = fmin_nan(ca.z, cb.z), bry = fmin_nan(ca.w, cb.w);
                 const float en = (tlx < brx && tly < bry) ? 1.0f : 0.0f;
                 const float inter = __fmul_rn(__fmul_rn(__fsub_rn(brx, tlx), __fsub_rn(bry, tly)), en);
-                const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, s_area[i]), inter));
+                const float iou = iou_from_parts(inter, __fadd_rn(area_a, s_area[i]));
                 if (iou != iou) { if (!is_nan) { best = iou; arg = g0 + i; is_nan = true; } }
                 else if (!is_nan && (!have || iou > best)) { best = iou; arg = g0 + i; have = true; }
             }
@@ -236,9 +249,12 @@ MYDET_API int mydet_iou_aabb_pairwise(const float* a, int64_t n, const float* b,
     if (n == 0 || k == 0) return 0;
     MYDET_REQUIRE(a && b && out, "NULL tensor pointer");
     MYDET_REQUIRE(((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0, "box arrays must be 16-byte aligned");
-    const dim3 grid((unsigned)((k + kIouCols - 1) / kIouCols), (unsigned)((n + kIouRows - 1) / kIouRows));
+    const bool vec = (k % 4 == 0) && ((uintptr_t)out & 15) == 0;
+    const long long per_cta = (long long)kIouCols * (vec ? 4 : 1);
+    const dim3 grid((unsigned)((k + per_cta - 1) / per_cta), (unsigned)((n + kIouRows - 1) / kIouRows));
     MYDET_REQUIRE(grid.y <= 65535, "too many rows for one launch");
-    iou_aabb_kernel<<<grid, kIouCols, 0, (cudaStream_t)stream>>>(a, n, b, k, xyxy, out);
+    if (vec) iou_aabb_kernel<4><<<grid, kIouCols, 0, (cudaStream_t)stream>>>(a, n, b, k, xyxy, out);
+    else iou_aabb_kernel<1><<<grid, kIouCols, 0, (cudaStream_t)stream>>>(a, n, b, k, xyxy, out);
     return launch_status("iou_aabb_kernel");
 }
 

@@ -693,8 +693,8 @@ __global__ void __launch_bounds__(kTile) mask_kernel(LargeWs w, const int* m, in
 #pragma unroll 4
                 for (int j = 0; j < lim; ++j) {
                     const float4 c4 = cbox[j];
-                    const float ovr = iou_corners(a.x, a.y, a.z, a.w, aarea, c4.x, c4.y, c4.z, c4.w, carea[j]);
-                    if (c0 + j > r && ccls[j] == ac && ovr > thr_f) bits |= 1ull << j;
+                    if (c0 + j > r && ccls[j] == ac && iou_corners_gt(a.x, a.y, a.z, a.w, aarea, c4.x, c4.y, c4.z, c4.w, carea[j], thr_f))
+                        bits |= 1ull << j;
                 }
             }
         }

@@ -849,7 +849,7 @@ __global__ void __maxnreg__(MYDET_PP_MAXNREG) postprocess_small_kernel(const PPP
                 }
                 const int r = lo, j = sseg[r] + (q - ppre[r]);
                 const float4 a = sbox[r], c4 = sbox[j];
-                if (iou_corners(c4.x, c4.y, c4.z, c4.w, sarea[j], a.x, a.y, a.z, a.w, sarea[r]) > thr_f)
+                if (iou_corners_gt(c4.x, c4.y, c4.z, c4.w, sarea[j], a.x, a.y, a.z, a.w, sarea[r], thr_f))
                     atomicOr(&mask[r * Wp + (j >> 5)], 1u << (j & 31));
             }
             pairs_done = true;
@@ -884,7 +884,7 @@ __global__ void __maxnreg__(MYDET_PP_MAXNREG) postprocess_small_kernel(const PPP
                 bool hit = false;
                 if (c < steps && j >= s0 && j < r) {
                     const float4 c4 = sbox[j];
-                    hit = iou_corners(c4.x, c4.y, c4.z, c4.w, sarea[j], a.x, a.y, a.z, a.w, aarea) > thr_f;
+                    hit = iou_corners_gt(c4.x, c4.y, c4.z, c4.w, sarea[j], a.x, a.y, a.z, a.w, aarea, thr_f);
                 }
                 const unsigned byte = (__ballot_sync(0xffffffffu, hit) >> gshift) & 0xffu;
                 if (part == 0 && c < steps) {

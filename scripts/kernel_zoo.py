@@ -125,6 +125,15 @@ def sec_iou(rot=False):
          pairs_per_s=n * k / us * 1e6, bound='HBM (output write)' if not rot else 'ALU (polygon clip per pair) / HBM write',
          algorithmic_bytes=algo, achieved_gbs=algo / us / 1e3, frac_of_hbm=algo / us / 1e3 / HBM,
          note='includes the torch allocation of the output matrix')
+    if not rot:                                     # anchor-vs-GT like: small boxes on a large canvas, almost every pair disjoint
+        a3 = torch.cat([torch.rand(n, 2, generator=gen) * 1000, torch.rand(n, 2, generator=gen) * 60 + 4], 1).to(DEV)
+        b3 = torch.cat([torch.rand(k, 2, generator=gen) * 1000, torch.rand(k, 2, generator=gen) * 60 + 4], 1).to(DEV)
+        us3 = timed(lambda i: ops.iou_aabb(a3, b3), iters=5)
+        emit('iou_sparse', workload=f'({n},4) x ({k},4), 4-64 px boxes on a 1000 px canvas', us_per_call=us3, pairs_per_s=n * k / us3 * 1e6,
+             bound='HBM (output write)', algorithmic_bytes=algo, achieved_gbs=algo / us3 / 1e3, frac_of_hbm=algo / us3 / 1e3 / HBM)
+        a4 = a3[:, :].contiguous(); b4 = b3[:k - 3].contiguous()          # k % 4 != 0: the scalar-store kernel
+        us4 = timed(lambda i: ops.iou_aabb(a4, b4), iters=5)
+        emit('iou_sparse_scalar', workload=f'({n},4) x ({k - 3},4)', us_per_call=us4, pairs_per_s=n * (k - 3) / us4 * 1e6)
     if not rot:                                     # the configs[3] shape: 8 525 anchors x 100 GT
         a2, b2 = a[:8525].contiguous(), b[:100].contiguous()
         us2 = timed(lambda i: ops.iou_aabb(a2, b2), iters=20)

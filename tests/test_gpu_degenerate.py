@@ -154,3 +154,43 @@ def test_exchange_publish_of_nothing_and_bad_arguments():
     assert L.mydet_exchange_wait(None, 8, 16, 4, None, None, stream) != 0
     torch.cuda.synchronize()
     assert int(buf.abs().sum()) == 0
+
+
+@pytest.mark.parametrize('k', [203, 204])
+@pytest.mark.parametrize('xyxy', [False, True])
+def test_iou_aabb_bit_pattern_on_disjoint_and_non_finite_pairs(k, xyxy):
+    """The pairwise kernels skip the divide of a disjoint pair (its quotient is the +-0 / NaN numerator itself when
+    area_a + area_b > 0): the BIT PATTERN of every element -- signed zeros, NaN positions -- equals the reference
+    formula's (bbox_ops.py:25-50, restated in oracle/iou.py on torch CPU), for the vector-store kernel (k % 4 == 0) and
+    the scalar one, with zero-size, negative-size, infinite and NaN boxes among ordinary ones; the row-max kernel
+    agrees with torch.max over that matrix."""
+    from mydetection_b200 import ops
+    from oracle import iou as oi
+    g = torch.Generator().manual_seed(k)
+    def boxes(n):
+        t = torch.cat([torch.rand(n, 2, generator=g) * 600, torch.rand(n, 2, generator=g) * 50 + 2], 1)
+        if xyxy:
+            t = torch.cat([t[:, :2], t[:, :2] + t[:, 2:]], 1)
+        return t
+    a, b = boxes(150), boxes(k)
+    a[3, 2:] = a[3, :2] if xyxy else 0.0                 # zero size
+    b[5, 2:] = b[5, :2] if xyxy else 0.0
+    a[4] = a[3]                                          # two zero-size boxes at the same place: 0 / 0
+    b[6] = a[3]
+    a[7, 2] = float('inf'); b[9, 3] = float('inf')
+    a[11, 0] = float('nan'); b[13, 2] = float('nan')
+    if xyxy:
+        a[15, 2:] = a[15, :2] - 5.0                      # negative extent: negative "area"
+    else:
+        a[15, 2] = -a[15, 2]
+    want = oi.bboxes_iou(a, b, xyxy=xyxy)
+    got = ops.iou_aabb(a.to(dev()), b.to(dev()), xyxy=xyxy).cpu()
+    nan_w, nan_g = torch.isnan(want), torch.isnan(got)
+    assert torch.equal(nan_w, nan_g)
+    assert torch.equal(got.view(torch.int32)[~nan_g], want.view(torch.int32)[~nan_w])
+    assert (want == 0).float().mean() > 0.9 and int(nan_w.sum()) > 0
+    # row-wise max / arg-max without the matrix: rows without a NaN (torch.max with NaN: covered in test_gpu_parity)
+    rows = ~nan_w.any(dim=1)
+    mx, arg = ops.iou_rowmax(a[None].to(dev()), b[None].to(dev()), xyxy=xyxy)
+    wmx, warg = want.max(dim=1)
+    assert torch.equal(mx[0].cpu()[rows], wmx[rows]) and torch.equal(arg[0].cpu()[rows], warg[rows])
