@@ -117,7 +117,7 @@ __device__ __forceinline__ double rot_iou_f64(const C* ax, const C* ay, const C*
     double inter = 0.0;
     if (areaA > 0.0 && areaB > 0.0) inter = clip_area<double, C>(ax, ay, bx, by, a2B >= 0.0 ? 1.0 : -1.0, (C)0, (C)0);
     const double uni = areaA + areaB - inter;
-    return uni > 0.0 ? inter / uni : 0.0;
+    return (inter > 0.0 && uni > 0.0) ? inter / uni : 0.0;      // a zero numerator would take the divide's slow path for the same 0
 }
 
 // Decision "IoU >= thr" (ge) or "IoU > thr": float32 clipping in box-local coordinates, and an
@@ -135,7 +135,7 @@ __device__ __forceinline__ bool rot_overlaps(const RotBox& A, const RotBox& B, d
     // (3) float32 clip around A's centre
     const float inter = clip_area<float>(A.x, A.y, B.x, B.y, B.area2 >= 0.f ? 1.f : -1.f, A.cx, A.cy);
     const float uni = aA + aB - inter;
-    const float iou = uni > 0.f ? inter / uni : 0.f;
+    const float iou = (inter > 0.f && uni > 0.f) ? inter / uni : 0.f;
     const float d = iou - (float)thr;
     if (fabsf(d) < 1e-3f) {
         const double e = rot_iou_f64(A.x, A.y, B.x, B.y);
