@@ -229,7 +229,11 @@ int mydet_detect(int kind, const mydet_level_t* levels, int n_levels, int batch,
                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* mydet_detect on a persistent workspace (see the conventions at the top): workspace_clean != 0 = the buffer was zeroed
- * once and has only been used by this entry point with this geometry since. */
+ * once and has only been used by this entry point with this geometry since.  On the single-kernel path (<= 1024
+ * survivors after top-k) the call is then two launches and no memset: the post-process zeroes the candidate counts it
+ * consumed.  In both entry points the post-process kernel is launched as a programmatic dependent of the decode kernel
+ * (it starts while the decode drains and waits before its first read); the environment variable MYDET_PDL=0 turns
+ * that off. */
 int mydet_detect_ws(int kind, const mydet_level_t* levels, int n_levels, int batch, int n_cls,
                     int n_param, float img_h, float img_w, float conf_thres, int topk,
                     double nms_thres, float* out_box, float* out_score, int64_t* out_cls,

@@ -81,7 +81,7 @@ static int postprocess_impl(const float* boxes, const float* scores, const void*
             if (reinterpret_cast<uintptr_t>(peers[q]) & 15) P.peer_vec = 0;
         P.peer_mc = static_cast<float*>(peer_mc); P.peer_self = peer_self; P.peer_protocol = peer_protocol ? 1 : 0;
         P.consume = consume; P.force_scan = (pp_flags & MYDET_PP_FORCE_SCAN) ? 1 : 0;
-        return launch_postprocess_small(P, batch, st);
+        return launch_postprocess_small(P, batch, st, (pp_flags & kPPFlagPdl) != 0);
     }
     MYDET_REQUIRE(n_peers == 0, "the fused exchange is implemented for the single-kernel path only (<= %d survivors)", MYDET_SMALL_K);
     LargeArgs A{boxes, scores, cls, cls_is_i64, src_idx, counts, batch, pitch, n_per_image, n_param, box_format,
@@ -169,10 +169,17 @@ static int detect_impl(int kind, const mydet_level_t* levels, int n_levels, int 
         return MYDET_ERR_WORKSPACE;
     }
     if (batch == 0) return 0;
+    // persistent clean workspace + single-kernel post-process: the post-process zeroes the candidate counts it consumed,
+    // so the counts are zero on entry of every call and the memset in front of the decode is not needed
+    const bool self_clean = (pp_flags & MYDET_PP_WS_CLEAN) && n_total > 0 && effective_k((int)n_total, topk) <= MYDET_SMALL_K;
     int rc = decode_compact_impl(kind, levels, n_levels, batch, n_cls, n_param, img_h, img_w, conf_thres, w.box, w.score,
-                                 w.cls, w.idx, w.count, (int32_t)n_total, /*state_clean=*/0, nullptr, st);
+                                 w.cls, w.idx, w.count, (int32_t)n_total, /*state_clean=*/self_clean ? 1 : 0, nullptr, st);
     if (rc) return rc;
-    // the decode already applied conf_thres; the post-process sees only survivors
+    if (self_clean) pp_flags |= MYDET_PP_CONSUME;
+    // the decode already applied conf_thres; the post-process sees only survivors.  It is launched as a programmatic
+    // dependent of the decode kernel (its launch latency and CTA ramp overlap the decode's tail); MYDET_PDL=0 turns that off.
+    static const bool pdl = [] { const char* e = getenv("MYDET_PDL"); return !(e && e[0] == '0'); }();
+    if (pdl) pp_flags |= kPPFlagPdl;
     return mydet_postprocess(w.box, w.score, w.cls, 0, w.idx, w.count, batch, n_total, (int)n_total, n_param,
                              MYDET_BOX_CXCYWH, -INFINITY, topk, nms_thres, out_box, out_score, out_cls, out_idx,
                              out_count, status, out_cap, w.rest, w.rest_bytes, pp_flags, st);

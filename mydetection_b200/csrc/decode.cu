@@ -361,6 +361,9 @@ __device__ __forceinline__ void decode_unit(const DecodeParams& P, const LevelDe
 template <int KIND, bool COMPACT>
 __global__ void __launch_bounds__(kDecodeThreads, MYDET_DECODE_MINBLOCKS)
 decode_kernel(const __grid_constant__ DecodeParams P) {
+    // a dependent launched programmatically behind this grid (the post-process of mydet_detect) may be scheduled once
+    // every CTA of this grid has started; it waits for this grid's completion before reading.  No-op otherwise.
+    asm volatile("griddepcontrol.launch_dependents;");
     // CTA -> level (levels are laid out back to back in CTA index space)
     int l = 0;
 #pragma unroll 1

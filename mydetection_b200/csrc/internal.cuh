@@ -37,7 +37,10 @@ struct PPParams {
     int consume;                // zero counts[b] once it has been read
     int force_scan;             // skip the sampled front end of the select (tests)
 };
-int launch_postprocess_small(const PPParams& P, int batch, cudaStream_t st);
+// pdl: programmatic dependent launch -- the kernel may be scheduled while its predecessor on the stream (the decode) is
+// still draining; it waits (griddepcontrol.wait) before its first global read.  Internal flag bit of pp_flags.
+constexpr int kPPFlagPdl = 1 << 16;
+int launch_postprocess_small(const PPParams& P, int batch, cudaStream_t st, bool pdl = false);
 
 // Gathered-detections buffer of the fused exchange, in 32-bit words (include/mydet.h):
 //   float rows[images_total][out_cap][P+2]; int32 counts[images_total];                      (the data)

@@ -112,6 +112,9 @@ __global__ void __maxnreg__(MYDET_PP_MAXNREG) postprocess_small_kernel(const PPP
     __shared__ int s_need, s_done, s_nsel, s_total, s_flags, s_bucket, s_ucount, s_top, s_nvalid;
     __shared__ unsigned s_seq;      // exchange protocol: the sequence number this launch publishes for the image
 
+    // launched as a programmatic dependent of the decode (mydet_detect): everything above overlapped its tail; the
+    // decode's stores are visible from here on.  A no-op for an ordinary launch.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     int n = P.n_per_image;
     int flags = 0;
     if (P.counts) {
@@ -1071,10 +1074,20 @@ size_t pp_small_smem_bytes(int kpad, int n_per_image) {
            (size_t)pp_cache_elems(n_per_image, kpad) * 8;
 }
 
-int launch_postprocess_small(const PPParams& P, int batch, cudaStream_t st) {
+int launch_postprocess_small(const PPParams& P, int batch, cudaStream_t st, bool pdl) {
     const size_t smem = pp_small_smem_bytes(P.kpad, P.n_per_image);
     MYDET_CUDA(cudaFuncSetAttribute(postprocess_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    postprocess_small_kernel<<<batch, kPPThreads, smem, st>>>(P);
+    if (!pdl) {
+        postprocess_small_kernel<<<batch, kPPThreads, smem, st>>>(P);
+        return launch_status("postprocess_small_kernel");
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)batch); cfg.blockDim = dim3(kPPThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    MYDET_CUDA(cudaLaunchKernelEx(&cfg, postprocess_small_kernel, P));
     return launch_status("postprocess_small_kernel");
 }
 

@@ -201,9 +201,44 @@ def sec_decode(kind):
          note='eager launch + a 4-byte-per-image memset; the lone-launch ramp is included')
 
 
+def sec_eager():
+    """The one-call path (mydet_detect: memset + decode + post-process on one stream), single image and batch 64:
+    GPU time per call with the calls queued back to back, and host wall clock of a call that is waited for."""
+    import time
+    YOLO_A = [[10, 13], [16, 30], [33, 23], [30, 61], [62, 45], [59, 119], [116, 90], [156, 198], [373, 326]]
+    for name, B in (('yolo', 1), ('yolo', 16), ('fcos2', 1), ('fcos2', 64)):
+        if name == 'yolo':
+            img, C, P = 608, 80, 4
+            raws = []
+            for s_ in (8, 16, 32):
+                m = img // s_
+                t = torch.randn(B, 3 * (P + 1 + C), m, m, generator=gen)
+                raws.append({k: v.to(DEV) for k, v in yolo_head_views(t, 3, P, C).items()})
+            pipe = pl.DetectionPipeline('YOLO', (8, 16, 32), C, (img, img), 0.005, 0.45, 512, anchors=[YOLO_A[0:3], YOLO_A[3:6], YOLO_A[6:9]])
+        else:
+            import bench
+            wl = bench.Workload(640, 2.0)
+            g2 = torch.Generator(device=DEV).manual_seed(5)
+            raws, _ = wl.make_batch(g2, DEV)
+            raws = [{k: v[:B] for k, v in r.items()} for r in raws]
+            pipe = pl.DetectionPipeline('FCOS2', bench.STRIDES, bench.N_CLS, (wl.img, wl.img), bench.CONF_THRES, bench.NMS_THRES, bench.TOPK)
+        bc = pipe.bind(raws)
+        us = timed(lambda i: bc.launch(), iters=50, warm=5)
+        torch.cuda.synchronize()
+        walls = []
+        for _ in range(50):
+            t0 = time.perf_counter()
+            bc.launch()
+            torch.cuda.synchronize()
+            walls.append((time.perf_counter() - t0) * 1e6)
+        walls.sort()
+        emit('eager', workload=f'{name} batch {B}: mydet_detect (memset + decode + post-process)', us_per_call_queued=us,
+             us_wall_sync_median=walls[len(walls) // 2], us_wall_sync_min=walls[0], pdl=os.environ.get('MYDET_PDL', '1'))
+
+
 SECTIONS = {'rot': sec_rot, 'rotbench': sec_rotbench, 'rot1': lambda: sec_rot(False, 1), 'rotclu': lambda: sec_rot(True), 'atss': sec_atss, 'fcos': lambda: sec_atss(True), 'rowmax': sec_rowmax,
             'iou': sec_iou, 'iourot': lambda: sec_iou(True), 'dense': sec_dense, 'pre': sec_pre,
-            'decode_yolo': lambda: sec_decode('yolo'), 'decode_rapid': lambda: sec_decode('rapid')}
+            'eager': sec_eager, 'decode_yolo': lambda: sec_decode('yolo'), 'decode_rapid': lambda: sec_decode('rapid')}
 
 if __name__ == '__main__':
     for name in (ARGS or list(SECTIONS)):
