@@ -1,5 +1,7 @@
-"""Developer tool: A/B of iou_aabb_kernel build variants (mydetection_b200/_tune/libmydet_<tag>.so, built with
--DIOU_SKIP / -DIOU_NAN / -DIOU_V4) on three workloads; one process per variant (MYDET_LIB)."""
+"""Developer tool: A/B of library build variants on the pairwise-IoU workloads.  Times ops.iou_aabb on three inputs for
+every mydetection_b200/_tune/libmydet_<tag>.so present (one process per variant, selected through MYDET_LIB) and for the
+default library.  The table in profiles/r2_history.md ("Late finding") was made with five temporary variants of
+iou_aabb_kernel (columns per thread x how the divide is skipped), built with `build.build(extra_flags=..., out=...)`."""
 import glob
 import os
 import subprocess
