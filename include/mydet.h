@@ -335,6 +335,25 @@ int mydet_atss_assign(const float* t_ltrb, const int64_t t_stride[4], int batch,
                       float* target_cls, float* thr_out, int thr_is_input, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* mydet_atss_assign for ALL pyramid levels in one call: the GT ordering and the adaptive thresholds are computed once and
+ * one grid covers the cells of every level (3 launches instead of 15 for five levels, and the few CTAs of the coarse
+ * levels fill the tail of the finest one).  levels: HOST array of n_levels descriptors, stride-ascending like strides /
+ * anchor_sides; every output is fully written, exactly as by n_levels calls of mydet_atss_assign.  thr_out optional. */
+typedef struct {
+    const float* t_ltrb;          /* this level's raw regression logits, logical (B,nH,nW,4)            */
+    int64_t t_stride[4];          /* element strides of b, h, w, p                                      */
+    uint8_t* positive;            /* (B,nH,nW)                                                          */
+    uint8_t* ignored;             /* (B,nH,nW)                                                          */
+    float* target_ltrb;           /* (B,nH,nW,4)                                                        */
+    float* target_conf;           /* (B,nH,nW)                                                          */
+    float* target_cls;            /* (B,nH,nW,C)                                                        */
+} mydet_atss_level_t;
+int mydet_atss_assign_levels(const mydet_atss_level_t* levels, int n_levels, const int32_t* strides,
+                             const float* anchor_sides, int batch, int img_h, int img_w, const float* gt_box,
+                             const int64_t* gt_cls, const int32_t* gt_count, int max_gt, int topk,
+                             float ignore_thres, int n_cls, float* thr_out, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
 /* Target assignment of FCOSLayer.forward (models/detlayers/fcos2.py:84-143), one pyramid level: the same
  * outputs and GT conventions as mydet_atss_assign, with FCOSLayer's rule for a positive cell -- the cell centre
  * lies strictly inside the GT shrunk by center_region (0.5 in the reference) and

@@ -32,6 +32,12 @@ class Level(ctypes.Structure):
                 ('stride', c_f32), ('anchor_w', c_f32 * MAX_ANCHORS), ('anchor_h', c_f32 * MAX_ANCHORS)]
 
 
+class AtssLevel(ctypes.Structure):
+    """mydet_atss_level_t"""
+    _fields_ = [('t_ltrb', c_vp), ('t_stride', c_i64 * 4), ('positive', c_vp), ('ignored', c_vp),
+                ('target_ltrb', c_vp), ('target_conf', c_vp), ('target_cls', c_vp)]
+
+
 # name -> (restype, argtypes); mirrors include/mydet.h one to one
 SIGNATURES = {
     'mydet_version': (c_int, []),
@@ -76,6 +82,8 @@ SIGNATURES = {
     'mydet_atss_assign': (c_int, [c_vp, ctypes.POINTER(c_i64), c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int32),
                                   ctypes.POINTER(c_f32), c_int, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_f32, c_int,
                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),
+    'mydet_atss_assign_levels': (c_int, [ctypes.POINTER(AtssLevel), c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(c_f32),
+                                         c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_f32, c_int, c_vp, c_vp, c_sz, c_vp]),
     'mydet_fcos_assign': (c_int, [c_vp, ctypes.POINTER(c_i64), c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int,
                                   c_f32, c_f32, c_f32, c_f32, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     'mydet_kf_initiate': (c_int, [c_vp, c_int, ctypes.POINTER(c_f64), c_vp, c_vp, c_vp, c_vp]),

@@ -463,3 +463,54 @@ def atss_assign(t_ltrb, level, strides, anchor_sides, img_hw, gt_box, gt_cls, gt
     _lib.check(rc, 'mydet_atss_assign')
     return {'PositiveMask': pos.view(torch.bool), 'IgnoredMask': ign.view(torch.bool), 'TargetLTRB': t_box, 'TargetConf': t_conf,
             'TargetCls': t_cls, 'thr': thr}
+
+
+def atss_assign_levels(t_ltrbs, strides, anchor_sides, img_hw, gt_box, gt_cls, gt_count, topk, ignore_thres, n_cls):
+    """Targets of ALL levels in one call (mydet_atss_assign_levels): t_ltrbs = list of (B,nH_l,nW_l,4) views, finest level
+    first.  Returns a list of dicts like atss_assign's (the 'thr' entry is shared); bit-identical to calling
+    atss_assign level by level, in 3 launches and 6 allocations instead of 15 and ~35."""
+    ts = [_dev(t, torch.float32, 't_ltrb') for t in t_ltrbs]
+    gt_box = _dev(gt_box, torch.float32, 'gt_box').contiguous()
+    gt_cls = _dev(gt_cls, torch.int64, 'gt_cls').contiguous()
+    gt_count = _dev(gt_count, torch.int32, 'gt_count').contiguous()
+    n_l = len(ts)
+    if n_l != len(strides) or n_l != len(anchor_sides):
+        raise ValueError('one t_ltrb view, stride and anchor side per level')
+    B, G, dev = ts[0].shape[0], gt_box.shape[1], ts[0].device
+    cells = [t.shape[1] * t.shape[2] for t in ts]
+    total = sum(cells)
+    # one allocation per kind; level l owns the contiguous block [B * sum(cells[:l]), B * sum(cells[:l+1]))
+    pos = torch.empty(B * total, dtype=torch.uint8, device=dev)
+    ign = torch.empty(B * total, dtype=torch.uint8, device=dev)
+    t_box = torch.empty(B * total * 4, dtype=torch.float32, device=dev)
+    t_conf = torch.empty(B * total, dtype=torch.float32, device=dev)
+    t_cls = torch.empty(B * total * n_cls, dtype=torch.float32, device=dev)
+    thr = torch.full((B, max(G, 1)), float('nan'), dtype=torch.float32, device=dev)
+    L = _lib.lib()
+    ws = _workspace(L.mydet_atss_workspace_bytes(B, G), dev)
+    lv = (_lib.AtssLevel * n_l)()
+    out, off = [], 0
+    for i, t in enumerate(ts):
+        n_h, n_w = t.shape[1], t.shape[2]
+        lo, hi = B * off, B * (off + cells[i])
+        views = {'PositiveMask': pos[lo:hi].view(B, n_h, n_w), 'IgnoredMask': ign[lo:hi].view(B, n_h, n_w),
+                 'TargetLTRB': t_box[lo * 4:hi * 4].view(B, n_h, n_w, 4), 'TargetConf': t_conf[lo:hi].view(B, n_h, n_w, 1),
+                 'TargetCls': t_cls[lo * n_cls:hi * n_cls].view(B, n_h, n_w, n_cls)}
+        lv[i].t_ltrb = t.data_ptr()
+        lv[i].t_stride[:] = list(t.stride())
+        lv[i].positive, lv[i].ignored = views['PositiveMask'].data_ptr(), views['IgnoredMask'].data_ptr()
+        lv[i].target_ltrb, lv[i].target_conf = views['TargetLTRB'].data_ptr(), views['TargetConf'].data_ptr()
+        lv[i].target_cls = views['TargetCls'].data_ptr()
+        views['PositiveMask'] = views['PositiveMask'].view(torch.bool)
+        views['IgnoredMask'] = views['IgnoredMask'].view(torch.bool)
+        views['thr'] = thr
+        out.append(views)
+        off += cells[i]
+    c_strides = (ctypes.c_int32 * n_l)(*[int(s) for s in strides])
+    c_sides = (ctypes.c_float * n_l)(*[float(s) for s in anchor_sides])
+    with torch.cuda.device(dev):
+        rc = L.mydet_atss_assign_levels(lv, n_l, c_strides, c_sides, B, int(img_hw[0]), int(img_hw[1]), _ptr(gt_box), _ptr(gt_cls),
+                                        _ptr(gt_count), G, int(topk), float(ignore_thres), int(n_cls), _ptr(thr), _ptr(ws),
+                                        ws.numel(), _stream())
+    _lib.check(rc, 'mydet_atss_assign_levels')
+    return out

@@ -97,6 +97,11 @@ def sec_atss(fcos=False):
         for li in range(5):
             ops.fcos_assign(ts[li], strides[li], img, gb, gc, gn, 0.5, lims[li], lims[li + 1], 0.7, 80)
 
+    if not fcos:
+        us_all = timed(lambda i: ops.atss_assign_levels(ts, strides, sides, img, gb, gc, gn, 9, 0.7, 80), iters=5, warm=1)
+        emit('atss_all_levels', workload=f'batch {B} @640, {G} GT / image, 5 levels ({cells} cells), mydet_atss_assign_levels', us_per_batch=us_all,
+             us_per_image=us_all / B, anchor_gt_pairs_per_s=B * cells * G / us_all * 1e6, algorithmic_bytes=algo,
+             achieved_gbs=algo / us_all / 1e3, frac_of_hbm=algo / us_all / 1e3 / HBM)
     us = timed(fc if fcos else atss, iters=5, warm=1)
     emit('fcos' if fcos else 'atss', workload=f'batch {B} @640, {G} GT / image, 5 levels ({cells} cells)', us_per_batch=us,
          us_per_image=us / B, anchor_gt_pairs_per_s=B * cells * G / us * 1e6, bound='HBM write of the target maps (memset-like) + ALU for the pair tests',

@@ -194,3 +194,38 @@ def test_iou_aabb_bit_pattern_on_disjoint_and_non_finite_pairs(k, xyxy):
     mx, arg = ops.iou_rowmax(a[None].to(dev()), b[None].to(dev()), xyxy=xyxy)
     wmx, warg = want.max(dim=1)
     assert torch.equal(mx[0].cpu()[rows], wmx[rows]) and torch.equal(arg[0].cpu()[rows], warg[rows])
+
+
+def test_atss_all_levels_in_one_call_equals_level_by_level():
+    """mydet_atss_assign_levels (one GT ordering, one threshold pass, ONE grid over the cells of every level) against
+    five calls of mydet_atss_assign (itself pinned to the reference's targets in test_gpu_configs / test_zz_fullmodel):
+    every output bit-identical, with images of 0, 1 and many GT boxes and non-contiguous (permuted NCHW) inputs."""
+    from mydetection_b200 import ops
+    d = dev()
+    g = torch.Generator().manual_seed(11)
+    strides, sides, img = [8, 16, 32, 64, 128], [24, 48, 96, 192, 384], (384, 512)
+    B, G, C = 4, 23, 7
+    gt_box = torch.cat([torch.rand(B, G, 1, generator=g) * img[1], torch.rand(B, G, 1, generator=g) * img[0],
+                        torch.rand(B, G, 2, generator=g) * 150 + 6], dim=2)
+    gt_cls = torch.randint(0, C, (B, G), generator=g)
+    gt_count = torch.tensor([G, 0, 1, 9], dtype=torch.int32)
+    gt_box[3, 0] = torch.tensor([-40.0, 100.0, 60.0, 60.0])          # a centre outside the image: the exhaustive candidate scan
+    gt_box[3, 1] = torch.tensor([2.0, 3.0, 30.0, 20.0])              # in the corner cell: the clipped 11 x 11 window
+    gt_box, gt_cls, gt_count = gt_box.to(d), gt_cls.to(d), gt_count.to(d)
+    ts = [(torch.randn(B, 4, img[0] // s, img[1] // s, generator=g) * 0.6).to(d).permute(0, 2, 3, 1) for s in strides]
+    want, thr = [], None
+    for li in range(len(strides)):
+        o = ops.atss_assign(ts[li], li, strides, sides, img, gt_box, gt_cls, gt_count, 9, 0.6, C, thr=thr)
+        thr = o['thr']
+        want.append(o)
+    got = ops.atss_assign_levels(ts, strides, sides, img, gt_box, gt_cls, gt_count, 9, 0.6, C)
+    assert len(got) == len(want)
+    n_pos = 0
+    for li, (a, b) in enumerate(zip(got, want)):
+        for k in ('PositiveMask', 'IgnoredMask', 'TargetLTRB', 'TargetConf', 'TargetCls'):
+            assert a[k].shape == b[k].shape and a[k].dtype == b[k].dtype, (li, k)
+            assert torch.equal(a[k], b[k]), (li, k)
+        n_pos += int(a['PositiveMask'].sum())
+    valid = torch.arange(G)[None, :] < gt_count.cpu()[:, None]
+    assert torch.equal(got[0]['thr'].cpu()[valid], want[0]['thr'].cpu()[valid])
+    assert n_pos > 50
