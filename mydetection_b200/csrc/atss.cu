@@ -100,13 +100,16 @@ __global__ void atss_threshold_kernel(AtssGeom G, const int* gt_count, int max_g
         const int n_w = G.img_w / s, n_h = G.img_h / s;
         const float fs = (float)s, half = __fmul_rn(0.5f, fs);
         // Candidates.  When the GT centre lies inside the image, the k (<= 16) nearest cell centres of a regular
-        // grid all lie within 5 cells of the cell that holds the centre: a 3x3 .. 1x9 block next to it already
-        // offers k points within 4.5 cells, every point outside the window is >= 5.5 cells away.  So only that
-        // (clipped) 11x11 window is searched -- with the same (distance, index) order, hence the same picks as the
-        // exhaustive scan over all n anchors (9 rounds x 6 400 anchors per GT at stride 8), which remains the
-        // path for centres outside the image.
+        // grid all lie within 5 cells of the cell that holds the centre, so only that (clipped) 11x11 window is
+        // searched -- with the same (distance, index) order, hence the same picks as the exhaustive scan over all n
+        // anchors (9 rounds x 6 400 anchors per GT at stride 8), which remains the path for centres outside the image
+        // and for grids too thin for the argument (tests/test_kernel_claims_cpu.py checks both windows by brute force).
         int r_lo = 0, c_lo = 0, w_rows = n_h, w_cols = n_w;
-        if (gt.x >= 0.f && gt.x <= (float)G.img_w && gt.y >= 0.f && gt.y <= (float)G.img_h) {
+        // the window argument needs an m x m block of cells (m = ceil(sqrt(k)) <= 4) next to the centre's cell INSIDE the
+        // grid: its centres are within (m - 0.5) sqrt(2) <= 4.95 cells, cells outside the window are >= 5.5 away.  A
+        // grid thinner than m (a 1 x 20 level: the 9 nearest of a corner reach 8.5 cells) takes the exhaustive scan.
+        const int m_blk = G.k <= 1 ? 1 : (G.k <= 4 ? 2 : (G.k <= 9 ? 3 : 4));
+        if (gt.x >= 0.f && gt.x <= (float)G.img_w && gt.y >= 0.f && gt.y <= (float)G.img_h && n_h >= m_blk && n_w >= m_blk) {
             const int col0 = min(max((int)floorf(gt.x / fs), 0), n_w - 1), row0 = min(max((int)floorf(gt.y / fs), 0), n_h - 1);
             // k <= 9 and the 3x3 block around the centre's cell lies inside the grid: those 9 centres are within
             // 1.5 sqrt(2) = 2.13 cells, every cell outside a 5x5 window is >= 2.5 cells away -- 25 candidates, one per lane

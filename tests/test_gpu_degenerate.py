@@ -229,3 +229,24 @@ def test_atss_all_levels_in_one_call_equals_level_by_level():
     valid = torch.arange(G)[None, :] < gt_count.cpu()[:, None]
     assert torch.equal(got[0]['thr'].cpu()[valid], want[0]['thr'].cpu()[valid])
     assert n_pos > 50
+
+
+def test_atss_threshold_on_grids_too_thin_for_the_candidate_window():
+    """A pyramid level of 1 x 20 or 2 x 12 cells (found by tests/test_kernel_claims_cpu.py): the k = 9 nearest anchors of a
+    corner GT reach 8.5 cells, outside the 11 x 11 window -- such grids take the exhaustive scan.  Against the oracle's
+    torch.topk over all anchors."""
+    from mydetection_b200 import ops
+    from oracle import atss as oa
+    for img, strides, sides in (((8, 160), [8], [24]), ((16, 96), [8], [24]), ((32, 256), [8, 16, 32], [24, 48, 96])):
+        pts = [(0, 0), (img[1], img[0]), (3.3, 2.2), (img[1] / 2 + 0.7, img[0] / 2 + 0.3), (img[1] - 1.9, 1.1), (17.1, img[0] - 0.6)]
+        gt = torch.tensor([[x, y, 30.0 + 3 * i, 12.0 + 2 * i] for i, (x, y) in enumerate(pts)], dtype=torch.float32)[None]
+        cls = torch.zeros(1, len(pts), dtype=torch.int64)
+        counts = torch.tensor([len(pts)], dtype=torch.int32)
+        k = 9 if len(strides) == 1 else 4                      # every level must hold at least k anchors
+        t = torch.zeros(1, img[0] // strides[0], img[1] // strides[0], 4)
+        out = ops.atss_assign(t.to(dev()), 0, strides, sides, img, gt.to(dev()), cls.to(dev()), counts.to(dev()), k, 0.7, 3)
+        anchors = oa.all_level_anchors(img, strides, sides)
+        for i in range(len(pts)):
+            got = float(out['thr'][0, i])
+            want = float(oa.atss_threshold_index_ties(gt[0, i], anchors, k))
+            assert abs(got - want) <= 2e-6 * max(1.0, abs(want)), (img, pts[i], got, want)

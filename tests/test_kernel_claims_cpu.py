@@ -1,0 +1,129 @@
+"""CPU: the arithmetic / geometric claims the kernels' shortcuts rest on, checked by brute force in float32 numpy.
+Nothing here runs device code; each test restates the shortcut exactly as the kernel source does and compares it with the
+unabridged computation (the reference's formula) on adversarial and random inputs."""
+import numpy as np
+
+f32 = np.float32
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# csrc/atss.cu, atss_threshold_kernel: candidate window of the k nearest anchor centres
+def _topk_by_distance_index(gx, gy, rows, cols, n_w, stride, k):
+    """(distance, flat index) order of the given cells, float32 arithmetic of the kernel / of fcos2.py:396."""
+    s, half = f32(stride), f32(0.5) * f32(stride)
+    ax = cols.astype(f32) * s + half
+    ay = rows.astype(f32) * s + half
+    dx, dy = f32(gx) - ax, f32(gy) - ay
+    d = dx * dx + dy * dy
+    idx = rows * n_w + cols
+    order = np.lexsort((idx, d))
+    return idx[order][:k]
+
+
+def _window(gx, gy, n_h, n_w, stride, k):
+    """The kernel's window: 5x5 when k <= 9 and the 3x3 block around the centre's cell fits, else 11x11, clipped; the whole
+    grid when it is thinner than ceil(sqrt(k)) (found by this test: on a 1 x 20 grid the 9 nearest of a corner reach 8.5 cells)."""
+    col0 = min(max(int(np.floor(f32(gx) / f32(stride))), 0), n_w - 1)
+    row0 = min(max(int(np.floor(f32(gy) / f32(stride))), 0), n_h - 1)
+    m_blk = 1 if k <= 1 else (2 if k <= 4 else (3 if k <= 9 else 4))
+    if n_h < m_blk or n_w < m_blk:                      # grid too thin for the window argument: exhaustive scan
+        rr, cc = np.meshgrid(np.arange(n_h), np.arange(n_w), indexing='ij')
+        return rr.ravel(), cc.ravel(), False
+    small = k <= 9 and col0 >= 1 and col0 + 1 <= n_w - 1 and row0 >= 1 and row0 + 1 <= n_h - 1
+    R = 2 if small else 5
+    c_lo, r_lo = max(col0 - R, 0), max(row0 - R, 0)
+    c_hi, r_hi = min(col0 + R, n_w - 1), min(row0 + R, n_h - 1)
+    rr, cc = np.meshgrid(np.arange(r_lo, r_hi + 1), np.arange(c_lo, c_hi + 1), indexing='ij')
+    return rr.ravel(), cc.ravel(), small
+
+
+def test_atss_candidate_window_holds_the_k_nearest_anchors():
+    rng = np.random.default_rng(0)
+    n_small = n_big = 0
+    for stride, n_h, n_w in ((8, 48, 80), (16, 24, 40), (32, 12, 20), (64, 6, 10), (128, 3, 5), (8, 3, 3), (8, 1, 20), (8, 20, 2), (8, 3, 30), (8, 4, 4), (8, 2, 9), (8, 30, 4)):
+        all_r, all_c = (a.ravel() for a in np.meshgrid(np.arange(n_h), np.arange(n_w), indexing='ij'))
+        W, H = n_w * stride, n_h * stride
+        pts = [(0, 0), (W, H), (0, H), (W, 0), (W / 2, 0), (stride, stride), (stride * 1.5, stride * 1.5), (W - 1e-3, H - 1e-3),
+               (stride * 2, stride * 2.5), (np.nextafter(f32(stride * 3), f32(0)), stride * 3)]
+        pts += [(rng.uniform(0, W), rng.uniform(0, H)) for _ in range(150)]
+        # cell boundaries and half cells, where distances tie
+        pts += [(stride * rng.integers(0, n_w + 1), stride * rng.integers(0, n_h + 1) + stride / 2 * rng.integers(0, 2)) for _ in range(60)]
+        for k in (1, 4, 9, 12, 16):
+            if n_h * n_w < k:
+                continue
+            for gx, gy in pts:
+                if not (0 <= gx <= W and 0 <= gy <= H):
+                    continue
+                wr, wc, small = _window(gx, gy, n_h, n_w, stride, k)
+                want = _topk_by_distance_index(gx, gy, all_r, all_c, n_w, stride, k)
+                got = _topk_by_distance_index(gx, gy, wr, wc, n_w, stride, k)
+                assert np.array_equal(got, want), (stride, n_h, n_w, k, gx, gy, small)
+                n_small += small
+                n_big += not small
+    assert n_small > 1000 and n_big > 1000
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# csrc/atss.cu, assign_body: per-CTA GT cull against the hull of the CTA's predicted boxes and cell centres
+def test_atss_gt_cull_never_drops_a_gt_that_could_matter():
+    rng = np.random.default_rng(1)
+    dropped = kept = 0
+    for trial in range(300):
+        stride = f32(rng.choice([8, 16, 32]))
+        n_w = int(rng.integers(3, 40))
+        cells = np.arange(int(rng.integers(1, 129))) + int(rng.integers(0, 50))
+        row, col = cells // n_w, cells % n_w
+        half = stride * f32(0.5)
+        gx = col.astype(f32) * stride + half
+        gy = row.astype(f32) * stride + half
+        t = rng.normal(0, 0.8, (cells.size, 4)).astype(f32)
+        if trial % 7 == 0:
+            t[rng.integers(0, cells.size)] = [np.nan, 0, 0, 0]
+        if trial % 11 == 0:
+            t[rng.integers(0, cells.size)] = [200.0, 0, 0, 0]            # exp overflows to inf
+        with np.errstate(over='ignore', invalid='ignore'):
+            l, tp, r, bt = (np.exp(t[:, i]).astype(f32) * stride for i in range(4))
+            pcx, pcy = gx + (r - l) * f32(0.5), gy + (bt - tp) * f32(0.5)
+            pw, ph = l + r, tp + bt
+            phw, phh = pw * f32(0.5), ph * f32(0.5)
+            px1, py1, px2, py2 = pcx - phw, pcy - phh, pcx + phw, pcy + phh
+            # hull: fminf / fmaxf drop NaN operands
+            hx1, hy1 = np.fmin(gx, px1).min(), np.fmin(gy, py1).min()
+            hx2, hy2 = np.fmax(gx, px2).max(), np.fmax(gy, py2).max()
+            G = 60
+            gt = np.concatenate([rng.uniform(-50, 400, (G, 2)), rng.uniform(0, 120, (G, 2))], axis=1).astype(f32)
+            gt[0] = [np.nan, 10, 20, 20]
+            gt[1, 2:] = 0
+            ghw, ghh = gt[:, 2] * f32(0.5), gt[:, 3] * f32(0.5)
+            g1x, g1y, g2x, g2y = gt[:, 0] - ghw, gt[:, 1] - ghh, gt[:, 0] + ghw, gt[:, 1] + ghh
+            keep = (np.fmax(hx1, g1x) <= np.fmin(hx2, g2x)) & (np.fmax(hy1, g1y) <= np.fmin(hy2, g2y))
+            for g in np.nonzero(~keep)[0]:
+                # iou_cxcywh_or_zero's overlap test (NaN-propagating max / min: np.maximum / np.minimum) fails for every cell
+                tlx, tly = np.maximum(px1, g1x[g]), np.maximum(py1, g1y[g])
+                brx, bry = np.minimum(px2, g2x[g]), np.minimum(py2, g2y[g])
+                assert not ((tlx < brx) & (tly < bry)).any(), (trial, g)
+                # and no cell centre lies strictly inside the GT (fcos2.py:321)
+                inside = (gx - g1x[g] > 0) & (gy - g1y[g] > 0) & (g2x[g] - gx > 0) & (g2y[g] - gy > 0)
+                assert not inside.any(), (trial, g)
+        dropped += int((~keep).sum())
+        kept += int(keep.sum())
+    assert dropped > 3000 and kept > 1000
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# csrc/common.cuh, iou_from_parts / iou_corners_gt: the divide is skipped where the numerator is a zero
+def test_zero_numerator_quotient_is_the_numerator():
+    sums = np.array([1e-38, 1e-30, 1.0, 3.5, 1e30, np.inf, np.finfo(f32).tiny, np.finfo(f32).max], dtype=f32)
+    for z in (f32(0.0), f32(-0.0)):
+        with np.errstate(all='ignore'):
+            q = z / (sums - z)
+        assert np.array_equal(q.view(np.int32), np.full_like(sums, z).view(np.int32)), (z, q)
+    # ... and NOT where area_a + area_b is not positive: the kernels divide there
+    with np.errstate(all='ignore'):
+        assert np.isnan(f32(0.0) / (f32(0.0) - f32(0.0)))
+        assert (f32(0.0) / (f32(-2.0) - f32(0.0))).view(np.int32) == f32(-0.0).view(np.int32)
+    # iou_corners_gt: inter == 0 gives 0, -0 or NaN -- never above a non-negative threshold
+    unis = np.array([-3.0, -0.0, 0.0, 2.0, np.inf, np.nan], dtype=f32)
+    with np.errstate(all='ignore'):
+        for thr in (f32(0.0), f32(0.45), f32(1.0)):
+            assert not (f32(0.0) / unis > thr).any()
