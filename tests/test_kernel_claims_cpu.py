@@ -127,3 +127,91 @@ def test_zero_numerator_quotient_is_the_numerator():
     with np.errstate(all='ignore'):
         for thr in (f32(0.0), f32(0.45), f32(1.0)):
             assert not (f32(0.0) / unis > thr).any()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# csrc/nms_large.cu, rot_broad_kernel / rot_narrow_kernel: a pair is dropped before the polygon clip by the circle test, the
+# area-ratio bound, the hull-overlap bound or the oriented-extent bound -- none may drop a pair whose exact IoU reaches thr
+def _rot_quantities(b):
+    """Per-box quantities as the gather kernel stores them (float32): corners, centre, radius, area, hull, half axes."""
+    import torch
+    from oracle import iou as oi
+    rad = b.clone()
+    rad[:, 4] = oi.deg2rad_f32(rad[:, 4])
+    v = oi.xywha2vertex(rad).numpy().astype(f32)                          # (N,4,2) tl,tr,br,bl
+    x, y = v[:, :, 0], v[:, :, 1]
+    bn = b.numpy().astype(f32)
+    r = f32(0.5) * np.sqrt(bn[:, 2] * bn[:, 2] + bn[:, 3] * bn[:, 3]).astype(f32)
+    xd, yd = x.astype(np.float64), y.astype(np.float64)
+    a2 = sum(xd[:, k] * yd[:, (k + 1) % 4] - xd[:, (k + 1) % 4] * yd[:, k] for k in range(4))
+    area = f32(0.5) * np.abs(a2.astype(f32))
+    hull = np.stack([x.min(1), y.min(1), x.max(1), y.max(1)], 1)
+    axes = np.stack([f32(0.5) * (x[:, 1] - x[:, 0]), f32(0.5) * (y[:, 1] - y[:, 0]),
+                     f32(0.5) * (x[:, 0] - x[:, 3]), f32(0.5) * (y[:, 0] - y[:, 3])], 1)
+    return bn[:, 0], bn[:, 1], r, area, hull, axes
+
+
+def _oriented_bound(ca, xa, cb, xb):
+    """oriented_overlap_bound of nms_large.cu, vectorised over pairs; c = (cx, cy, r, area), x = (Hx, Hy, Vx, Vy)."""
+    dx, dy = cb[0] - ca[0], cb[1] - ca[1]
+    hh, vh = np.abs(xb[0] * xa[0] + xb[1] * xa[1]), np.abs(xb[2] * xa[0] + xb[3] * xa[1])
+    hv, vv = np.abs(xb[0] * xa[2] + xb[1] * xa[3]), np.abs(xb[2] * xa[2] + xb[3] * xa[3])
+
+    def frame(h2, v2, ph, pv, eh, ev, area):
+        ox = np.minimum(h2, ph + eh) - np.maximum(-h2, ph - eh)
+        oy = np.minimum(v2, pv + ev) - np.maximum(-v2, pv - ev)
+        return np.maximum(ox, f32(0)) * np.maximum(oy, f32(0)) * f32(4) / area
+    ua = frame(xa[0] * xa[0] + xa[1] * xa[1], xa[2] * xa[2] + xa[3] * xa[3], dx * xa[0] + dy * xa[1], dx * xa[2] + dy * xa[3],
+               hh + vh, hv + vv, ca[3])
+    ub = frame(xb[0] * xb[0] + xb[1] * xb[1], xb[2] * xb[2] + xb[3] * xb[3], dx * xb[0] + dy * xb[1], dx * xb[2] + dy * xb[3],
+               hh + hv, vh + vv, cb[3])
+    return np.minimum(ua, ub)
+
+
+def test_rotated_culls_never_drop_a_pair_that_reaches_the_threshold():
+    import torch
+    from oracle import iou as oi
+    g = torch.Generator().manual_seed(7)
+    n = 700
+    boxes = []
+    # clusters of similar boxes (IoUs on both sides of every threshold), thin boxes, tiny and huge ones, all angles
+    for _ in range(14):
+        c = torch.rand(2, generator=g) * 300 + 100
+        wh = torch.rand(2, generator=g) * torch.tensor([180.0, 60.0]) + 4
+        ang = torch.rand(1, generator=g) * 360 - 180
+        k = n // 14
+        boxes.append(torch.cat([c + torch.randn(k, 2, generator=g) * wh.min() * 0.4, wh * torch.exp(torch.randn(k, 2, generator=g) * 0.25),
+                                ang + torch.randn(k, 1, generator=g) * 25], 1))
+    b = torch.cat(boxes).float()
+    b[::97, 4] = 0.0
+    b[5::97, 4] = 90.0
+    b[11::97, 2:4] = b[11::97, 2:4].flip(1)
+    cx, cy, r, area, hull, axes = _rot_quantities(b)
+    exact = oi.iou_rot(b, b).numpy()
+    i, j = np.triu_indices(b.shape[0], 1)
+    ca = (cx[i], cy[i], r[i], area[i])
+    cb = (cx[j], cy[j], r[j], area[j])
+    with np.errstate(all='ignore'):
+        # (1) circumscribed circles: rot_broad_kernel, mr = r * 1.00001 + 1e-3, rr = r_other * 1.00001 + mr
+        dx, dy = ca[0] - cb[0], ca[1] - cb[1]
+        rr = cb[2] * f32(1.00001) + (ca[2] * f32(1.00001) + f32(1e-3))
+        circle_drop = ~(dx * dx + dy * dy <= rr * rr)
+        assert exact[i, j][circle_drop].max(initial=0.0) == 0.0
+        ub_o = _oriented_bound(ca, axes[i].T, cb, axes[j].T)
+        ix = np.minimum(hull[i, 2], hull[j, 2]) - np.maximum(hull[i, 0], hull[j, 0])
+        iy = np.minimum(hull[i, 3], hull[j, 3]) - np.maximum(hull[i, 1], hull[j, 1])
+        ub_h = (ix + f32(2e-3)) * (iy + f32(2e-3))
+        n_dropped = 0
+        for thr in (0.05, 0.3, 0.45, 0.5, 0.7, 0.95):
+            t = f32(thr)
+            ratio_drop = ~(np.minimum(ca[3], cb[3]) * f32(1.0001) >= t * np.maximum(ca[3], cb[3]))           # (2)
+            hull_drop = ~((ix > f32(-1e-3)) & (iy > f32(-1e-3))) | (ub_h * f32(1.0001) < t * (ca[3] + cb[3] - ub_h))   # (3)
+            orient_drop = ub_o * f32(1.001) + f32(1e-2) < t * (ca[3] + cb[3] - ub_o)                           # (4)
+            for name, drop in (('ratio', ratio_drop), ('hull', hull_drop), ('oriented', orient_drop)):
+                worst = exact[i, j][drop].max(initial=0.0)
+                assert worst < thr, (name, thr, worst)
+                n_dropped += int(drop.sum())
+        # the oriented bound is an upper bound of the intersection area itself
+        inter = exact[i, j] * (area[i].astype(np.float64) + area[j]) / (1.0 + exact[i, j])
+        assert (inter <= ub_o.astype(np.float64) * 1.001 + 1e-2).all()
+    assert n_dropped > 100000 and (exact[i, j] > 0.5).sum() > 500 and (exact[i, j] > 0.05).sum() > 5000
