@@ -129,6 +129,8 @@ int mydet_decode_compact(int kind, const mydet_level_t* levels, int n_levels, in
  *   src_idx  optional (B,pitch) i32: value reported in out_idx instead of the slot number
  *   counts   optional (B) i32: valid candidates per image (clamped to n_per_image); else all
  *   conf_thres: candidates with score < conf_thres (or NaN) are ignored; pass -INFINITY for none
+ *   nms_thres  torchvision's rule: a box is dropped iff its IoU with a kept, higher-scored box of its class is > nms_thres.
+ *            A negative threshold (which disjoint boxes pass: 0 > thr) is honoured; it takes the all-pairs kernels.
  *   topk     > 0: keep the topk best survivors before NMS (reference: 512); <= 0: no cap
  *   outputs  out_box (B,out_cap,P), out_score (B,out_cap), out_cls (B,out_cap) i64,
  *            out_idx (B,out_cap) i32, out_count (B) i32; rows ordered class ascending, then score

@@ -811,7 +811,7 @@ __global__ void __launch_bounds__(kTile) mask_rot_kernel(LargeWs w, const int* m
             const int c0 = ct * kTile;
             if (c0 >= mb) break;
             unsigned long long bits = ((unsigned long long)bits32[ct - ct_lo][t][1] << 32) | bits32[ct - ct_lo][t][0];
-            if (thr_d <= 0.0 && ge_mode) {           // degenerate threshold: every later box is suppressed
+            if (ge_mode ? (thr_d <= 0.0) : (thr_d < 0.0)) {   // degenerate threshold: every later box is suppressed
                 bits = 0ull;
                 const int lim = min(kTile, mb - c0);
                 for (int j = 0; j < lim; ++j) if (c0 + j > r) bits |= 1ull << j;
@@ -1876,9 +1876,11 @@ int run_large(const LargeArgs& A, void* workspace, size_t workspace_bytes, cudaS
     const int B = A.batch, n = A.n;
     MYDET_CUDA(cudaMemsetAsync(w.m, 0, sizeof(int) * (size_t)B, st));
     if (A.status) MYDET_CUDA(cudaMemsetAsync(A.status, 0, sizeof(int) * (size_t)B, st));
-    // Morton-ordered mask (n <= 65 536).  The degenerate "IoU >= 0" threshold of the rotated API suppresses
-    // disjoint boxes too, which patch culling would miss: it keeps the score-ordered kernel.
-    const bool spatial = n <= kSpatialMaxN && !(A.rot && A.ge && A.thr <= 0.0);
+    // Morton-ordered mask (n <= 65 536).  A degenerate threshold that a DISJOINT pair passes ("IoU >= 0" of the rotated
+    // API, a negative threshold with torchvision's "IoU > thr") suppresses boxes that patch culling never pairs up:
+    // such calls keep the score-ordered all-pairs kernels.
+    const bool disjoint_suppresses = (A.rot && A.ge) ? (A.thr <= 0.0) : (A.thr < 0.0);
+    const bool spatial = n <= kSpatialMaxN && !disjoint_suppresses;
     KeyParams K{A.scores, A.cls, A.counts, A.src_idx, A.pitch, n, A.cls_is_i64, (A.cls && !A.rot) ? 1 : 0, A.conf_thres, A.status,
                 A.boxes, A.n_param, A.box_format, spatial ? w.skeys : nullptr};
     keys_kernel<<<dim3((n + 255) / 256, B), 256, 0, st>>>(K, w.keys, w.m);

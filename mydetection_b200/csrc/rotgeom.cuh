@@ -126,11 +126,11 @@ __device__ __forceinline__ bool rot_overlaps(const RotBox& A, const RotBox& B, d
     // (1) circumscribed circles apart => empty intersection (slack covers float32 rounding)
     const float dx = A.cx - B.cx, dy = A.cy - B.cy;
     const float rr = (A.r + B.r) * 1.00001f + 1e-3f;
-    if (dx * dx + dy * dy > rr * rr) return ge ? (0.0 >= thr) : false;
+    if (dx * dx + dy * dy > rr * rr) return ge ? (0.0 >= thr) : (0.0 > thr);
     // (2) IoU <= min(area)/max(area)
     const float aA = 0.5f * fabsf(A.area2), aB = 0.5f * fabsf(B.area2);
     const float lo = fminf(aA, aB), hi = fmaxf(aA, aB);
-    if (!(lo > 0.f)) return ge ? (0.0 >= thr) : false;
+    if (!(lo > 0.f)) return ge ? (0.0 >= thr) : (0.0 > thr);
     if ((double)lo * 1.0001 < thr * (double)hi) return false;
     // (3) float32 clip around A's centre
     const float inter = clip_area<float>(A.x, A.y, B.x, B.y, B.area2 >= 0.f ? 1.f : -1.f, A.cx, A.cy);
