@@ -1969,6 +1969,10 @@ int run_large(const LargeArgs& A, void* workspace, size_t workspace_bytes, cudaS
         votes_kernel<<<dim3((n + 127) / 128, B), 128, 0, st>>>(w, w.m, n, A.votes, A.pitch, spatial ? 1 : 0);
     }
     if (spatial && A.ws_clean) mask_cleanup_kernel<<<dim3(32, B), 256, 0, st>>>(w, n);
+    // the all-pairs kernels write whole mask rows; a persistent workspace is handed back clean all the same (a later call
+    // of the same geometry with an ordinary threshold takes the spatial path and relies on it)
+    if (!spatial && A.ws_clean && n <= kSpatialMaxN)
+        MYDET_CUDA(cudaMemsetAsync(w.mask, 0, (size_t)B * n * w.words * sizeof(unsigned long long), st));
     return launch_status("large NMS pipeline");
 }
 
