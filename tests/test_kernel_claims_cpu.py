@@ -215,3 +215,34 @@ def test_rotated_culls_never_drop_a_pair_that_reaches_the_threshold():
         inter = exact[i, j] * (area[i].astype(np.float64) + area[j]) / (1.0 + exact[i, j])
         assert (inter <= ub_o.astype(np.float64) * 1.001 + 1e-2).all()
     assert n_dropped > 100000 and (exact[i, j] > 0.5).sum() > 500 and (exact[i, j] > 0.05).sum() > 5000
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# csrc/common.cuh: float_at_or_below / float_at_or_above (torchvision compares a float32 IoU with a float64 threshold; the
+# kernels compare with ONE float) and float_key (order-preserving float -> uint32 of the sort / select keys)
+def test_float_threshold_and_sort_key_identities():
+    rng = np.random.default_rng(3)
+    ts = np.concatenate([rng.uniform(-1, 2, 2000), [0.0, 0.5, 0.45, 0.3, 1.0, 1e-45, -1e-45, 0.1, 0.7, 1 / 3]])
+    for t in ts:
+        lo = f32(t)
+        if np.float64(lo) > t:
+            lo = np.nextafter(lo, f32(-np.inf))                      # float_at_or_below
+        hi = f32(t)
+        if np.float64(hi) < t:
+            hi = np.nextafter(hi, f32(np.inf))                       # float_at_or_above
+        xs = np.array([lo, hi, np.nextafter(lo, f32(-np.inf)), np.nextafter(lo, f32(np.inf)), np.nextafter(hi, f32(np.inf)),
+                       np.nextafter(hi, f32(-np.inf)), f32(0), f32(1), f32(-0.0)], dtype=f32)
+        xs = np.concatenate([xs, rng.uniform(-1, 2, 50).astype(f32)])
+        assert np.array_equal(xs.astype(np.float64) > t, xs > lo), t
+        assert np.array_equal(xs.astype(np.float64) >= t, xs >= hi), t
+
+    def float_key(s):
+        u = (s + f32(0.0)).view(np.uint32)
+        return np.where(u & np.uint32(0x80000000), ~u, u | np.uint32(0x80000000))
+    vals = np.concatenate([rng.normal(0, 1, 5000).astype(f32), rng.uniform(0, 1, 5000).astype(f32),
+                           np.array([0.0, -0.0, np.inf, -np.inf, 1e-45, -1e-45, np.finfo(f32).max, np.finfo(f32).min, 1.0, -1.0], dtype=f32)])
+    keys = float_key(vals)
+    order = np.argsort(vals, kind='stable')
+    sv, sk = vals[order], keys[order]
+    assert (np.diff(sk.astype(np.int64)) >= 0).all()                              # monotone
+    assert ((np.diff(sk.astype(np.int64)) == 0) == (np.diff(sv) == 0)).all()      # equal keys <=> equal floats (-0 == +0)
