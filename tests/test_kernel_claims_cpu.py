@@ -246,3 +246,48 @@ def test_float_threshold_and_sort_key_identities():
     sv, sk = vals[order], keys[order]
     assert (np.diff(sk.astype(np.int64)) >= 0).all()                              # monotone
     assert ((np.diff(sk.astype(np.int64)) == 0) == (np.diff(sv) == 0)).all()      # equal keys <=> equal floats (-0 == +0)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# csrc/nms_large.cu, lazy narrow phase (rot_filter / rot_clip<0> / rot_clip<1>): greedy NMS on the REDUCED suppression matrix
+# -- pairs under a root first, pairs with a dead member never evaluated -- keeps the same boxes as on the full matrix
+def test_lazy_root_first_matrix_gives_the_greedy_set():
+    rng = np.random.default_rng(5)
+
+    def greedy(M):
+        n = M.shape[0]
+        kept = np.zeros(n, dtype=bool)
+        for i in range(n):                       # rank order: 0 = best score; M[j, i], j < i: j suppresses i if kept
+            kept[i] = not (M[:i, i] & kept[:i]).any()
+        return kept
+
+    total_pairs = evaluated = 0
+    for trial in range(120):
+        n = int(rng.integers(2, 160))
+        n_obj = int(rng.integers(1, 8))
+        obj = rng.integers(0, n_obj, n)
+        # true overlaps: mostly inside an object's cluster, some across; listed pairs = a superset (the bound is conservative)
+        p_in, p_out = rng.uniform(0.2, 0.95), rng.uniform(0.0, 0.05)
+        same = obj[:, None] == obj[None, :]
+        O = np.triu((rng.random((n, n)) < np.where(same, p_in, p_out)), 1)
+        L = O | np.triu(rng.random((n, n)) < 0.1, 1)
+        want = greedy(O)
+        has_higher = L.any(axis=0)               # filter: the lower box of every listed pair is marked
+        root = ~has_higher
+        M = np.zeros_like(O)
+        dead = np.zeros(n, dtype=bool)
+        for j, i in zip(*np.nonzero(L)):         # clip<0>: pairs whose higher-scored box is a root
+            if root[j]:
+                evaluated += 1
+                if O[j, i]:
+                    M[j, i] = True
+                    dead[i] = True
+        for j, i in zip(*np.nonzero(L)):         # clip<1>: the rest, except pairs with a dead member
+            if not root[j] and not dead[j] and not dead[i]:
+                evaluated += 1
+                if O[j, i]:
+                    M[j, i] = True
+        total_pairs += int(L.sum())
+        assert np.array_equal(greedy(M), want), trial
+        assert want[root].all()                  # roots are certainly kept
+    assert evaluated < 0.6 * total_pairs         # and the reduction is real on clustered input
