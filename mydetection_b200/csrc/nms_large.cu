@@ -1217,7 +1217,7 @@ __global__ void __launch_bounds__(kBroadWarps * 32) rot_broad_kernel(LargeWs w, 
 // scaled by the half lengths (no square root): with H, V the half-axis vectors of A and d the centre offset, the overlap
 // of the two intervals along H is  min(|H|^2, d.H + E) - max(-|H|^2, d.H - E),  E = |H_B.H| + |V_B.H|,  in units of |H|.
 // On the bench workload this bound removes 78 % of the pairs the axis-aligned hull bound lets through (138 k -> 30 k per
-// 10 000-box image; none of the removed pairs reaches the threshold: /tmp probe in profiles/r2_rotated_nms.md).
+// 10 000-box image; that none of the removed pairs reaches the threshold is checked by brute force in tests/test_kernel_claims_cpu.py).
 __device__ __forceinline__ float oriented_overlap_bound(const float4 ca, const float4 xa, const float4 cb, const float4 xb) {
     const float dx = cb.x - ca.x, dy = cb.y - ca.y;
     const float hh_ = fabsf(xb.x * xa.x + xb.y * xa.y), vh_ = fabsf(xb.z * xa.x + xb.w * xa.y);   // |H_B.H_A|, |V_B.H_A|
