@@ -234,6 +234,39 @@ def test_header_is_plain_c(tmp_path):
         assert res.returncode == 0, res.stdout
 
 
+def test_ctypes_descriptors_have_the_c_layout(tmp_path):
+    """The two descriptor structs that cross the ABI by pointer (mydet_level_t, mydet_atss_level_t): size and every field
+    offset of the ctypes mirror equal what a C compiler gives the header's structs."""
+    import subprocess
+    from mydetection_b200 import _lib
+    fields = {'mydet_level_t': (_lib.Level, ['bbox', 'conf', 'cls', 'bbox_stride', 'conf_stride', 'cls_stride', 'n_anchor', 'n_h', 'n_w',
+                                             'stride', 'anchor_w', 'anchor_h']),
+              'mydet_atss_level_t': (_lib.AtssLevel, ['t_ltrb', 't_stride', 'positive', 'ignored', 'target_ltrb', 'target_conf', 'target_cls'])}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "mydet.h"', 'int main(void) {']
+    for name, (_, names) in fields.items():
+        lines.append(f'    printf("{name} %zu", sizeof({name}));')
+        for f in names:
+            lines.append(f'    printf(" %zu", offsetof({name}, {f}));')
+        lines.append('    printf("\\n");')
+    lines += ['    return 0;', '}']
+    src, exe = tmp_path / 'layout.c', tmp_path / 'layout'
+    src.write_text('\n'.join(lines) + '\n')
+    res = subprocess.run(['gcc', '-std=c99', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0, res.stdout
+    out = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True, check=True).stdout.split('\n')
+    seen = 0
+    for line in out:
+        tok = line.split()
+        if not tok:
+            continue
+        cls, names = fields[tok[0]]
+        want = [ctypes.sizeof(cls)] + [getattr(cls, f).offset for f in names]
+        assert [int(v) for v in tok[1:]] == want, (tok[0], tok[1:], want)
+        seen += 1
+    assert seen == 2
+
+
 def test_reference_copy_and_dropin_graft():
     """oracle/fetch_ref.py's copy is byte-identical to the manifest, the reference imports from it with the three
     third-party stand-ins, and dropin.install() completes the mirror with what lies outside the hot path (tracklets,
