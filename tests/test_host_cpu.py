@@ -31,6 +31,39 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib().mydet_version() == 100
 
 
+def test_binding_signatures_match_the_header_prototypes():
+    """Every prototype of include/mydet.h against _lib.SIGNATURES, argument by argument: same count, pointers bound as
+    pointers, and every scalar with the ctypes type of its C type (a float passed as c_int, or a missing argument, would
+    otherwise only show on a GPU)."""
+    from mydetection_b200 import _lib
+    text = open(os.path.join(ROOT, 'include', 'mydet.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    protos = re.findall(r'^\s*((?:const\s+)?[A-Za-z_][A-Za-z0-9_]*\s*\*?)\s*\b(mydet_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;', text, flags=re.M | re.S)
+    scalar = {'int': ctypes.c_int, 'int32_t': ctypes.c_int32, 'int64_t': ctypes.c_int64, 'float': ctypes.c_float,
+              'double': ctypes.c_double, 'size_t': ctypes.c_size_t}
+    seen = set()
+    for ret, name, args in protos:
+        seen.add(name)
+        restype, argtypes = _lib.SIGNATURES[name]
+        ret = ret.strip()
+        if '*' in ret:
+            assert restype is ctypes.c_char_p, name
+        else:
+            assert ctypes.sizeof(restype) == ctypes.sizeof(scalar[ret]), (name, ret)
+        args = args.strip()
+        params = [] if args in ('', 'void') else [a.strip() for a in args.split(',')]
+        assert len(params) == len(argtypes), (name, len(params), len(argtypes))
+        for k, (c_decl, bound) in enumerate(zip(params, argtypes)):
+            is_ptr = '*' in c_decl or '[' in c_decl
+            bound_is_ptr = bound is ctypes.c_void_p or bound is ctypes.c_char_p or hasattr(bound, '_type_') and not isinstance(bound._type_, str)
+            assert is_ptr == bound_is_ptr, (name, k, c_decl, bound)
+            if not is_ptr:
+                ctype = scalar[c_decl.replace('const', '').split()[0]]
+                assert bound is ctype or (ctypes.sizeof(bound) == ctypes.sizeof(ctype) and
+                                          (bound in (ctypes.c_float, ctypes.c_double)) == (ctype in (ctypes.c_float, ctypes.c_double))), (name, k, c_decl, bound)
+    assert seen == set(_lib.SIGNATURES), sorted(set(_lib.SIGNATURES) ^ seen)
+
+
 def test_library_is_sm100a_only():
     from mydetection_b200 import _lib
     import subprocess
