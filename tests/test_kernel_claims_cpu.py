@@ -291,3 +291,52 @@ def test_lazy_root_first_matrix_gives_the_greedy_set():
         assert np.array_equal(greedy(M), want), trial
         assert want[root].all()                  # roots are certainly kept
     assert evaluated < 0.6 * total_pairs         # and the reduction is real on clustered input
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# csrc/postprocess_small.cu, register-resident front end: the exact top-K through a 2048-bin histogram that is LINEAR over
+# the score range -- bins above the K-th score's bin are taken whole, that bin's candidates are ranked by (score, index)
+def test_histogram_select_is_the_exact_top_k():
+    rng = np.random.default_rng(9)
+    BINS = 2048
+
+    def select(s, thr, K):
+        valid = s >= thr                                                   # NaN fails
+        if valid.sum() <= K:
+            return np.nonzero(valid)[0]
+        smin, smax = s[valid].min(), s[valid].max()
+        with np.errstate(all='ignore'):
+            scale = f32(BINS - 1) / (smax - smin) if smax > smin else f32(0)
+            b = np.nan_to_num((s - smin) * scale, nan=0.0, posinf=3e9, neginf=-3e9)      # cvt.rzi: NaN -> 0, saturating
+        b = np.clip(b.astype(np.int64), 0, BINS - 1)
+        hist = np.bincount(b[valid], minlength=BINS)
+        above = hist[::-1].cumsum()[::-1] - hist                           # candidates in bins above each bin
+        T = int(np.nonzero((above < K) & (K <= above + hist))[0][0])
+        need = K - above[T]
+        sure = np.nonzero(valid & (b > T))[0]
+        und = np.nonzero(valid & (b == T))[0]
+        und = und[np.lexsort((und, -s[und].astype(np.float64)))][:need]    # score descending, index ascending
+        return np.concatenate([sure, und])
+
+    for trial in range(400):
+        n = int(rng.integers(1, 9217))
+        kind = trial % 6
+        if kind == 0:
+            s = rng.random(n).astype(f32)
+        elif kind == 1:
+            s = (1 / (1 + np.exp(-rng.normal(-3, 2, n)))).astype(f32)      # detector scores: piled up near 0
+        elif kind == 2:
+            s = rng.choice(np.array([0.1, 0.2, 0.2000001, 0.5, 0.9], dtype=f32), n)      # heavy ties
+        elif kind == 3:
+            s = (f32(0.5) + rng.integers(0, 3, n).astype(f32) * np.finfo(f32).eps).astype(f32)   # range of two ulps
+        elif kind == 4:
+            s = rng.normal(0, 1e-38, n).astype(f32)                        # denormal range: the scale overflows
+        else:
+            s = rng.random(n).astype(f32)
+            s[rng.integers(0, n, max(1, n // 50))] = np.nan
+        thr = f32(rng.choice([-1.0, 0.0, 0.005, 0.3]))
+        K = int(rng.choice([1, 7, 100, 512, 1024]))
+        got = np.sort(select(s, thr, K))
+        valid = np.nonzero(s >= thr)[0]
+        want = np.sort(valid[np.lexsort((valid, -s[valid].astype(np.float64)))][:K])
+        assert np.array_equal(got, want), (trial, kind, n, K)
