@@ -419,6 +419,7 @@ MYDET_API int mydet_atss_assign(const float* t_ltrb, const int64_t t_stride[4], 
     }
     if (batch == 0) return 0;
     MYDET_REQUIRE(t_ltrb && gt_count && positive && ignored && target_ltrb && target_conf && target_cls, "NULL tensor pointer");
+    MYDET_REQUIRE((reinterpret_cast<uintptr_t>(target_ltrb) & 15) == 0, "target_ltrb must be 16-byte aligned (written as 128-bit vectors)");
     MYDET_REQUIRE(max_gt == 0 || (gt_box && gt_cls), "NULL GT pointer");
     AtssWs w;
     const size_t need = carve_atss(w, workspace, batch, max_gt);
@@ -459,6 +460,7 @@ MYDET_API int mydet_fcos_assign(const float* t_ltrb, const int64_t t_stride[4], 
     MYDET_REQUIRE(max_gt <= 2048, "more than 2048 GT boxes per image");
     if (batch == 0) return 0;
     MYDET_REQUIRE(t_ltrb && gt_count && positive && ignored && target_ltrb && target_conf && target_cls, "NULL tensor pointer");
+    MYDET_REQUIRE((reinterpret_cast<uintptr_t>(target_ltrb) & 15) == 0, "target_ltrb must be 16-byte aligned (written as 128-bit vectors)");
     MYDET_REQUIRE(max_gt == 0 || (gt_box && gt_cls), "NULL GT pointer");
     AtssWs w;
     const size_t need = carve_atss(w, workspace, batch, max_gt);
@@ -517,6 +519,7 @@ MYDET_API int mydet_atss_assign_levels(const mydet_atss_level_t* levels, int n_l
     for (int i = 0; i < n_levels; ++i) {
         const mydet_atss_level_t& L = levels[i];
         MYDET_REQUIRE(L.t_ltrb && L.positive && L.ignored && L.target_ltrb && L.target_conf && L.target_cls, "NULL tensor pointer in level %d", i);
+        MYDET_REQUIRE((reinterpret_cast<uintptr_t>(L.target_ltrb) & 15) == 0, "target_ltrb of level %d must be 16-byte aligned (written as 128-bit vectors)", i);
         AssignParams& P = A.lv[i];
         P.t = L.t_ltrb; P.ts_b = L.t_stride[0]; P.ts_h = L.t_stride[1]; P.ts_w = L.t_stride[2]; P.ts_p = L.t_stride[3];
         P.n_h = img_h / strides[i]; P.n_w = img_w / strides[i]; P.n_cls = n_cls; P.max_gt = max_gt;
