@@ -105,6 +105,19 @@ def test_atss_gt_cull_never_drops_a_gt_that_could_matter():
                 # and no cell centre lies strictly inside the GT (fcos2.py:321)
                 inside = (gx - g1x[g] > 0) & (gy - g1y[g] > 0) & (g2x[g] - gx > 0) & (g2y[g] - gy > 0)
                 assert not inside.any(), (trial, g)
+            # FCOS mode (fcos2.py:113-133): the positive test is "centre strictly inside the GT scaled by center_region", and
+            # the cull box is the union of the GT and that region (center_region may exceed 1)
+            for cr in (f32(0.5), f32(1.0), f32(1.7)):
+                chw, chh = (gt[:, 2] * cr) * f32(0.5), (gt[:, 3] * cr) * f32(0.5)
+                uhw, uhh = np.fmax(ghw, chw), np.fmax(ghh, chh)
+                keep_f = (np.fmax(hx1, gt[:, 0] - uhw) <= np.fmin(hx2, gt[:, 0] + uhw)) & \
+                         (np.fmax(hy1, gt[:, 1] - uhh) <= np.fmin(hy2, gt[:, 1] + uhh))
+                for g in np.nonzero(~keep_f)[0]:
+                    centre = (gx > gt[g, 0] - chw[g]) & (gx < gt[g, 0] + chw[g]) & (gy > gt[g, 1] - chh[g]) & (gy < gt[g, 1] + chh[g])
+                    assert not centre.any(), (trial, g, cr)
+                    tlx, tly = np.maximum(px1, gt[g, 0] - ghw[g]), np.maximum(py1, gt[g, 1] - ghh[g])
+                    brx, bry = np.minimum(px2, gt[g, 0] + ghw[g]), np.minimum(py2, gt[g, 1] + ghh[g])
+                    assert not ((tlx < brx) & (tly < bry)).any(), (trial, g, cr)
         dropped += int((~keep).sum())
         kept += int(keep.sum())
     assert dropped > 3000 and kept > 1000
